@@ -1,0 +1,70 @@
+"""ctypes binding of libape_b200.so (the C-ABI declared in include/ape_b200.h).
+
+The library is built in-tree by `make` / `__graft_entry__.build()`; there is no CPU
+fallback: if it is missing, importing this module raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libape_b200.so")
+
+APE_DTYPE_F32, APE_DTYPE_F16, APE_DTYPE_BF16 = 0, 1, 2
+_DTYPE_CODE = {torch.float32: APE_DTYPE_F32, torch.float16: APE_DTYPE_F16, torch.bfloat16: APE_DTYPE_BF16}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+        "ape_b200 has no CPU / PyTorch fallback."
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+
+lib.ape_abi_version.restype = _i
+lib.ape_abi_version.argtypes = []
+lib.ape_last_error.restype = ctypes.c_char_p
+lib.ape_last_error.argtypes = []
+lib.ape_launch_count.restype = ctypes.c_uint64
+lib.ape_launch_count.argtypes = []
+lib.ape_msda_fwd.restype = _i
+lib.ape_msda_fwd.argtypes = [_vp] * 6 + [_i] * 8 + [_vp]
+lib.ape_msda_fwd_variant.restype = _i
+lib.ape_msda_fwd_variant.argtypes = [_vp] * 6 + [_i] * 9 + [_vp]
+lib.ape_msda_fused_fwd.restype = _i
+lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
+
+# every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
+EXPORTS = (
+    "ape_abi_version",
+    "ape_last_error",
+    "ape_launch_count",
+    "ape_msda_fwd",
+    "ape_msda_fwd_variant",
+    "ape_msda_fused_fwd",
+)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dt]
+    except KeyError:
+        raise RuntimeError(f"ape_b200: unsupported dtype {dt} (float32 / float16 / bfloat16 only)") from None
+
+
+def check(status: int, what: str) -> None:
+    """Convert a non-zero C-ABI status into RuntimeError (the reference only printf's launch
+    errors, ms_deform_im2col_cuda.cuh:948-952; we raise)."""
+    if status != 0:
+        msg = lib.ape_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def current_stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.ape_launch_count())

@@ -1,0 +1,513 @@
+// msda_fwd.cu — multi-scale deformable attention forward for sm_100a (B200).
+//
+// Replaces torch.ops.ape.ms_deform_attn_forward
+//   (ape/layers/csrc/MsDeformAttn/ms_deform_attn_cuda.cu:21-81, kernel
+//    ape/layers/csrc/MsDeformAttn/ms_deform_im2col_cuda.cuh:237-299)
+// and, in the fused entry point, the softmax + sampling-location arithmetic of
+//   ape/layers/multi_scale_deform_attn.py:283-311.
+//
+// Design (B200-first, not a translation of the reference's thread-per-scalar kernel):
+//   * a "row" is one (b, q, h) output vector of D channels.  One lane owns 16 bytes of a row
+//     (4 fp32 / 8 fp16|bf16 channels), so a row is LPR = D*sizeof(T)/16 lanes and every corner
+//     fetch is one 128-bit load per lane — a full 128 B line per fp32 row of D=32.
+//   * a CTA owns a tile of QT queries x HT heads.  Phase 1: all threads cooperatively read the
+//     tile's sampling locations / attention weights with coalesced streaming loads and turn each
+//     sample into 4 corner indices (int32, in 16-byte units, -1 = outside) and 4 fp32 weights
+//     (bilinear x attention) staged in shared memory.  Phase 2: every lane walks the L*P samples
+//     of its row, reads index/weight quads with two broadcast LDS.128, issues U*4 independent
+//     LDG.128 gathers before consuming them, and accumulates in fp32 registers.  No shuffles
+//     are needed because a lane owns its channels outright.
+//   * HT=1 makes a CTA's rows 32..64 consecutive queries of ONE head, so neighbouring queries
+//     (pixels, in the encoder) re-use each other's texels out of L1; HT=H keeps all heads of a few
+//     queries together (better when queries are spatially unrelated, e.g. the decoder).
+//   * spatial_shapes / level_start_index stay int64 device tensors at the boundary (as in the
+//     reference op) and are converted once per CTA into int32 shared memory.
+//   * the output is written exactly once with 128-bit stores; no pre-zeroing
+//     (the reference does at::zeros + overwrite, ms_deform_attn_cuda.cu:55).
+#include "common.cuh"
+
+namespace ape {
+namespace {
+
+constexpr int kMaxLevels = 16;
+
+struct MsdaParams {
+  const void *value;
+  const int64_t *shapes;
+  const int64_t *starts;
+  const void *loc;    // plain: sampling locations; fused: raw offsets
+  const void *attn;   // plain: attention weights;  fused: raw logits
+  const float *ref;   // fused only
+  void *out;
+  int64_t offs_row_stride;   // fused: elements between consecutive (b,q) rows of `loc`
+  int64_t logit_row_stride;  // fused: elements between consecutive (b,q) rows of `attn`
+  int B, S, H, L, Q, P;
+  int ht_log2;  // log2(heads per CTA)
+  int ref_dim;  // fused: 2 or 4
+};
+
+__host__ __device__ constexpr int threads_for(int lpr) { return lpr >= 4 ? 256 : 64 * lpr; }
+
+// One sampling point -> 4 corner indices + 4 weights.  Follows ms_deform_im2col_cuda.cuh:279-291
+// (in-range test) and :36-80 (corner validity, weights).  `x`,`y` are normalised locations.
+__device__ __forceinline__ void make_sample(float x, float y, float a, int Hl, int Wl, int start,
+                                            int h, int H, int lpr, int4 &off, float4 &w) {
+  const float h_im = y * (float)Hl - 0.5f;
+  const float w_im = x * (float)Wl - 0.5f;
+  off = make_int4(-1, -1, -1, -1);
+  w = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl) {
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    const int h_low = (int)hf, w_low = (int)wf;
+    const int h_high = h_low + 1, w_high = w_low + 1;
+    const float lh = h_im - hf, lw = w_im - wf;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    const int row_lo = start + h_low * Wl, row_hi = row_lo + Wl;
+    const bool hl_ok = h_low >= 0, hh_ok = h_high <= Hl - 1;
+    const bool wl_ok = w_low >= 0, wh_ok = w_high <= Wl - 1;
+    if (hl_ok && wl_ok) { off.x = ((row_lo + w_low) * H + h) * lpr;  w.x = hh * hw * a; }
+    if (hl_ok && wh_ok) { off.y = ((row_lo + w_high) * H + h) * lpr; w.y = hh * lw * a; }
+    if (hh_ok && wl_ok) { off.z = ((row_hi + w_low) * H + h) * lpr;  w.z = lh * hw * a; }
+    if (hh_ok && wh_ok) { off.w = ((row_hi + w_high) * H + h) * lpr; w.w = lh * lw * a; }
+  }
+}
+
+// Phase 2: gather + accumulate + store for one lane.
+template <typename T, int LPR, int U>
+__device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_off,
+                                            const float4 *s_w, int lps, int b, int q0, int h0) {
+  using E = Elem<T>;
+  constexpr int VEC = E::kVec;
+  const int LP = p.L * p.P;
+  const int r = threadIdx.x / LPR, c = threadIdx.x % LPR;
+  const int ht_mask = (1 << p.ht_log2) - 1;
+  const int q = q0 + (r >> p.ht_log2), h = h0 + (r & ht_mask);
+  if (q >= p.Q) return;
+
+  const uint4 *vb = reinterpret_cast<const uint4 *>(p.value) + (size_t)b * p.S * p.H * LPR + c;
+  const int4 *ro = s_off + r * lps;
+  const float4 *rw = s_w + r * lps;
+
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  for (int s0 = 0; s0 < LP; s0 += U) {
+    int4 o[U];
+    float4 w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (s0 + u < LP) {
+        o[u] = ro[s0 + u];
+        w[u] = rw[s0 + u];
+      } else {
+        o[u] = make_int4(-1, -1, -1, -1);
+        w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint4 v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int oo[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[u][k] = make_uint4(0u, 0u, 0u, 0u);
+        if (oo[k] >= 0) v[u][k] = ldg_nc_v4(vb + oo[k]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[VEC];
+        E::unpack(v[u][k], f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(ww[k], f[i], acc[i]);
+      }
+    }
+  }
+  uint4 *ob = reinterpret_cast<uint4 *>(p.out) + (((size_t)b * p.Q + q) * p.H + h) * LPR + c;
+  stg_stream_v4(ob, E::pack(acc));
+}
+
+// grid = (q_tiles * head_tiles, B); dynamic smem = R*lps*(16+16) bytes.
+template <typename T, int LPR, int U>
+__global__ void __launch_bounds__(threads_for(LPR))
+msda_fwd_kernel(const MsdaParams p) {
+  using E = Elem<T>;
+  constexpr int NT = threads_for(LPR);
+  constexpr int R = NT / LPR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_lvl[kMaxLevels * 3];
+
+  const int LP = p.L * p.P;
+  const int lps = LP | 1;  // odd stride (in 16 B units): conflict-free broadcast reads
+  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
+  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
+
+  const int tid = threadIdx.x;
+  if (tid < p.L) {
+    s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
+    s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
+    s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+  }
+  __syncthreads();
+
+  const int HT = 1 << p.ht_log2;
+  const int QT = R >> p.ht_log2;
+  const int head_tiles = p.H >> p.ht_log2;
+  const int b = blockIdx.y;
+  const int q0 = (blockIdx.x / head_tiles) * QT;
+  const int h0 = (blockIdx.x % head_tiles) * HT;
+
+  const T *loc = reinterpret_cast<const T *>(p.loc);
+  const T *attn = reinterpret_cast<const T *>(p.attn);
+  for (int i = tid; i < R * LP; i += NT) {
+    const int r = i / LP, s = i - r * LP;
+    const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+    int4 off = make_int4(-1, -1, -1, -1);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < p.Q) {
+      const int l = s / p.P;
+      const size_t e = (((size_t)b * p.Q + q) * p.H + h) * LP + s;
+      const float2 xy = E::load2(loc + 2 * e);
+      const float a = E::load1(attn + e);
+      make_sample(xy.x, xy.y, a, s_lvl[l * 3], s_lvl[l * 3 + 1], s_lvl[l * 3 + 2], h, p.H, LPR,
+                  off, w);
+    }
+    s_off[r * lps + s] = off;
+    s_w[r * lps + s] = w;
+  }
+  __syncthreads();
+  gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0, h0);
+}
+
+// Fused variant: softmax(logits) over L*P, loc = f(ref, offsets), then the same gather.
+// TO = element type of the offsets/logits tensors (output of the sampling_offsets /
+// attention_weights linears).
+template <typename T, typename TO, int LPR, int U>
+__global__ void __launch_bounds__(threads_for(LPR))
+msda_fused_fwd_kernel(const MsdaParams p) {
+  using EO = Elem<TO>;
+  constexpr int NT = threads_for(LPR);
+  constexpr int R = NT / LPR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_lvl[kMaxLevels * 3];
+  __shared__ float s_max[R], s_rinv[R];
+
+  const int LP = p.L * p.P;
+  const int lps = LP | 1;
+  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
+  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
+  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * (sizeof(int4) + sizeof(float4)));
+
+  const int tid = threadIdx.x;
+  if (tid < p.L) {
+    s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
+    s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
+    s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+  }
+  const int HT = 1 << p.ht_log2;
+  const int QT = R >> p.ht_log2;
+  const int head_tiles = p.H >> p.ht_log2;
+  const int b = blockIdx.y;
+  const int q0 = (blockIdx.x / head_tiles) * QT;
+  const int h0 = (blockIdx.x % head_tiles) * HT;
+
+  const TO *offs = reinterpret_cast<const TO *>(p.loc);
+  const TO *logits = reinterpret_cast<const TO *>(p.attn);
+
+  // stage logits (coalesced), then one thread per row reduces max / sum(exp)
+  for (int i = tid; i < R * LP; i += NT) {
+    const int r = i / LP, s = i - r * LP;
+    const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+    float v = 0.f;
+    if (q < p.Q) v = EO::load1(logits + ((size_t)b * p.Q + q) * p.logit_row_stride + (size_t)h * LP + s);
+    s_logit[r * lps + s] = v;
+  }
+  __syncthreads();
+  if (tid < R) {
+    const float *row = s_logit + tid * lps;
+    float m = row[0];
+    for (int s = 1; s < LP; ++s) m = fmaxf(m, row[s]);
+    float sum = 0.f;
+    for (int s = 0; s < LP; ++s) sum += expf(row[s] - m);
+    s_max[tid] = m;
+    s_rinv[tid] = 1.f / sum;
+  }
+  __syncthreads();
+
+  for (int i = tid; i < R * LP; i += NT) {
+    const int r = i / LP, s = i - r * LP;
+    const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+    int4 off = make_int4(-1, -1, -1, -1);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < p.Q) {
+      const int l = s / p.P;
+      const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1];
+      const size_t bq = (size_t)b * p.Q + q;
+      const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
+      const float a = expf(s_logit[r * lps + s] - s_max[r]) * s_rinv[r];
+      const float *rp = p.ref + (bq * p.L + l) * p.ref_dim;
+      float x, y;
+      if (p.ref_dim == 2) {
+        // multi_scale_deform_attn.py:298-303: ref + off / (W_l, H_l)
+        x = rp[0] + o.x / (float)Wl;
+        y = rp[1] + o.y / (float)Hl;
+      } else {
+        // multi_scale_deform_attn.py:304-311: ref_xy + off / P * ref_wh * 0.5
+        x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
+        y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
+      }
+      make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR, off, w);
+    }
+    s_off[r * lps + s] = off;
+    s_w[r * lps + s] = w;
+  }
+  __syncthreads();
+  gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0, h0);
+}
+
+// Scalar fallback for shapes the vector path does not cover (D*sizeof(T) not a power-of-two
+// multiple of 16 B, L > 16, or tiles that do not fit shared memory).  One thread per output
+// scalar, fp32 accumulation.  Correctness path only.
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fwd_scalar_kernel(const MsdaParams p, int D, long long n) {
+  using E = Elem<T>;
+  const T *value = reinterpret_cast<const T *>(p.value);
+  const T *loc = reinterpret_cast<const T *>(p.loc);
+  const T *attn = reinterpret_cast<const T *>(p.attn);
+  T *out = reinterpret_cast<T *>(p.out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % D);
+    const long long row = idx / D;  // (b*Q+q)*H+h
+    const int h = (int)(row % p.H);
+    const int b = (int)(row / ((long long)p.H * p.Q));
+    const T *vb = value + (size_t)b * p.S * p.H * D;
+    float acc = 0.f;
+    const int LP = p.L * p.P;
+    for (int l = 0; l < p.L; ++l) {
+      const int Hl = (int)p.shapes[2 * l], Wl = (int)p.shapes[2 * l + 1], st = (int)p.starts[l];
+      for (int pt = 0; pt < p.P; ++pt) {
+        const size_t e = (size_t)row * LP + l * p.P + pt;
+        const float x = E::to_f(loc[2 * e]), y = E::to_f(loc[2 * e + 1]), a = E::to_f(attn[e]);
+        int4 off;
+        float4 w;
+        make_sample(x, y, a, Hl, Wl, st, h, p.H, 1, off, w);  // lpr=1 -> index of (s,h) row
+        if (off.x >= 0) acc = fmaf(w.x, E::to_f(vb[(size_t)off.x * D + c]), acc);
+        if (off.y >= 0) acc = fmaf(w.y, E::to_f(vb[(size_t)off.y * D + c]), acc);
+        if (off.z >= 0) acc = fmaf(w.z, E::to_f(vb[(size_t)off.z * D + c]), acc);
+        if (off.w >= 0) acc = fmaf(w.w, E::to_f(vb[(size_t)off.w * D + c]), acc);
+      }
+    }
+    out[idx] = E::from_f(acc);
+  }
+}
+
+// ---- host dispatch ---------------------------------------------------------------------------
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return APE_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+  return APE_OK;
+}
+
+template <typename T, int LPR, int U>
+int launch_plain(const MsdaParams &p, cudaStream_t st) {
+  constexpr int NT = threads_for(LPR), R = NT / LPR;
+  const int lps = (p.L * p.P) | 1;
+  const size_t smem = (size_t)R * lps * 32;
+  auto k = msda_fwd_kernel<T, LPR, U>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int QT = R >> p.ht_log2;
+  dim3 grid((unsigned)(((p.Q + QT - 1) / QT) * (p.H >> p.ht_log2)), (unsigned)p.B);
+  k<<<grid, NT, smem, st>>>(p);
+  return check_launch("msda_fwd_kernel");
+}
+
+template <typename T, typename TO, int LPR, int U>
+int launch_fused(const MsdaParams &p, cudaStream_t st) {
+  constexpr int NT = threads_for(LPR), R = NT / LPR;
+  const int lps = (p.L * p.P) | 1;
+  const size_t smem = (size_t)R * lps * 36;
+  auto k = msda_fused_fwd_kernel<T, TO, LPR, U>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int QT = R >> p.ht_log2;
+  dim3 grid((unsigned)(((p.Q + QT - 1) / QT) * (p.H >> p.ht_log2)), (unsigned)p.B);
+  k<<<grid, NT, smem, st>>>(p);
+  return check_launch("msda_fused_fwd_kernel");
+}
+
+template <typename T, int U>
+int dispatch_lpr_plain(int lpr, const MsdaParams &p, cudaStream_t st) {
+  switch (lpr) {
+    case 1: return launch_plain<T, 1, U>(p, st);
+    case 2: return launch_plain<T, 2, U>(p, st);
+    case 4: return launch_plain<T, 4, U>(p, st);
+    case 8: return launch_plain<T, 8, U>(p, st);
+    case 16: return launch_plain<T, 16, U>(p, st);
+    case 32: return launch_plain<T, 32, U>(p, st);
+  }
+  return fail(APE_ERR_UNSUPPORTED, "msda: lanes-per-row %d", lpr);
+}
+
+template <typename T, typename TO>
+int dispatch_lpr_fused(int lpr, const MsdaParams &p, cudaStream_t st) {
+  switch (lpr) {
+    case 2: return launch_fused<T, TO, 2, 4>(p, st);
+    case 4: return launch_fused<T, TO, 4, 4>(p, st);
+    case 8: return launch_fused<T, TO, 8, 4>(p, st);
+    case 16: return launch_fused<T, TO, 16, 4>(p, st);
+  }
+  return fail(APE_ERR_UNSUPPORTED, "msda_fused: lanes-per-row %d (head dim * elem size must be 32..256 B)", lpr);
+}
+
+template <typename T>
+int launch_scalar(const MsdaParams &p, int D, cudaStream_t st) {
+  const long long n = (long long)p.B * p.Q * p.H * D;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (blocks < 1) blocks = 1;
+  msda_fwd_scalar_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(p, D, n);
+  return check_launch("msda_fwd_scalar_kernel");
+}
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+int validate(const void *value, const int64_t *shapes, const int64_t *starts, const void *loc,
+             const void *attn, void *out, int B, int S, int H, int D, int L, int Q, int P, int dtype) {
+  if (dtype != APE_DTYPE_F32 && dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16)
+    return fail(APE_ERR_INVALID_ARG, "msda: unknown dtype %d", dtype);
+  if (B < 0 || S < 0 || Q < 0 || H <= 0 || D <= 0 || L <= 0 || P <= 0)
+    return fail(APE_ERR_INVALID_ARG, "msda: bad sizes B=%d S=%d H=%d D=%d L=%d Q=%d P=%d", B, S, H, D, L, Q, P);
+  if ((long long)S * H * D >= (1LL << 31))
+    return fail(APE_ERR_UNSUPPORTED, "msda: S*H*D=%lld exceeds int32 indexing", (long long)S * H * D);
+  if (B > 65535) return fail(APE_ERR_UNSUPPORTED, "msda: B=%d > 65535", B);
+  if (B == 0 || Q == 0) return APE_OK;
+  if (!value || !shapes || !starts || !loc || !attn || !out)
+    return fail(APE_ERR_NULL_PTR, "msda: null pointer argument");
+  return APE_OK;
+}
+
+// default tile mapping: one head per CTA when there are enough queries for neighbouring
+// queries to share texels (encoder: queries are pixels); all heads together otherwise.
+int default_ht(int H, int Q, int R) {
+  if (!is_pow2(H)) return 1;
+  if (Q >= 4 * R) return 1;
+  int ht = H;
+  while (ht > R) ht >>= 1;
+  return ht;
+}
+
+}  // namespace
+}  // namespace ape
+
+using namespace ape;
+
+extern "C" int ape_msda_fwd_variant(const void *value, const int64_t *shapes, const int64_t *starts,
+                                    const void *loc, const void *attn, void *out, int B, int S, int H,
+                                    int D, int L, int Q, int P, int dtype, int variant, void *stream) {
+  if (int rc = validate(value, shapes, starts, loc, attn, out, B, S, H, D, L, Q, P, dtype)) return rc;
+  if (B == 0 || Q == 0) return APE_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MsdaParams p{};
+  p.value = value; p.shapes = shapes; p.starts = starts; p.loc = loc; p.attn = attn; p.out = out;
+  p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P;
+
+  const int esize = dtype_size(dtype);
+  const int row_bytes = D * esize;
+  const int lpr = row_bytes / 16;
+  const bool vec_ok = (row_bytes % 16 == 0) && is_pow2(lpr) && lpr <= 32 && L <= kMaxLevels;
+  bool scalar = !vec_ok || (variant >= 0 && (variant & 0x1000));
+  int ht = 0, unroll = 4;
+  if (!scalar) {
+    const int R = threads_for(lpr) / lpr;
+    const size_t smem = (size_t)R * ((L * P) | 1) * 32;
+    if (smem > 200 * 1024) scalar = true;
+    ht = default_ht(H, Q, R);
+    if (variant >= 0) {
+      const int vh = variant & 0xff, vu = (variant >> 8) & 0xf;
+      if (vh) {
+        if (!is_pow2(vh) || H % vh != 0 || vh > R)
+          return fail(APE_ERR_INVALID_ARG, "msda: heads_per_cta=%d invalid for H=%d R=%d", vh, H, R);
+        ht = vh;
+      }
+      if (vu) {
+        if (vu != 1 && vu != 2 && vu != 4) return fail(APE_ERR_INVALID_ARG, "msda: unroll=%d", vu);
+        unroll = vu;
+      }
+    }
+  }
+  if (scalar) {
+    switch (dtype) {
+      case APE_DTYPE_F32: return launch_scalar<float>(p, D, st);
+      case APE_DTYPE_F16: return launch_scalar<__half>(p, D, st);
+      default: return launch_scalar<__nv_bfloat16>(p, D, st);
+    }
+  }
+  p.ht_log2 = ilog2(ht);
+#define APE_MSDA_DISPATCH(T)                                            \
+  switch (unroll) {                                                     \
+    case 1: return dispatch_lpr_plain<T, 1>(lpr, p, st);                \
+    case 2: return dispatch_lpr_plain<T, 2>(lpr, p, st);                \
+    default: return dispatch_lpr_plain<T, 4>(lpr, p, st);               \
+  }
+  switch (dtype) {
+    case APE_DTYPE_F32: APE_MSDA_DISPATCH(float)
+    case APE_DTYPE_F16: APE_MSDA_DISPATCH(__half)
+    default: APE_MSDA_DISPATCH(__nv_bfloat16)
+  }
+#undef APE_MSDA_DISPATCH
+}
+
+extern "C" int ape_msda_fwd(const void *value, const int64_t *shapes, const int64_t *starts,
+                            const void *loc, const void *attn, void *out, int B, int S, int H, int D,
+                            int L, int Q, int P, int dtype, void *stream) {
+  return ape_msda_fwd_variant(value, shapes, starts, loc, attn, out, B, S, H, D, L, Q, P, dtype, -1, stream);
+}
+
+extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, const int64_t *starts,
+                                  const void *offsets, int64_t offs_row_stride, const void *logits,
+                                  int64_t logit_row_stride, const float *ref, int ref_dim, void *out,
+                                  int B, int S, int H, int D, int L, int Q, int P, int dtype,
+                                  int offs_dtype, void *stream) {
+  if (int rc = validate(value, shapes, starts, offsets, logits, out, B, S, H, D, L, Q, P, dtype)) return rc;
+  if (offs_dtype != APE_DTYPE_F32 && offs_dtype != APE_DTYPE_F16 && offs_dtype != APE_DTYPE_BF16)
+    return fail(APE_ERR_INVALID_ARG, "msda_fused: unknown offs_dtype %d", offs_dtype);
+  if (ref_dim != 2 && ref_dim != 4)
+    return fail(APE_ERR_INVALID_ARG, "msda_fused: last dim of reference_points must be 2 or 4, got %d", ref_dim);
+  if (offs_row_stride < (int64_t)H * L * P * 2 || logit_row_stride < (int64_t)H * L * P)
+    return fail(APE_ERR_INVALID_ARG, "msda_fused: row strides smaller than a row");
+  if (B == 0 || Q == 0) return APE_OK;
+  if (!ref) return fail(APE_ERR_NULL_PTR, "msda_fused: null reference_points");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MsdaParams p{};
+  p.value = value; p.shapes = shapes; p.starts = starts; p.loc = offsets; p.attn = logits; p.ref = ref;
+  p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
+  p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
+  const int row_bytes = D * dtype_size(dtype);
+  const int lpr = row_bytes / 16;
+  if (row_bytes % 16 != 0 || !is_pow2(lpr) || L > kMaxLevels)
+    return fail(APE_ERR_UNSUPPORTED, "msda_fused: D=%d dtype=%d L=%d not supported", D, dtype, L);
+  const int R = threads_for(lpr) / lpr;
+  if ((size_t)R * ((L * P) | 1) * 36 > 200 * 1024)
+    return fail(APE_ERR_UNSUPPORTED, "msda_fused: L*P=%d too large for shared memory", L * P);
+  p.ht_log2 = ilog2(default_ht(H, Q, R));
+#define APE_FUSED_DISPATCH(T)                                                           \
+  switch (offs_dtype) {                                                                 \
+    case APE_DTYPE_F32: return dispatch_lpr_fused<T, float>(lpr, p, st);                \
+    case APE_DTYPE_F16: return dispatch_lpr_fused<T, __half>(lpr, p, st);               \
+    default: return dispatch_lpr_fused<T, __nv_bfloat16>(lpr, p, st);                   \
+  }
+  switch (dtype) {
+    case APE_DTYPE_F32: APE_FUSED_DISPATCH(float)
+    case APE_DTYPE_F16: APE_FUSED_DISPATCH(__half)
+    default: APE_FUSED_DISPATCH(__nv_bfloat16)
+  }
+#undef APE_FUSED_DISPATCH
+}

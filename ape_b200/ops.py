@@ -1,0 +1,135 @@
+"""Operator surface of the reference's native library, backed by libape_b200.so.
+
+Registers `torch.ops.ape.ms_deform_attn_forward` / `ms_deform_attn_backward` with the
+reference's schemas (ape/layers/csrc/vision.cpp:76-79, ms_deform_attn.h:21-28,42-50) so
+`MultiScaleDeformableAttnFunction` (ape/layers/multi_scale_deform_attn.py:32-81) works unchanged.
+CUDA tensors only: like the reference (`AT_ERROR("Not implemented on the CPU")`,
+ms_deform_attn.h:39) there is no CPU implementation."""
+import torch
+
+from . import _lib
+
+_NS = "ape"
+_FWD_SCHEMA = (
+    "ms_deform_attn_forward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+    "Tensor sampling_loc, Tensor attn_weight, int im2col_step) -> Tensor"
+)
+_BWD_SCHEMA = (
+    "ms_deform_attn_backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
+    "Tensor sampling_loc, Tensor attn_weight, Tensor grad_output, int im2col_step) -> Tensor[]"
+)
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    # same asserts as ms_deform_attn_cuda.cu:29-39
+    for name, t in (
+        ("value", value),
+        ("spatial_shapes", spatial_shapes),
+        ("level_start_index", level_start_index),
+        ("sampling_loc", sampling_loc),
+        ("attn_weight", attn_weight),
+    ):
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+    _require(value.dim() == 4, "value must be [B,S,H,D]")
+    _require(sampling_loc.dim() == 6 and sampling_loc.size(-1) == 2, "sampling_loc must be [B,Q,H,L,P,2]")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes / level_start_index must be int64")
+    _require(sampling_loc.dtype == value.dtype and attn_weight.dtype == value.dtype,
+             "sampling_loc / attn_weight must have value's dtype")
+    B, S, H, D = value.shape
+    _, Q, H2, L, P, _ = sampling_loc.shape
+    _require(H2 == H and sampling_loc.size(0) == B, "sampling_loc shape does not match value")
+    _require(tuple(attn_weight.shape) == (B, Q, H, L, P), "attn_weight must be [B,Q,H,L,P]")
+    _require(spatial_shapes.shape == (L, 2) and level_start_index.shape == (L,), "bad level tensors")
+    return B, S, H, D, L, Q, P
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step=64, variant=-1):
+    """out[B,Q,H*D]; `im2col_step` is accepted for signature parity and ignored (it only
+    chunks the batch in the reference host code, ms_deform_attn_cuda.cu:51-62)."""
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")  # ms_deform_attn.h:39
+    B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib.ape_msda_fwd_variant(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+            B, S, H, D, L, Q, P, _lib.dtype_code(value.dtype), int(variant), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_msda_fwd")
+    return out
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets,
+                                 attention_logits, reference_points, num_points):
+    """Fused tail of MultiScaleDeformableAttention.forward (multi_scale_deform_attn.py:283-348).
+
+    value [B,S,H,D]; sampling_offsets [B,Q,>=H*L*P*2] and attention_logits [B,Q,>=H*L*P] are the
+    raw linear outputs (may be column slices of one wider GEMM output: only the last dim needs
+    unit stride); reference_points [B,Q,L,2|4] fp32."""
+    B, S, H, D = value.shape
+    L = spatial_shapes.shape[0]
+    Q = sampling_offsets.shape[1]
+    P = int(num_points)
+    _require(value.is_cuda and value.is_contiguous(), "value must be a contiguous CUDA tensor")
+    _require(sampling_offsets.dtype == attention_logits.dtype, "offsets/logits dtype mismatch")
+    _require(sampling_offsets.stride(-1) == 1 and attention_logits.stride(-1) == 1, "unit inner stride required")
+    _require(sampling_offsets.stride(0) == Q * sampling_offsets.stride(1), "offsets batch stride")
+    _require(attention_logits.stride(0) == Q * attention_logits.stride(1), "logits batch stride")
+    ref = reference_points
+    _require(ref.dtype == torch.float32 and ref.is_contiguous(), "reference_points must be contiguous fp32")
+    _require(ref.shape[:3] == (B, Q, L), "reference_points must be [B,Q,L,2|4]")
+    out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib.ape_msda_fused_fwd(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_offsets.data_ptr(), sampling_offsets.stride(1),
+            attention_logits.data_ptr(), attention_logits.stride(1),
+            ref.data_ptr(), ref.shape[-1], out.data_ptr(),
+            B, S, H, D, L, Q, P, _lib.dtype_code(value.dtype), _lib.dtype_code(sampling_offsets.dtype),
+            _lib.current_stream_ptr())
+    _lib.check(rc, "ape_msda_fused_fwd")
+    return out
+
+
+def _ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                             grad_output, im2col_step):
+    raise RuntimeError(
+        "ape_b200: ms_deform_attn_backward is not implemented (inference engine; SURVEY.md §8f row 4)")
+
+
+def _register():
+    try:
+        lib = torch.library.Library(_NS, "DEF")
+    except Exception:  # namespace already defined in this process (e.g. the reference's ape._C)
+        lib = torch.library.Library(_NS, "FRAGMENT")
+    defined = []
+    for schema in (_FWD_SCHEMA, _BWD_SCHEMA):
+        try:
+            lib.define(schema)
+            defined.append(schema.split("(")[0])
+        except RuntimeError:
+            pass  # already defined by someone else: leave theirs in place
+
+    def _fwd(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+        return ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
+
+    def _fwd_cpu(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+        raise RuntimeError("Not implemented on the CPU")
+
+    if "ms_deform_attn_forward" in defined:
+        lib.impl("ms_deform_attn_forward", _fwd, "CUDA")
+        lib.impl("ms_deform_attn_forward", _fwd_cpu, "CPU")
+    if "ms_deform_attn_backward" in defined:
+        lib.impl("ms_deform_attn_backward", _ms_deform_attn_backward, "CompositeExplicitAutograd")
+    return lib
+
+
+_LIBRARY = _register()

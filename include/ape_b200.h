@@ -1,0 +1,106 @@
+/*
+ * ape_b200.h — C-ABI of libape_b200.so, the sm_100a (B200) kernels behind APE's
+ * detection forward pass.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers and sizes, a
+ * `cudaStream_t` passed as `void*`, never allocates, never synchronises, and is
+ * safe to call under CUDA-graph capture.  Return value: 0 = ok, <0 = invalid
+ * argument (text in ape_last_error()), >0 = a cudaError_t from the launch.
+ *
+ * Reference interfaces replaced (paths relative to the APE repository):
+ *   ape_msda_fwd            <- torch.ops.ape.ms_deform_attn_forward
+ *                              ape/layers/csrc/vision.cpp:76-79 (registration)
+ *                              ape/layers/csrc/MsDeformAttn/ms_deform_attn.h:21-40 (dispatch)
+ *                              ape/layers/csrc/MsDeformAttn/ms_deform_attn_cuda.cu:21-81 (host)
+ *                              ape/layers/csrc/MsDeformAttn/ms_deform_im2col_cuda.cuh:237-299 (kernel)
+ *   ape_msda_fused_fwd      <- MultiScaleDeformableAttention.forward tail
+ *                              ape/layers/multi_scale_deform_attn.py:283-348
+ *                              (softmax + sampling-location arithmetic + gather in one launch)
+ * The Python side that binds these (ctypes) and registers the reference's
+ * operator names lives in ape_b200/_lib.py and ape_b200/ops.py; the binding a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef APE_B200_H_
+#define APE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APE_ABI_VERSION 1
+
+/* element types accepted by the kernels (value of the `dtype` argument) */
+#define APE_DTYPE_F32 0
+#define APE_DTYPE_F16 1
+#define APE_DTYPE_BF16 2
+
+/* status codes (<0); positive return values are cudaError_t */
+#define APE_OK 0
+#define APE_ERR_INVALID_ARG (-1)
+#define APE_ERR_UNSUPPORTED (-2)
+#define APE_ERR_NULL_PTR (-3)
+
+int ape_abi_version(void);
+
+/* Text of the last non-zero status returned on the calling thread ("" if none). */
+const char *ape_last_error(void);
+
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t ape_launch_count(void);
+
+/*
+ * Multi-scale deformable attention, forward.
+ *
+ *   out[b,q,h,:] = sum_{l<L} sum_{p<P} attn[b,q,h,l,p] *
+ *                  bilinear_zero_pad(value_l[b,:,h,:], loc[b,q,h,l,p] * (W_l,H_l) - 0.5)
+ *
+ * value   [B,S,H,D]      contiguous, dtype
+ * spatial_shapes [L,2]   int64 (H_l, W_l), DEVICE memory (as in the reference op)
+ * level_start    [L]     int64, DEVICE memory
+ * loc     [B,Q,H,L,P,2]  contiguous, dtype, (x,y) normalised to [0,1]
+ * attn    [B,Q,H,L,P]    contiguous, dtype
+ * out     [B,Q,H*D]      contiguous, dtype; fully overwritten (no pre-zeroing needed)
+ *
+ * Accumulation is always fp32 (the reference accumulates in `dtype`,
+ * ms_deform_im2col_cuda.cuh:270).  Sample kept iff h_im>-1 && w_im>-1 &&
+ * h_im<H_l && w_im<W_l (…cuh:285-291), per-corner validity as …cuh:56-78.
+ */
+int ape_msda_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                 const void *loc, const void *attn, void *out, int B, int S, int H, int D, int L,
+                 int Q, int P, int dtype, void *stream);
+
+/*
+ * Same contract as ape_msda_fwd but selects a kernel variant explicitly
+ * (used by bench.py / tests to sweep mappings; `variant` < 0 = default).
+ *   variant = heads_per_cta (1,2,4,8) | unroll<<8 ; 0x1000 = scalar fallback kernel
+ */
+int ape_msda_fwd_variant(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                         const void *loc, const void *attn, void *out, int B, int S, int H, int D,
+                         int L, int Q, int P, int dtype, int variant, void *stream);
+
+/*
+ * Fused tail of MultiScaleDeformableAttention.forward (multi_scale_deform_attn.py:283-348):
+ * takes the raw outputs of the sampling_offsets / attention_weights linears and the
+ * reference points, performs softmax over L*P, the sampling-location arithmetic and
+ * the gather in one launch (sampling locations and attention weights never touch HBM).
+ *
+ * value     [B,S,H,D]        dtype
+ * offsets   [B,Q,H,L,P,2]    offs_dtype (raw linear output), row stride `offs_row_stride` elements per (b,q)
+ * logits    [B,Q,H,L*P]      offs_dtype (raw linear output), row stride `logit_row_stride` elements per (b,q)
+ * ref       [B,Q,L,ref_dim]  fp32, ref_dim 2 (points) or 4 (boxes cx,cy,w,h)
+ *   ref_dim 2: loc = ref + off / (W_l,H_l)                      (…py:298-303)
+ *   ref_dim 4: loc = ref_xy + off / P * ref_wh * 0.5            (…py:304-311)
+ * out       [B,Q,H*D]        dtype
+ */
+int ape_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                       const void *offsets, int64_t offs_row_stride, const void *logits,
+                       int64_t logit_row_stride, const float *ref, int ref_dim, void *out, int B,
+                       int S, int H, int D, int L, int Q, int P, int dtype, int offs_dtype,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APE_B200_H_ */
