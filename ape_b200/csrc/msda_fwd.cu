@@ -48,31 +48,43 @@ struct MsdaParams {
 
 __host__ __device__ constexpr int threads_for(int lpr) { return lpr >= 4 ? 256 : 64 * lpr; }
 
-// One sampling point -> 4 corner indices + 4 weights.  Follows ms_deform_im2col_cuda.cuh:279-291
+// floor(i / d) for 0 <= i < 2^20 given inv = 1/d (float): (i + 0.5) * inv never lands on the wrong
+// side of an integer for these ranges, and costs 3 instructions instead of a ~20-instruction idiv.
+__device__ __forceinline__ int fast_div(int i, float inv) { return __float2int_rz(((float)i + 0.5f) * inv); }
+
+// One sampling point -> 4 corner byte offsets + 4 weights.  Follows ms_deform_im2col_cuda.cuh:279-291
 // (in-range test) and :36-80 (corner validity, weights).  `x`,`y` are normalised locations.
+// Offsets are ALWAYS valid addresses (coordinates clamped into the level) and corners / samples the
+// reference skips get weight 0, so phase 2 needs no predicates.  The only observable difference:
+// a NaN/Inf texel next to the border is multiplied by 0 instead of being skipped (finite inputs:
+// identical results).
 __device__ __forceinline__ void make_sample(float x, float y, float a, int Hl, int Wl, int start,
-                                            int h, int H, int lpr, int4 &off, float4 &w) {
+                                            int h, int H, int row_bytes, int4 &off, float4 &w) {
   const float h_im = y * (float)Hl - 0.5f;
   const float w_im = x * (float)Wl - 0.5f;
-  off = make_int4(-1, -1, -1, -1);
-  w = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl) {
-    const float hf = floorf(h_im), wf = floorf(w_im);
-    const int h_low = (int)hf, w_low = (int)wf;
-    const int h_high = h_low + 1, w_high = w_low + 1;
-    const float lh = h_im - hf, lw = w_im - wf;
-    const float hh = 1.f - lh, hw = 1.f - lw;
-    const int row_lo = start + h_low * Wl, row_hi = row_lo + Wl;
-    const bool hl_ok = h_low >= 0, hh_ok = h_high <= Hl - 1;
-    const bool wl_ok = w_low >= 0, wh_ok = w_high <= Wl - 1;
-    if (hl_ok && wl_ok) { off.x = ((row_lo + w_low) * H + h) * lpr;  w.x = hh * hw * a; }
-    if (hl_ok && wh_ok) { off.y = ((row_lo + w_high) * H + h) * lpr; w.y = hh * lw * a; }
-    if (hh_ok && wl_ok) { off.z = ((row_hi + w_low) * H + h) * lpr;  w.z = lh * hw * a; }
-    if (hh_ok && wh_ok) { off.w = ((row_hi + w_high) * H + h) * lpr; w.w = lh * lw * a; }
-  }
+  const bool in_range = h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl;
+  const float hf = floorf(h_im), wf = floorf(w_im);
+  const float lh = h_im - hf, lw = w_im - wf;
+  const float hh = 1.f - lh, hw = 1.f - lw;
+  // saturating float->int conversions (NaN -> 0), then clamp into the level
+  const int h_low = __float2int_rd(h_im), w_low = __float2int_rd(w_im);
+  const bool hl_ok = in_range && h_low >= 0, hh_ok = in_range && h_low < Hl - 1;
+  const bool wl_ok = w_low >= 0, wh_ok = w_low < Wl - 1;
+  const int hc = min(max(h_low, -1), Hl - 1), wc = min(max(w_low, -1), Wl - 1);
+  const int y0 = max(hc, 0), y1 = min(hc + 1, Hl - 1);
+  const int x0 = max(wc, 0), x1 = min(wc + 1, Wl - 1);
+  const int r0 = start + y0 * Wl, r1 = start + y1 * Wl;
+  off.x = ((r0 + x0) * H + h) * row_bytes;
+  off.y = ((r0 + x1) * H + h) * row_bytes;
+  off.z = ((r1 + x0) * H + h) * row_bytes;
+  off.w = ((r1 + x1) * H + h) * row_bytes;
+  w.x = (hl_ok && wl_ok) ? hh * hw * a : 0.f;
+  w.y = (hl_ok && wh_ok) ? hh * lw * a : 0.f;
+  w.z = (hh_ok && wl_ok) ? lh * hw * a : 0.f;
+  w.w = (hh_ok && wh_ok) ? lh * lw * a : 0.f;
 }
 
-// Phase 2: gather + accumulate + store for one lane.
+// Phase 2: gather + accumulate + store for one lane.  The host guarantees LP % U == 0.
 template <typename T, int LPR, int U>
 __device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_off,
                                             const float4 *s_w, int lps, int b, int q0, int h0) {
@@ -84,7 +96,7 @@ __device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_o
   const int q = q0 + (r >> p.ht_log2), h = h0 + (r & ht_mask);
   if (q >= p.Q) return;
 
-  const uint4 *vb = reinterpret_cast<const uint4 *>(p.value) + (size_t)b * p.S * p.H * LPR + c;
+  const char *vb = reinterpret_cast<const char *>(p.value) + ((size_t)b * p.S * p.H * LPR + c) * 16;
   const int4 *ro = s_off + r * lps;
   const float4 *rw = s_w + r * lps;
 
@@ -92,28 +104,22 @@ __device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_o
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
+#pragma unroll 1
   for (int s0 = 0; s0 < LP; s0 += U) {
     int4 o[U];
     float4 w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (s0 + u < LP) {
-        o[u] = ro[s0 + u];
-        w[u] = rw[s0 + u];
-      } else {
-        o[u] = make_int4(-1, -1, -1, -1);
-        w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      o[u] = ro[s0 + u];
+      w[u] = rw[s0 + u];
     }
     uint4 v[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int oo[4] = {o[u].x, o[u].y, o[u].z, o[u].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[u][k] = make_uint4(0u, 0u, 0u, 0u);
-        if (oo[k] >= 0) v[u][k] = ldg_nc_v4(vb + oo[k]);
-      }
+      v[u][0] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].x));
+      v[u][1] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].y));
+      v[u][2] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].z));
+      v[u][3] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].w));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -163,17 +169,18 @@ msda_fwd_kernel(const MsdaParams p) {
 
   const T *loc = reinterpret_cast<const T *>(p.loc);
   const T *attn = reinterpret_cast<const T *>(p.attn);
+  const float inv_lp = 1.f / (float)LP, inv_p = 1.f / (float)p.P;
   for (int i = tid; i < R * LP; i += NT) {
-    const int r = i / LP, s = i - r * LP;
+    const int r = fast_div(i, inv_lp), s = i - r * LP;  // exact for i < 2^20
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    int4 off = make_int4(-1, -1, -1, -1);
+    int4 off = make_int4(0, 0, 0, 0);
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < p.Q) {
-      const int l = s / p.P;
+      const int l = fast_div(s, inv_p);
       const size_t e = (((size_t)b * p.Q + q) * p.H + h) * LP + s;
       const float2 xy = E::load2(loc + 2 * e);
       const float a = E::load1(attn + e);
-      make_sample(xy.x, xy.y, a, s_lvl[l * 3], s_lvl[l * 3 + 1], s_lvl[l * 3 + 2], h, p.H, LPR,
+      make_sample(xy.x, xy.y, a, s_lvl[l * 3], s_lvl[l * 3 + 1], s_lvl[l * 3 + 2], h, p.H, LPR * 16,
                   off, w);
     }
     s_off[r * lps + s] = off;
@@ -219,8 +226,9 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   const TO *logits = reinterpret_cast<const TO *>(p.attn);
 
   // stage logits (coalesced), then one thread per row reduces max / sum(exp)
+  const float inv_lp = 1.f / (float)LP, inv_p = 1.f / (float)p.P;
   for (int i = tid; i < R * LP; i += NT) {
-    const int r = i / LP, s = i - r * LP;
+    const int r = fast_div(i, inv_lp), s = i - r * LP;
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
     float v = 0.f;
     if (q < p.Q) v = EO::load1(logits + ((size_t)b * p.Q + q) * p.logit_row_stride + (size_t)h * LP + s);
@@ -239,12 +247,12 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   __syncthreads();
 
   for (int i = tid; i < R * LP; i += NT) {
-    const int r = i / LP, s = i - r * LP;
+    const int r = fast_div(i, inv_lp), s = i - r * LP;
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    int4 off = make_int4(-1, -1, -1, -1);
+    int4 off = make_int4(0, 0, 0, 0);
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < p.Q) {
-      const int l = s / p.P;
+      const int l = fast_div(s, inv_p);
       const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1];
       const size_t bq = (size_t)b * p.Q + q;
       const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
@@ -260,7 +268,7 @@ msda_fused_fwd_kernel(const MsdaParams p) {
         x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
         y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
       }
-      make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR, off, w);
+      make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR * 16, off, w);
     }
     s_off[r * lps + s] = off;
     s_w[r * lps + s] = w;
@@ -296,11 +304,11 @@ msda_fwd_scalar_kernel(const MsdaParams p, int D, long long n) {
         const float x = E::to_f(loc[2 * e]), y = E::to_f(loc[2 * e + 1]), a = E::to_f(attn[e]);
         int4 off;
         float4 w;
-        make_sample(x, y, a, Hl, Wl, st, h, p.H, 1, off, w);  // lpr=1 -> index of (s,h) row
-        if (off.x >= 0) acc = fmaf(w.x, E::to_f(vb[(size_t)off.x * D + c]), acc);
-        if (off.y >= 0) acc = fmaf(w.y, E::to_f(vb[(size_t)off.y * D + c]), acc);
-        if (off.z >= 0) acc = fmaf(w.z, E::to_f(vb[(size_t)off.z * D + c]), acc);
-        if (off.w >= 0) acc = fmaf(w.w, E::to_f(vb[(size_t)off.w * D + c]), acc);
+        make_sample(x, y, a, Hl, Wl, st, h, p.H, 1, off, w);  // row_bytes=1 -> index of the (s,h) row
+        if (w.x != 0.f) acc = fmaf(w.x, E::to_f(vb[(size_t)off.x * D + c]), acc);
+        if (w.y != 0.f) acc = fmaf(w.y, E::to_f(vb[(size_t)off.y * D + c]), acc);
+        if (w.z != 0.f) acc = fmaf(w.z, E::to_f(vb[(size_t)off.z * D + c]), acc);
+        if (w.w != 0.f) acc = fmaf(w.w, E::to_f(vb[(size_t)off.w * D + c]), acc);
       }
     }
     out[idx] = E::from_f(acc);
@@ -357,11 +365,21 @@ int dispatch_lpr_plain(int lpr, const MsdaParams &p, cudaStream_t st) {
 
 template <typename T, typename TO>
 int dispatch_lpr_fused(int lpr, const MsdaParams &p, cudaStream_t st) {
-  switch (lpr) {
-    case 2: return launch_fused<T, TO, 2, 4>(p, st);
-    case 4: return launch_fused<T, TO, 4, 4>(p, st);
-    case 8: return launch_fused<T, TO, 8, 4>(p, st);
-    case 16: return launch_fused<T, TO, 16, 4>(p, st);
+  const int LP = p.L * p.P;
+  if (LP % 2 != 0) {
+    switch (lpr) {
+      case 2: return launch_fused<T, TO, 2, 1>(p, st);
+      case 4: return launch_fused<T, TO, 4, 1>(p, st);
+      case 8: return launch_fused<T, TO, 8, 1>(p, st);
+      case 16: return launch_fused<T, TO, 16, 1>(p, st);
+    }
+  } else {
+    switch (lpr) {
+      case 2: return launch_fused<T, TO, 2, 2>(p, st);
+      case 4: return launch_fused<T, TO, 4, 2>(p, st);
+      case 8: return launch_fused<T, TO, 8, 2>(p, st);
+      case 16: return launch_fused<T, TO, 16, 2>(p, st);
+    }
   }
   return fail(APE_ERR_UNSUPPORTED, "msda_fused: lanes-per-row %d (head dim * elem size must be 32..256 B)", lpr);
 }
@@ -424,7 +442,8 @@ extern "C" int ape_msda_fwd_variant(const void *value, const int64_t *shapes, co
   const int lpr = row_bytes / 16;
   const bool vec_ok = (row_bytes % 16 == 0) && is_pow2(lpr) && lpr <= 32 && L <= kMaxLevels;
   bool scalar = !vec_ok || (variant >= 0 && (variant & 0x1000));
-  int ht = 0, unroll = 4;
+  const int LP = L * P;
+  int ht = 0, unroll = (LP % 4 == 0) ? 4 : (LP % 2 == 0) ? 2 : 1;
   if (!scalar) {
     const int R = threads_for(lpr) / lpr;
     const size_t smem = (size_t)R * ((L * P) | 1) * 32;
@@ -438,7 +457,8 @@ extern "C" int ape_msda_fwd_variant(const void *value, const int64_t *shapes, co
         ht = vh;
       }
       if (vu) {
-        if (vu != 1 && vu != 2 && vu != 4) return fail(APE_ERR_INVALID_ARG, "msda: unroll=%d", vu);
+        if ((vu != 1 && vu != 2 && vu != 4) || LP % vu != 0)
+          return fail(APE_ERR_INVALID_ARG, "msda: unroll=%d must be 1, 2 or 4 and divide L*P=%d", vu, LP);
         unroll = vu;
       }
     }

@@ -1,0 +1,374 @@
+"""Meta-architecture of the engine: `DeformableDETRSegmVL` (+ `SomeThing` wrapper).
+
+Mirror of ape/modeling/ape_deta/deformable_detr_segm_vl.py:33-164 (constructor), :166-726
+(forward, inference branch), :728-750 (mask features), :759-810 (inference), :846-872
+(pre/post-process), ape/modeling/ape_deta/deformable_detr.py:22-296 (base constructor),
+ape/modeling/ape_deta/fast_rcnn.py:97-201 (threshold + class-aware NMS + top-k) and
+ape/modeling/ape_deta/ape_deta.py:20-40 (`SomeThing`).  Same constructor keywords, same
+`forward(batched_inputs, do_postprocess)` contract (list of dicts in, list of dicts with
+"instances" out, results on CPU), same parameter names incl. the shared `class_embed` /
+`bbox_embed` aliases under `transformer.decoder`.
+
+Scope: inference of box detections for "name" and "phrase"/"text" prompts.
+Training, mask / semantic / panoptic post-processing and mask prompts raise NotImplementedError
+(next rows of §8f) — loudly, never silently."""
+import copy
+import math
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torchvision
+
+from ..layers import VisionLanguageAlign
+from ..layers.common import MLP, ConvNorm, box_cxcywh_to_xyxy, inverse_sigmoid
+from ..structures import Boxes, Instances
+
+
+class PositionEmbeddingSine(nn.Module):
+    """detrex PositionEmbeddingSine."""
+
+    def __init__(self, num_pos_feats=64, temperature=10000, scale=2 * math.pi, eps=1e-6, offset=0.0, normalize=False):
+        super().__init__()
+        self.num_pos_feats, self.temperature, self.normalize = num_pos_feats, temperature, normalize
+        self.scale, self.eps, self.offset = scale, eps, offset
+
+    def forward(self, mask):
+        not_mask = ~mask
+        y = not_mask.cumsum(1, dtype=torch.float32)
+        x = not_mask.cumsum(2, dtype=torch.float32)
+        if self.normalize:
+            y = (y + self.offset) / (y[:, -1:, :] + self.eps) * self.scale
+            x = (x + self.offset) / (x[:, :, -1:] + self.eps) * self.scale
+        dim_t = torch.arange(self.num_pos_feats, dtype=torch.float32, device=mask.device)
+        dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / self.num_pos_feats)
+        px = x[:, :, :, None] / dim_t
+        py = y[:, :, :, None] / dim_t
+        B, H, W = mask.shape
+        px = torch.stack((px[:, :, :, 0::2].sin(), px[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        py = torch.stack((py[:, :, :, 0::2].sin(), py[:, :, :, 1::2].cos()), dim=4).view(B, H, W, -1)
+        return torch.cat((py, px), dim=3).permute(0, 3, 1, 2)
+
+
+class ChannelMapper(nn.Module):
+    """detrex ChannelMapper: per level `convs.{i}.conv` (1x1, bias) + `convs.{i}.norm` (GroupNorm)."""
+
+    class _ConvNormAct(nn.Module):
+        def __init__(self, cin, cout, kernel_size, norm_layer):
+            super().__init__()
+            self.conv = nn.Conv2d(cin, cout, kernel_size, padding=(kernel_size - 1) // 2)
+            self.norm = norm_layer
+
+        def forward(self, x):
+            return self.norm(self.conv(x))
+
+    def __init__(self, input_shapes, in_features, out_channels, kernel_size=1, norm_layer=None, num_outs=None, **kw):
+        super().__init__()
+        if num_outs is not None and num_outs != len(in_features):
+            raise NotImplementedError("ape_b200.ChannelMapper: extra output levels are not used by APE")
+        self.in_features = in_features
+        self.convs = nn.ModuleList([self._ConvNormAct(input_shapes[f].channels, out_channels, kernel_size,
+                                                      copy.deepcopy(norm_layer)) for f in in_features])
+
+    def forward(self, inputs):
+        return tuple(self.convs[i](inputs[f]) for i, f in enumerate(self.in_features))
+
+
+def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, nms_thresh, topk_per_image):
+    """fast_rcnn.py:97-201 (hard-NMS branch).  Returns (boxes, scores, classes, query indices)."""
+    valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)
+    if not valid.all():
+        boxes, scores = boxes[valid], scores[valid]
+    scores = scores[:, :-1]
+    h, w = image_shape
+    boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
+                         boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1)
+    filter_mask = scores > score_thresh
+    filter_inds = filter_mask.nonzero()
+    boxes = boxes[filter_inds[:, 0]]
+    scores = scores[filter_mask]
+    keep = torchvision.ops.boxes.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
+    if topk_per_image >= 0:
+        keep = keep[:topk_per_image]
+    boxes, scores, filter_inds = boxes[keep], scores[keep], filter_inds[keep]
+    return boxes, scores, filter_inds[:, 1], filter_inds[:, 0]
+
+
+def detector_postprocess(result: Instances, out_h, out_w):
+    """detectron2 detector_postprocess for box fields: rescale, clip, drop empty boxes."""
+    sx, sy = out_w / result.image_size[1], out_h / result.image_size[0]
+    b = result.pred_boxes.tensor.clone()
+    b[:, 0::2] *= sx
+    b[:, 1::2] *= sy
+    b = torch.stack((b[:, 0].clamp(min=0, max=out_w), b[:, 1].clamp(min=0, max=out_h),
+                     b[:, 2].clamp(min=0, max=out_w), b[:, 3].clamp(min=0, max=out_h)), dim=-1)
+    keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    return Instances((out_h, out_w), pred_boxes=Boxes(b[keep]), scores=result.scores[keep],
+                     pred_classes=result.pred_classes[keep])
+
+
+class _Criterion(nn.Module):
+    """Inference-only stand-in for DeformableCriterion entries of the `criterion` list."""
+
+    loss_class_type = "focal_loss"
+
+    def __init__(self, num_classes):
+        super().__init__()
+        self.num_classes = num_classes
+
+
+class DeformableDETRSegmVL(nn.Module):
+    def __init__(
+        self,
+        # DeformableDETRSegmVL (deformable_detr_segm_vl.py:63-90)
+        instance_on: bool = True, semantic_on: bool = False, panoptic_on: bool = False, freeze_detr=False,
+        input_shapes=None, mask_in_features=None, mask_encode_level=0, stuff_dataset_learn_thing: bool = True,
+        stuff_prob_thing: float = -1.0, name_prompt_fusion_type: str = "none", name_prompt_fusion_text=None,
+        test_mask_on: bool = True, semantic_post_nms: bool = True, panoptic_post_nms: bool = True,
+        aux_mask: bool = False, panoptic_configs=None,
+        # DeformableDETR (deformable_detr.py:52-88)
+        backbone=None, position_embedding=None, neck=None, transformer=None, embed_dim=256, num_classes=80,
+        num_queries=900, criterion=None, pixel_mean=(123.675, 116.280, 103.530), pixel_std=(58.395, 57.120, 57.375),
+        aux_loss=True, with_box_refine=False, as_two_stage=False, select_box_nums_for_evaluation=100,
+        select_box_nums_for_evaluation_list=None, input_format="RGB", vis_period=0, output_dir=None,
+        dataset_names=(), dataset_metas=(), dataset_prompts=None, embed_dim_language=512,
+        text_feature_batch_repeat=True, text_feature_bank=False, text_feature_bank_reset=False,
+        text_feature_bank_random_size=False, text_feature_reduce_type="last",
+        text_feature_reduce_before_fusion=True, expression_cumulative_gt_class=True, test_nms_thresh=0.7,
+        test_score_thresh=0.0, last_class_embed_use_mlp=False, openset_classifier="VisionLanguageAlign",
+        vocabulary=None,
+    ):
+        super().__init__()
+        if not (with_box_refine and as_two_stage) or openset_classifier != "VisionLanguageAlign" or aux_mask \
+                or last_class_embed_use_mlp:
+            raise NotImplementedError("ape_b200: only the two-stage, box-refine, VisionLanguageAlign configuration")
+        self.backbone, self.position_embedding, self.neck, self.transformer = backbone, position_embedding, neck, transformer
+        self.num_queries, self.num_classes = num_queries, num_classes
+        self.embed_dim_language = embed_dim_language
+        nd = transformer.decoder.num_layers
+        cls = VisionLanguageAlign(embed_dim, embed_dim_language)
+        box = MLP(embed_dim, embed_dim, 4, 3)
+        nn.init.constant_(box.layers[-1].weight.data, 0)
+        nn.init.constant_(box.layers[-1].bias.data, 0)
+        self.class_embed = nn.ModuleList([copy.deepcopy(cls) for _ in range(nd + 1)])
+        self.bbox_embed = nn.ModuleList([copy.deepcopy(box) for _ in range(nd + 1)])
+        self.criterion = nn.ModuleList(criterion if criterion is not None else [_Criterion(num_classes)])
+        # shared with the decoder, exactly as deformable_detr.py:158-200 (aliases appear in state_dict)
+        transformer.decoder.bbox_embed = self.bbox_embed
+        transformer.decoder.class_embed = self.class_embed
+        bias_value = -math.log((1 - 0.01) / 0.01)
+        transformer.decoder.class_embed[-1] = nn.Linear(embed_dim, 1)
+        transformer.decoder.class_embed[-1].bias.data = torch.ones(1) * bias_value
+        if transformer.proposal_ambiguous:
+            transformer.decoder.bbox_embed_ambiguous = nn.ModuleList(
+                [copy.deepcopy(self.bbox_embed[-1]) for _ in range(transformer.proposal_ambiguous)])
+            transformer.decoder.class_embed_ambiguous = nn.ModuleList(
+                [copy.deepcopy(self.class_embed[-1]) for _ in range(transformer.proposal_ambiguous)])
+
+        self.aux_loss, self.with_box_refine, self.as_two_stage = aux_loss, with_box_refine, as_two_stage
+        self.select_box_nums_for_evaluation = select_box_nums_for_evaluation
+        self.select_box_nums_for_evaluation_list = select_box_nums_for_evaluation_list
+        self.test_topk_per_image = select_box_nums_for_evaluation
+        self.test_nms_thresh, self.test_score_thresh = test_nms_thresh, test_score_thresh
+        self.input_format = input_format
+        self.register_buffer("pixel_mean", torch.tensor(pixel_mean).view(-1, 1, 1), False)
+        self.register_buffer("pixel_std", torch.tensor(pixel_std).view(-1, 1, 1), False)
+        self.dataset_names = list(dataset_names)
+        self.dataset_prompts = dataset_prompts
+        # class-name vocabulary per dataset (the reference reads detectron2's MetadataCatalog,
+        # deformable_detr.py:232-262; the engine takes the lists directly)
+        self.vocabulary = vocabulary if vocabulary is not None else {}
+        self.dataset_name_to_idx = {k: i for i, k in enumerate(self.dataset_names)}
+        self.eval_dataset_id = -1
+        self.eval_dataset_entity = ""
+        self.text_feature_bank, self.text_feature_bank_reset = text_feature_bank, text_feature_bank_reset
+        self.text_feature_batch_repeat = text_feature_batch_repeat
+        self.text_feature_reduce_before_fusion = text_feature_reduce_before_fusion
+        if text_feature_bank:
+            bank = torch.zeros((len(self.criterion), max(c.num_classes for c in self.criterion), embed_dim_language))
+            self.register_buffer("features_phrase_bank", bank, False)
+
+        self.instance_on, self.semantic_on, self.panoptic_on = instance_on, semantic_on, panoptic_on
+        self.test_mask_on = test_mask_on
+        self.input_shapes, self.mask_in_features, self.mask_encode_level = input_shapes, mask_in_features, mask_encode_level
+        hidden = transformer.embed_dim
+        in_ch = input_shapes[mask_in_features[0]].channels
+        self.lateral_conv = ConvNorm(in_ch, hidden, 1, bias=False, norm=nn.GroupNorm(32, hidden))
+        self.output_conv = ConvNorm(hidden, hidden, 3, padding=1, bias=False, norm=nn.GroupNorm(32, hidden), activation=F.relu)
+        self.mask_conv = ConvNorm(hidden, hidden, 1, bias=False)
+        self.mask_embed = MLP(hidden, hidden, hidden, 3)
+        self.name_prompt_fusion_type = name_prompt_fusion_type
+        self.name_prompt_fusion_text = name_prompt_fusion_text
+        if name_prompt_fusion_type == "zero":
+            self.name_prompt_fusion_feature = nn.Parameter(torch.zeros(1, 1, embed_dim_language), requires_grad=False)
+        elif name_prompt_fusion_type == "learnable":
+            self.name_prompt_fusion_feature = nn.Parameter(torch.randn(1, 1, embed_dim_language))
+        else:
+            self.name_prompt_fusion_feature = None
+        self.model_language = None
+        self._text_cache = {}
+
+    # -- plumbing ----------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    def set_model_language(self, model_language):
+        # kept out of the module tree like the reference (ape_deta.py:31-33 deletes its own handle)
+        object.__setattr__(self, "model_language", model_language)
+
+    def set_eval_dataset(self, dataset_name):
+        """deformable_detr.py:524-549."""
+        for d in self.dataset_names:
+            if sum([dd in dataset_name for dd in d.split("+")]):
+                self.eval_dataset_id = self.dataset_name_to_idx[d]
+                break
+        else:
+            self.eval_dataset_id = -1
+
+    def preprocess_image(self, batched_inputs):
+        """:846-855 + ImageList.from_tensors with padding_constraints square_size (pads AFTER normalising)."""
+        sq = self.backbone.padding_constraints.get("square_size", 0)
+        imgs = [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in imgs]
+        H = max(s[0] for s in sizes) if sq <= 0 else sq
+        W = max(s[1] for s in sizes) if sq <= 0 else sq
+        batch = torch.zeros((len(imgs), 3, H, W), dtype=self.pixel_mean.dtype, device=self.device)
+        masks = torch.ones((len(imgs), H, W), dtype=self.pixel_mean.dtype, device=self.device)
+        for i, im in enumerate(imgs):
+            h, w = sizes[i]
+            batch[i, :, :h, :w] = (im.to(self.pixel_mean.dtype) - self.pixel_mean) / self.pixel_std
+            masks[i, :h, :w] = 0
+        return batch, masks, sizes
+
+    # -- text routing (:166-360) -------------------------------------------------------------------
+    def _text_features(self, batched_inputs):
+        dataset_id = self.eval_dataset_id
+        if dataset_id >= 0:
+            prompt = self.dataset_prompts[dataset_id]
+        elif "prompt" in batched_inputs[0]:
+            prompt = batched_inputs[0]["prompt"]
+        else:
+            prompt = "name"
+        if prompt == "expression":
+            raise NotImplementedError("ape_b200: expression prompts (SURVEY.md §8f)")
+        self.test_topk_per_image = self.select_box_nums_for_evaluation
+        if self.select_box_nums_for_evaluation_list is not None:
+            self.test_topk_per_image = self.select_box_nums_for_evaluation_list[dataset_id]
+        text_list = None
+        if prompt == "text":
+            texts = [x["text_prompt"] for x in batched_inputs]
+            text_list = [x.strip() for x in ",".join(texts).split(",")]
+            text_list = [x for x in text_list if len(x) > 0]
+            prompt = "phrase" if any(x.count(" ") >= 1 for x in text_list) else "name"
+        bs = len(batched_inputs)
+        if prompt == "name":
+            if text_list:
+                cache = False
+            elif dataset_id >= 0:
+                text_list, cache = list(self.vocabulary[self.dataset_names[dataset_id]]), True
+            else:
+                text_list = []
+                for d in self.dataset_names:
+                    text_list += list(self.vocabulary[d])
+                text_list, cache = text_list[:1203], True  # (:249-251)
+            key = tuple(text_list)
+            if cache and key in self._text_cache:
+                features_l = self._text_cache[key]
+            else:
+                features_l = self.model_language.forward_text(text_list, cache=cache)["last_hidden_state_eot"]
+                if cache:
+                    self._text_cache[key] = features_l
+            features_l = features_l.to(self.device).unsqueeze(0).repeat(bs, 1, 1)
+            if self.name_prompt_fusion_text is not None and self.name_prompt_fusion_text[dataset_id]:
+                fusion = features_l
+            elif self.name_prompt_fusion_feature is not None:
+                fusion = self.name_prompt_fusion_feature.repeat(bs, 1, 1)
+            else:
+                fusion = None
+            return prompt, features_l, fusion
+        # phrase (:292-337)
+        if not text_list:
+            raise NotImplementedError("ape_b200: phrase prompts need `text_prompt` at inference")
+        features_l = self.model_language.forward_text(text_list)["last_hidden_state_eot"].to(self.device)
+        if self.text_feature_bank and not self.text_feature_bank_reset and 0 <= dataset_id < len(self.dataset_names):
+            n = self.criterion[dataset_id].num_classes
+            features_l = torch.cat([features_l, self.features_phrase_bank[dataset_id]], dim=0)[: max(len(text_list), n)]
+            self.features_phrase_bank[dataset_id, :n] = features_l[:n]
+        elif self.text_feature_bank and self.text_feature_bank_reset:
+            n = self.criterion[dataset_id].num_classes
+            features_l = torch.cat([features_l.to(self.features_phrase_bank.dtype),
+                                    self.features_phrase_bank[dataset_id] * 0], dim=0)[: max(len(text_list), n)]
+        features_l = features_l.unsqueeze(0).repeat(bs, 1, 1)
+        fusion = features_l
+        if self.name_prompt_fusion_feature is not None:
+            fusion = fusion + 0.0 * self.name_prompt_fusion_feature
+        return prompt, features_l, fusion
+
+    # -- forward -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, batched_inputs: List[Dict], do_postprocess=True):
+        if self.training:
+            raise NotImplementedError("ape_b200 is an inference engine (SURVEY.md §8f row 4)")
+        if "mask_prompt" in batched_inputs[0]:
+            raise NotImplementedError("ape_b200: mask prompts")
+        prompt, features_l, fusion = self._text_features(batched_inputs)
+        images, img_masks, image_sizes = self.preprocess_image(batched_inputs)
+        features = self.backbone(images)
+        feats = self.neck({f: features[f] for f in self.neck.in_features})
+        masks = [F.interpolate(img_masks[None], size=f.shape[-2:]).to(torch.bool).squeeze(0) for f in feats]
+        pos = [self.position_embedding(m).to(images.dtype) for m in masks]
+        (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory,
+         fusion_out) = self.transformer(feats, masks, pos, None, fusion, None, None)
+        if prompt == "name":
+            features_l = 1.0 * features_l + 0.0 * fusion_out  # (:446)
+        else:
+            features_l = 0.0 * features_l + 1.0 * fusion_out  # (:448)
+        # only the last decoder level feeds inference (:514-523); levels 0..n-2 are aux outputs
+        lvl = inter_states.shape[0] - 1
+        reference = init_reference if lvl == 0 else inter_references[lvl - 1]
+        box_cls = self.class_embed[lvl](inter_states[lvl], features_l)
+        box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
+        self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
+                                 init_reference=init_reference, inter_references=inter_references,
+                                 features=features, neck=feats)
+        if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
+            raise NotImplementedError("ape_b200: mask / semantic / panoptic heads are the next §8 rows; construct "
+                                      "with test_mask_on=False, semantic_on=False, panoptic_on=False (boxes only)")
+        results = self.inference(box_cls, box_pred, image_sizes)
+        if not do_postprocess:
+            return results, None, None
+        out = []
+        for r, inp, size in zip(results, batched_inputs, image_sizes):
+            h, w = inp.get("height", size[0]), inp.get("width", size[1])
+            out.append({"instances": detector_postprocess(r, h, w).to("cpu")})
+        return out
+
+    def inference(self, box_cls, box_pred, image_sizes):
+        """:759-810 + fast_rcnn.py:40-95."""
+        results = []
+        zeros = torch.zeros((box_cls.size(1), 1), device=box_cls.device, dtype=box_cls.dtype)
+        for b, (h, w) in enumerate(image_sizes):
+            scores = torch.cat((box_cls[b].sigmoid(), zeros), dim=1)
+            scale = torch.tensor([w, h, w, h], dtype=box_pred.dtype, device=box_pred.device)
+            boxes = box_cxcywh_to_xyxy(box_pred[b]) * scale
+            bx, sc, cl, qi = fast_rcnn_inference_single_image(boxes.float(), scores.float(), (h, w), self.test_score_thresh,
+                                                              self.test_nms_thresh, self.test_topk_per_image)
+            results.append(Instances((h, w), pred_boxes=Boxes(bx), scores=sc, pred_classes=cl, query_index=qi))
+        return results
+
+
+class SomeThing(nn.Module):
+    """ape_deta.py:20-40."""
+
+    def __init__(self, model_vision, model_language, **kwargs):
+        super().__init__()
+        self.model_vision = model_vision
+        self.model_vision.set_model_language(model_language)
+
+    def forward(self, batched_inputs, do_postprocess=True):
+        return self.model_vision(batched_inputs, do_postprocess=do_postprocess)
+
+    def set_eval_dataset(self, dataset_name):
+        self.model_vision.set_eval_dataset(dataset_name)

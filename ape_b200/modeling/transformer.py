@@ -1,0 +1,328 @@
+"""Deformable VL transformer (encoder with VisionLanguageFusion, two-stage proposal selection,
+decoder with iterative box refinement).
+
+Mirror of ape/modeling/ape_deta/deformable_transformer_vl.py (`DeformableDetrTransformerEncoderVL`
+:20-121, `DeformableDetrTransformerDecoderVL` :124-255, `DeformableDetrTransformerVL` :258-699) and
+of the detrex containers it is built from (BaseTransformerLayer / TransformerLayerSequence / FFN /
+MultiheadAttention): same constructor arguments, same forward signatures,
+same parameter names (`layers.{i}.attentions.{j}`, `layers.{i}.ffns.0.layers.{0.0,1}`,
+`layers.{i}.norms.{k}`, `vl_layers.{i}.b_attn…`, `level_embeds`, `enc_output`, `pos_trans`, …)."""
+import copy
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torchvision
+
+from ..layers import MultiScaleDeformableAttention
+from ..layers.common import FFN, box_cxcywh_to_xyxy, inverse_sigmoid
+
+
+class _SelfAttention(nn.Module):
+    """detrex MultiheadAttention wrapper (parameters under `.attn`): q = k = x + pos, v = x."""
+
+    def __init__(self, embed_dim, num_heads):
+        super().__init__()
+        self.embed_dim, self.num_heads = embed_dim, num_heads
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=0.0, batch_first=True)
+
+    def forward(self, x, pos):
+        E, nh = self.embed_dim, self.num_heads
+        w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
+        qk = F.linear(x + pos, w[: 2 * E], b[: 2 * E])
+        v = F.linear(x, w[2 * E:], b[2 * E:])
+        B, N, _ = x.shape
+        q, k = qk[..., :E], qk[..., E:]
+        q, k, v = (t.reshape(B, N, nh, E // nh).transpose(1, 2) for t in (q, k, v))
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, E)
+        return x + self.attn.out_proj(o)
+
+
+class _EncoderLayer(nn.Module):
+    """BaseTransformerLayer(("self_attn","norm","ffn","norm")) with an MSDA self-attention."""
+
+    def __init__(self, embed_dim, num_heads, ffn_dim, num_levels):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.pre_norm = False
+        self.attentions = nn.ModuleList([MultiScaleDeformableAttention(
+            embed_dim=embed_dim, num_heads=num_heads, dropout=0.0, batch_first=True, num_levels=num_levels)])
+        self.ffns = nn.ModuleList([FFN(embed_dim, ffn_dim)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed_dim), nn.LayerNorm(embed_dim)])
+
+    def forward(self, query, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+        x = self.attentions[0](query, None, query, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
+                               reference_points=reference_points, spatial_shapes=spatial_shapes,
+                               level_start_index=level_start_index)
+        x = self.norms[0](x)
+        x = self.ffns[0](x)
+        return self.norms[1](x)
+
+
+class _DecoderLayer(nn.Module):
+    """BaseTransformerLayer(("self_attn","norm","cross_attn","norm","ffn","norm"))."""
+
+    def __init__(self, embed_dim, num_heads, ffn_dim, num_levels):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.pre_norm = False
+        self.attentions = nn.ModuleList([
+            _SelfAttention(embed_dim, num_heads),
+            MultiScaleDeformableAttention(embed_dim=embed_dim, num_heads=num_heads, dropout=0.0, batch_first=True,
+                                          num_levels=num_levels)])
+        self.ffns = nn.ModuleList([FFN(embed_dim, ffn_dim)])
+        self.norms = nn.ModuleList([nn.LayerNorm(embed_dim) for _ in range(3)])
+
+    def forward(self, query, value, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+        x = self.attentions[0](query, query_pos)
+        x = self.norms[0](x)
+        x = self.attentions[1](x, None, value, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
+                               reference_points=reference_points, spatial_shapes=spatial_shapes,
+                               level_start_index=level_start_index)
+        x = self.norms[1](x)
+        x = self.ffns[0](x)
+        return self.norms[2](x)
+
+
+class DeformableDetrTransformerEncoderVL(nn.Module):
+    def __init__(self, embed_dim=256, num_heads=8, feedforward_dim=1024, attn_dropout=0.1, ffn_dropout=0.1,
+                 num_layers=6, post_norm=False, num_feature_levels=4, vl_layer=None, use_act_checkpoint=False,
+                 pytorch_attn=False):
+        super().__init__()
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([_EncoderLayer(embed_dim, num_heads, feedforward_dim, num_feature_levels)
+                                     for _ in range(num_layers)])
+        self.embed_dim = embed_dim
+        self.pre_norm = False
+        self.post_norm_layer = nn.LayerNorm(embed_dim) if post_norm else None
+        self.vl_layers = nn.ModuleList([copy.deepcopy(vl_layer) for _ in range(num_layers)])
+
+    def forward(self, query, key, value, query_l, attention_mask_l, query_pos=None, key_pos=None, attn_masks=None,
+                query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        for vl_layer, layer in zip(self.vl_layers, self.layers):
+            if vl_layer is not None and query_l is not None:
+                query, query_l = vl_layer(query, query_l, attention_mask_v=query_key_padding_mask,
+                                          attention_mask_l=attention_mask_l)
+            query = layer(query, query_pos, query_key_padding_mask, kwargs["reference_points"],
+                          kwargs["spatial_shapes"], kwargs["level_start_index"])
+        if self.post_norm_layer is not None:
+            query = self.post_norm_layer(query)
+        return query, query_l
+
+
+class DeformableDetrTransformerDecoderVL(nn.Module):
+    def __init__(self, embed_dim=256, num_heads=8, feedforward_dim=1024, attn_dropout=0.1, ffn_dropout=0.1,
+                 num_layers=6, return_intermediate=True, num_feature_levels=4, use_act_checkpoint=False,
+                 look_forward_twice=False, pytorch_attn=False):
+        super().__init__()
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([_DecoderLayer(embed_dim, num_heads, feedforward_dim, num_feature_levels)
+                                     for _ in range(num_layers)])
+        self.return_intermediate = return_intermediate
+        self.bbox_embed = None
+        self.class_embed = None
+        self.look_forward_twice = look_forward_twice
+
+    def forward(self, query, key, value, query_pos=None, key_pos=None, attn_masks=None, query_key_padding_mask=None,
+                key_padding_mask=None, reference_points=None, valid_ratios=None, **kwargs):
+        output = query
+        intermediate, intermediate_ref = [], []
+        for i, layer in enumerate(self.layers):
+            if reference_points.shape[-1] == 4:
+                ref_in = reference_points[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+            else:
+                ref_in = reference_points[:, :, None] * valid_ratios[:, None]
+            output = layer(output, value, query_pos, key_padding_mask, ref_in, kwargs["spatial_shapes"],
+                           kwargs["level_start_index"])
+            if self.bbox_embed is not None:
+                tmp = self.bbox_embed[i](output)
+                if reference_points.shape[-1] == 4:
+                    new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()
+                else:
+                    new_ref = tmp
+                    new_ref[..., :2] = tmp[..., :2] + inverse_sigmoid(reference_points)
+                    new_ref = new_ref.sigmoid()
+                reference_points = new_ref.detach()
+            if self.return_intermediate:
+                intermediate.append(output)
+                intermediate_ref.append(new_ref if self.look_forward_twice else reference_points)
+        if self.return_intermediate:
+            return torch.stack(intermediate), torch.stack(intermediate_ref)
+        return output, reference_points
+
+
+class DeformableDetrTransformerVL(nn.Module):
+    def __init__(self, encoder=None, decoder=None, num_feature_levels=4, as_two_stage=False,
+                 two_stage_num_proposals=300, assign_first_stage=False, pre_nms_topk=1000, nms_thresh_enc=0.9,
+                 proposal_ambiguous=0):
+        super().__init__()
+        if not (as_two_stage and assign_first_stage):
+            raise NotImplementedError("ape_b200: only the two-stage / assign_first_stage configuration APE uses")
+        self.encoder, self.decoder = encoder, decoder
+        self.num_feature_levels = num_feature_levels
+        self.as_two_stage = as_two_stage
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.assign_first_stage = assign_first_stage
+        self.pre_nms_topk = pre_nms_topk
+        self.nms_thresh_enc = nms_thresh_enc
+        self.proposal_ambiguous = proposal_ambiguous
+        self.embed_dim = encoder.embed_dim
+        E = self.embed_dim
+        self.level_embeds = nn.Parameter(torch.Tensor(num_feature_levels, E))
+        self.enc_output = nn.Linear(E, E)
+        self.enc_output_norm = nn.LayerNorm(E)
+        self.pos_trans = nn.Linear(E * 2, E * 2)
+        self.pos_trans_norm = nn.LayerNorm(E * 2)
+        self.pix_trans = nn.Linear(E, E)
+        self.pix_trans_norm = nn.LayerNorm(E)
+        self.init_weights()
+
+    def init_weights(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MultiScaleDeformableAttention):
+                m.init_weights()
+        nn.init.normal_(self.level_embeds)
+
+    # -- deformable_transformer_vl.py:321-369 ----------------------------------------------------
+    def gen_encoder_output_proposals(self, memory, memory_padding_mask, spatial_shapes, mask_prompt_flatten=None):
+        N, S, C = memory.shape
+        dev = memory.device
+        proposals, level_ids = [], []
+        cur = 0
+        for lvl, (H, W) in enumerate(spatial_shapes):
+            m = memory_padding_mask[:, cur:cur + H * W].view(N, H, W, 1)
+            valid_H = torch.sum(~m[:, :, 0, 0], 1)
+            valid_W = torch.sum(~m[:, 0, :, 0], 1)
+            gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
+                                    torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
+            grid = torch.cat([gx.unsqueeze(-1), gy.unsqueeze(-1)], -1)
+            scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N, 1, 1, 2)
+            grid = (grid.unsqueeze(0).expand(N, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+            proposals.append(torch.cat((grid, wh), -1).view(N, -1, 4))
+            cur += H * W
+            level_ids.append(grid.new_ones(H * W, dtype=torch.long) * lvl)
+        out = torch.cat(proposals, 1)
+        valid = ((out > 0.01) & (out < 0.99)).all(-1, keepdim=True)
+        out = torch.log(out / (1 - out))
+        out = out.masked_fill(memory_padding_mask.unsqueeze(-1), float("inf"))
+        out = out.masked_fill(~valid, float("inf"))
+        mem = memory.masked_fill(memory_padding_mask.unsqueeze(-1), float(0)).masked_fill(~valid, float(0))
+        if mask_prompt_flatten is not None:
+            out = out.masked_fill(~mask_prompt_flatten.unsqueeze(-1), float("inf"))
+            mem = mem.masked_fill(~mask_prompt_flatten.unsqueeze(-1), float(0))
+        mem = self.enc_output_norm(self.enc_output(mem))
+        return mem, out.to(mem.dtype), torch.cat(level_ids)
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        pts = []
+        for lvl, (H, W) in enumerate(spatial_shapes):
+            ry, rx = torch.meshgrid(torch.linspace(0.5, H - 0.5, H, dtype=torch.float32, device=device),
+                                    torch.linspace(0.5, W - 0.5, W, dtype=torch.float32, device=device), indexing="ij")
+            ry = ry.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H)
+            rx = rx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W)
+            pts.append(torch.stack((rx, ry), -1))
+        ref = torch.cat(pts, 1)
+        return ref[:, :, None] * valid_ratios[:, None]
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        _, H, W = mask.shape
+        vh = torch.sum(~mask[:, :, 0], 1).float() / H
+        vw = torch.sum(~mask[:, 0, :], 1).float() / W
+        return torch.stack([vw, vh], -1)
+
+    @staticmethod
+    def get_proposal_pos_embed(proposals, num_pos_feats=128, temperature=10000):
+        dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=proposals.device)
+        dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+        proposals = proposals.sigmoid() * (2 * math.pi)
+        pos = proposals[:, :, :, None] / dim_t
+        return torch.stack((pos[:, :, :, 0::2].sin(), pos[:, :, :, 1::2].cos()), dim=4).flatten(2)
+
+    def select_proposals(self, logit, coord_unact, level_ids, n_levels):
+        """deformable_transformer_vl.py:569-625 for one image -> LongTensor[two_stage_num_proposals]."""
+        topk = self.two_stage_num_proposals
+        boxes = box_cxcywh_to_xyxy(coord_unact.sigmoid()).clamp(0, 1)
+        pre = []
+        for lvl in range(n_levels):
+            lvl_mask = level_ids == lvl
+            pre.append(torch.topk(logit.sigmoid() * lvl_mask, min(self.pre_nms_topk, logit.size(0)))[1])
+        pre = torch.cat(pre)
+        post = torchvision.ops.boxes.batched_nms(boxes[pre].float(), logit[pre].float(), level_ids[pre],
+                                                 self.nms_thresh_enc)
+        keep = pre[post]
+        if len(keep) < topk:
+            keep = torch.topk(logit, min(topk, logit.size(0)))[1]
+        q_per_l = topk // n_levels
+        ordered = level_ids[keep][None] == torch.arange(n_levels, device=level_ids.device)[:, None]
+        km = (ordered & (ordered.cumsum(1) <= q_per_l)).any(0)
+        if km.sum() < topk:
+            num_to_add = topk - km.sum()
+            pad = (~km).nonzero()[:num_to_add]
+            km[pad] = True
+        return keep[km]
+
+    def forward(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, query_embed, query_l,
+                attention_mask_l, multi_level_masks_prompt, **kwargs):
+        feat_flatten, mask_flatten, pos_flatten, shapes = [], [], [], []
+        for lvl, (feat, mask, pos) in enumerate(zip(multi_level_feats, multi_level_masks, multi_level_pos_embeds)):
+            bs, c, h, w = feat.shape
+            shapes.append((h, w))
+            feat_flatten.append(feat.flatten(2).transpose(1, 2))
+            mask_flatten.append(mask.flatten(1))
+            pos_flatten.append(pos.flatten(2).transpose(1, 2) + self.level_embeds[lvl].view(1, 1, -1))
+        feat_flatten = torch.cat(feat_flatten, 1)
+        mask_flatten = torch.cat(mask_flatten, 1)
+        pos_flatten = torch.cat(pos_flatten, 1)
+        dev = feat_flatten.device
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in multi_level_masks], 1).to(feat_flatten.dtype)
+        if multi_level_masks_prompt is not None:
+            mask_prompt_flatten = torch.cat([m.flatten(1) for m in multi_level_masks_prompt], 1)
+        else:
+            mask_prompt_flatten = None
+        reference_points = self.get_reference_points(shapes, valid_ratios, dev).to(feat_flatten.dtype)
+
+        memory, query_l = self.encoder(
+            query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
+            query_pos=pos_flatten, query_key_padding_mask=mask_flatten, spatial_shapes=spatial_shapes,
+            reference_points=reference_points, level_start_index=level_start_index, valid_ratios=valid_ratios)
+
+        bs, _, c = memory.shape
+        output_memory, output_proposals, level_ids = self.gen_encoder_output_proposals(
+            memory, mask_flatten, shapes, mask_prompt_flatten)
+        nd = self.decoder.num_layers
+        enc_cls = self.decoder.class_embed[nd](output_memory)
+        enc_coord = self.decoder.bbox_embed[nd](output_memory) + output_proposals
+        if self.proposal_ambiguous:
+            cls_all = torch.stack([enc_cls] + [m(output_memory) for m in self.decoder.class_embed_ambiguous], dim=1)
+            coord_all = torch.stack([enc_coord] + [m(output_memory) + output_proposals
+                                                   for m in self.decoder.bbox_embed_ambiguous], dim=1)
+            idx = torch.argmax(cls_all, dim=1, keepdim=True)
+            enc_cls = torch.gather(cls_all, 1, idx).squeeze(1)
+            enc_coord = torch.gather(coord_all, 1, idx.repeat(1, 1, 1, 4)).squeeze(1)
+        logit = enc_cls[..., 0]
+        topk_proposals = torch.stack([self.select_proposals(logit[b], enc_coord[b], level_ids, len(shapes))
+                                      for b in range(bs)])
+        topk_unact = torch.gather(enc_coord, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).detach()
+        reference = topk_unact.sigmoid()
+        init_reference_out = reference
+        pos_trans_out = self.pos_trans_norm(self.pos_trans(self.get_proposal_pos_embed(topk_unact).to(topk_unact.dtype)))
+        query_pos, query = torch.split(pos_trans_out, c, dim=2)
+        topk_feats = torch.gather(output_memory, 1, topk_proposals.unsqueeze(-1).expand(-1, -1, c)).detach()
+        query = query + self.pix_trans_norm(self.pix_trans(topk_feats))
+
+        inter_states, inter_references = self.decoder(
+            query=query, key=None, value=memory, query_pos=query_pos, key_padding_mask=mask_flatten,
+            reference_points=reference, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+            valid_ratios=valid_ratios)
+        self.last_topk_proposals = topk_proposals  # kept for parity tests (bit-exact index requirement)
+        return (inter_states, init_reference_out, inter_references, enc_cls, enc_coord, output_proposals.sigmoid(),
+                memory, query_l)

@@ -1,0 +1,97 @@
+"""Generates tests/golden/model_mini_*.npz by running the REFERENCE model (unmodified files from
+/root/reference under oracle/refshim.py) on the MINI spec with name-derived synthetic weights
+(oracle/synth.py).  Build container only:   python tests/golden/gen_model_golden.py
+
+Recorded per case: backbone pyramid, neck outputs, encoder memory, two-stage outputs and the
+selected proposal indices, decoder states / references, logits, boxes and the final detections
+(boxes, scores, classes, kept query indices) — the boundary tensors of SURVEY.md §8(a) rows
+a4-a18."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from ape_b200 import configs  # noqa: E402
+from oracle import ref_model, synth  # noqa: E402
+
+CASES = {
+    # name: (list of (h, w, out_h, out_w), text_prompt or None)
+    "single": ([(48, 64, 96, 128)], None),
+    "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
+    "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
+}
+
+
+def main():
+    spec = configs.MINI
+    model, names = ref_model.build_reference_model(spec)
+    synth.fill_state_dict(model)
+    cap = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            cap[name] = out
+        return f
+
+    model.backbone.register_forward_hook(hook("backbone"))
+    model.neck.register_forward_hook(hook("neck"))
+    model.transformer.register_forward_hook(hook("transformer"))
+    model.transformer.encoder.register_forward_hook(hook("encoder"))
+    for i, layer in enumerate(model.transformer.encoder.vl_layers):
+        layer.register_forward_hook(hook(f"vlf{i}"))
+
+    for cname, (sizes, text) in CASES.items():
+        inputs = []
+        for i, (h, w, oh, ow) in enumerate(sizes):
+            d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
+            if text is not None:
+                d["prompt"] = "text"
+                d["text_prompt"] = text
+            inputs.append(d)
+        cap.clear()
+        # record the proposal indices the reference really selected: it gathers the chosen boxes with
+        # torch.gather(enc_outputs_coord_unact, 1, topk_proposals[..., None].repeat(1, 1, 4))
+        # (deformable_transformer_vl.py:627-629)
+        gathered = []
+        orig_gather = torch.gather
+
+        def spy(inp, dim, index, *a, **k):
+            if index.dim() == 3 and index.shape[-1] == 4 and index.shape[1] == spec["num_queries"]:
+                gathered.append(index[..., 0].clone())
+            return orig_gather(inp, dim, index, *a, **k)
+
+        torch.gather = spy
+        try:
+            with torch.no_grad():
+                out = model(inputs)
+        finally:
+            torch.gather = orig_gather
+        (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory, feats_l) = cap["transformer"]
+        assert len(gathered) == 1
+        topk = gathered[0]
+        assert torch.equal(orig_gather(enc_coord_unact, 1, topk.unsqueeze(-1).repeat(1, 1, 4)).sigmoid(), init_reference)
+        # large per-token tensors are stored for every 4th token / channel only (fixture size)
+        rec = {f"backbone.{k}": v[:, ::4] for k, v in cap["backbone"].items()}
+        rec.update({f"neck.{i}": v[:, ::8] for i, v in enumerate(cap["neck"])})
+        rec.update(memory=memory[:, ::4], inter_states=inter_states, init_reference=init_reference,
+                   inter_references=inter_references, enc_outputs_class=enc_cls,
+                   enc_outputs_coord_unact=enc_coord_unact, topk_proposals=topk)
+        for i in range(len(model.transformer.encoder.vl_layers)):
+            rec[f"vlf{i}.v"] = cap[f"vlf{i}"][0][:, ::8]
+            rec[f"vlf{i}.l"] = cap[f"vlf{i}"][1]
+        for b, o in enumerate(out):
+            inst = o["instances"]
+            rec[f"det{b}.boxes"] = inst.pred_boxes.tensor
+            rec[f"det{b}.scores"] = inst.scores
+            rec[f"det{b}.classes"] = inst.pred_classes
+        # logits/boxes of the last decoder level, recomputed exactly as deformable_detr_segm_vl.py:485-503
+        np.savez_compressed(os.path.join(HERE, f"model_mini_{cname}.npz"),
+                            **{k: v.detach().cpu().numpy() for k, v in rec.items()})
+        print(cname, {k: tuple(v.shape) for k, v in rec.items() if k.startswith(("memory", "inter_states", "det", "topk"))})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+"""GPU parity of the engine's full detection forward (ape_b200.modeling) against
+(1) golden tensors recorded from the REFERENCE model on the MINI spec, and
+(2) the oracle's CPU port (oracle/ape_forward.py) at MINI and at the full APE-L_D 1024^2 size.
+Weights: name-derived synthetic (oracle/synth.py); fp32, TF32 off."""
+import pytest
+import torch
+
+from conftest import load_golden
+from ape_b200 import configs
+from oracle import ape_forward as AF
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CASES = {
+    "single": ([(48, 64, 96, 128)], None),
+    "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
+    "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
+}
+
+
+def _build(spec):
+    from ape_b200.modeling import build_model
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = build_model(spec)
+    synth.fill_state_dict(m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def mini():
+    m = _build(configs.MINI)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    return m.to(DEV), sd
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_mini_matches_reference_golden(case, mini):
+    model, _ = mini
+    sizes, text = CASES[case]
+    g = load_golden(f"model_mini_{case}.npz")
+    inputs = []
+    for i, (h, w, oh, ow) in enumerate(sizes):
+        d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
+        if text:
+            d.update(prompt="text", text_prompt=text)
+        inputs.append(d)
+    out = model(inputs)
+    lo = model.last_outputs
+    tol = dict(rtol=2e-3, atol=2e-3)
+    for k in ("p2", "p3", "p4", "p5", "p6"):
+        torch.testing.assert_close(lo["features"][k][:, ::4].cpu(), g[f"backbone.{k}"], **tol)
+    for i in range(5):
+        torch.testing.assert_close(lo["neck"][i][:, ::8].cpu(), g[f"neck.{i}"], **tol)
+    torch.testing.assert_close(lo["memory"][:, ::4].cpu(), g["memory"], **tol)
+    # bit-exact: proposal indices selected by top-k + NMS + per-level quota
+    assert torch.equal(model.transformer.last_topk_proposals.cpu(), g["topk_proposals"])
+    torch.testing.assert_close(lo["init_reference"].cpu(), g["init_reference"], **tol)
+    torch.testing.assert_close(lo["inter_states"].cpu(), g["inter_states"], rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(lo["inter_references"].cpu(), g["inter_references"], **tol)
+    for b, o in enumerate(out):
+        inst = o["instances"]
+        assert inst.pred_boxes.tensor.device.type == "cpu"  # results are handed back on the host like the reference
+        assert torch.equal(inst.pred_classes, g[f"det{b}.classes"])  # bit-exact kept (query, class) pairs
+        torch.testing.assert_close(inst.scores, g[f"det{b}.scores"], rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(inst.pred_boxes.tensor, g[f"det{b}.boxes"], rtol=1e-3, atol=2e-2)
+
+
+def test_mini_matches_oracle_port(mini):
+    model, sd = mini
+    spec = configs.MINI
+    images = [synth.image(56, 64, seed=7), synth.image(64, 33, seed=8)]
+    outs = [(112, 128), (64, 33)]
+    res, taps = AF.forward(images, outs, synth.text_features(8192, spec["lang_dim"])[: spec["num_classes"]], sd, spec)
+    out = model([{"image": im, "height": o[0], "width": o[1]} for im, o in zip(images, outs)])
+    assert torch.equal(model.transformer.last_topk_proposals.cpu(), taps["topk_proposals"])
+    torch.testing.assert_close(model.last_outputs["pred_logits"].cpu(), taps["pred_logits"], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(model.last_outputs["pred_boxes"].cpu(), taps["pred_boxes"], rtol=1e-3, atol=1e-4)
+    for r, o in zip(res, out):
+        assert torch.equal(o["instances"].pred_classes, r["classes"])
+        assert torch.equal(o["instances"].query_index, r["query_index"])
+        torch.testing.assert_close(o["instances"].scores, r["scores"], rtol=1e-3, atol=1e-5)
+
+
+def test_no_cpu_fallback(mini):
+    model, _ = mini
+    with pytest.raises(RuntimeError):
+        model.transformer.encoder.layers[0].attentions[0](
+            torch.zeros(1, 4, 256), reference_points=torch.zeros(1, 4, 5, 2),
+            spatial_shapes=torch.tensor([[2, 2]]), level_start_index=torch.tensor([0]))
+
+
+@pytest.mark.slow
+def test_ape_l_d_1024_matches_oracle_port_stagewise():
+    """BASELINE.json config 2 (APE-L_D, 1024^2, 1203 names, boxes only, B=1), fp32: the oracle port runs on
+    the host cores (about a minute), the engine on the GPU; same name-derived weights."""
+    spec = configs.APE_L_D
+    model = _build(spec)
+    sd = {k: v for k, v in model.state_dict().items()}
+    img = synth.image(1024, 768, seed=0)
+    text = synth.text_features(8192, spec["lang_dim"])[:1203]
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    res, taps = AF.forward([img], [(1024, 768)], text, sd, spec)
+    model = model.to(DEV)
+    model.vocabulary = {model.dataset_names[0]: [f"c{i}" for i in range(1203)]}
+    out = model([{"image": img, "height": 1024, "width": 768}])
+    lo = model.last_outputs
+    for k in ("p2", "p4", "p6"):
+        torch.testing.assert_close(lo["features"][k].cpu(), taps[f"backbone.{k}"], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(lo["memory"].cpu(), taps["memory"], rtol=2e-3, atol=2e-3)
+    sel, want = model.transformer.last_topk_proposals.cpu(), taps["topk_proposals"]
+    same = (sel == want).float().mean().item()
+    assert same == 1.0, f"proposal indices differ ({same:.3f} equal)"
+    torch.testing.assert_close(lo["pred_logits"].cpu(), taps["pred_logits"], rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(lo["pred_boxes"].cpu(), taps["pred_boxes"], rtol=1e-3, atol=1e-3)
+    inst = out[0]["instances"]
+    assert torch.equal(inst.pred_classes, res[0]["classes"])
+    assert torch.equal(inst.query_index, res[0]["query_index"])

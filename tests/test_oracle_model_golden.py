@@ -1,0 +1,62 @@
+"""CPU: pins the oracle's port of the detection forward (oracle/ape_forward.py) against golden
+tensors produced by the REFERENCE's own files run under oracle/refshim.py on the MINI spec
+(tests/golden/gen_model_golden.py).  Weights are a pure function of (name, shape) (oracle/synth.py),
+so only outputs are stored."""
+import pytest
+import torch
+
+from conftest import load_golden
+from ape_b200 import configs
+from oracle import ape_forward as AF
+from oracle import synth
+
+CASES = {
+    "single": ([(48, 64, 96, 128)], None),
+    "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
+    "phrase": ([(64, 48, 64, 48)], 3),
+}
+
+
+def mini_state_dict():
+    """Reference-named state_dict for the MINI spec, shapes taken from the golden generator's
+    model; here rebuilt from the engine's own module tree (same names by construction)."""
+    from ape_b200.modeling import build_model
+
+    m = build_model(configs.MINI)
+    synth.fill_state_dict(m)
+    return {k: v.clone() for k, v in m.state_dict().items()}
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return mini_state_dict()
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_port_matches_reference_golden(case, sd):
+    spec = configs.MINI
+    sizes, n_phrase = CASES[case]
+    g = load_golden(f"model_mini_{case}.npz")
+    images = [synth.image(h, w, seed=i) for i, (h, w, _, _) in enumerate(sizes)]
+    outs = [(oh, ow) for (_, _, oh, ow) in sizes]
+    n_text = n_phrase if n_phrase else spec["num_classes"]
+    text = synth.text_features(8192, spec["lang_dim"])[:n_text]
+    res, taps = AF.forward(images, outs, text, sd, spec, phrase=bool(n_phrase))
+    tol = dict(rtol=2e-4, atol=2e-4)
+    for k in ("p2", "p3", "p4", "p5", "p6"):
+        torch.testing.assert_close(taps[f"backbone.{k}"][:, ::4], g[f"backbone.{k}"], **tol)
+    for i in range(5):
+        torch.testing.assert_close(taps[f"neck.{i}"][:, ::8], g[f"neck.{i}"], **tol)
+    for i in range(spec["enc_layers"]):
+        torch.testing.assert_close(taps[f"vlf{i}.v"][:, ::8], g[f"vlf{i}.v"], **tol)
+        torch.testing.assert_close(taps[f"vlf{i}.l"], g[f"vlf{i}.l"], **tol)
+    torch.testing.assert_close(taps["memory"][:, ::4], g["memory"], **tol)
+    # bit-exact requirement: selected proposal indices (deformable_transformer_vl.py:569-625)
+    assert torch.equal(taps["topk_proposals"], g["topk_proposals"])
+    torch.testing.assert_close(taps["init_reference"], g["init_reference"], **tol)
+    torch.testing.assert_close(taps["inter_states"], g["inter_states"], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(taps["inter_references"], g["inter_references"], **tol)
+    for b, r in enumerate(res):
+        assert torch.equal(r["classes"], g[f"det{b}.classes"])  # bit-exact: kept (query, class) pairs
+        torch.testing.assert_close(r["scores"], g[f"det{b}.scores"], rtol=1e-3, atol=1e-5)
+        torch.testing.assert_close(r["boxes"], g[f"det{b}.boxes"], rtol=1e-3, atol=1e-2)
