@@ -36,6 +36,9 @@ lib.ape_msda_fwd_variant.argtypes = [_vp] * 6 + [_i] * 9 + [_vp]
 lib.ape_msda_fused_fwd.restype = _i
 lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
 
+lib.ape_gemm_tn.restype = _i
+lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
+
 # every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = (
     "ape_abi_version",
@@ -44,6 +47,7 @@ EXPORTS = (
     "ape_msda_fwd",
     "ape_msda_fwd_variant",
     "ape_msda_fused_fwd",
+    "ape_gemm_tn",
 )
 
 

@@ -1,0 +1,329 @@
+// gemm_tc.cu — C[M,N] = A[M,K] · W[N,K]^T (+bias, activation, residual) on the 5th-gen tensor
+// cores of sm_100a: TMA-staged 128-byte-swizzled operand tiles, tcgen05.mma issued by one thread
+// with fp32 accumulators in TMEM, tcgen05.ld epilogue.  Hand-written (no CUTLASS/cuBLAS).
+//
+// This is the dense workhorse behind the reference's nn.Linear calls on the detection path:
+//   ViT q/k/v/proj and SwiGLU w1/w2/w3      ape/modeling/backbone/vit_eva_clip.py:225-232,266-267,125-132
+//   encoder/decoder FFN and MSDA projections  ape/modeling/ape_deta/deformable_transformer_vl.py:36-54,
+//                                              ape/layers/multi_scale_deform_attn.py:278-295,353
+//   VisionLanguageAlign contraction            ape/layers/vision_language_align.py:36-48
+// `W` is consumed in nn.Linear's own [out_features, in_features] layout: both operands are K-major.
+//
+// Kernel shape (persistent, warp-specialised, 192 threads, 1 CTA / SM):
+//   warp 0     TMA producer   : STAGES-deep ring of {A 128x64, B BNx64} 16-bit tiles, mbarrier full/empty
+//   warp 1     MMA issuer     : 4 x tcgen05.mma (M=128, N=BN, K=16) per stage; owns the TMEM allocation
+//   warps 2-5  epilogue       : TMEM quadrant (warp_id % 4) -> registers -> bias/act/residual -> global
+//   TMEM holds two BN-column accumulators so tile i's epilogue overlaps tile i+1's main loop.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace ape {
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
+
+struct GemmParams {
+  void *C;
+  const float *bias;
+  const void *residual;
+  long long ldc, ldr;
+  int M, N, K;
+  int m_blocks, n_blocks, k_blocks;
+  int out_dtype;  // APE_DTYPE_*
+  int act;
+  uint32_t idesc;
+};
+
+template <int BN, int STAGES>
+struct alignas(1024) GemmSmem {
+  uint8_t a[STAGES][BM * BK * 2];
+  uint8_t b[STAGES][BN * BK * 2];
+  uint64_t full[STAGES], empty[STAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float act_fn(float x, int act) {
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
+template <typename TO>
+__device__ __forceinline__ void store_row(TO *dst, const float *v, int n) {  // n <= 32 contiguous outputs
+  if (n == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<uint4 *>(dst)[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]),
+                                                       __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4 *>(dst)[i] = Elem<TO>::pack(v + 8 * i);
+    }
+  } else {
+    for (int i = 0; i < n; ++i) dst[i] = Elem<TO>::from_f(v[i]);
+  }
+}
+
+template <typename TO>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32_t *r, int m, int n0) {
+  // r: 32 fp32 accumulators of row m, columns n0..n0+31
+  float v[32];
+  const int nvalid = min(32, p.N - n0);
+  if (nvalid <= 0) return;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (p.bias != nullptr) {
+    if (nvalid == 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+      for (int i = 0; i < nvalid; ++i) v[i] += __ldg(p.bias + n0 + i);
+    }
+  }
+  TO *C = reinterpret_cast<TO *>(p.C);
+  if (p.act == ACT_SWIGLU) {
+    // interleaved (gate, up) column pairs -> silu(gate) * up, N/2 outputs (vit_eva_clip.py:126-128)
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float g = v[2 * i];
+      o[i] = g / (1.f + __expf(-g)) * v[2 * i + 1];
+    }
+    TO *dst = C + (size_t)m * p.ldc + n0 / 2;
+    const int no = nvalid / 2;
+    if (no == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 && sizeof(TO) == 2) {
+      reinterpret_cast<uint4 *>(dst)[0] = Elem<TO>::pack(o);
+      reinterpret_cast<uint4 *>(dst)[1] = Elem<TO>::pack(o + 8);
+    } else {
+      for (int i = 0; i < no; ++i) dst[i] = Elem<TO>::from_f(o[i]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = act_fn(v[i], p.act);
+  if (p.residual != nullptr) {
+    const TO *res = reinterpret_cast<const TO *>(p.residual) + (size_t)m * p.ldr + n0;
+    for (int i = 0; i < nvalid; ++i) v[i] += Elem<TO>::to_f(res[i]);
+  }
+  store_row<TO>(C + (size_t)m * p.ldc + n0, v, nvalid);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using Smem = GemmSmem<BN, STAGES>;
+  Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int num_tiles = p.m_blocks * p.n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&map_a);
+    tc::prefetch_tensormap(&map_b);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(&s.full[i], 1);
+      tc::mbar_init(&s.empty[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s.tmem_full[i], 1);
+      tc::mbar_init(&s.tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&s.tmem_base, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          tc::mbar_wait(&s.empty[stage], phase ^ 1);
+          tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
+          tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
+          tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        tc::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          tc::mbar_wait(&s.full[stage], phase);
+          tc::fence_after_sync();
+          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(s.a[stage]));
+          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(s.b[stage]));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
+            tc::mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
+          }
+          tc::mma_commit(&s.empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit(&s.tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp % 4;  // TMEM lane quadrant this warp may access
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
+      const int m = m_blk * BM + quad * 32 + lane;
+      tc::mbar_wait(&s.tmem_full[acc], acc_phase);
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, r);
+        tc::tmem_ld_wait();
+        if (m < p.M) {
+          const int n0 = n_blk * BN + c * 32;
+          if (p.out_dtype == APE_DTYPE_F32) epilogue_chunk<float>(p, r, m, n0);
+          else if (p.out_dtype == APE_DTYPE_F16) epilogue_chunk<__half>(p, r, m, n0);
+          else epilogue_chunk<__nv_bfloat16>(p, r, m, n0);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [rows, K] 16-bit row-major matrix with pitch `ld` elements; box = 64 (K) x box_rows, 128 B swizzle.
+int make_map(CUtensorMap *map, const void *base, int dtype, long long rows, long long K, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return fail(APE_ERR_UNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return APE_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmParams &p, cudaStream_t st) {
+  using Smem = GemmSmem<BN, STAGES>;
+  const size_t smem = sizeof(Smem) + 1024;
+  auto k = gemm_tc_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "gemm: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  p.n_blocks = (p.N + BN - 1) / BN;
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  k<<<grid, 192, smem, st>>>(ma, mb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace
+}  // namespace ape
+
+using namespace ape;
+
+extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
+                           const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
+                           int out_dtype, int act, int tile_n, void *stream) {
+  if (in_dtype != APE_DTYPE_F16 && in_dtype != APE_DTYPE_BF16)
+    return fail(APE_ERR_INVALID_ARG, "gemm: operands must be fp16 or bf16 (got dtype %d)", in_dtype);
+  if (out_dtype != APE_DTYPE_F32 && out_dtype != APE_DTYPE_F16 && out_dtype != APE_DTYPE_BF16)
+    return fail(APE_ERR_INVALID_ARG, "gemm: bad out_dtype %d", out_dtype);
+  if (act < 0 || act > ACT_SWIGLU) return fail(APE_ERR_INVALID_ARG, "gemm: bad activation %d", act);
+  if (M < 0 || N <= 0 || K <= 0) return fail(APE_ERR_INVALID_ARG, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return APE_OK;
+  if (!A || !W || !C) return fail(APE_ERR_NULL_PTR, "gemm: null pointer argument");
+  if ((lda * 2) % 16 || (ldw * 2) % 16 || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return fail(APE_ERR_INVALID_ARG, "gemm: A/W base and row pitch must be 16-byte aligned (TMA)");
+  if (lda < K || ldw < K) return fail(APE_ERR_INVALID_ARG, "gemm: row pitch smaller than K");
+  if (act == ACT_SWIGLU && ((N & 1) || residual)) return fail(APE_ERR_INVALID_ARG, "gemm: swiglu needs even N, no residual");
+  if (residual && out_dtype == APE_DTYPE_F32 && false) return APE_ERR_INVALID_ARG;
+  const int bn = tile_n > 0 ? tile_n : (N >= 1536 ? 256 : 128);
+  if (bn != 128 && bn != 256) return fail(APE_ERR_INVALID_ARG, "gemm: tile_n must be 128 or 256");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap ma, mb;
+  if (int rc = make_map(&ma, A, in_dtype, M, K, lda, BM)) return rc;
+  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, bn)) return rc;
+  GemmParams p{};
+  p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  p.m_blocks = (M + BM - 1) / BM;
+  p.k_blocks = (K + BK - 1) / BK;
+  p.out_dtype = out_dtype; p.act = act;
+  p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
+  if (bn == 256) return launch_gemm<256, 4>(ma, mb, p, st);
+  return launch_gemm<128, 6>(ma, mb, p, st);
+}

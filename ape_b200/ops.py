@@ -10,6 +10,28 @@ import torch
 from . import _lib
 
 _NS = "ape"
+
+# bench.py sets this to a list to collect (tag, start_event, end_event) around every launch of the
+# library's kernels on the current stream (None = off, zero overhead).
+PROFILE_EVENTS = None
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE_EVENTS is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_EVENTS is not None:
+            self.b.record()
+            PROFILE_EVENTS.append((self.tag, self.a, self.b))
+        return False
 _FWD_SCHEMA = (
     "ms_deform_attn_forward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
     "Tensor sampling_loc, Tensor attn_weight, int im2col_step) -> Tensor"
@@ -87,7 +109,8 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
     _require(ref.dtype == torch.float32 and ref.is_contiguous(), "reference_points must be contiguous fp32")
     _require(ref.shape[:3] == (B, Q, L), "reference_points must be [B,Q,L,2|4]")
     out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _timed(("msda_fused", B, S, Q, L, P, value.element_size(),
+                                                  sampling_offsets.element_size())):
         rc = _lib.lib.ape_msda_fused_fwd(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_offsets.data_ptr(), sampling_offsets.stride(1),
@@ -97,6 +120,44 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
             _lib.current_stream_ptr())
     _lib.check(rc, "ape_msda_fused_fwd")
     return out
+
+
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu": 3}
+
+
+def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0):
+    """act(x @ weight.T + bias) (+ residual) on the tcgen05 tensor cores (ape_gemm_tn).
+
+    x [..., K] and weight [N, K] fp16/bf16 with unit inner stride; bias fp32 [N] (or None); residual
+    [..., N] of the output dtype.  act="swiglu": weight rows are interleaved (gate_j, up_j) pairs and the
+    result has N/2 columns."""
+    _require(x.is_cuda and weight.is_cuda, "linear_tc: CUDA tensors only")
+    _require(x.dtype == weight.dtype and x.dtype in (torch.float16, torch.bfloat16), "linear_tc: fp16/bf16 operands")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    _require(weight.shape[1] == K and x.stride(-1) == 1 and weight.stride(-1) == 1, "linear_tc: bad operand layout")
+    x2 = x.reshape(-1, K)
+    if x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    _require(weight.stride(0) % 8 == 0 and weight.data_ptr() % 16 == 0, "linear_tc: weight rows must be 16-byte aligned")
+    M = x2.shape[0]
+    out_dtype = out_dtype or x.dtype
+    n_out = N // 2 if act == "swiglu" else N
+    out = torch.empty((M, n_out), dtype=out_dtype, device=x.device)
+    res_ptr, ldr = None, 0
+    if residual is not None:
+        r2 = residual.reshape(-1, n_out)
+        _require(r2.dtype == out_dtype and r2.stride(1) == 1, "linear_tc: residual must match the output dtype")
+        res_ptr, ldr = r2.data_ptr(), r2.stride(0)
+    if bias is not None:
+        _require(bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N, "linear_tc: bias must be fp32 [N]")
+    with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
+        rc = _lib.lib.ape_gemm_tn(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
+                                  out.stride(0), bias.data_ptr() if bias is not None else None, res_ptr, ldr,
+                                  M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
+                                  _lib.current_stream_ptr())
+    _lib.check(rc, "ape_gemm_tn")
+    return out.view(*x.shape[:-1], n_out)
 
 
 def _ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

@@ -6,8 +6,12 @@
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
 synthetic input.  Workloads:
 
+  ape_l_d  (default) BASELINE.json configs[1]: the whole APE-L_D detection forward at 1024², 1203-name
+           vocabulary, boxes only, batch 1 per GPU -> images/sec.  Synthetic image, random-init weights
+           of the real architecture (380 M parameters), seeded synthetic text features (the text tower
+           is a cached input of this path).
   msda     ms_deform_attn forward at the APE-L_D 1024² encoder shape (B=1 per GPU, Q=S=87 296,
-           5 levels, 8 heads x 32, 4 points, fp32) — BASELINE.json's "ms_deform_attn HBM GB/s"
+           5 levels, 8 heads x 32, 4 points) — BASELINE.json's "ms_deform_attn HBM GB/s"
            half of the metric; algorithmic bytes per call as SURVEY.md §8(d).
 
 `value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
@@ -22,6 +26,7 @@ per GPU); launched by torchrun, NCCL is used only for the barrier and the max-ov
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -126,12 +131,194 @@ def cpu_reference_arm(steps, warmup):
                       "multi_scale_deformable_attn_pytorch, all host threads", "ms_per_step": dt * 1e3}
 
 
+def fused_msda_bytes(B, S, Q, L, e, eo):
+    """Algorithmic bytes of one fused MSDA launch: value read once, raw offsets + logits
+    read once (instead of materialised locations / weights), fp32 reference points, output written once."""
+    return e * B * S * H * D + eo * B * Q * H * L * P * 3 + 4 * B * Q * L * 2 + e * B * Q * H * D + 24 * L
+
+
+def cpu_model_arm(steps, n_text=1203, sd=None):
+    """Reference arm for the ape_l_d workload: the oracle's CPU port of the reference forward
+    (oracle/ape_forward.py; /root/reference itself cannot travel to the GPU box), fp32, all host threads.
+    `sd`: state_dict of the already calibrated engine model (same weights as the GPU arm); when None the
+    same synthetic weights are built and the same score calibration is done with the port itself."""
+    import copy
+
+    from ape_b200 import configs, synthetic
+    from ape_b200.modeling import build_model
+    from oracle import ape_forward as AF
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = copy.deepcopy(configs.APE_L_D)
+    spec["test_score_thresh"] = 0.1
+    text = synthetic.text_features(8192, spec["lang_dim"])[:n_text]
+    if sd is None:
+        m = build_model(spec, num_text=n_text)  # parameter container only; the port is functional over its state_dict
+        synthetic.fill_state_dict(m)
+        sd = m.state_dict()
+        _, taps = AF.forward([synthetic.image(1024, 1024, seed=99)], [(1024, 1024)], text, sd, spec)
+        kth = torch.topk(taps["pred_logits"].flatten(), 500).values[-1]
+        sd[f"class_embed.{spec['dec_layers'] - 1}.bias0"].add_(math.log(0.1 / 0.9) - kth)
+    else:
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    img = torch.randint(0, 256, (3, 1024, 1024), generator=torch.Generator().manual_seed(0)).to(torch.float32)
+    n = max(1, min(steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        res, _ = AF.forward([img], [(1024, 1024)], text, sd, spec)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} whole-image forward(s) of the oracle port (APE-L_D 1024^2, {n_text} names, fp32), all host threads",
+            "ms_per_step": dt * 1e3, "detections": int(res[0]["scores"].numel())}
+
+
+def model_bench(args, rank, local_rank, world):
+    from ape_b200 import configs
+
+    n_text = 1203
+    config = {"workload": "APE-L_D detection forward, 1024x1024 image, 1203-name vocabulary, boxes only, batch 1 per GPU",
+              "weights": "random init of the real architecture (380 M params)", "text": "seeded synthetic features (text tower out of path)",
+              "l2": "per-step working set (weights 1.5 GB fp32 + activations) >> 126 MB L2",
+              "dense_ops": "torch library kernels (cuBLAS/cuDNN/SDPA) this round; ms_deform_attn = libape_b200 fused kernel",
+              "parallelism": f"dp{args.gpus} (one image per GPU, no data-path collective; results gathered by the caller)"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_model_arm(args.steps, n_text)
+        print(json.dumps({"impl": "reference", "metric": "images_per_sec", "value": cb["value"], "unit": "images/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in ape_b200)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    import ape_b200
+    from ape_b200 import ops
+    from ape_b200.modeling import build_model
+
+    from ape_b200 import synthetic
+
+    tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    model = build_model(configs.APE_L_D, num_text=n_text)
+    synthetic.fill_state_dict(model)  # non-degenerate random weights (nothing the reference zero-inits stays 0)
+    model.test_score_thresh = 0.1     # SURVEY.md 8(d) config 2 (README recipe --confidence-threshold 0.1)
+    model = model.to(dev)
+    if tdt != torch.float32:
+        model = model.to(tdt)
+    # Untrained weights put every score near the 0.01 prior, so nothing would reach the 0.1 threshold and
+    # the selection stage would be skipped.  Shift the classifier bias once so that ~500 of the 1.08 M
+    # (query, class) scores pass, as with a trained detector; identical for every step.
+    model([{"image": synthetic.image(1024, 1024, seed=99), "height": 1024, "width": 1024}])
+    lg = model.last_outputs["pred_logits"].float().flatten()
+    kth = torch.topk(lg, 500).values[-1]
+    with torch.no_grad():
+        model.class_embed[len(model.class_embed) - 2].bias0.add_((math.log(0.1 / 0.9) - kth).to(model.class_embed[0].bias0.dtype))
+    config["selection"] = "test_score_thresh 0.1, bias calibrated so ~500 of 1.08M scores pass; NMS 0.7; top-300"
+    g = torch.Generator().manual_seed(rank)
+    NIMG = 4
+    host_imgs = [torch.randint(0, 256, (3, 1024, 1024), generator=g).to(torch.float32).pin_memory() for _ in range(NIMG)]
+    dev_imgs = [t.to(dev) for t in host_imgs]
+
+    def step(i, host):
+        img = host_imgs[i % NIMG] if host else dev_imgs[i % NIMG]
+        return model([{"image": img, "height": 1024, "width": 1024}])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        step(i, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE_EVENTS = []
+    n0 = ape_b200._lib.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    for i in range(args.steps):
+        out = step(i, False)
+    b.record()
+    barrier()
+    launches = ape_b200._lib.launch_count() - n0
+    total_ms = a.elapsed_time(b)
+    events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
+    enc = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] == t[2]]
+    dec = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] != t[2]]
+    # e2e: pinned host image in, detections out on the host (the model's public call does both)
+    e2e_steps = max(3, min(args.steps, 10))
+    step(0, True)
+    barrier()
+    a.record()
+    for i in range(e2e_steps):
+        out = step(i, True)
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        peak, peak_src = peaks()
+        tag, _ = enc[0]
+        _, B, S, Q, L, _, e, eo = tag
+        enc_ms = sum(x for _, x in enc) / len(enc)
+        nbytes = fused_msda_bytes(B, S, Q, L, e, eo)
+        achieved = nbytes / (enc_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(f"msda_fused_enc_{args.dtype}")
+        inst = out[0]["instances"]
+        d2h = sum(v.tensor.numel() * 4 if hasattr(v, "tensor") else v.numel() * v.element_size()
+                  for v in inst.get_fields().values())
+        line = {
+            "metric": "images_per_sec", "value": world * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
+            "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "msda_fused_fwd_kernel (encoder, Q=S)",
+                         "algorithmic_bytes_per_launch": nbytes, "launch_ms": enc_ms,
+                         "launches_per_step": len(enc) / args.steps,
+                         "share_of_step": enc_ms * len(enc) / args.steps / ms_per_step,
+                         "decoder_launch_ms": (sum(x for _, x in dec) / len(dec)) if dec else None},
+            "e2e": {"value": world * 1e3 / e2e_ms, "unit": "images/s", "h2d_bytes_per_step": host_imgs[0].numel() * 4,
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_model_arm(1, n_text, sd=model.state_dict())
+            line["detections_per_image"] = {"engine": len(inst), "cpu_port": cb["detections"]}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="msda")
+    ap.add_argument("--workload", default="ape_l_d", choices=["ape_l_d", "msda"])
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -147,6 +334,9 @@ def main():
     config = {"workload": "ms_deform_attn_forward APE-L_D 1024^2 encoder shape (B=1/GPU, Q=S=87296, L=5, H=8, D=32, P=4)",
               "loc": "uniform(0,1) seed 3 (SURVEY 8d)", "l2": "4 rotating input sets (1.4 GB fp32) > 126 MB L2",
               "parallelism": f"dp{args.gpus} (one image per GPU, no data-path collective)"}
+
+    if args.workload == "ape_l_d":
+        return model_bench(args, rank, local_rank, world)
 
     if args.impl == "reference":
         if rank != 0:

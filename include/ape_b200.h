@@ -100,6 +100,21 @@ int ape_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const i
                        int S, int H, int D, int L, int Q, int P, int dtype, int offs_dtype,
                        void *stream);
 
+/*
+ * Tensor-core linear layer: C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), tcgen05 / TMA / TMEM.
+ * Replaces the nn.Linear (cuBLAS) calls of the detection path (vit_eva_clip.py:225-232,266-267,125-132;
+ * deformable_transformer_vl.py:36-54; multi_scale_deform_attn.py:278-295,353; vision_language_align.py:36-48).
+ *
+ * A [M,K] and W [N,K] (nn.Linear weight layout) are fp16 or bf16 (in_dtype), K contiguous, row pitches
+ * lda / ldw in elements (16-byte aligned rows).  fp32 accumulation in tensor memory.
+ * bias: fp32 [N] or NULL.  residual: [M,N] of out_dtype with pitch ldr, or NULL.
+ * act: 0 none, 1 ReLU, 2 GELU(erf), 3 SwiGLU over interleaved (gate, up) column pairs -> C is [M, N/2].
+ * out_dtype: APE_DTYPE_* of C (pitch ldc elements).  tile_n: 0 = auto, or 128 / 256.
+ */
+int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
+                const void *residual, int64_t ldr, int M, int N, int K, int in_dtype, int out_dtype, int act,
+                int tile_n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

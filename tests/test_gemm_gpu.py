@@ -1,0 +1,88 @@
+"""GPU: the tcgen05/TMA/TMEM linear layer (ape_gemm_tn) against a plain PyTorch fp32 reference of
+the same op on the same (16-bit rounded) operands.  Tolerance: fp32 accumulation over K terms of
+16-bit products -> relative 2e-3 on fp16/bf16 outputs (output rounding), 1e-4 on fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import ape_b200
+
+    return ape_b200.ops
+
+
+def ref_linear(x, w, b=None, act=None, residual=None):
+    y = F.linear(x.float(), w.float(), b)
+    if act == "relu":
+        y = F.relu(y)
+    elif act == "gelu":
+        y = F.gelu(y)
+    elif act == "swiglu":
+        y = F.silu(y[..., 0::2]) * y[..., 1::2]
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def rnd(*shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,tile", [
+    (128, 128, 64, 128), (128, 256, 64, 256), (256, 256, 128, 0), (384, 512, 1024, 128),
+    (4096, 3072, 1024, 256),   # ViT-L fused q/k/v projection
+    (4096, 1024, 1024, 128),   # ViT-L attention output projection
+    (900, 256, 256, 0),        # decoder tokens: M not a multiple of 128
+    (1000, 1203, 256, 0),      # LVIS vocabulary: N not a multiple of the tile
+    (300, 96, 200, 128),       # K not a multiple of 64 (TMA zero-fills the tail)
+])
+def test_plain_gemm(ops, dtype, M, N, K, tile):
+    x = rnd(M, K, dtype=dtype, seed=1)
+    w = rnd(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    y = ops.linear_tc(x, w, tile_n=tile)
+    assert y.dtype == dtype and y.shape == (M, N)
+    torch.testing.assert_close(y.float(), ref_linear(x, w), rtol=1e-2, atol=1e-2 if dtype == torch.bfloat16 else 2e-3)
+    y32 = ops.linear_tc(x, w, out_dtype=torch.float32, tile_n=tile)
+    torch.testing.assert_close(y32, ref_linear(x, w), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("act", [None, "relu", "gelu", "swiglu"])
+def test_epilogues(ops, act):
+    M, N, K = 640, 512, 320
+    dtype = torch.float16
+    x = rnd(M, K, dtype=dtype, seed=3)
+    w = rnd(N, K, dtype=dtype, seed=4, scale=K ** -0.5)
+    b = rnd(N, dtype=torch.float32, seed=5)
+    y = ops.linear_tc(x, w, b, act=act, out_dtype=torch.float32)
+    torch.testing.assert_close(y, ref_linear(x, w, b, act), rtol=2e-4, atol=2e-4)
+    if act != "swiglu":
+        res = rnd(M, N, dtype=dtype, seed=6)
+        y = ops.linear_tc(x, w, b, act=act, residual=res)
+        torch.testing.assert_close(y.float(), ref_linear(x, w, b, act, res), rtol=2e-3, atol=4e-3)
+
+
+def test_padded_pitch_and_batched_input(ops):
+    # K = 2730 (SwiGLU hidden of ViT-L) stored with a 2752-element pitch; leading batch dims are flattened
+    K, Kp, N = 2730, 2752, 1024
+    buf = torch.zeros(2, 64, Kp, dtype=torch.bfloat16, device=DEV)
+    buf[..., :K] = rnd(2, 64, K, dtype=torch.bfloat16, seed=7)
+    wbuf = torch.zeros(N, Kp, dtype=torch.bfloat16, device=DEV)
+    wbuf[:, :K] = rnd(N, K, dtype=torch.bfloat16, seed=8, scale=K ** -0.5)
+    y = ops.linear_tc(buf[..., :K], wbuf[:, :K], out_dtype=torch.float32)
+    assert y.shape == (2, 64, N)
+    torch.testing.assert_close(y, ref_linear(buf[..., :K], wbuf[:, :K]), rtol=1e-4, atol=1e-4)
+
+
+def test_rejects_bad_arguments(ops):
+    x = rnd(128, 64, dtype=torch.float32, seed=1)
+    with pytest.raises(RuntimeError):
+        ops.linear_tc(x, x)  # fp32 operands are not a tensor-core format here
+    with pytest.raises(RuntimeError):
+        ops.linear_tc(x.cpu().half(), x.cpu().half())  # no CPU path
