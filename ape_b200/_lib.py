@@ -39,6 +39,11 @@ lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i,
 lib.ape_gemm_tn.restype = _i
 lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
 
+lib.ape_layernorm.restype = _i
+lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp]
+lib.ape_rope_qk.restype = _i
+lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+
 # every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = (
     "ape_abi_version",
@@ -48,6 +53,8 @@ EXPORTS = (
     "ape_msda_fwd_variant",
     "ape_msda_fused_fwd",
     "ape_gemm_tn",
+    "ape_layernorm",
+    "ape_rope_qk",
 )
 
 

@@ -1,0 +1,197 @@
+// norm_rope.cu — row-wise kernels around the tensor-core GEMMs of the ViT / transformer blocks:
+//   * LayerNorm over the last dim (fp32 statistics, 16-bit or fp32 IO, optional row gather so that
+//     window partition / un-partition (utils_eva02.py:19-63) costs no extra pass),
+//   * 2-D rotary embedding applied in place to the q and k thirds of a fused [M, 3C] qkv buffer
+//     (VisionRotaryEmbeddingFast, utils_eva02.py:307-346; rotate_half :248-252).
+// All HBM-bound: one warp per row, 128-bit loads, data held in registers between the two passes.
+#include "common.cuh"
+
+namespace ape {
+namespace {
+
+template <typename T>
+struct Vec8 {  // 8 elements of T as raw storage
+  static constexpr int kBytes = 8 * sizeof(T);
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float *f) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    Elem<T>::unpack(v, f);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T *p, const float *f) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4 *>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4 *>(p) = Elem<T>::pack(f);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  MAXV = max 8-element vectors per lane (C <= 256 * MAXV).
+// y[out_row(r)] = LN(x[r]) * w + b;  out_row = gather ? row_map[r] : r.
+template <typename TI, typename TO, int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy,
+                 const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ row_map,
+                 int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const TI *xr = x + (size_t)warp * ldx;
+  // rows are padded to a multiple of 8 elements (host-checked pitch); elements >= C are ignored on
+  // input and written as 0 (keeps the K-padding of the next GEMM's operand clean, e.g. C = 2730)
+  const int nvec = (C + 7) >> 3;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      load8<TI>(xr + 8 * j, v[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (8 * j + k >= C) v[i][k] = 0.f;
+        sum += v[i][k];
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = (8 * j + k < C) ? v[i][k] - mean : 0.f;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  const int orow = row_map ? row_map[warp] : warp;
+  TO *yr = y + (size_t)orow * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      float o[8];
+      if (8 * j + 8 <= C) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(w + 8 * j)), w1 = __ldg(reinterpret_cast<const float4 *>(w + 8 * j) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(b + 8 * j)), b1 = __ldg(reinterpret_cast<const float4 *>(b + 8 * j) + 1);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * ww[k] + bb[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          o[k] = (8 * j + k < C) ? (v[i][k] - mean) * rstd * __ldg(w + 8 * j + k) + __ldg(b + 8 * j + k) : 0.f;
+      }
+      store8<TO>(yr + 8 * j, o);
+    }
+  }
+}
+
+// In-place 2-D RoPE on the q and k parts of qkv [M, 3*C] (C = heads*hd); cos/sin [npos, hd] fp32;
+// token m uses position pos_map ? pos_map[m] : m % npos.  t' = t*cos + rotate_half(t)*sin with
+// rotate_half pairing (2i, 2i+1) -> (-t[2i+1], t[2i]).  One thread per 8 channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rope_qk_kernel(T *__restrict__ qkv, long long ld, const float *__restrict__ cosr, const float *__restrict__ sinr,
+               const int *__restrict__ pos_map, int M, int C, int hd, int npos) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vec_per_row = 2 * C / 8;  // q and k only
+  if (idx >= (long long)M * vec_per_row) return;
+  const int m = (int)(idx / vec_per_row), j = (int)(idx % vec_per_row);
+  const int col = j * 8;           // column inside [0, 2C)
+  const int d = col % hd;          // channel inside the head (hd % 8 == 0)
+  const int pos = pos_map ? pos_map[m] : m % npos;
+  T *p = qkv + (size_t)m * ld + col;
+  float t[8], o[8];
+  load8<T>(p, t);
+  const float *c = cosr + (size_t)pos * hd + d, *s = sinr + (size_t)pos * hd + d;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    o[i] = t[i] * c[i] - t[i + 1] * s[i];
+    o[i + 1] = t[i + 1] * c[i + 1] + t[i] * s[i + 1];
+  }
+  store8<T>(p, o);
+}
+
+template <typename TI, typename TO>
+int launch_ln(const void *x, long long ldx, void *y, long long ldy, const float *w, const float *b, const int *row_map,
+              int rows, int C, float eps, cudaStream_t st) {
+  const int blocks = (rows + 7) / 8;
+  if (C <= 1024 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0)
+    layernorm_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+  else
+    layernorm_kernel<TI, TO, 16><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+  return check_launch("layernorm_kernel");
+}
+
+}  // namespace
+}  // namespace ape
+
+using namespace ape;
+
+extern "C" int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
+                             const int *row_map, int rows, int C, float eps, int in_dtype, int out_dtype, void *stream) {
+  if (rows < 0 || C <= 0 || C > 4096) return fail(APE_ERR_INVALID_ARG, "layernorm: rows=%d C=%d (C <= 4096)", rows, C);
+  if (ldx < ((C + 7) & ~7) || ldy < ((C + 7) & ~7))
+    return fail(APE_ERR_INVALID_ARG, "layernorm: row pitch must cover C rounded up to 8 elements");
+  if (rows == 0) return APE_OK;
+  if (!x || !y || !weight || !bias) return fail(APE_ERR_NULL_PTR, "layernorm: null pointer argument");
+  const int ie = dtype_size(in_dtype), oe = dtype_size(out_dtype);
+  if ((ldx * ie) % 16 || (ldy * oe) % 16 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(APE_ERR_INVALID_ARG, "layernorm: rows must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define APE_LN(TI, TO) return launch_ln<TI, TO>(x, ldx, y, ldy, weight, bias, row_map, rows, C, eps, st)
+  if (in_dtype == APE_DTYPE_F32) {
+    if (out_dtype == APE_DTYPE_F32) APE_LN(float, float);
+    if (out_dtype == APE_DTYPE_F16) APE_LN(float, __half);
+    if (out_dtype == APE_DTYPE_BF16) APE_LN(float, __nv_bfloat16);
+  } else if (in_dtype == APE_DTYPE_F16) {
+    if (out_dtype == APE_DTYPE_F32) APE_LN(__half, float);
+    if (out_dtype == APE_DTYPE_F16) APE_LN(__half, __half);
+  } else if (in_dtype == APE_DTYPE_BF16) {
+    if (out_dtype == APE_DTYPE_F32) APE_LN(__nv_bfloat16, float);
+    if (out_dtype == APE_DTYPE_BF16) APE_LN(__nv_bfloat16, __nv_bfloat16);
+  }
+#undef APE_LN
+  return fail(APE_ERR_UNSUPPORTED, "layernorm: dtype pair (%d -> %d) not supported", in_dtype, out_dtype);
+}
+
+extern "C" int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_table, const int *pos_map,
+                           int M, int C, int head_dim, int npos, int dtype, void *stream) {
+  if (M < 0 || C <= 0 || head_dim <= 0 || head_dim % 8 != 0 || C % head_dim != 0 || npos <= 0)
+    return fail(APE_ERR_INVALID_ARG, "rope: M=%d C=%d head_dim=%d npos=%d", M, C, head_dim, npos);
+  if (M == 0) return APE_OK;
+  if (!qkv || !cos_table || !sin_table) return fail(APE_ERR_NULL_PTR, "rope: null pointer argument");
+  if ((ld * dtype_size(dtype)) % 16 || (reinterpret_cast<uintptr_t>(qkv) & 15))
+    return fail(APE_ERR_INVALID_ARG, "rope: rows must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = (long long)M * (2 * C / 8);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == APE_DTYPE_F32)
+    rope_qk_kernel<float><<<blocks, 256, 0, st>>>((float *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+  else if (dtype == APE_DTYPE_F16)
+    rope_qk_kernel<__half><<<blocks, 256, 0, st>>>((__half *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+  else if (dtype == APE_DTYPE_BF16)
+    rope_qk_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16 *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+  else
+    return fail(APE_ERR_INVALID_ARG, "rope: unknown dtype %d", dtype);
+  return check_launch("rope_qk_kernel");
+}

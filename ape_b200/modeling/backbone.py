@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from ..layers.common import ConvNorm, LayerNorm2d
 
 
@@ -198,11 +199,118 @@ class ViT(nn.Module):
                 for n in self._out_features}
 
     def forward(self, x):
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and self._engine_ok(x):
+            return {self._out_features[0]: self._engine_forward(x)}
+        # fp32 (strict-parity) path on PyTorch library kernels
         x = self.patch_embed(x)
         x = x + get_abs_pos(self.pos_embed, self.pretrain_use_cls_token, (x.shape[1], x.shape[2])).to(x.dtype)
         for blk in self.blocks:
             x = blk(x)
         return {self._out_features[0]: x.permute(0, 3, 1, 2)}
+
+    # ---------------------------------------------------------------------------------------------
+    # Engine path (fp16 / bf16): libape_b200 kernels — tcgen05 GEMMs with fused bias / SwiGLU /
+    # residual epilogues, LayerNorm and RoPE kernels; tokens stay in WINDOW-MAJOR order for the
+    # whole network (attention is permutation-equivariant once the RoPE table follows the tokens), so
+    # window_partition / window_unpartition (utils_eva02.py:19-63) cost one permutation at the
+    # patch embedding and one at the end instead of two copies per block.
+    # ---------------------------------------------------------------------------------------------
+    def _engine_ok(self, x):
+        ws = next((b.window_size for b in self.blocks if b.window_size > 0), 0)
+        g = x.shape[-1] // self.patch_embed.proj.kernel_size[0]
+        return x.shape[-1] == x.shape[-2] and (ws == 0 or g % ws == 0)
+
+    def _pack(self, dtype, device):
+        """Weights re-laid out once for the kernels (fused qkv, interleaved SwiGLU pairs, K padded to 8)."""
+        key = (dtype, str(device), tuple(p._version for p in self.parameters()))
+        if getattr(self, "_packed_key", None) == key:
+            return self._packed
+        f32 = dict(dtype=torch.float32, device=device)
+        packed = {"blocks": []}
+        with torch.no_grad():
+            pw = self.patch_embed.proj.weight
+            packed["patch_w"] = pw.reshape(pw.shape[0], -1).to(device, dtype).contiguous()
+            packed["patch_b"] = self.patch_embed.proj.bias.to(**f32).contiguous()
+            for blk in self.blocks:
+                a, m = blk.attn, blk.mlp
+                hid = m.w1.weight.shape[0]
+                hid_p = (hid + 7) // 8 * 8
+                w12 = torch.stack([m.w1.weight, m.w2.weight], 1).reshape(2 * hid, -1)  # rows (w1_j, w2_j)
+                b12 = torch.stack([m.w1.bias, m.w2.bias], 1).reshape(2 * hid)
+                w3 = torch.zeros(m.w3.weight.shape[0], hid_p, dtype=dtype, device=device)
+                w3[:, :hid] = m.w3.weight
+                packed["blocks"].append(dict(
+                    n1w=blk.norm1.weight.to(**f32), n1b=blk.norm1.bias.to(**f32),
+                    wqkv=torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).to(device, dtype).contiguous(),
+                    bqkv=torch.cat([a.q_bias, torch.zeros_like(a.v_bias), a.v_bias]).to(**f32).contiguous(),
+                    lnw=a.inner_attn_ln.weight.to(**f32), lnb=a.inner_attn_ln.bias.to(**f32),
+                    wproj=a.proj.weight.to(device, dtype).contiguous(), bproj=a.proj.bias.to(**f32).contiguous(),
+                    n2w=blk.norm2.weight.to(**f32), n2b=blk.norm2.bias.to(**f32),
+                    w12=w12.to(device, dtype).contiguous(), b12=b12.to(**f32).contiguous(),
+                    fw=m.ffn_ln.weight.to(**f32).contiguous(), fb=m.ffn_ln.bias.to(**f32).contiguous(),
+                    w3=w3, b3=m.w3.bias.to(**f32).contiguous(), hid=hid, hid_p=hid_p))
+        self._packed, self._packed_key = packed, key
+        self._geom = {}
+        return packed
+
+    def _geometry(self, B, g, ws, dtype, device):
+        """Per input geometry: window-major token permutation, abs-pos table, RoPE position maps."""
+        k = (B, g, ws, dtype, str(device))
+        if k in self._geom:
+            return self._geom[k]
+        nw = g // ws if ws else 1
+        w = ws if ws else g
+        ids = torch.arange(g * g, device=device).view(nw, w, nw, w).permute(0, 2, 1, 3).reshape(-1)  # window-major -> raster
+        pos = get_abs_pos(self.pos_embed.detach().float(), self.pretrain_use_cls_token, (g, g)).reshape(g * g, -1)
+        geo = dict(ids=ids, pos=pos[ids].to(dtype).repeat(B, 1).contiguous(),
+                   glb_map=ids.to(torch.int32).repeat(B).contiguous(), inv=torch.argsort(ids))
+        self._geom[k] = geo
+        return geo
+
+    def _engine_forward(self, img):
+        B, _, Hh, Ww = img.shape
+        ps = self.patch_embed.proj.kernel_size[0]
+        g = Hh // ps
+        ws = next((b.window_size for b in self.blocks if b.window_size > 0), 0)
+        dtype, dev = img.dtype, img.device
+        pk = self._pack(dtype, dev)
+        geo = self._geometry(B, g, ws, dtype, dev)
+        C = self.pos_embed.shape[-1]
+        heads = self.blocks[0].attn.num_heads
+        hd = C // heads
+        nw = g // ws if ws else 1
+        w = ws if ws else g
+        # patch embedding as a GEMM over window-major im2col rows; abs-pos added as the epilogue residual
+        cols = img.view(B, 3, nw, w, ps, nw, w, ps).permute(0, 2, 5, 3, 6, 1, 4, 7).reshape(B * g * g, 3 * ps * ps)
+        x = ops.linear_tc(cols, pk["patch_w"], pk["patch_b"], residual=geo["pos"])
+        M = x.shape[0]
+        rope_win = (self.rope_win.freqs_cos.float().contiguous(), self.rope_win.freqs_sin.float().contiguous())
+        rope_glb = (self.rope_glb.freqs_cos.float().contiguous(), self.rope_glb.freqs_sin.float().contiguous())
+        hid_p = pk["blocks"][0]["hid_p"]
+        hbuf = torch.empty((M, hid_p), dtype=dtype, device=dev)
+        hbuf2 = torch.empty((M, hid_p), dtype=dtype, device=dev)
+        for blk, p in zip(self.blocks, pk["blocks"]):
+            h = ops.layernorm(x, p["n1w"], p["n1b"], eps=1e-6)
+            qkv = ops.linear_tc(h, p["wqkv"], p["bqkv"])
+            if blk.window_size > 0:
+                ops.rope_qk_(qkv, rope_win[0], rope_win[1], C, hd)  # position = index inside the window
+                nb, n = B * nw * nw, w * w
+            else:
+                ops.rope_qk_(qkv, rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
+                nb, n = B, g * g
+            q5 = qkv.view(nb, n, 3, heads, hd)
+            o = F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
+                                               q5[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
+            o = o.transpose(1, 2).reshape(M, C)
+            a = ops.layernorm(o, p["lnw"], p["lnb"], eps=1e-6)
+            x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x)
+            h = ops.layernorm(x, p["n2w"], p["n2b"], eps=1e-6)
+            ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]])
+            ops.layernorm(hbuf[:, :p["hid"]], p["fw"], p["fb"], eps=1e-6, out=hbuf2[:, :p["hid"]])
+            x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x)
+        # back to raster order, NCHW
+        x = x.view(B, g * g, C)[:, geo["inv"]]
+        return x.view(B, g, g, C).permute(0, 3, 1, 2)
 
 
 class LastLevelMaxPool(nn.Module):

@@ -208,6 +208,11 @@ class DeformableDETRSegmVL(nn.Module):
             self.name_prompt_fusion_feature = None
         self.model_language = None
         self._text_cache = {}
+        # Numeric mode of the engine.  Parameters stay fp32 (checkpoint precision); with a 16-bit
+        # engine_dtype the backbone runs on libape_b200's tensor-core kernels and the remaining library
+        # ops run under autocast — the reference's own eval recipe casts the whole model to fp16
+        # (tools/train_net.py:641-642).  float32 = strict-parity mode on fp32 library kernels.
+        self.engine_dtype = torch.float32
 
     # -- plumbing ----------------------------------------------------------------------------------
     @property
@@ -315,12 +320,16 @@ class DeformableDETRSegmVL(nn.Module):
             raise NotImplementedError("ape_b200: mask prompts")
         prompt, features_l, fusion = self._text_features(batched_inputs)
         images, img_masks, image_sizes = self.preprocess_image(batched_inputs)
-        features = self.backbone(images)
-        feats = self.neck({f: features[f] for f in self.neck.in_features})
-        masks = [F.interpolate(img_masks[None], size=f.shape[-2:]).to(torch.bool).squeeze(0) for f in feats]
-        pos = [self.position_embedding(m).to(images.dtype) for m in masks]
-        (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory,
-         fusion_out) = self.transformer(feats, masks, pos, None, fusion, None, None)
+        low = self.engine_dtype != torch.float32
+        with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
+            features = self.backbone(images.to(self.engine_dtype))
+            feats = self.neck({f: features[f] for f in self.neck.in_features})
+            masks = [F.interpolate(img_masks[None], size=f.shape[-2:]).to(torch.bool).squeeze(0) for f in feats]
+            pos = [self.position_embedding(m).to(feats[0].dtype) for m in masks]
+            (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory,
+             fusion_out) = self.transformer(feats, masks, pos, None, fusion, None, None)
+        inter_states, init_reference, inter_references = inter_states.float(), init_reference.float(), inter_references.float()
+        fusion_out = fusion_out.float() if fusion_out is not None else None
         if prompt == "name":
             features_l = 1.0 * features_l + 0.0 * fusion_out  # (:446)
         else:

@@ -125,7 +125,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu": 3}
 
 
-def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0):
+def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0, out=None):
     """act(x @ weight.T + bias) (+ residual) on the tcgen05 tensor cores (ape_gemm_tn).
 
     x [..., K] and weight [N, K] fp16/bf16 with unit inner stride; bias fp32 [N] (or None); residual
@@ -141,9 +141,15 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
         x2 = x2.contiguous()
     _require(weight.stride(0) % 8 == 0 and weight.data_ptr() % 16 == 0, "linear_tc: weight rows must be 16-byte aligned")
     M = x2.shape[0]
-    out_dtype = out_dtype or x.dtype
     n_out = N // 2 if act == "swiglu" else N
-    out = torch.empty((M, n_out), dtype=out_dtype, device=x.device)
+    if out is None:
+        out_dtype = out_dtype or x.dtype
+        out = torch.empty((M, n_out), dtype=out_dtype, device=x.device)
+        ret_view = True
+    else:
+        _require(out.dim() == 2 and out.shape == (M, n_out) and out.stride(1) == 1 and out.is_cuda, "linear_tc: bad `out`")
+        out_dtype = out.dtype
+        ret_view = False
     res_ptr, ldr = None, 0
     if residual is not None:
         r2 = residual.reshape(-1, n_out)
@@ -157,7 +163,40 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
                                   M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
                                   _lib.current_stream_ptr())
     _lib.check(rc, "ape_gemm_tn")
-    return out.view(*x.shape[:-1], n_out)
+    return out.view(*x.shape[:-1], n_out) if ret_view else out
+
+
+def layernorm(x, weight, bias, eps=1e-5, out_dtype=None, row_map=None, out=None):
+    """LayerNorm over the last dim (ape_layernorm).  x [..., C] with unit inner stride and uniform row
+    pitch; weight / bias fp32.  row_map: int32 [rows] output row of each input row (or None)."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C) if x.dim() != 2 else x
+    _require(x2.is_cuda and x2.stride(1) == 1, "layernorm: CUDA tensor with unit inner stride")
+    _require(weight.dtype == torch.float32 and bias.dtype == torch.float32, "layernorm: fp32 weight / bias")
+    rows = x2.shape[0]
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty((rows, C), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device), _timed(("layernorm", rows, C)):
+        rc = _lib.lib.ape_layernorm(x2.data_ptr(), x2.stride(0), out.data_ptr(), out.stride(0), weight.data_ptr(),
+                                    bias.data_ptr(), row_map.data_ptr() if row_map is not None else None, rows, C,
+                                    float(eps), _lib.dtype_code(x2.dtype), _lib.dtype_code(out.dtype),
+                                    _lib.current_stream_ptr())
+    _lib.check(rc, "ape_layernorm")
+    return out if x.dim() == 2 or out.shape[1] != C else out.view(*x.shape[:-1], C)
+
+
+def rope_qk_(qkv, cos, sin, num_channels, head_dim, pos_map=None):
+    """In-place 2-D RoPE on the q and k thirds of qkv [M, 3*num_channels] (ape_rope_qk)."""
+    _require(qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1, "rope: qkv must be a 2-D CUDA tensor")
+    _require(cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[1] == head_dim,
+             "rope: cos/sin must be contiguous fp32 [npos, head_dim]")
+    with torch.cuda.device(qkv.device), _timed(("rope_qk", qkv.shape[0], num_channels)):
+        rc = _lib.lib.ape_rope_qk(qkv.data_ptr(), qkv.stride(0), cos.data_ptr(), sin.data_ptr(),
+                                  pos_map.data_ptr() if pos_map is not None else None, qkv.shape[0], num_channels,
+                                  head_dim, cos.shape[0], _lib.dtype_code(qkv.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_rope_qk")
+    return qkv
 
 
 def _ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

@@ -115,6 +115,23 @@ int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C,
                 const void *residual, int64_t ldr, int M, int N, int K, int in_dtype, int out_dtype, int act,
                 int tile_n, void *stream);
 
+/*
+ * LayerNorm over the last dimension (nn.LayerNorm / inner_attn_ln / ffn_ln of vit_eva_clip.py:505-523,266,130;
+ * norms of the detrex transformer layers).  fp32 statistics; x [rows, C] pitch ldx (in_dtype), y pitch ldy
+ * (out_dtype); weight/bias fp32 [C].  Pitches must cover C rounded up to 8 elements; padding elements
+ * are written as 0.  row_map (int32 [rows], device) or NULL: output row of input row r (window partition).
+ */
+int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
+                  const int *row_map, int rows, int C, float eps, int in_dtype, int out_dtype, void *stream);
+
+/*
+ * In-place 2-D rotary embedding on the q and k thirds of a fused qkv buffer [M, 3*C] (pitch ld):
+ * t' = t*cos + rotate_half(t)*sin (VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346).
+ * cos/sin fp32 [npos, head_dim]; token m uses row pos_map[m] (int32, device) or m % npos when NULL.
+ */
+int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_table, const int *pos_map, int M,
+                int C, int head_dim, int npos, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,73 @@
+"""GPU: LayerNorm and 2-D RoPE kernels against plain PyTorch fp32 references of the same ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import ape_b200
+
+    return ape_b200.ops
+
+
+@pytest.mark.parametrize("C", [256, 1024, 2730, 64, 4096])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_layernorm(ops, C, dtype):
+    g = torch.Generator().manual_seed(C)
+    rows = 777
+    pitch = (C + 7) // 8 * 8 + 16
+    buf = torch.zeros(rows, pitch, dtype=dtype, device=DEV)
+    buf[:, :C] = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(dtype).to(DEV)
+    buf[:, C:] = 7.0  # garbage in the padding must not influence the statistics
+    x = buf[:, :C]
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    out = torch.full((rows, pitch), 3.0, dtype=dtype, device=DEV)
+    y = ops.layernorm(x, w, b, eps=1e-6, out=out[:, :C])
+    want = F.layer_norm(x.float(), (C,), w, b, 1e-6)
+    tol = {torch.float32: 1e-5, torch.float16: 4e-3, torch.bfloat16: 3e-2}[dtype]
+    torch.testing.assert_close(y.float(), want, rtol=tol, atol=tol)
+    pad_end = (C + 7) // 8 * 8
+    assert (out[:, C:pad_end] == 0).all()  # alignment padding zeroed
+    assert (out[:, pad_end:] == 3.0).all()  # nothing written beyond
+
+
+def test_layernorm_row_map_and_dtype_change(ops):
+    rows, C = 64, 256
+    x = torch.randn(rows, C, device=DEV)
+    w, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    perm = torch.randperm(rows, device=DEV).to(torch.int32)
+    y = ops.layernorm(x, w, b, out_dtype=torch.float16, row_map=perm)
+    want = torch.empty_like(x)
+    want[perm.long()] = F.layer_norm(x, (C,))
+    torch.testing.assert_close(y.float(), want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_rope_matches_reference_formula(ops, dtype):
+    heads, hd, npos, M = 4, 64, 16, 48
+    C = heads * hd
+    g = torch.Generator().manual_seed(0)
+    qkv = torch.randn(M, 3 * C, generator=g).to(dtype).to(DEV)
+    ang = torch.randn(npos, hd, generator=g)
+    cos, sin = ang.cos().to(DEV), ang.sin().to(DEV)
+    pos = torch.randint(0, npos, (M,), generator=g).to(torch.int32).to(DEV)
+
+    def ref(t, p):  # utils_eva02.py:248-252,346
+        t = t.float().view(M, heads, hd)
+        x = t.reshape(M, heads, hd // 2, 2)
+        rot = torch.stack((-x[..., 1], x[..., 0]), -1).flatten(-2)
+        return (t * cos[p][:, None] + rot * sin[p][:, None]).reshape(M, C)
+
+    for pm in (pos, None):
+        buf = qkv.clone()
+        ops.rope_qk_(buf, cos, sin, C, hd, pos_map=pm)
+        p = pos.long() if pm is not None else torch.arange(M, device=DEV) % npos
+        tol = 1e-5 if dtype == torch.float32 else 4e-3
+        torch.testing.assert_close(buf[:, :C].float(), ref(qkv[:, :C], p), rtol=tol, atol=tol)
+        torch.testing.assert_close(buf[:, C:2 * C].float(), ref(qkv[:, C:2 * C], p), rtol=tol, atol=tol)
+        assert torch.equal(buf[:, 2 * C:], qkv[:, 2 * C:])  # v untouched
