@@ -65,6 +65,11 @@ class FFN(nn.Module):
         )
 
     def forward(self, x):
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
+            from .. import ops  # tensor-core path: ReLU and the residual add live in the GEMM epilogues
+
+            h = ops.linear_module_tc(self.layers[0][0], x, act="relu")
+            return ops.linear_module_tc(self.layers[1], h, residual=x.contiguous())
         return x + self.layers[1](F.relu(self.layers[0][0](x)))
 
 

@@ -113,18 +113,27 @@ class MultiScaleDeformableAttention(nn.Module):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
                 reference_points.shape[-1]))
 
-        value = self.value_proj(value)
+        engine = query.dtype in (torch.float16, torch.bfloat16) and value.dtype == query.dtype
+        wq, bq = self._query_side_weights()
+        if engine:
+            # tensor-core path: tcgen05 GEMMs (fp32 accumulate), fused gather kernel, residual in the epilogue
+            value = ops.linear_module_tc(self.value_proj, value)
+            key = ("q", query.dtype, wq._version, wq.data_ptr())
+            if getattr(self, "_q16", (None,))[0] != key:
+                self._q16 = (key, wq.to(query.dtype).contiguous(), bq.float().contiguous())
+            qo = ops.linear_tc(query, self._q16[1], self._q16[2])
+        else:
+            value = self.value_proj(value)
+            qo = F.linear(query, wq, bq)  # [B,Q, H*L*P*2 + H*L*P]
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], float(0))
         value = value.view(bs, num_value, self.num_heads, -1).contiguous()
-
-        wq, bq = self._query_side_weights()
-        qo = F.linear(query, wq, bq)  # [B,Q, H*L*P*2 + H*L*P]
         n_off = self.num_heads * self.num_levels * self.num_points * 2
         output = ops.ms_deform_attn_fused_forward(
             value, spatial_shapes, level_start_index, qo[..., :n_off], qo[..., n_off:],
             reference_points.to(torch.float32).contiguous(), self.num_points)
-
+        if engine and self.batch_first and identity.dtype == output.dtype:
+            return ops.linear_module_tc(self.output_proj, output, residual=identity.contiguous())
         output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)

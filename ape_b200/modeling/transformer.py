@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torchvision
 
+from .. import ops
 from ..layers import MultiScaleDeformableAttention
 from ..layers.common import FFN, box_cxcywh_to_xyxy, inverse_sigmoid
 
@@ -55,6 +56,10 @@ class _EncoderLayer(nn.Module):
         x = self.attentions[0](query, None, query, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
                                reference_points=reference_points, spatial_shapes=spatial_shapes,
                                level_start_index=level_start_index)
+        if x.dtype in (torch.float16, torch.bfloat16):  # engine path: libape_b200 LayerNorm kernel
+            x = ops.layernorm_module(self.norms[0], x)
+            x = self.ffns[0](x)
+            return ops.layernorm_module(self.norms[1], x)
         x = self.norms[0](x)
         x = self.ffns[0](x)
         return self.norms[1](x)
@@ -100,10 +105,24 @@ class DeformableDetrTransformerEncoderVL(nn.Module):
 
     def forward(self, query, key, value, query_l, attention_mask_l, query_pos=None, key_pos=None, attn_masks=None,
                 query_key_padding_mask=None, key_padding_mask=None, **kwargs):
+        engine_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+        if engine_dtype is not None:
+            query, query_pos = query.to(engine_dtype), query_pos.to(engine_dtype)
         for vl_layer, layer in zip(self.vl_layers, self.layers):
             if vl_layer is not None and query_l is not None:
-                query, query_l = vl_layer(query, query_l, attention_mask_v=query_key_padding_mask,
-                                          attention_mask_l=attention_mask_l)
+                if engine_dtype is not None and query_l.shape[1] == 1 and attention_mask_l is None:
+                    b = vl_layer.b_attn
+                    v = ops.layernorm_module(b.layer_norm_v, query)
+                    with torch.autocast("cuda", enabled=False):
+                        ln_l = b.layer_norm_l(query_l.float())
+                        dv, dl = b.single_token(v, ln_l)
+                        query = v + (b.gamma_v.float() * dv.float()).to(v.dtype)
+                        query_l = ln_l + b.gamma_l.float() * dl
+                else:
+                    query, query_l = vl_layer(query, query_l, attention_mask_v=query_key_padding_mask,
+                                              attention_mask_l=attention_mask_l)
+                    if engine_dtype is not None:
+                        query = query.to(engine_dtype)
             query = layer(query, query_pos, query_key_padding_mask, kwargs["reference_points"],
                           kwargs["spatial_shapes"], kwargs["level_start_index"])
         if self.post_norm_layer is not None:

@@ -166,6 +166,32 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
     return out.view(*x.shape[:-1], n_out) if ret_view else out
 
 
+def packed(module, dtype, extra=None):
+    """(weight in `dtype`, fp32 bias) of an nn.Linear / nn.LayerNorm-like module, cached on the module and
+    refreshed when its parameters change (load_state_dict, .to()).  LayerNorm weights stay fp32."""
+    w, b = module.weight, getattr(module, "bias", None)
+    key = (dtype, w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+    cache = module.__dict__.get("_ape_packed")
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            wd = w.detach().to(dtype if w.dim() >= 2 else torch.float32).contiguous()
+            bd = None if b is None else b.detach().to(torch.float32).contiguous()
+        cache = (key, wd, bd)
+        module.__dict__["_ape_packed"] = cache
+    return cache[1], cache[2]
+
+
+def linear_module_tc(module, x, act=None, residual=None, out_dtype=None):
+    """nn.Linear forward on the tensor cores (weights packed once per dtype)."""
+    w, b = packed(module, x.dtype)
+    return linear_tc(x, w, b, act=act, residual=residual, out_dtype=out_dtype)
+
+
+def layernorm_module(module, x, out_dtype=None):
+    w, b = packed(module, x.dtype)
+    return layernorm(x, w, b, eps=module.eps, out_dtype=out_dtype)
+
+
 def layernorm(x, weight, bias, eps=1e-5, out_dtype=None, row_map=None, out=None):
     """LayerNorm over the last dim (ape_layernorm).  x [..., C] with unit inner stride and uniform row
     pitch; weight / bias fp32.  row_map: int32 [rows] output row of each input row (or None)."""

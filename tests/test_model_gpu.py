@@ -83,7 +83,8 @@ def test_mini_matches_oracle_port(mini):
     outs = [(112, 128), (64, 33)]
     res, taps = AF.forward(images, outs, synth.text_features(8192, spec["lang_dim"])[: spec["num_classes"]], sd, spec)
     out = model([{"image": im, "height": o[0], "width": o[1]} for im, o in zip(images, outs)])
-    assert torch.equal(model.transformer.last_topk_proposals.cpu(), taps["topk_proposals"])
+    valid = (taps["init_reference"] < 1).all(-1)  # see test_mini_matches_reference_golden: ties among padded proposals
+    assert torch.equal(model.transformer.last_topk_proposals.cpu()[valid], taps["topk_proposals"][valid])
     torch.testing.assert_close(model.last_outputs["pred_logits"].cpu(), taps["pred_logits"], rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(model.last_outputs["pred_boxes"].cpu(), taps["pred_boxes"], rtol=1e-3, atol=1e-4)
     for r, o in zip(res, out):
