@@ -9,10 +9,12 @@
 //   VisionLanguageAlign contraction            ape/layers/vision_language_align.py:36-48
 // `W` is consumed in nn.Linear's own [out_features, in_features] layout: both operands are K-major.
 //
-// Kernel shape (persistent, warp-specialised, 192 threads, 1 CTA / SM):
+// Kernel shape (persistent, warp-specialised, 320 threads, 1 CTA / SM):
 //   warp 0     TMA producer   : STAGES-deep ring of {A 128x64, B BNx64} 16-bit tiles, mbarrier full/empty
 //   warp 1     MMA issuer     : 4 x tcgen05.mma (M=128, N=BN, K=16) per stage; owns the TMEM allocation
-//   warps 2-5  epilogue       : TMEM quadrant (warp_id % 4) -> registers -> bias/act/residual -> global
+//   warps 2-9  epilogue       : TMEM quadrant (warp_id % 4), column half ((warp_id-2)/4): tcgen05.ld ->
+//                               bias/act/residual in registers -> 16-bit pack -> 128B-swizzled smem slab
+//                               (32 rows x 64 cols) -> TMA store (coalesced, clips the M/N edges)
 //   TMEM holds two BN-column accumulators so tile i's epilogue overlaps tile i+1's main loop.
 #include "common.cuh"
 #include "tc.cuh"
@@ -33,6 +35,7 @@ struct GemmParams {
   int m_blocks, n_blocks, k_blocks;
   int out_dtype;  // APE_DTYPE_*
   int act;
+  int tma_store;  // 16-bit output with 16-byte aligned rows: epilogue goes through smem + TMA store
   uint32_t idesc;
 };
 
@@ -40,10 +43,13 @@ template <int BN, int STAGES>
 struct alignas(1024) GemmSmem {
   uint8_t a[STAGES][BM * BK * 2];
   uint8_t b[STAGES][BN * BK * 2];
+  uint8_t c[8][32 * 128];  // per epilogue warp: 32 rows x 64 16-bit columns, 128-byte swizzle (1024 B aligned)
   uint64_t full[STAGES], empty[STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
+
+constexpr int kThreads = 320;
 
 __device__ __forceinline__ float act_fn(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
@@ -115,10 +121,130 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
   store_row<TO>(C + (size_t)m * p.ldc + n0, v, nvalid);
 }
 
+
+// 64 accumulator columns of one row -> +bias, activation, +residual (all fp32) in place.
+template <typename TO>
+__device__ __forceinline__ void finish64(const GemmParams &p, float *v, int m, int n0) {
+  if (p.bias != nullptr) {
+    if (n0 + 64 <= p.N) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
+        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+    }
+  }
+  if (p.act == ACT_RELU || p.act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = act_fn(v[i], p.act);
+  }
+  if (p.residual != nullptr && m < p.M) {
+    const TO *res = reinterpret_cast<const TO *>(p.residual) + (size_t)m * p.ldr + n0;
+    if (n0 + 64 <= p.N && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float f[8];
+        Elem<TO>::unpack(__ldg(reinterpret_cast<const uint4 *>(res) + i), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[8 * i + k] += f[k];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i)
+        if (n0 + i < p.N) v[i] += Elem<TO>::to_f(res[i]);
+    }
+  }
+}
+
+// Epilogue of one warp for its (32 rows) x (BN/2 accumulator columns) part of a tile, 16-bit output,
+// staged through a swizzled shared-memory slab and written with TMA stores.
+template <typename TO, int BN>
+__device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab,
+                                             uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk) {
+  const int row0 = m_blk * BM + quad * 32;
+  const int m = row0 + lane;
+  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16);
+  uint8_t *my_row = slab + lane * 128;
+  constexpr int HALF = BN / 2;
+  if (p.act == ACT_SWIGLU) {
+    // 128 accumulator columns (64 gate/up pairs) -> 64 output columns = one slab
+#pragma unroll 1
+    for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 128) {
+      if (lane == 0) tc::tma_store_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[64];
+        tc::tmem_ld_32x32b_x32(trow + c0 + hh * 64, r);
+        tc::tmem_ld_32x32b_x32(trow + c0 + hh * 64 + 32, r + 32);
+        tc::tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+        GemmParams q = p;
+        q.residual = nullptr;
+        const int n0 = n_blk * BN + c0 + hh * 64;
+        // bias only (activation is the gate below)
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+        }
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float g = v[2 * i];
+          o[i] = g / (1.f + __expf(-g)) * v[2 * i + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = hh * 4 + j;
+          *reinterpret_cast<uint4 *>(my_row + ((chunk ^ (lane & 7)) << 4)) = Elem<TO>::pack(o + 8 * j);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tc::tma_store_2d(map_c, slab, (n_blk * BN + c0) / 2, row0);
+        tc::tma_store_commit();
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 64) {
+    const int n0 = n_blk * BN + c0;
+    if (n0 >= p.N) break;
+    uint32_t r[64];
+    tc::tmem_ld_32x32b_x32(trow + c0, r);
+    tc::tmem_ld_32x32b_x32(trow + c0 + 32, r + 32);
+    tc::tmem_ld_wait();
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+    finish64<TO>(p, v, m, n0);
+    if (lane == 0) tc::tma_store_wait_read0();  // previous store of this warp has drained the slab
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4 *>(my_row + ((j ^ (lane & 7)) << 4)) = Elem<TO>::pack(v + 8 * j);
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_store_2d(map_c, slab, n0, row0);
+      tc::tma_store_commit();
+    }
+  }
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   using Smem = GemmSmem<BN, STAGES>;
   Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,6 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(&map_a);
     tc::prefetch_tensormap(&map_b);
+    if (p.tma_store) tc::prefetch_tensormap(&map_c);
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       tc::mbar_init(&s.full[i], 1);
@@ -139,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&s.tmem_full[i], 1);
-      tc::mbar_init(&s.tmem_empty[i], 4);  // one arrival per epilogue warp
+      tc::mbar_init(&s.tmem_empty[i], 8);  // one arrival per epilogue warp
     }
     tc::fence_mbar_init();
   }
@@ -195,24 +322,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp % 4;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp % 4;        // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) / 4;  // which half of the tile's columns
+    uint8_t *slab = s.c[warp - 2];
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
-      const int m = m_blk * BM + quad * 32 + lane;
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
+      if (p.tma_store) {
+        if (p.out_dtype == APE_DTYPE_F16)
+          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+        else
+          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+      } else {
+        const int m = m_blk * BM + quad * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, r);
-        tc::tmem_ld_wait();
-        if (m < p.M) {
-          const int n0 = n_blk * BN + c * 32;
-          if (p.out_dtype == APE_DTYPE_F32) epilogue_chunk<float>(p, r, m, n0);
-          else if (p.out_dtype == APE_DTYPE_F16) epilogue_chunk<__half>(p, r, m, n0);
-          else epilogue_chunk<__nv_bfloat16>(p, r, m, n0);
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, r);
+          tc::tmem_ld_wait();
+          if (m < p.M) {
+            const int n0 = n_blk * BN + c * 32;
+            if (p.out_dtype == APE_DTYPE_F32) epilogue_chunk<float>(p, r, m, n0);
+            else if (p.out_dtype == APE_DTYPE_F16) epilogue_chunk<__half>(p, r, m, n0);
+            else epilogue_chunk<__nv_bfloat16>(p, r, m, n0);
+          }
         }
       }
       tc::fence_before_sync();
@@ -220,6 +356,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) tc::mbar_arrive(&s.tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA exits
+    __syncwarp();
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -247,12 +385,13 @@ EncodeTiledFn get_encoder() {
 }
 
 // [rows, K] 16-bit row-major matrix with pitch `ld` elements; box = 64 (K) x box_rows, 128 B swizzle.
-int make_map(CUtensorMap *map, const void *base, int dtype, long long rows, long long K, long long ld, int box_rows) {
+int make_map(CUtensorMap *map, const void *base, int dtype, long long rows, long long K, long long ld, int box_rows,
+             int box_cols = BK) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) return fail(APE_ERR_UNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -273,7 +412,7 @@ int num_sms() {
 }
 
 template <int BN, int STAGES>
-int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmParams &p, cudaStream_t st) {
+int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, GemmParams &p, cudaStream_t st) {
   using Smem = GemmSmem<BN, STAGES>;
   const size_t smem = sizeof(Smem) + 1024;
   auto k = gemm_tc_kernel<BN, STAGES>;
@@ -286,7 +425,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, GemmParams &p, cud
   p.n_blocks = (p.N + BN - 1) / BN;
   const int tiles = p.m_blocks * p.n_blocks;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  k<<<grid, 192, smem, st>>>(ma, mb, p);
+  k<<<grid, kThreads, smem, st>>>(ma, mb, mc, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -324,6 +463,13 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
   p.k_blocks = (K + BK - 1) / BK;
   p.out_dtype = out_dtype; p.act = act;
   p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
-  if (bn == 256) return launch_gemm<256, 4>(ma, mb, p, st);
-  return launch_gemm<128, 6>(ma, mb, p, st);
+  // 16-bit outputs with 16-byte aligned rows leave through shared memory + TMA stores
+  const int n_out = act == ACT_SWIGLU ? N / 2 : N;
+  CUtensorMap mc = ma;
+  p.tma_store = out_dtype != APE_DTYPE_F32 && (ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                (act != ACT_SWIGLU || bn == 256);
+  if (p.tma_store)
+    if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 64)) return rc;
+  if (bn == 256) return launch_gemm<256, 4>(ma, mb, mc, p, st);
+  return launch_gemm<128, 6>(ma, mb, mc, p, st);
 }

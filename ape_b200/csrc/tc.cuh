@@ -57,6 +57,19 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
+// 2-D tile store shared -> global (bulk async group); out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores of this thread have finished READING shared memory (buffer reusable)
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before issuing a store
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- tcgen05 ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)

@@ -104,8 +104,9 @@ def detector_postprocess(result: Instances, out_h, out_w):
     b = torch.stack((b[:, 0].clamp(min=0, max=out_w), b[:, 1].clamp(min=0, max=out_h),
                      b[:, 2].clamp(min=0, max=out_w), b[:, 3].clamp(min=0, max=out_h)), dim=-1)
     keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+    extra = {k: v[keep] for k, v in result.get_fields().items() if k not in ("pred_boxes", "scores", "pred_classes")}
     return Instances((out_h, out_w), pred_boxes=Boxes(b[keep]), scores=result.scores[keep],
-                     pred_classes=result.pred_classes[keep])
+                     pred_classes=result.pred_classes[keep], **extra)
 
 
 class _Criterion(nn.Module):
@@ -213,6 +214,8 @@ class DeformableDETRSegmVL(nn.Module):
         # ops run under autocast — the reference's own eval recipe casts the whole model to fp16
         # (tools/train_net.py:641-642).  float32 = strict-parity mode on fp32 library kernels.
         self.engine_dtype = torch.float32
+        self.use_cuda_graphs = False  # capture the static stages once per input geometry (16-bit engine mode)
+        self._geo_cache, self._graph_cache = {}, {}
 
     # -- plumbing ----------------------------------------------------------------------------------
     @property
@@ -321,24 +324,29 @@ class DeformableDETRSegmVL(nn.Module):
         prompt, features_l, fusion = self._text_features(batched_inputs)
         images, img_masks, image_sizes = self.preprocess_image(batched_inputs)
         low = self.engine_dtype != torch.float32
+        geo = self._geometry(images.shape, image_sizes, img_masks)
+        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
-            features = self.backbone(images.to(self.engine_dtype))
-            feats = self.neck({f: features[f] for f in self.neck.in_features})
-            masks = [F.interpolate(img_masks[None], size=f.shape[-2:]).to(torch.bool).squeeze(0) for f in feats]
-            pos = [self.position_embedding(m).to(feats[0].dtype) for m in masks]
-            (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory,
-             fusion_out) = self.transformer(feats, masks, pos, None, fusion, None, None)
-        inter_states, init_reference, inter_references = inter_states.float(), init_reference.float(), inter_references.float()
-        fusion_out = fusion_out.float() if fusion_out is not None else None
-        if prompt == "name":
-            features_l = 1.0 * features_l + 0.0 * fusion_out  # (:446)
-        else:
-            features_l = 0.0 * features_l + 1.0 * fusion_out  # (:448)
-        # only the last decoder level feeds inference (:514-523); levels 0..n-2 are aux outputs
-        lvl = inter_states.shape[0] - 1
-        reference = init_reference if lvl == 0 else inter_references[lvl - 1]
-        box_cls = self.class_embed[lvl](inter_states[lvl], features_l)
-        box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
+            if graphs:
+                memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._graphed(
+                    ("encode", tuple(images.shape), tuple(image_sizes)), self._stage_encode, (images, fusion), (geo,))
+            else:
+                memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+            topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
+            self.transformer.last_topk_proposals = topk
+            if prompt == "name":
+                if fusion_out is not None:
+                    features_l = 1.0 * features_l + 0.0 * fusion_out.float()  # (:446)
+            else:
+                features_l = 0.0 * features_l + 1.0 * fusion_out.float()  # (:448)
+            if graphs:
+                # memory / output_memory / enc_coord are the encode graph's static outputs: constants of this graph
+                box_cls, box_pred, inter_states, init_reference, inter_references = self._graphed(
+                    ("decode", memory.data_ptr(), tuple(image_sizes), tuple(features_l.shape)), self._stage_decode,
+                    (topk, features_l), (memory, output_memory, enc_coord, geo))
+            else:
+                box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
+                    topk, features_l, memory, output_memory, enc_coord, geo)
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
@@ -353,6 +361,69 @@ class DeformableDETRSegmVL(nn.Module):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
             out.append({"instances": detector_postprocess(r, h, w).to("cpu")})
         return out
+
+    # -- stages (static shapes, no host synchronisation: CUDA-graph capturable) -----------------------------
+    def _geometry(self, batch_shape, image_sizes, img_masks):
+        """Padding masks, sine position embeddings (:375-392) and the transformer's geometric constants for
+        one (batch shape, image sizes) combination; cached — they do not depend on pixel values."""
+        key = (tuple(batch_shape), tuple(image_sizes))
+        geo = self._geo_cache.get(key)
+        if geo is None:
+            strides = [self.backbone._out_feature_strides[f] for f in self.neck.in_features]
+            H, W = batch_shape[-2], batch_shape[-1]
+            shapes = [(-(-H // s), -(-W // s)) for s in strides]
+            masks = [F.interpolate(img_masks[None], size=sh).to(torch.bool).squeeze(0) for sh in shapes]
+            pos = [self.position_embedding(m).to(torch.float32) for m in masks]
+            geo = self.transformer.geometry(shapes, masks, pos)
+            if len(self._geo_cache) > 16:
+                self._geo_cache.clear()
+            self._geo_cache[key] = geo
+        return geo
+
+    def _stage_encode(self, images, fusion, geo):
+        features = self.backbone(images.to(self.engine_dtype))
+        feats = self.neck({f: features[f] for f in self.neck.in_features})
+        memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(feats, geo, fusion)
+        return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats
+
+    def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo):
+        inter_states, init_reference, inter_references = self.transformer.stage_decode(
+            memory, output_memory, enc_coord, topk, geo)
+        inter_states, init_reference, inter_references = inter_states.float(), init_reference.float(), inter_references.float()
+        # only the last decoder level feeds inference (:514-523); levels 0..n-2 are aux outputs
+        lvl = inter_states.shape[0] - 1
+        reference = init_reference if lvl == 0 else inter_references[lvl - 1]
+        with torch.autocast("cuda", enabled=False):
+            box_cls = self.class_embed[lvl](inter_states[lvl], features_l.float())
+            box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
+        return box_cls, box_pred, inter_states, init_reference, inter_references
+
+    def _graphed(self, key, fn, tensor_args, const_args):
+        """Run fn(*tensor_args, *const_args) through a CUDA graph captured once per key: inputs are copied into
+        static buffers, the replay reuses the captured launch sequence (about 2 000 kernel launches per image
+        otherwise dominate the wall clock).  Outputs are static buffers, valid until the next replay of `key`."""
+        entry = self._graph_cache.get(key)
+        if entry is None:
+            static_in = [t.clone() for t in tensor_args]
+            # autocast's weight-cast cache must be off while capturing: cached casts would be freed when the
+            # autocast region ends while the graph still reads them
+            with torch.autocast("cuda", dtype=self.engine_dtype, cache_enabled=False):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):  # warm-up: packs weights, fills caches, sets kernel attributes
+                        fn(*static_in, *const_args)
+                torch.cuda.current_stream().wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = fn(*static_in, *const_args)
+            entry = (graph, static_in, static_out)
+            self._graph_cache[key] = entry
+        graph, static_in, static_out = entry
+        for dst, src in zip(static_in, tensor_args):
+            dst.copy_(src)
+        graph.replay()
+        return static_out
 
     def inference(self, box_cls, box_pred, image_sizes):
         """:759-810 + fast_rcnn.py:40-95."""

@@ -287,36 +287,63 @@ class DeformableDetrTransformerVL(nn.Module):
             km[pad] = True
         return keep[km]
 
-    def forward(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, query_embed, query_l,
-                attention_mask_l, multi_level_masks_prompt, **kwargs):
-        feat_flatten, mask_flatten, pos_flatten, shapes = [], [], [], []
-        for lvl, (feat, mask, pos) in enumerate(zip(multi_level_feats, multi_level_masks, multi_level_pos_embeds)):
-            bs, c, h, w = feat.shape
-            shapes.append((h, w))
-            feat_flatten.append(feat.flatten(2).transpose(1, 2))
-            mask_flatten.append(mask.flatten(1))
-            pos_flatten.append(pos.flatten(2).transpose(1, 2) + self.level_embeds[lvl].view(1, 1, -1))
-        feat_flatten = torch.cat(feat_flatten, 1)
-        mask_flatten = torch.cat(mask_flatten, 1)
-        pos_flatten = torch.cat(pos_flatten, 1)
-        dev = feat_flatten.device
+    # -- staged forward ------------------------------------------------------------------------------
+    # forward() = geometry() [pure function of the padded-image geometry, cacheable] -> stage_encode()
+    # [static shapes, no host sync: CUDA-graph capturable] -> stage_select() [top-k / NMS, data dependent]
+    # -> stage_decode() [static shapes again].
+    def geometry(self, shapes, multi_level_masks, multi_level_pos_embeds):
+        """Everything that depends only on the feature-map shapes and the padding masks
+        (deformable_transformer_vl.py:435-477 and the anchor part of :321-353)."""
+        dev = multi_level_masks[0].device
+        mask_flatten = torch.cat([m.flatten(1) for m in multi_level_masks], 1)
+        pos_flatten = torch.cat([p.flatten(2).transpose(1, 2) for p in multi_level_pos_embeds], 1)
         spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=dev)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
-        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in multi_level_masks], 1).to(feat_flatten.dtype)
-        if multi_level_masks_prompt is not None:
-            mask_prompt_flatten = torch.cat([m.flatten(1) for m in multi_level_masks_prompt], 1)
-        else:
-            mask_prompt_flatten = None
-        reference_points = self.get_reference_points(shapes, valid_ratios, dev).to(feat_flatten.dtype)
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in multi_level_masks], 1).to(torch.float32)
+        reference_points = self.get_reference_points(shapes, valid_ratios, dev).to(torch.float32)
+        N = mask_flatten.shape[0]
+        proposals, level_ids = [], []
+        cur = 0
+        for lvl, (H, W) in enumerate(shapes):
+            m = mask_flatten[:, cur:cur + H * W].view(N, H, W, 1)
+            valid_H = torch.sum(~m[:, :, 0, 0], 1)
+            valid_W = torch.sum(~m[:, 0, :, 0], 1)
+            gy, gx = torch.meshgrid(torch.linspace(0, H - 1, H, dtype=torch.float32, device=dev),
+                                    torch.linspace(0, W - 1, W, dtype=torch.float32, device=dev), indexing="ij")
+            grid = torch.cat([gx.unsqueeze(-1), gy.unsqueeze(-1)], -1)
+            scale = torch.cat([valid_W.unsqueeze(-1), valid_H.unsqueeze(-1)], 1).view(N, 1, 1, 2)
+            grid = (grid.unsqueeze(0).expand(N, -1, -1, -1) + 0.5) / scale
+            wh = torch.ones_like(grid) * 0.05 * (2.0 ** lvl)
+            proposals.append(torch.cat((grid, wh), -1).view(N, -1, 4))
+            cur += H * W
+            level_ids.append(grid.new_ones(H * W, dtype=torch.long) * lvl)
+        out = torch.cat(proposals, 1)
+        valid = ((out > 0.01) & (out < 0.99)).all(-1, keepdim=True)
+        out = torch.log(out / (1 - out))
+        out = out.masked_fill(mask_flatten.unsqueeze(-1), float("inf")).masked_fill(~valid, float("inf"))
+        return dict(shapes=list(shapes), mask_flatten=mask_flatten, pos_flatten=pos_flatten, spatial_shapes=spatial_shapes,
+                    level_start_index=level_start_index, valid_ratios=valid_ratios, reference_points=reference_points,
+                    output_proposals=out, proposal_invalid=mask_flatten.unsqueeze(-1) | ~valid,
+                    level_ids=torch.cat(level_ids), has_padding=bool(mask_flatten.any()))
 
+    def stage_encode(self, multi_level_feats, geo, query_l, attention_mask_l=None, mask_prompt_flatten=None):
+        feat_flatten = torch.cat([f.flatten(2).transpose(1, 2) for f in multi_level_feats], 1)
+        lvl_embed = torch.cat([self.level_embeds[i].view(1, 1, -1).expand(1, h * w, -1)
+                               for i, (h, w) in enumerate(geo["shapes"])], 1)
+        pos_flatten = geo["pos_flatten"] + lvl_embed
         memory, query_l = self.encoder(
             query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
-            query_pos=pos_flatten, query_key_padding_mask=mask_flatten, spatial_shapes=spatial_shapes,
-            reference_points=reference_points, level_start_index=level_start_index, valid_ratios=valid_ratios)
-
-        bs, _, c = memory.shape
-        output_memory, output_proposals, level_ids = self.gen_encoder_output_proposals(
-            memory, mask_flatten, shapes, mask_prompt_flatten)
+            query_pos=pos_flatten, query_key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
+            spatial_shapes=geo["spatial_shapes"], reference_points=geo["reference_points"],
+            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"])
+        # gen_encoder_output_proposals (:354-369): zero the memory of invalid anchors, project, normalise
+        output_proposals = geo["output_proposals"]
+        invalid = geo["proposal_invalid"]
+        if mask_prompt_flatten is not None:
+            output_proposals = output_proposals.masked_fill(~mask_prompt_flatten.unsqueeze(-1), float("inf"))
+            invalid = invalid | ~mask_prompt_flatten.unsqueeze(-1)
+        output_memory = self.enc_output_norm(self.enc_output(memory.masked_fill(invalid, float(0))))
+        output_proposals = output_proposals.to(output_memory.dtype)
         nd = self.decoder.num_layers
         enc_cls = self.decoder.class_embed[nd](output_memory)
         enc_coord = self.decoder.bbox_embed[nd](output_memory) + output_proposals
@@ -327,21 +354,41 @@ class DeformableDetrTransformerVL(nn.Module):
             idx = torch.argmax(cls_all, dim=1, keepdim=True)
             enc_cls = torch.gather(cls_all, 1, idx).squeeze(1)
             enc_coord = torch.gather(coord_all, 1, idx.repeat(1, 1, 1, 4)).squeeze(1)
-        logit = enc_cls[..., 0]
-        topk_proposals = torch.stack([self.select_proposals(logit[b], enc_coord[b], level_ids, len(shapes))
-                                      for b in range(bs)])
-        topk_unact = torch.gather(enc_coord, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).detach()
+        return memory, query_l, output_memory, enc_cls, enc_coord
+
+    def stage_select(self, enc_cls, enc_coord, geo):
+        logit = enc_cls[..., 0].float()
+        coord = enc_coord.float()
+        return torch.stack([self.select_proposals(logit[b], coord[b], geo["level_ids"], len(geo["shapes"]))
+                            for b in range(logit.shape[0])])
+
+    def stage_decode(self, memory, output_memory, enc_coord, topk_proposals, geo):
+        c = memory.shape[-1]
+        topk_unact = torch.gather(enc_coord.float(), 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).detach()
         reference = topk_unact.sigmoid()
-        init_reference_out = reference
         pos_trans_out = self.pos_trans_norm(self.pos_trans(self.get_proposal_pos_embed(topk_unact).to(topk_unact.dtype)))
         query_pos, query = torch.split(pos_trans_out, c, dim=2)
         topk_feats = torch.gather(output_memory, 1, topk_proposals.unsqueeze(-1).expand(-1, -1, c)).detach()
         query = query + self.pix_trans_norm(self.pix_trans(topk_feats))
-
         inter_states, inter_references = self.decoder(
-            query=query, key=None, value=memory, query_pos=query_pos, key_padding_mask=mask_flatten,
-            reference_points=reference, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
-            valid_ratios=valid_ratios)
+            query=query, key=None, value=memory, query_pos=query_pos,
+            key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
+            reference_points=reference, spatial_shapes=geo["spatial_shapes"],
+            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"])
+        return inter_states, reference, inter_references
+
+    def forward(self, multi_level_feats, multi_level_masks, multi_level_pos_embeds, query_embed, query_l,
+                attention_mask_l, multi_level_masks_prompt, **kwargs):
+        shapes = [(int(f.shape[2]), int(f.shape[3])) for f in multi_level_feats]
+        geo = kwargs.get("geometry") or self.geometry(shapes, multi_level_masks, multi_level_pos_embeds)
+        mask_prompt_flatten = None
+        if multi_level_masks_prompt is not None:
+            mask_prompt_flatten = torch.cat([m.flatten(1) for m in multi_level_masks_prompt], 1)
+        memory, query_l, output_memory, enc_cls, enc_coord = self.stage_encode(
+            multi_level_feats, geo, query_l, attention_mask_l, mask_prompt_flatten)
+        topk_proposals = self.stage_select(enc_cls, enc_coord, geo)
+        inter_states, init_reference_out, inter_references = self.stage_decode(
+            memory, output_memory, enc_coord, topk_proposals, geo)
         self.last_topk_proposals = topk_proposals  # kept for parity tests (bit-exact index requirement)
-        return (inter_states, init_reference_out, inter_references, enc_cls, enc_coord, output_proposals.sigmoid(),
-                memory, query_l)
+        return (inter_states, init_reference_out, inter_references, enc_cls, enc_coord,
+                geo["output_proposals"].sigmoid(), memory, query_l)

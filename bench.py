@@ -214,6 +214,7 @@ def model_bench(args, rank, local_rank, world):
     model.test_score_thresh = 0.1     # SURVEY.md 8(d) config 2 (README recipe --confidence-threshold 0.1)
     model = model.to(dev)
     model.engine_dtype = tdt  # parameters stay fp32; 16-bit = tensor-core engine path
+    model.use_cuda_graphs = tdt != torch.float32 and not args.no_graphs
     # Untrained weights put every score near the 0.01 prior, so nothing would reach the 0.1 threshold and
     # the selection stage would be skipped.  Shift the classifier bias once so that ~500 of the 1.08 M
     # (query, class) scores pass, as with a trained detector; identical for every step.
@@ -322,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="disable CUDA-graph capture of the static stages")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

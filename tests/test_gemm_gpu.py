@@ -68,6 +68,44 @@ def test_epilogues(ops, act):
         torch.testing.assert_close(y.float(), ref_linear(x, w, b, act, res), rtol=2e-3, atol=4e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_vit_swiglu_shape_16bit_out(ops, dtype):
+    """ViT-L SwiGLU up-projection: interleaved (w1_j, w2_j) rows, N = 2*2730, 16-bit output through the
+    shared-memory + TMA-store epilogue into a 2752-pitch buffer (N/2 = 2730 is not a multiple of 8)."""
+    M, K, hid = 4096, 1024, 2730
+    x = rnd(M, K, dtype=dtype, seed=11)
+    w = rnd(2 * hid, K, dtype=dtype, seed=12, scale=K ** -0.5)
+    b = rnd(2 * hid, dtype=torch.float32, seed=13)
+    buf = torch.full((M, 2752), 9.0, dtype=dtype, device=DEV)
+    y = ops.linear_tc(x, w, b, act="swiglu", out=buf[:, :hid])
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    torch.testing.assert_close(y.float(), ref_linear(x, w, b, "swiglu"), rtol=tol, atol=tol)
+    assert (buf[:, hid:] == 9.0).all()  # TMA store clips at N/2: padding untouched
+
+
+@pytest.mark.parametrize("tile", [128, 256])
+def test_tma_store_epilogue_edges(ops, tile):
+    # M and N both ragged, bias + relu + residual, 16-bit output with an aligned pitch
+    M, N, K = 777, 840, 192
+    dtype = torch.float16
+    x = rnd(M, K, dtype=dtype, seed=21)
+    w = rnd(N, K, dtype=dtype, seed=22, scale=K ** -0.5)
+    b = rnd(N, dtype=torch.float32, seed=23)
+    res = rnd(M, N, dtype=dtype, seed=24)
+    y = ops.linear_tc(x, w, b, act="relu", residual=res, tile_n=tile)
+    torch.testing.assert_close(y.float(), ref_linear(x, w, b, "relu", res), rtol=4e-3, atol=4e-3)
+
+
+def test_many_tiles_per_cta_ring_wraparound(ops):
+    # 87 296 encoder tokens x FFN: 682 x 8 tiles over 148 persistent CTAs, K = 2048 (32 k-blocks)
+    M, N, K = 87296, 256, 2048
+    x = rnd(M, K, dtype=torch.float16, seed=31, scale=0.5)
+    w = rnd(N, K, dtype=torch.float16, seed=32, scale=K ** -0.5)
+    y = ops.linear_tc(x, w)
+    idx = torch.randint(0, M, (2048,), device=DEV)
+    torch.testing.assert_close(y[idx].float(), ref_linear(x[idx], w), rtol=4e-3, atol=4e-3)
+
+
 def test_padded_pitch_and_batched_input(ops):
     # K = 2730 (SwiGLU hidden of ViT-L) stored with a 2752-element pitch; leading batch dims are flattened
     K, Kp, N = 2730, 2752, 1024

@@ -122,6 +122,23 @@ def test_engine_fp16_mode_end_to_end(mini):
     assert len(out[0]["instances"]) == len(res[0]["scores"])
 
 
+def test_cuda_graph_mode_equals_eager(mini):
+    model, _ = mini
+    inputs = [{"image": synth.image(64, 64, seed=3), "height": 64, "width": 64}]
+    model.engine_dtype = torch.float16
+    try:
+        eager = model(inputs)
+        le = model.last_outputs["pred_logits"].clone()
+        model.use_cuda_graphs = True
+        for seed in (3, 4, 3):  # first call captures, later calls replay (with a different image in between)
+            out = model([{"image": synth.image(64, 64, seed=seed), "height": 64, "width": 64}])
+        lg = model.last_outputs["pred_logits"].clone()
+    finally:
+        model.engine_dtype, model.use_cuda_graphs = torch.float32, False
+    torch.testing.assert_close(lg, le, rtol=0, atol=0)
+    assert torch.equal(out[0]["instances"].pred_classes, eager[0]["instances"].pred_classes)
+
+
 def test_no_cpu_fallback(mini):
     model, _ = mini
     with pytest.raises(RuntimeError):
