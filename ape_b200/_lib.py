@@ -44,6 +44,11 @@ lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctype
 lib.ape_rope_qk.restype = _i
 lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 
+lib.ape_nms_workspace_bytes.restype = _i64
+lib.ape_nms_workspace_bytes.argtypes = [_i]
+lib.ape_nms_sorted.restype = _i
+lib.ape_nms_sorted.argtypes = [_vp, _i, ctypes.c_float, _vp, _vp, _vp, _vp]
+
 # every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = (
     "ape_abi_version",
@@ -55,6 +60,8 @@ EXPORTS = (
     "ape_gemm_tn",
     "ape_layernorm",
     "ape_rope_qk",
+    "ape_nms_workspace_bytes",
+    "ape_nms_sorted",
 )
 
 

@@ -1,0 +1,119 @@
+// nms.cu — greedy hard-NMS over score-sorted boxes (torchvision.ops.nms semantics), used by
+//   the two-stage proposal selection   ape/modeling/ape_deta/deformable_transformer_vl.py:591-596
+//   the final class-aware NMS           ape/modeling/ape_deta/fast_rcnn.py:192 (detectron2 batched_nms)
+// Two launches: (1) upper-triangular IoU>thr bit matrix, 64x64 boxes per CTA; (2) one CTA scans the
+// sorted list in chunks of 64: a single thread resolves the 64x64 diagonal block in registers, then all
+// threads OR the rows of the boxes kept in that chunk into the suppression bitset (coalesced 8-byte
+// loads) — the serial dependency is 64 steps per chunk instead of one global round trip per box.
+// IoU arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction):
+//   inter / (area_a + area_b - inter) > thr, widths/heights clamped at 0, as torchvision's devIoU.
+#include "common.cuh"
+
+namespace ape {
+namespace {
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter)) > thr;
+}
+
+// grid (col_blocks, row_blocks), 64 threads; mask[row * col_blocks + cb] bit j = IoU(row, cb*64+j) > thr, j > row
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__ boxes, int n, float thr,
+                                                      unsigned long long *__restrict__ mask, int col_blocks) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;  // lower triangle never read
+  __shared__ float4 cols[64];
+  const int t = threadIdx.x;
+  const int col = cb * 64 + t;
+  if (col < n) cols[t] = boxes[col];
+  __syncthreads();
+  const int row = rb * 64 + t;
+  if (row >= n) return;
+  const float4 a = boxes[row];
+  const int ncols = min(64, n - cb * 64);
+  unsigned long long bits = 0;
+  for (int j = (rb == cb) ? t + 1 : 0; j < ncols; ++j)
+    if (iou_gt(a, cols[j], thr)) bits |= 1ull << j;
+  mask[(size_t)row * col_blocks + cb] = bits;
+}
+
+// single CTA; keep[i] = 1 iff sorted box i survives; *count = number kept.
+__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
+                                                       unsigned char *__restrict__ keep, int *__restrict__ count) {
+  extern __shared__ unsigned long long removed[];  // col_blocks words
+  __shared__ unsigned long long s_keepbits;
+  __shared__ int s_total;
+  const int t = threadIdx.x;
+  for (int w = t; w < col_blocks; w += blockDim.x) removed[w] = 0;
+  if (t == 0) s_total = 0;
+  __syncthreads();
+  for (int c = 0; c < col_blocks; ++c) {
+    const int base = c * 64;
+    const int nb = min(64, n - base);
+    if (t == 0) {
+      unsigned long long rem = removed[c], kept = 0;
+      for (int i = 0; i < nb; ++i) {
+        if (!((rem >> i) & 1ull)) {
+          kept |= 1ull << i;
+          rem |= mask[(size_t)(base + i) * col_blocks + c];  // diagonal block: bits j > i only
+        }
+      }
+      s_keepbits = kept;
+      s_total += __popcll(kept);
+    }
+    __syncthreads();
+    const unsigned long long kept = s_keepbits;
+    if (t < nb) keep[base + t] = (unsigned char)((kept >> t) & 1ull);
+    // suppress later chunks: OR the rows of every box kept in this chunk
+    for (int w = c + 1 + t; w < col_blocks; w += blockDim.x) {
+      unsigned long long acc = removed[w], k = kept;
+      while (k) {
+        const int i = __ffsll((long long)k) - 1;
+        k &= k - 1;
+        acc |= mask[(size_t)(base + i) * col_blocks + w];
+      }
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (t == 0) *count = s_total;
+}
+
+}  // namespace
+}  // namespace ape
+
+using namespace ape;
+
+extern "C" int64_t ape_nms_workspace_bytes(int n) {
+  const int64_t cb = (n + 63) / 64;
+  return (int64_t)n * cb * 8;
+}
+
+extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *workspace, uint8_t *keep,
+                              int *count, void *stream) {
+  if (n < 0) return fail(APE_ERR_INVALID_ARG, "nms: n=%d", n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    if (count) cudaMemsetAsync(count, 0, sizeof(int), st);
+    return APE_OK;
+  }
+  if (!boxes_sorted || !workspace || !keep || !count) return fail(APE_ERR_NULL_PTR, "nms: null pointer argument");
+  if (reinterpret_cast<uintptr_t>(boxes_sorted) & 15) return fail(APE_ERR_INVALID_ARG, "nms: boxes must be 16-byte aligned");
+  const int cb = (n + 63) / 64;
+  if ((size_t)cb * 8 > 200 * 1024) return fail(APE_ERR_UNSUPPORTED, "nms: n=%d too large for the single-CTA scan", n);
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes_sorted), n, iou_threshold,
+                                               reinterpret_cast<unsigned long long *>(workspace), cb);
+  if (int rc = check_launch("nms_mask_kernel")) return rc;
+  const size_t smem = (size_t)cb * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  nms_scan_kernel<<<1, 256, smem, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
+  return check_launch("nms_scan_kernel");
+}

@@ -225,6 +225,34 @@ def rope_qk_(qkv, cos, sin, num_channels, head_dim, pos_map=None):
     return qkv
 
 
+def nms(boxes, scores, iou_threshold):
+    """torchvision.ops.nms replacement: indices of kept boxes, sorted by descending score."""
+    _require(boxes.is_cuda and boxes.dim() == 2 and boxes.shape[1] == 4, "nms: boxes must be CUDA [n,4]")
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    order = scores.sort(0, descending=True)[1]  # same ordering call as torchvision's nms kernel wrapper
+    sb = boxes.float().index_select(0, order).contiguous()
+    ws = torch.empty((int(_lib.lib.ape_nms_workspace_bytes(n)),), dtype=torch.uint8, device=boxes.device)
+    keep = torch.empty((n,), dtype=torch.uint8, device=boxes.device)
+    count = torch.empty((1,), dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device), _timed(("nms", n)):
+        rc = _lib.lib.ape_nms_sorted(sb.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
+                                     count.data_ptr(), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_nms_sorted")
+    return order[keep.bool()]
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """detectron2 / torchvision batched_nms (coordinate-offset trick, boxes.float()) on ape_nms_sorted."""
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    boxes = boxes.float()
+    max_coordinate = boxes.max()
+    offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+    return nms(boxes + offsets[:, None], scores, iou_threshold)
+
+
 def _ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                              grad_output, im2col_step):
     raise RuntimeError(

@@ -132,6 +132,16 @@ int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, const float 
 int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_table, const int *pos_map, int M,
                 int C, int head_dim, int npos, int dtype, void *stream);
 
+/*
+ * Greedy hard NMS over boxes already sorted by descending score (torchvision.ops.nms semantics; replaces the
+ * nms call inside batched_nms of deformable_transformer_vl.py:591-596 and fast_rcnn.py:192).
+ * boxes_sorted [n,4] fp32 xyxy (16-byte aligned); keep [n] bytes (1 = survives); *count = survivors (device int).
+ * workspace: ape_nms_workspace_bytes(n) bytes of device memory.
+ */
+int64_t ape_nms_workspace_bytes(int n);
+int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *workspace, uint8_t *keep, int *count,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif
