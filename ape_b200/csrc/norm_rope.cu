@@ -105,6 +105,48 @@ layernorm_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, lo
   }
 }
 
+// Wide rows (C > 1024, e.g. the 2730-wide SwiGLU hidden): same contract, but the row is re-read from
+// L1/L2 for the variance and normalisation passes instead of being held in 128 registers per lane —
+// 8 resident warps per SM could not cover HBM latency.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+layernorm_wide_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy,
+                      const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ row_map,
+                      int rows, int C, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const TI *xr = x + (size_t)warp * ldx;
+  const int nvec = (C + 7) >> 3;
+  float sum = 0.f;
+  for (int j = lane; j < nvec; j += 32) {
+    float v[8];
+    load8<TI>(xr + 8 * j, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += (8 * j + k < C) ? v[k] : 0.f;
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+  for (int j = lane; j < nvec; j += 32) {
+    float v[8];
+    load8<TI>(xr + 8 * j, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = (8 * j + k < C) ? v[k] - mean : 0.f;
+      sq += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  TO *yr = y + (size_t)(row_map ? row_map[warp] : warp) * ldy;
+  for (int j = lane; j < nvec; j += 32) {
+    float v[8], o[8];
+    load8<TI>(xr + 8 * j, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      o[k] = (8 * j + k < C) ? (v[k] - mean) * rstd * __ldg(w + 8 * j + k) + __ldg(b + 8 * j + k) : 0.f;
+    store8<TO>(yr + 8 * j, o);
+  }
+}
+
 // In-place 2-D RoPE on the q and k parts of qkv [M, 3*C] (C = heads*hd); cos/sin [npos, hd] fp32;
 // token m uses position pos_map ? pos_map[m] : m % npos.  t' = t*cos + rotate_half(t)*sin with
 // rotate_half pairing (2i, 2i+1) -> (-t[2i+1], t[2i]).  One thread per 8 channels.
@@ -137,8 +179,10 @@ int launch_ln(const void *x, long long ldx, void *y, long long ldy, const float 
   const int blocks = (rows + 7) / 8;
   if (C <= 1024 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0)
     layernorm_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
-  else
+  else if (x == y)  // in place: the single-read register variant is required
     layernorm_kernel<TI, TO, 16><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+  else
+    layernorm_wide_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
   return check_launch("layernorm_kernel");
 }
 

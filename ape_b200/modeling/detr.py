@@ -21,6 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torchvision
 
+from .. import ops
 from ..layers import VisionLanguageAlign
 from ..layers.common import MLP, ConvNorm, box_cxcywh_to_xyxy, inverse_sigmoid
 from ..structures import Boxes, Instances
@@ -88,7 +89,7 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
     filter_inds = filter_mask.nonzero()
     boxes = boxes[filter_inds[:, 0]]
     scores = scores[filter_mask]
-    keep = torchvision.ops.boxes.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
+    keep = ops.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
     if topk_per_image >= 0:
         keep = keep[:topk_per_image]
     boxes, scores, filter_inds = boxes[keep], scores[keep], filter_inds[keep]

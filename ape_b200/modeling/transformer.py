@@ -273,8 +273,7 @@ class DeformableDetrTransformerVL(nn.Module):
             lvl_mask = level_ids == lvl
             pre.append(torch.topk(logit.sigmoid() * lvl_mask, min(self.pre_nms_topk, logit.size(0)))[1])
         pre = torch.cat(pre)
-        post = torchvision.ops.boxes.batched_nms(boxes[pre].float(), logit[pre].float(), level_ids[pre],
-                                                 self.nms_thresh_enc)
+        post = ops.batched_nms(boxes[pre].float(), logit[pre].float(), level_ids[pre], self.nms_thresh_enc)
         keep = pre[post]
         if len(keep) < topk:
             keep = torch.topk(logit, min(topk, logit.size(0)))[1]
