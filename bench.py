@@ -182,7 +182,7 @@ def model_bench(args, rank, local_rank, world):
               "l2": "per-step working set (weights 1.5 GB fp32 + activations) >> 126 MB L2",
               "dense_ops": "ViT linears/LayerNorm/RoPE + ms_deform_attn = libape_b200 kernels (tcgen05 GEMM); attention, convs, "
                            "encoder/decoder linears, top-k/NMS = torch library kernels this round",
-              "parallelism": f"dp{args.gpus} (one image per GPU, no data-path collective; results gathered by the caller)"}
+              "parallelism": f"dp{args.gpus} (one image per GPU; one NCCL gather of packed detections per step when N>1)"}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -229,9 +229,14 @@ def model_bench(args, rank, local_rank, world):
     host_imgs = [torch.randint(0, 256, (3, 1024, 1024), generator=g).to(torch.float32).pin_memory() for _ in range(NIMG)]
     dev_imgs = [t.to(dev) for t in host_imgs]
 
+    from ape_b200 import parallel
+
     def step(i, host):
         img = host_imgs[i % NIMG] if host else dev_imgs[i % NIMG]
-        return model([{"image": img, "height": 1024, "width": 1024}])
+        out = model([{"image": img, "height": 1024, "width": 1024}])
+        if world > 1:  # the one collective of the path: packed detections -> rank 0 (NCCL over NVLink)
+            parallel.gather_detections([o["instances"] for o in out], 300, dev, dst=0)
+        return out
 
     def barrier():
         torch.cuda.synchronize()
