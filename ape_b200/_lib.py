@@ -36,11 +36,17 @@ lib.ape_msda_fwd_variant.argtypes = [_vp] * 6 + [_i] * 9 + [_vp]
 lib.ape_msda_fused_fwd.restype = _i
 lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
 
+lib.ape_msda_fused_self_fwd.restype = _i
+lib.ape_msda_fused_self_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 8 + [_vp]
 lib.ape_gemm_tn.restype = _i
 lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
 
 lib.ape_layernorm.restype = _i
 lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp]
+lib.ape_groupnorm_workspace_bytes.restype = _i64
+lib.ape_groupnorm_workspace_bytes.argtypes = [_i, _i, _i]
+lib.ape_groupnorm_nhwc.restype = _i
+lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _i, _vp]
 lib.ape_rope_qk.restype = _i
 lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 
@@ -57,9 +63,12 @@ EXPORTS = (
     "ape_msda_fwd",
     "ape_msda_fwd_variant",
     "ape_msda_fused_fwd",
+    "ape_msda_fused_self_fwd",
     "ape_gemm_tn",
     "ape_layernorm",
     "ape_rope_qk",
+    "ape_groupnorm_workspace_bytes",
+    "ape_groupnorm_nhwc",
     "ape_nms_workspace_bytes",
     "ape_nms_sorted",
 )

@@ -87,14 +87,12 @@ __device__ __forceinline__ void make_sample(float x, float y, float a, int Hl, i
 // Phase 2: gather + accumulate + store for one lane.  The host guarantees LP % U == 0.
 template <typename T, int LPR, int U>
 __device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_off,
-                                            const float4 *s_w, int lps, int b, int q0, int h0) {
+                                            const float4 *s_w, int lps, int b, int q, int h) {
   using E = Elem<T>;
   constexpr int VEC = E::kVec;
   const int LP = p.L * p.P;
   const int r = threadIdx.x / LPR, c = threadIdx.x % LPR;
-  const int ht_mask = (1 << p.ht_log2) - 1;
-  const int q = q0 + (r >> p.ht_log2), h = h0 + (r & ht_mask);
-  if (q >= p.Q) return;
+  if (q < 0 || q >= p.Q) return;
 
   const char *vb = reinterpret_cast<const char *>(p.value) + ((size_t)b * p.S * p.H * LPR + c) * 16;
   const int4 *ro = s_off + r * lps;
@@ -187,7 +185,10 @@ msda_fwd_kernel(const MsdaParams p) {
     s_w[r * lps + s] = w;
   }
   __syncthreads();
-  gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0, h0);
+  {
+    const int r = tid / LPR;
+    gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
+  }
 }
 
 // Fused variant: softmax(logits) over L*P, loc = f(ref, offsets), then the same gather.
@@ -274,7 +275,131 @@ msda_fused_fwd_kernel(const MsdaParams p) {
     s_w[r * lps + s] = w;
   }
   __syncthreads();
-  gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0, h0);
+  {
+    const int r = tid / LPR;
+    gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
+  }
+}
+
+// Fused, spatially tiled variant for self-attention over the feature pyramid itself (Q == S, query i IS
+// pixel i of the level structure — the encoder).  Same arithmetic as msda_fused_fwd_kernel; only the
+// work -> CTA mapping changes: a persistent CTA owns a contiguous run of 16x16-pixel super-tiles of one
+// (image, head, level) and walks each in 8x4 / 8x8 sub-tiles, so the texels its queries sample (own
+// neighbourhood at every level) stay resident in that SM's L1 instead of being re-fetched from L2 by
+// whichever SM happens to run the next strip of the raster order.
+template <typename T, typename TO, int LPR, int U>
+__global__ void __launch_bounds__(threads_for(LPR))
+msda_fused_tiled_kernel(const MsdaParams p, int units_per_cta, int total_units) {
+  using EO = Elem<TO>;
+  constexpr int NT = threads_for(LPR);
+  constexpr int R = NT / LPR;
+  constexpr int SW = 8, SH = R / SW;  // sub-tile: 8 wide, 4 (fp32) or 8 (16-bit) rows of pixels
+  constexpr int TS = 16;              // super-tile edge in pixels
+  static_assert(R % SW == 0 && TS % SH == 0, "tile geometry");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_lvl[kMaxLevels * 3];
+  __shared__ int s_tiles[kMaxLevels + 1];
+  __shared__ float s_max[R], s_rinv[R];
+
+  const int LP = p.L * p.P;
+  const int lps = LP | 1;
+  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
+  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
+  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * (sizeof(int4) + sizeof(float4)));
+
+  const int tid = threadIdx.x;
+  if (tid < p.L) {
+    s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
+    s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
+    s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int l = 0; l < p.L; ++l) {
+      s_tiles[l] = acc;
+      acc += ((s_lvl[l * 3] + TS - 1) / TS) * ((s_lvl[l * 3 + 1] + TS - 1) / TS);
+    }
+    s_tiles[p.L] = acc;
+  }
+  __syncthreads();
+  const int tiles = s_tiles[p.L];
+  const float inv_lp = 1.f / (float)LP, inv_p = 1.f / (float)p.P;
+  const TO *offs = reinterpret_cast<const TO *>(p.loc);
+  const TO *logits = reinterpret_cast<const TO *>(p.attn);
+
+  const int u_end = min(total_units, (int)(blockIdx.x + 1) * units_per_cta);
+  for (int u = blockIdx.x * units_per_cta; u < u_end; ++u) {
+    // unit -> (image, head, level, super-tile); tiles of one (image, head) are consecutive
+    const int b = u / (p.H * tiles);
+    const int rem = u - b * p.H * tiles;
+    const int h = rem / tiles, t = rem - h * tiles;
+    int l = 0;
+    while (l + 1 < p.L && t >= s_tiles[l + 1]) ++l;
+    const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1], start = s_lvl[l * 3 + 2];
+    const int txn = (Wl + TS - 1) / TS;
+    const int tl = t - s_tiles[l];
+    const int ty0 = (tl / txn) * TS, tx0 = (tl % txn) * TS;
+#pragma unroll 1
+    for (int sub = 0; sub < (TS / SH) * (TS / SW); ++sub) {
+      const int y0 = ty0 + (sub / (TS / SW)) * SH, x0 = tx0 + (sub % (TS / SW)) * SW;
+      if (y0 >= Hl || x0 >= Wl) continue;  // CTA-uniform
+      // stage logits (one 2*LP-byte run per query), then per-row softmax statistics
+      for (int i = tid; i < R * LP; i += NT) {
+        const int r = fast_div(i, inv_lp), s = i - r * LP;
+        const int qy = y0 + r / SW, qx = x0 + r % SW;
+        float v = 0.f;
+        if (qy < Hl && qx < Wl) {
+          const size_t bq = (size_t)b * p.Q + start + qy * Wl + qx;
+          v = EO::load1(logits + bq * p.logit_row_stride + (size_t)h * LP + s);
+        }
+        s_logit[r * lps + s] = v;
+      }
+      __syncthreads();
+      if (tid < R) {
+        const float *row = s_logit + tid * lps;
+        float m = row[0];
+        for (int s = 1; s < LP; ++s) m = fmaxf(m, row[s]);
+        float sum = 0.f;
+        for (int s = 0; s < LP; ++s) sum += expf(row[s] - m);
+        s_max[tid] = m;
+        s_rinv[tid] = 1.f / sum;
+      }
+      __syncthreads();
+      for (int i = tid; i < R * LP; i += NT) {
+        const int r = fast_div(i, inv_lp), s = i - r * LP;
+        const int qy = y0 + r / SW, qx = x0 + r % SW;
+        int4 off = make_int4(0, 0, 0, 0);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qy < Hl && qx < Wl) {
+          const int ls = fast_div(s, inv_p);
+          const int Hs = s_lvl[ls * 3], Ws = s_lvl[ls * 3 + 1];
+          const size_t bq = (size_t)b * p.Q + start + qy * Wl + qx;
+          const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
+          const float a = expf(s_logit[r * lps + s] - s_max[r]) * s_rinv[r];
+          const float *rp = p.ref + (bq * p.L + ls) * p.ref_dim;
+          float x, y;
+          if (p.ref_dim == 2) {
+            x = rp[0] + o.x / (float)Ws;
+            y = rp[1] + o.y / (float)Hs;
+          } else {
+            x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
+            y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
+          }
+          make_sample(x, y, a, Hs, Ws, s_lvl[ls * 3 + 2], h, p.H, LPR * 16, off, w);
+        }
+        s_off[r * lps + s] = off;
+        s_w[r * lps + s] = w;
+      }
+      __syncthreads();
+      {
+        const int r = tid / LPR;
+        const int qy = y0 + r / SW, qx = x0 + r % SW;
+        gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, (qy < Hl && qx < Wl) ? start + qy * Wl + qx : -1, h);
+      }
+      __syncthreads();  // smem is rewritten by the next sub-tile
+    }
+  }
 }
 
 // Scalar fallback for shapes the vector path does not cover (D*sizeof(T) not a power-of-two
@@ -348,6 +473,24 @@ int launch_fused(const MsdaParams &p, cudaStream_t st) {
   dim3 grid((unsigned)(((p.Q + QT - 1) / QT) * (p.H >> p.ht_log2)), (unsigned)p.B);
   k<<<grid, NT, smem, st>>>(p);
   return check_launch("msda_fused_fwd_kernel");
+}
+
+// tile count of the level structure is only known on the device; bound it from S: every 16x16 super-tile
+// but the ragged edge ones holds 256 pixels, and a level adds at most (H/16 + W/16 + 1) ragged tiles.
+template <typename T, typename TO, int LPR, int U>
+int launch_fused_tiled(const MsdaParams &p, int total_tiles_per_head_image, cudaStream_t st) {
+  constexpr int NT = threads_for(LPR), R = NT / LPR;
+  const int lps = (p.L * p.P) | 1;
+  const size_t smem = (size_t)R * lps * 36;
+  auto k = msda_fused_tiled_kernel<T, TO, LPR, U>;
+  if (int rc = set_smem(k, smem)) return rc;
+  const int total_units = p.B * p.H * total_tiles_per_head_image;
+  int ctas = 148 * 4;
+  if (ctas > total_units) ctas = total_units;
+  const int per = (total_units + ctas - 1) / ctas;
+  ctas = (total_units + per - 1) / per;
+  k<<<ctas, NT, smem, st>>>(p, per, total_units);
+  return check_launch("msda_fused_tiled_kernel");
 }
 
 template <typename T, int U>
@@ -530,4 +673,52 @@ extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, cons
     default: APE_FUSED_DISPATCH(__nv_bfloat16)
   }
 #undef APE_FUSED_DISPATCH
+}
+
+// Encoder self-attention variant: queries are the pixels of the level structure (Q == S).  Takes the level
+// shapes on the HOST as well (the caller built them; no device round trip) to size the persistent grid.
+extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes, const int64_t *starts,
+                                       const int *host_shapes, const void *offsets, int64_t offs_row_stride,
+                                       const void *logits, int64_t logit_row_stride, const float *ref, int ref_dim,
+                                       void *out, int B, int S, int H, int D, int L, int P, int dtype, int offs_dtype,
+                                       void *stream) {
+  const int Q = S;
+  if (int rc = validate(value, shapes, starts, offsets, logits, out, B, S, H, D, L, Q, P, dtype)) return rc;
+  if (!host_shapes) return fail(APE_ERR_NULL_PTR, "msda_self: null host_shapes");
+  if (ref_dim != 2 && ref_dim != 4) return fail(APE_ERR_INVALID_ARG, "msda_self: ref_dim must be 2 or 4");
+  if (offs_row_stride < (int64_t)H * L * P * 2 || logit_row_stride < (int64_t)H * L * P)
+    return fail(APE_ERR_INVALID_ARG, "msda_self: row strides smaller than a row");
+  long long total = 0;
+  int tiles = 0;
+  for (int l = 0; l < L; ++l) {
+    const int h = host_shapes[2 * l], w = host_shapes[2 * l + 1];
+    if (h <= 0 || w <= 0) return fail(APE_ERR_INVALID_ARG, "msda_self: bad level shape");
+    total += (long long)h * w;
+    tiles += ((h + 15) / 16) * ((w + 15) / 16);
+  }
+  if (total != S) return fail(APE_ERR_INVALID_ARG, "msda_self: level shapes do not sum to S=%d", S);
+  if (B == 0 || S == 0) return APE_OK;
+  if (!ref) return fail(APE_ERR_NULL_PTR, "msda_self: null reference_points");
+  const int row_bytes = D * dtype_size(dtype);
+  const int lpr = row_bytes / 16;
+  const int LP = L * P;
+  if ((lpr != 4 && lpr != 8) || L > kMaxLevels || (offs_dtype != dtype && offs_dtype != APE_DTYPE_F32))
+    // shapes outside the tuned encoder configuration take the generic fused kernel (same results)
+    return ape_msda_fused_fwd(value, shapes, starts, offsets, offs_row_stride, logits, logit_row_stride, ref, ref_dim,
+                              out, B, S, H, D, L, Q, P, dtype, offs_dtype, stream);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MsdaParams p{};
+  p.value = value; p.shapes = shapes; p.starts = starts; p.loc = offsets; p.attn = logits; p.ref = ref;
+  p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
+  p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
+#define APE_TILED(T, TO, LPR)                                                              \
+  return (LP % 2 == 0) ? launch_fused_tiled<T, TO, LPR, 2>(p, tiles, st) : launch_fused_tiled<T, TO, LPR, 1>(p, tiles, st)
+  if (dtype == APE_DTYPE_F32) { APE_TILED(float, float, 8); }
+  if (dtype == APE_DTYPE_F16) {
+    if (offs_dtype == APE_DTYPE_F16) { APE_TILED(__half, __half, 4); }
+    APE_TILED(__half, float, 4);
+  }
+  if (offs_dtype == APE_DTYPE_BF16) { APE_TILED(__nv_bfloat16, __nv_bfloat16, 4); }
+  APE_TILED(__nv_bfloat16, float, 4);
+#undef APE_TILED
 }

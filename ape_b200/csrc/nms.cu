@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__
 __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
                                                        unsigned char *__restrict__ keep, int *__restrict__ count) {
   extern __shared__ unsigned long long removed[];  // col_blocks words
+  __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keepbits;
   __shared__ int s_total;
   const int t = threadIdx.x;
@@ -55,12 +56,15 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long 
   for (int c = 0; c < col_blocks; ++c) {
     const int base = c * 64;
     const int nb = min(64, n - base);
+    // stage the 64x64 diagonal block so the serial resolution below never waits on global memory
+    if (t < nb) s_diag[t] = mask[(size_t)(base + t) * col_blocks + c];
+    __syncthreads();
     if (t == 0) {
       unsigned long long rem = removed[c], kept = 0;
       for (int i = 0; i < nb; ++i) {
         if (!((rem >> i) & 1ull)) {
           kept |= 1ull << i;
-          rem |= mask[(size_t)(base + i) * col_blocks + c];  // diagonal block: bits j > i only
+          rem |= s_diag[i];  // diagonal block: bits j > i only
         }
       }
       s_keepbits = kept;

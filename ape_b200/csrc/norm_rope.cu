@@ -239,3 +239,125 @@ extern "C" int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const 
     return fail(APE_ERR_INVALID_ARG, "rope: unknown dtype %d", dtype);
   return check_launch("rope_qk_kernel");
 }
+
+// ---- GroupNorm over token-major (NHWC) activations ------------------------------------------------
+// The neck's ChannelMapper (detrex; configs/…1080k.py:42-55) applies GroupNorm(32, 256) to each 1x1-conv
+// output.  With activations kept as [B, HW, C] rows (what the encoder consumes) the statistics of a group
+// span all HW rows x C/G channels.  Deterministic two-level reduction: (1) each CTA reduces a strip of rows
+// to per-group partial (sum, sum of squares), (2) one small kernel folds the partials in a fixed order and
+// emits mean / rstd, (3) normalise.  One thread owns 8 consecutive channels (= one group when C/G == 8).
+namespace ape {
+namespace {
+
+constexpr int kGnRowsPerCta = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const T *__restrict__ x, long long ldx, int rows_per_image, int C, int cpg,
+                  float *__restrict__ partial /* [B, strips, C/8, 2] */) {
+  const int vec_per_row = C / 8;
+  const int b = blockIdx.y, strip = blockIdx.x;
+  const int r0 = strip * kGnRowsPerCta, r1 = min(rows_per_image, r0 + kGnRowsPerCta);
+  // thread t: vector column v = t % vec_per_row, row offset t / vec_per_row (host guarantees 256 % vec_per_row == 0)
+  const int v = threadIdx.x % vec_per_row, ro = threadIdx.x / vec_per_row, rstep = 256 / vec_per_row;
+  float s = 0.f, ss = 0.f;
+  for (int r = r0 + ro; r < r1; r += rstep) {
+    float f[8];
+    load8<T>(x + ((size_t)b * rows_per_image + r) * ldx + 8 * v, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += f[k]; ss += f[k] * f[k]; }
+  }
+  __shared__ float sh[256][2];
+  sh[threadIdx.x][0] = s;
+  sh[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < vec_per_row) {
+    float a = 0.f, c = 0.f;
+    for (int j = threadIdx.x; j < 256; j += vec_per_row) { a += sh[j][0]; c += sh[j][1]; }
+    float *dst = partial + (((size_t)b * gridDim.x + strip) * vec_per_row + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = c;
+  }
+}
+
+// one thread per (b, group): fold strips and the C/G/8 vector columns of the group
+__global__ void gn_finalize_kernel(const float *__restrict__ partial, int B, int strips, int vec_per_row, int vec_per_group,
+                                   float count, float eps, float *__restrict__ stats /* [B, G, 2] mean, rstd */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = vec_per_row / vec_per_group;
+  if (idx >= B * G) return;
+  const int b = idx / G, g = idx % G;
+  double s = 0.0, ss = 0.0;
+  for (int st = 0; st < strips; ++st)
+    for (int v = 0; v < vec_per_group; ++v) {
+      const float *p = partial + (((size_t)b * strips + st) * vec_per_row + g * vec_per_group + v) * 2;
+      s += p[0];
+      ss += p[1];
+    }
+  const double mean = s / count;
+  const double var = fmax(ss / count - mean * mean, 0.0);
+  stats[idx * 2] = (float)mean;
+  stats[idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy, const float *__restrict__ w,
+                const float *__restrict__ bias, const float *__restrict__ stats, int rows_per_image, long long total_rows,
+                int C, int vec_per_group) {
+  const int vec_per_row = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rows * vec_per_row) return;
+  const long long row = idx / vec_per_row;
+  const int v = (int)(idx % vec_per_row);
+  const int b = (int)(row / rows_per_image);
+  const int G = vec_per_row / vec_per_group;
+  const float mean = stats[(b * G + v / vec_per_group) * 2], rstd = stats[(b * G + v / vec_per_group) * 2 + 1];
+  float f[8], o[8];
+  load8<TI>(x + (size_t)row * ldx + 8 * v, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = (f[k] - mean) * rstd * __ldg(w + 8 * v + k) + __ldg(bias + 8 * v + k);
+  store8<TO>(y + (size_t)row * ldy + 8 * v, o);
+}
+
+}  // namespace
+}  // namespace ape
+
+extern "C" int64_t ape_groupnorm_workspace_bytes(int B, int rows_per_image, int C) {
+  const int64_t strips = (rows_per_image + ape::kGnRowsPerCta - 1) / ape::kGnRowsPerCta;
+  return ((int64_t)B * strips * (C / 8) * 2 + (int64_t)B * C) * 4;
+}
+
+extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
+                                  void *workspace, int B, int rows_per_image, int C, int groups, float eps, int in_dtype,
+                                  int out_dtype, void *stream) {
+  using namespace ape;
+  if (B < 0 || rows_per_image <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || (C / groups) % 8 != 0 || 256 % (C / 8) != 0)
+    return fail(APE_ERR_UNSUPPORTED, "groupnorm: C=%d groups=%d (channels per group must be a multiple of 8, C/8 must divide 256)", C, groups);
+  if (B == 0) return APE_OK;
+  if (!x || !y || !weight || !bias || !workspace) return fail(APE_ERR_NULL_PTR, "groupnorm: null pointer argument");
+  if ((ldx * dtype_size(in_dtype)) % 16 || (ldy * dtype_size(out_dtype)) % 16)
+    return fail(APE_ERR_INVALID_ARG, "groupnorm: rows must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int strips = (rows_per_image + kGnRowsPerCta - 1) / kGnRowsPerCta;
+  const int vpr = C / 8, vpg = C / groups / 8;
+  float *partial = reinterpret_cast<float *>(workspace);
+  float *stats = partial + (size_t)B * strips * vpr * 2;
+  if (in_dtype == APE_DTYPE_F32) gn_partial_kernel<float><<<dim3(strips, B), 256, 0, st>>>((const float *)x, ldx, rows_per_image, C, C / groups, partial);
+  else if (in_dtype == APE_DTYPE_F16) gn_partial_kernel<__half><<<dim3(strips, B), 256, 0, st>>>((const __half *)x, ldx, rows_per_image, C, C / groups, partial);
+  else gn_partial_kernel<__nv_bfloat16><<<dim3(strips, B), 256, 0, st>>>((const __nv_bfloat16 *)x, ldx, rows_per_image, C, C / groups, partial);
+  if (int rc = check_launch("gn_partial_kernel")) return rc;
+  gn_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(partial, B, strips, vpr, vpg, (float)rows_per_image * (C / groups), eps, stats);
+  if (int rc = check_launch("gn_finalize_kernel")) return rc;
+  const long long total_rows = (long long)B * rows_per_image;
+  const unsigned blocks = (unsigned)((total_rows * vpr + 255) / 256);
+#define APE_GN(TI, TO) gn_apply_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, stats, rows_per_image, total_rows, C, vpg)
+  if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_F32) APE_GN(float, float);
+  else if (in_dtype == APE_DTYPE_F16 && out_dtype == APE_DTYPE_F16) APE_GN(__half, __half);
+  else if (in_dtype == APE_DTYPE_BF16 && out_dtype == APE_DTYPE_BF16) APE_GN(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == APE_DTYPE_F16 && out_dtype == APE_DTYPE_F32) APE_GN(__half, float);
+  else if (in_dtype == APE_DTYPE_BF16 && out_dtype == APE_DTYPE_F32) APE_GN(__nv_bfloat16, float);
+  else return fail(APE_ERR_UNSUPPORTED, "groupnorm: dtype pair (%d -> %d) not supported", in_dtype, out_dtype);
+#undef APE_GN
+  return check_launch("gn_apply_kernel");
+}

@@ -131,7 +131,8 @@ class MultiScaleDeformableAttention(nn.Module):
         n_off = self.num_heads * self.num_levels * self.num_points * 2
         output = ops.ms_deform_attn_fused_forward(
             value, spatial_shapes, level_start_index, qo[..., :n_off], qo[..., n_off:],
-            reference_points.to(torch.float32).contiguous(), self.num_points)
+            reference_points.to(torch.float32).contiguous(), self.num_points,
+            host_shapes=kwargs.get("host_shapes"))
         if engine and self.batch_first and identity.dtype == output.dtype:
             return ops.linear_module_tc(self.output_proj, output, residual=identity.contiguous())
         output = self.output_proj(output)

@@ -215,6 +215,7 @@ class DeformableDETRSegmVL(nn.Module):
         # ops run under autocast — the reference's own eval recipe casts the whole model to fp16
         # (tools/train_net.py:641-642).  float32 = strict-parity mode on fp32 library kernels.
         self.engine_dtype = torch.float32
+        self.profile_stages = False   # record CUDA-event stage times of the last forward in self.stage_ms
         self.use_cuda_graphs = False  # capture the static stages once per input geometry (16-bit engine mode)
         self._geo_cache, self._graph_cache = {}, {}
 
@@ -322,8 +323,18 @@ class DeformableDETRSegmVL(nn.Module):
             raise NotImplementedError("ape_b200 is an inference engine (SURVEY.md §8f row 4)")
         if "mask_prompt" in batched_inputs[0]:
             raise NotImplementedError("ape_b200: mask prompts")
+        marks = [] if self.profile_stages else None
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         prompt, features_l, fusion = self._text_features(batched_inputs)
         images, img_masks, image_sizes = self.preprocess_image(batched_inputs)
+        mark("preprocess")
         low = self.engine_dtype != torch.float32
         geo = self._geometry(images.shape, image_sizes, img_masks)
         graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
@@ -333,8 +344,10 @@ class DeformableDETRSegmVL(nn.Module):
                     ("encode", tuple(images.shape), tuple(image_sizes)), self._stage_encode, (images, fusion), (geo,))
             else:
                 memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+            mark("encode")
             topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
             self.transformer.last_topk_proposals = topk
+            mark("select")
             if prompt == "name":
                 if fusion_out is not None:
                     features_l = 1.0 * features_l + 0.0 * fusion_out.float()  # (:446)
@@ -354,6 +367,7 @@ class DeformableDETRSegmVL(nn.Module):
         if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
             raise NotImplementedError("ape_b200: mask / semantic / panoptic heads are the next §8 rows; construct "
                                       "with test_mask_on=False, semantic_on=False, panoptic_on=False (boxes only)")
+        mark("decode")
         results = self.inference(box_cls, box_pred, image_sizes)
         if not do_postprocess:
             return results, None, None
@@ -361,6 +375,10 @@ class DeformableDETRSegmVL(nn.Module):
         for r, inp, size in zip(results, batched_inputs, image_sizes):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
             out.append({"instances": detector_postprocess(r, h, w).to("cpu")})
+        mark("inference")
+        if marks is not None:
+            torch.cuda.synchronize()
+            self.stage_ms = {n: marks[i - 1][1].elapsed_time(e) for i, (n, e) in enumerate(marks) if i > 0}
         return out
 
     # -- stages (static shapes, no host synchronisation: CUDA-graph capturable) -----------------------------

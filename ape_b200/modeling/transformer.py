@@ -52,10 +52,11 @@ class _EncoderLayer(nn.Module):
         self.ffns = nn.ModuleList([FFN(embed_dim, ffn_dim)])
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dim), nn.LayerNorm(embed_dim)])
 
-    def forward(self, query, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+    def forward(self, query, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index,
+                host_shapes=None):
         x = self.attentions[0](query, None, query, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
                                reference_points=reference_points, spatial_shapes=spatial_shapes,
-                               level_start_index=level_start_index)
+                               level_start_index=level_start_index, host_shapes=host_shapes)
         if x.dtype in (torch.float16, torch.bfloat16):  # engine path: libape_b200 LayerNorm kernel
             x = ops.layernorm_module(self.norms[0], x)
             x = self.ffns[0](x)
@@ -124,7 +125,7 @@ class DeformableDetrTransformerEncoderVL(nn.Module):
                     if engine_dtype is not None:
                         query = query.to(engine_dtype)
             query = layer(query, query_pos, query_key_padding_mask, kwargs["reference_points"],
-                          kwargs["spatial_shapes"], kwargs["level_start_index"])
+                          kwargs["spatial_shapes"], kwargs["level_start_index"], kwargs.get("host_shapes"))
         if self.post_norm_layer is not None:
             query = self.post_norm_layer(query)
         return query, query_l
@@ -334,7 +335,7 @@ class DeformableDetrTransformerVL(nn.Module):
             query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
             query_pos=pos_flatten, query_key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
             spatial_shapes=geo["spatial_shapes"], reference_points=geo["reference_points"],
-            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"])
+            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"], host_shapes=geo["shapes"])
         # gen_encoder_output_proposals (:354-369): zero the memory of invalid anchors, project, normalise
         output_proposals = geo["output_proposals"]
         invalid = geo["proposal_invalid"]

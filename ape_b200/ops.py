@@ -5,9 +5,13 @@ reference's schemas (ape/layers/csrc/vision.cpp:76-79, ms_deform_attn.h:21-28,42
 `MultiScaleDeformableAttnFunction` (ape/layers/multi_scale_deform_attn.py:32-81) works unchanged.
 CUDA tensors only: like the reference (`AT_ERROR("Not implemented on the CPU")`,
 ms_deform_attn.h:39) there is no CPU implementation."""
+import ctypes
+
 import torch
 
 from . import _lib
+
+_DISABLE_TILED = False  # tests / sweeps flip this to compare the two encoder kernels
 
 _NS = "ape"
 
@@ -90,7 +94,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets,
-                                 attention_logits, reference_points, num_points):
+                                 attention_logits, reference_points, num_points, host_shapes=None):
     """Fused tail of MultiScaleDeformableAttention.forward (multi_scale_deform_attn.py:283-348).
 
     value [B,S,H,D]; sampling_offsets [B,Q,>=H*L*P*2] and attention_logits [B,Q,>=H*L*P] are the
@@ -109,6 +113,18 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
     _require(ref.dtype == torch.float32 and ref.is_contiguous(), "reference_points must be contiguous fp32")
     _require(ref.shape[:3] == (B, Q, L), "reference_points must be [B,Q,L,2|4]")
     out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
+    if host_shapes is not None and Q == S and not _DISABLE_TILED:
+        # self-attention over the pyramid (encoder): spatially tiled persistent kernel
+        hs = (ctypes.c_int * (2 * L))(*[int(v) for hw in host_shapes for v in hw])
+        with torch.cuda.device(value.device), _timed(("msda_fused", B, S, Q, L, P, value.element_size(),
+                                                      sampling_offsets.element_size())):
+            rc = _lib.lib.ape_msda_fused_self_fwd(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs,
+                sampling_offsets.data_ptr(), sampling_offsets.stride(1), attention_logits.data_ptr(),
+                attention_logits.stride(1), ref.data_ptr(), ref.shape[-1], out.data_ptr(), B, S, H, D, L, P,
+                _lib.dtype_code(value.dtype), _lib.dtype_code(sampling_offsets.dtype), _lib.current_stream_ptr())
+        _lib.check(rc, "ape_msda_fused_self_fwd")
+        return out
     with torch.cuda.device(value.device), _timed(("msda_fused", B, S, Q, L, P, value.element_size(),
                                                   sampling_offsets.element_size())):
         rc = _lib.lib.ape_msda_fused_fwd(
@@ -210,6 +226,20 @@ def layernorm(x, weight, bias, eps=1e-5, out_dtype=None, row_map=None, out=None)
                                     _lib.current_stream_ptr())
     _lib.check(rc, "ape_layernorm")
     return out if x.dim() == 2 or out.shape[1] != C else out.view(*x.shape[:-1], C)
+
+
+def groupnorm_nhwc(x, weight, bias, groups, eps=1e-5, out_dtype=None):
+    """GroupNorm over token-major activations x [B, rows, C] (ape_groupnorm_nhwc); weight / bias fp32 [C]."""
+    _require(x.is_cuda and x.dim() == 3 and x.is_contiguous(), "groupnorm_nhwc: contiguous CUDA [B, rows, C]")
+    B, rows, C = x.shape
+    out = torch.empty((B, rows, C), dtype=out_dtype or x.dtype, device=x.device)
+    ws = torch.empty((int(_lib.lib.ape_groupnorm_workspace_bytes(B, rows, C)),), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device), _timed(("groupnorm", B, rows, C)):
+        rc = _lib.lib.ape_groupnorm_nhwc(x.data_ptr(), C, out.data_ptr(), C, weight.data_ptr(), bias.data_ptr(),
+                                         ws.data_ptr(), B, rows, C, int(groups), float(eps), _lib.dtype_code(x.dtype),
+                                         _lib.dtype_code(out.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_groupnorm_nhwc")
+    return out
 
 
 def rope_qk_(qkv, cos, sin, num_channels, head_dim, pos_map=None):

@@ -262,6 +262,13 @@ def model_bench(args, rank, local_rank, world):
     # Per-kernel durations for the roofline object: CUDA events cannot be recorded inside a graph replay, so
     # the same steps are run a few more times eagerly (same kernels, same inputs, same stream) with an event
     # pair around every launch of our library; launches per step are counted here too.
+    model.profile_stages = True
+    stage_acc = {}
+    for i in range(5):
+        step(i, False)
+        for k, v in model.stage_ms.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / 5
+    model.profile_stages = False
     graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False
     step(0, False)
     barrier()
@@ -322,6 +329,7 @@ def model_bench(args, rank, local_rank, world):
             "e2e": {"value": world * 1e3 / e2e_ms, "unit": "images/s", "h2d_bytes_per_step": host_imgs[0].numel() * 4,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks,
+            "stage_ms": {k: round(v, 3) for k, v in stage_acc.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_model_arm(1, n_text, sd=model.state_dict())

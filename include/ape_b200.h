@@ -101,6 +101,16 @@ int ape_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const i
                        void *stream);
 
 /*
+ * ape_msda_fused_fwd for self-attention over the feature pyramid itself (the encoder: Q == S, query i is pixel i
+ * of the level structure).  Identical results; the work is tiled spatially (16x16-pixel super-tiles walked by
+ * persistent CTAs) so sampled texels are re-used out of L1.  host_shapes: int32 [L,2] (H_l, W_l) on the HOST.
+ */
+int ape_msda_fused_self_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+                            const int *host_shapes, const void *offsets, int64_t offs_row_stride, const void *logits,
+                            int64_t logit_row_stride, const float *ref, int ref_dim, void *out, int B, int S, int H,
+                            int D, int L, int P, int dtype, int offs_dtype, void *stream);
+
+/*
  * Tensor-core linear layer: C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), tcgen05 / TMA / TMEM.
  * Replaces the nn.Linear (cuBLAS) calls of the detection path (vit_eva_clip.py:225-232,266-267,125-132;
  * deformable_transformer_vl.py:36-54; multi_scale_deform_attn.py:278-295,353; vision_language_align.py:36-48).
@@ -123,6 +133,16 @@ int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C,
  */
 int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
                   const int *row_map, int rows, int C, float eps, int in_dtype, int out_dtype, void *stream);
+
+/*
+ * GroupNorm over token-major activations x [B, rows_per_image, C] (the neck's GroupNorm(32, 256) after each
+ * 1x1 conv, configs/…1080k.py:42-55): statistics per (image, group) over all rows x C/groups channels, fp32,
+ * deterministic.  workspace: ape_groupnorm_workspace_bytes(B, rows_per_image, C) bytes.
+ */
+int64_t ape_groupnorm_workspace_bytes(int B, int rows_per_image, int C);
+int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
+                       void *workspace, int B, int rows_per_image, int C, int groups, float eps, int in_dtype,
+                       int out_dtype, void *stream);
 
 /*
  * In-place 2-D rotary embedding on the q and k thirds of a fused qkv buffer [M, 3*C] (pitch ld):

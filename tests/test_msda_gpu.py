@@ -227,3 +227,25 @@ def test_fused_entry_equals_unfused_composition(ape):
         got = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :H * L * P * 2],
                                                    qo[..., H * L * P * 2:], ref, P)
         torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shapes", [[(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], [(16, 16), (8, 8)], [(33, 17)]])
+def test_tiled_self_attention_kernel_equals_generic_fused(ape, dtype, shapes):
+    """ape_msda_fused_self_fwd (spatially tiled persistent CTAs, encoder case Q == S) must reproduce
+    ape_msda_fused_fwd bit for bit: the per-row arithmetic is identical, only the work mapping differs."""
+    B, H, D, P = 2, 8, 32, 4
+    L = len(shapes)
+    g = torch.Generator().manual_seed(17)
+    ss = torch.tensor(shapes)
+    st = O.level_start_index(ss)
+    S = int((ss[:, 0] * ss[:, 1]).sum())
+    value = torch.randn(B, S, H, D, generator=g).to(DEV, dtype)
+    qo = torch.cat([torch.randn(B, S, H * L * P * 2, generator=g) * 3, torch.randn(B, S, H * L * P, generator=g)], -1).to(DEV, dtype)
+    n_off = H * L * P * 2
+    for ref_dim in (2, 4):
+        ref = torch.rand(B, S, L, ref_dim, generator=g).to(DEV)
+        a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
+        b = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P,
+                                                 host_shapes=shapes)
+        assert torch.equal(a, b)

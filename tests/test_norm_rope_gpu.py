@@ -71,3 +71,18 @@ def test_rope_matches_reference_formula(ops, dtype):
         torch.testing.assert_close(buf[:, :C].float(), ref(qkv[:, :C], p), rtol=tol, atol=tol)
         torch.testing.assert_close(buf[:, C:2 * C].float(), ref(qkv[:, C:2 * C], p), rtol=tol, atol=tol)
         assert torch.equal(buf[:, 2 * C:], qkv[:, 2 * C:])  # v untouched
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("rows", [1, 100, 4096, 65536])
+def test_groupnorm_nhwc(ops, dtype, rows):
+    B, C, G = 2, 256, 32
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(B, rows, C, generator=g) * 1.5 + 0.3).to(dtype).to(DEV)
+    w = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    y = ops.groupnorm_nhwc(x, w, b, G, eps=1e-5)
+    want = F.group_norm(x.float().transpose(1, 2), G, w, b, 1e-5).transpose(1, 2)
+    tol = 2e-5 if dtype == torch.float32 else 4e-3
+    torch.testing.assert_close(y.float(), want, rtol=tol, atol=tol)
+    assert torch.equal(y, ops.groupnorm_nhwc(x, w, b, G, eps=1e-5))  # deterministic
