@@ -50,6 +50,10 @@ lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, 
 lib.ape_rope_qk.restype = _i
 lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 
+lib.ape_vlf_pool_workspace_bytes.restype = _i64
+lib.ape_vlf_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
+lib.ape_vlf_pool.restype = _i
+lib.ape_vlf_pool.argtypes = [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i)] + [_i] * 6 + [_vp]
 lib.ape_nms_workspace_bytes.restype = _i64
 lib.ape_nms_workspace_bytes.argtypes = [_i]
 lib.ape_nms_sorted.restype = _i
@@ -69,6 +73,8 @@ EXPORTS = (
     "ape_rope_qk",
     "ape_groupnorm_workspace_bytes",
     "ape_groupnorm_nhwc",
+    "ape_vlf_pool_workspace_bytes",
+    "ape_vlf_pool",
     "ape_nms_workspace_bytes",
     "ape_nms_sorted",
 )

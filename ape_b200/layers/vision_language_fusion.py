@@ -104,14 +104,24 @@ class BiAttentionBlock(nn.Module):
         a = self.attn
         nh, hd = a.num_heads, a.head_dim
         with torch.autocast("cuda", enabled=False):
-            vf, lf = v.float(), l.float()
-            B, S, _ = vf.shape
+            lf = l.float()
+            B, S, _ = v.shape
             k = F.linear(lf, a.l_proj.weight.float(), a.l_proj.bias.float()).view(B, nh, hd)
             val_l = F.linear(lf, a.values_l_proj.weight.float(), a.values_l_proj.bias.float())       # [B,1,E]
             dv = F.linear(val_l, a.out_v_proj.weight.float(), a.out_v_proj.bias.float())             # [B,1,v_dim]
             wq = a.v_proj.weight.float().view(nh, hd, -1)                                            # [nh,hd,v_dim]
             qa = torch.einsum("bhd,hdc->bhc", k, wq) * a.scale                                       # [B,nh,v_dim]
             qc = torch.einsum("bhd,hd->bh", k, a.v_proj.bias.float().view(nh, hd)) * a.scale         # [B,nh]
+            if v.is_cuda and nh <= 8 and a.clamp_min_for_underflow and a.clamp_max_for_overflow and \
+                    (v.shape[-1] % 256 == 0 or v.dtype == torch.float32) and v.shape[-1] % 32 == 0 and B * nh <= 64:
+                from .. import ops  # fused pooling kernels: v is read twice in its own dtype, nothing else of size S
+
+                pooled = ops.vlf_pool(v.contiguous(), qa, qc, a.stable_softmax_2d)
+                wvv = a.values_v_proj.weight.float().view(nh, hd, -1)
+                out_l = torch.einsum("bhc,hdc->bhd", pooled, wvv) + a.values_v_proj.bias.float().view(nh, hd)
+                dl = F.linear(out_l.reshape(B, 1, nh * hd), a.out_l_proj.weight.float(), a.out_l_proj.bias.float())
+                return dv.to(v.dtype), dl.to(l.dtype)
+            vf = v.float()
             w = torch.einsum("bsc,bhc->bhs", vf, qa) + qc[..., None]                                 # [B,nh,S]
             if a.stable_softmax_2d:
                 w = w - w.max()

@@ -268,6 +268,9 @@ class ViT(nn.Module):
         return geo
 
     def _engine_forward(self, img):
+        return self._engine_tokens(img).permute(0, 3, 1, 2)  # NCHW view over NHWC memory (channels_last)
+
+    def _engine_tokens(self, img):
         B, _, Hh, Ww = img.shape
         ps = self.patch_embed.proj.kernel_size[0]
         g = Hh // ps
@@ -308,9 +311,33 @@ class ViT(nn.Module):
             ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]])
             ops.layernorm(hbuf[:, :p["hid"]], p["fw"], p["fb"], eps=1e-6, out=hbuf2[:, :p["hid"]])
             x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x)
-        # back to raster order, NCHW
-        x = x.view(B, g * g, C)[:, geo["inv"]]
-        return x.view(B, g, g, C).permute(0, 3, 1, 2)
+        # back to raster order: [B, g, g, C] tokens (NHWC memory)
+        return x.view(B, g * g, C)[:, geo["inv"]].view(B, g, g, C)
+
+
+def _convT_as_gemm(ct, dtype):
+    """ConvTranspose2d(k=2, s=2) as a GEMM over tokens: weight [(dy,dx,co), ci], bias tiled 4x (cached)."""
+    key = ("ct", dtype, ct.weight._version, ct.weight.data_ptr())
+    c = ct.__dict__.get("_ape_packed")
+    if c is None or c[0] != key:
+        with torch.no_grad():
+            w = ct.weight.detach().permute(2, 3, 1, 0).reshape(-1, ct.weight.shape[0]).to(dtype).contiguous()
+            b = ct.bias.detach().float().repeat(4).contiguous()
+        c = (key, w, b)
+        ct.__dict__["_ape_packed"] = c
+    return c[1], c[2]
+
+
+def _conv_weights(conv, dtype):
+    key = ("cv", dtype, conv.weight._version, conv.weight.data_ptr())
+    c = conv.__dict__.get("_ape_packed")
+    if c is None or c[0] != key:
+        with torch.no_grad():
+            w = conv.weight.detach().to(dtype)
+            w = w.reshape(w.shape[0], -1).contiguous() if w.shape[-1] == 1 else w.contiguous(memory_format=torch.channels_last)
+        c = (key, w)
+        conv.__dict__["_ape_packed"] = c
+    return c[1]
 
 
 class LastLevelMaxPool(nn.Module):
@@ -377,7 +404,77 @@ class SimpleFeaturePyramid(nn.Module):
         return {n: ShapeSpec(channels=self._out_feature_channels[n], stride=self._out_feature_strides[n])
                 for n in self._out_features}
 
+    # Engine path: activations stay token-major (NHWC) from the ViT to the encoder.  2x2/stride-2 transposed
+    # convolutions and 1x1 convolutions are tcgen05 GEMMs over tokens; the pixel shuffle of a transposed conv is
+    # folded into the row map of the LayerNorm kernel that follows it; channels-first LayerNorm (detectron2 "LN")
+    # is a row LayerNorm in this layout; only the 3x3 convolutions still go to cuDNN (channels_last, no copies).
+    def _shuffle_map(self, B, g, device):
+        key = (B, g, str(device))
+        cache = self.__dict__.setdefault("_maps", {})
+        if key not in cache:
+            b, y, x, dy, dx = torch.meshgrid(torch.arange(B), torch.arange(g), torch.arange(g), torch.arange(2),
+                                             torch.arange(2), indexing="ij")
+            cache[key] = (b * (4 * g * g) + (2 * y + dy) * (2 * g) + 2 * x + dx).reshape(-1).to(device, torch.int32)
+        return cache[key]
+
+    def _engine_forward(self, img):
+        tok = self.net._engine_tokens(img)  # [B, g, g, C]
+        B, g, _, C = tok.shape
+        dt, dev = tok.dtype, tok.device
+        results = {}
+        for scale, seq, name in zip(self.scale_factors, self.stages, self._out_features):
+            mods = list(seq)
+            if scale == 4.0:
+                ct1, ln, _, ct2, c1, c3 = mods
+                w, b = _convT_as_gemm(ct1, dt)
+                y = ops.linear_tc(tok.view(-1, C), w, b).view(-1, C // 2)            # rows (t, dy, dx)
+                lw, lb = ops.packed(ln, dt)
+                y = ops.layernorm(y, lw, lb, eps=ln.eps, row_map=self._shuffle_map(B, g, dev))  # -> raster 2g x 2g
+                y = F.gelu(y)
+                w, b = _convT_as_gemm(ct2, dt)
+                y = ops.linear_tc(y, w, b).view(-1, C // 4)                          # rows (t2, dy, dx), t2 raster 2g
+                y = ops.linear_tc(y, _conv_weights(c1, dt))                          # 1x1 conv commutes with the shuffle
+                nw, nb = ops.packed(c1.norm, dt)
+                y = ops.layernorm(y, nw, nb, eps=c1.norm.eps, row_map=self._shuffle_map(B, 2 * g, dev))
+                hw = 4 * g
+            elif scale == 2.0:
+                ct1, c1, c3 = mods
+                w, b = _convT_as_gemm(ct1, dt)
+                y = ops.linear_tc(tok.view(-1, C), w, b).view(-1, C // 2)
+                y = ops.linear_tc(y, _conv_weights(c1, dt))
+                nw, nb = ops.packed(c1.norm, dt)
+                y = ops.layernorm(y, nw, nb, eps=c1.norm.eps, row_map=self._shuffle_map(B, g, dev))
+                hw = 2 * g
+            else:
+                if scale == 1.0:
+                    c1, c3 = mods
+                    src, hw = tok.view(-1, C), g
+                elif scale == 0.5:
+                    _, c1, c3 = mods
+                    src = F.max_pool2d(tok.permute(0, 3, 1, 2), kernel_size=2, stride=2).permute(0, 2, 3, 1).reshape(-1, C)
+                    hw = g // 2
+                else:
+                    raise NotImplementedError(f"scale_factor={scale} is not supported yet.")
+                y = ops.linear_tc(src, _conv_weights(c1, dt))
+                nw, nb = ops.packed(c1.norm, dt)
+                y = ops.layernorm(y, nw, nb, eps=c1.norm.eps)
+            ch = y.shape[-1]
+            z = F.conv2d(y.view(B, hw, hw, ch).permute(0, 3, 1, 2), _conv_weights(c3, dt), padding=1)  # cuDNN NHWC
+            z = z.permute(0, 2, 3, 1)
+            if not z.is_contiguous():
+                z = z.contiguous()
+            nw, nb = ops.packed(c3.norm, dt)
+            z = ops.layernorm(z.view(-1, ch), nw, nb, eps=c3.norm.eps)
+            results[name] = z.view(B, hw, hw, ch).permute(0, 3, 1, 2)
+        top = self.top_block(results[self.top_block.in_feature])
+        for n, t in zip(self._out_features[len(self.stages):], top):
+            results[n] = t
+        return {n: results[n] for n in self._out_features}
+
     def forward(self, x):
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and hasattr(self.net, "_engine_ok") \
+                and self.net._engine_ok(x) and isinstance(self.top_block, LastLevelMaxPool):
+            return self._engine_forward(x)
         feats = self.net(x)
         f = feats[self.in_feature]
         results = [stage(f) for stage in self.stages]

@@ -73,6 +73,21 @@ class ChannelMapper(nn.Module):
                                                       copy.deepcopy(norm_layer)) for f in in_features])
 
     def forward(self, inputs):
+        first = inputs[self.in_features[0]]
+        if first.is_cuda and first.dtype in (torch.float16, torch.bfloat16) and \
+                all(c.conv.kernel_size == (1, 1) and isinstance(c.norm, nn.GroupNorm) for c in self.convs):
+            # engine path: 1x1 conv = tcgen05 GEMM over tokens, GroupNorm kernel on the token-major layout
+            outs = []
+            for conv, f in zip(self.convs, self.in_features):
+                x = inputs[f]
+                B, C, H, W = x.shape
+                tok = x.permute(0, 2, 3, 1).reshape(B * H * W, C)  # free when x is channels_last (engine backbone)
+                w, b = ops.packed(conv.conv, tok.dtype)
+                y = ops.linear_tc(tok, w.view(w.shape[0], -1), b)
+                gw, gb = ops.packed(conv.norm, tok.dtype)
+                y = ops.groupnorm_nhwc(y.view(B, H * W, -1), gw, gb, conv.norm.num_groups, conv.norm.eps)
+                outs.append(y.view(B, H, W, -1).permute(0, 3, 1, 2))
+            return tuple(outs)
         return tuple(self.convs[i](inputs[f]) for i, f in enumerate(self.in_features))
 
 

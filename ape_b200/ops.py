@@ -255,6 +255,26 @@ def rope_qk_(qkv, cos, sin, num_channels, head_dim, pos_map=None):
     return qkv
 
 
+def vlf_pool(v, qa, qc, stable_softmax_2d=True):
+    """sum_s softmax_s(v_s . qa[h] + qc[h]) * v_s for every head -> fp32 [B, NH, C]  (ape_vlf_pool)."""
+    _require(v.is_cuda and v.dim() == 3 and v.is_contiguous(), "vlf_pool: contiguous CUDA [B,S,C]")
+    B, S, C = v.shape
+    NH = qa.shape[1]
+    qa = qa.float().contiguous()
+    qc = qc.float().contiguous()
+    nbytes = int(_lib.lib.ape_vlf_pool_workspace_bytes(B, S, C, NH))
+    ws = torch.empty((nbytes // 4,), dtype=torch.float32, device=v.device)
+    ptr, strips = ctypes.c_void_p(), ctypes.c_int()
+    with torch.cuda.device(v.device), _timed(("vlf_pool", B, S, C, NH)):
+        rc = _lib.lib.ape_vlf_pool(v.data_ptr(), qa.data_ptr(), qc.data_ptr(), ws.data_ptr(), ctypes.byref(ptr),
+                                   ctypes.byref(strips), B, S, C, NH, 1 if stable_softmax_2d else 0,
+                                   _lib.dtype_code(v.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_vlf_pool")
+    off = (ptr.value - ws.data_ptr()) // 4
+    part = ws[off: off + B * strips.value * NH * (C + 1)].view(B, strips.value, NH, C + 1).sum(1)  # fixed order
+    return part[..., :C] / part[..., C:]
+
+
 def nms(boxes, scores, iou_threshold):
     """torchvision.ops.nms replacement: indices of kept boxes, sorted by descending score."""
     _require(boxes.is_cuda and boxes.dim() == 2 and boxes.shape[1] == 4, "nms: boxes must be CUDA [n,4]")

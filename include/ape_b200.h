@@ -153,6 +153,17 @@ int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_
                 int C, int head_dim, int npos, int dtype, void *stream);
 
 /*
+ * Language-side attention pooling of VisionLanguageFusion for a single language token ("name" prompts):
+ * softmax over the S vision tokens of scores t[s,h] = v_s . qa[h] + qc[h] (with the reference's global-max shift
+ * and +-5e4 clamps, fuse_helper.py:88-110) and the p-weighted sum of v.  v [B,S,C] dtype; qa [B,NH,C], qc [B,NH] fp32.
+ * Results are left as per-strip partials in the workspace: *partial_out -> [B, *strips_out, NH, C+1] fp32
+ * (last column = sum of exp).  workspace: ape_vlf_pool_workspace_bytes(B,S,C,NH) bytes.
+ */
+int64_t ape_vlf_pool_workspace_bytes(int B, int S, int C, int NH);
+int ape_vlf_pool(const void *v, const float *qa, const float *qc, void *workspace, float **partial_out, int *strips_out,
+                 int B, int S, int C, int NH, int stable_softmax_2d, int dtype, void *stream);
+
+/*
  * Greedy hard NMS over boxes already sorted by descending score (torchvision.ops.nms semantics; replaces the
  * nms call inside batched_nms of deformable_transformer_vl.py:591-596 and fast_rcnn.py:192).
  * boxes_sorted [n,4] fp32 xyxy (16-byte aligned); keep [n] bytes (1 = survives); *count = survivors (device int).
