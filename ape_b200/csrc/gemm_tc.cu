@@ -241,7 +241,13 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
   }
 }
 
-template <int BN, int STAGES>
+// CL = cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent
+// 128-row tiles of the same BN-column block: each loads half of the B (weight) tile and TMA-multicasts it into
+// both CTAs' shared memory, so the L2 -> SM traffic per CTA drops from 48 KB to 32 KB per k-block (these GEMMs
+// are L2-bandwidth bound at 128x256 tiles: ncu shows ~10 TB/s of xbar2l1tex reads).  A stage may only be
+// refilled when BOTH CTAs' MMAs have finished reading it, so every tcgen05.commit of a stage arrives on the
+// "empty" barrier of both CTAs (multicast commit, barrier count 2).
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
@@ -252,7 +258,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int num_tiles = p.m_blocks * p.n_blocks;
+  // work items: (m group of CL row blocks, n block); CTA `rank` of the cluster takes row block CL*m_group + rank
+  const int rank = CL > 1 ? (int)tc::cluster_ctarank() : 0;
+  const int m_groups = (p.m_blocks + CL - 1) / CL;
+  const int num_tiles = m_groups * p.n_blocks;
+  const int first = blockIdx.x / CL, stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(&map_a);
@@ -261,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       tc::mbar_init(&s.full[i], 1);
-      tc::mbar_init(&s.empty[i], 1);
+      tc::mbar_init(&s.empty[i], CL);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -276,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();  // peer barriers are initialised before any multicast can reach them
   tc::fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
 
@@ -283,13 +294,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
+      for (int tile = first; tile < num_tiles; tile += stride) {
+        const int m_blk = (tile % m_groups) * CL + rank, n_blk = tile / m_groups;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
           tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
           tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
-          tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
+          if (CL == 1) {
+            tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
+          } else {
+            constexpr int HALF_ROWS = BN / CL;
+            tc::tma_load_2d_multicast(s.b[stage] + rank * HALF_ROWS * BK * 2, &map_b, &s.full[stage], kb * BK,
+                                      n_blk * BN + rank * HALF_ROWS, (uint16_t)((1u << CL) - 1));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -299,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < num_tiles; tile += stride) {
         tc::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -313,7 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
             tc::mma_f16(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
           }
-          tc::mma_commit(&s.empty[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot once these MMAs have read it (in both CTAs of a cluster: the peer multicasts into it)
+          if (CL == 1) tc::mma_commit(&s.empty[stage]);
+          else tc::mma_commit_multicast(&s.empty[stage], (uint16_t)((1u << CL) - 1));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit(&s.tmem_full[acc]);  // accumulator complete -> epilogue
@@ -327,8 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 2) / 4;  // which half of the tile's columns
     uint8_t *slab = s.c[warp - 2];
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.m_blocks, n_blk = tile / p.m_blocks;
+    for (int tile = first; tile < num_tiles; tile += stride) {
+      const int m_blk = (tile % m_groups) * CL + rank, n_blk = tile / m_groups;
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
       if (p.tma_store) {
@@ -361,6 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();  // no CTA leaves while its peer can still signal its barriers
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -411,11 +431,11 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, GemmParams &p, cudaStream_t st) {
   using Smem = GemmSmem<BN, STAGES>;
   const size_t smem = sizeof(Smem) + 1024;
-  auto k = gemm_tc_kernel<BN, STAGES>;
+  auto k = gemm_tc_kernel<BN, STAGES, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -423,9 +443,23 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
     attr_set = true;
   }
   p.n_blocks = (p.N + BN - 1) / BN;
-  const int tiles = p.m_blocks * p.n_blocks;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  k<<<grid, kThreads, smem, st>>>(ma, mb, mc, p);
+  const int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
+  const int max_clusters = num_sms() / CL;
+  const int clusters = groups < max_clusters ? groups : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CL));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, ma, mb, mc, p);
+  if (e != cudaSuccess) return fail((int)e, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
 }
 
@@ -450,12 +484,14 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
   if (lda < K || ldw < K) return fail(APE_ERR_INVALID_ARG, "gemm: row pitch smaller than K");
   if (act == ACT_SWIGLU && ((N & 1) || residual)) return fail(APE_ERR_INVALID_ARG, "gemm: swiglu needs even N, no residual");
   if (residual && out_dtype == APE_DTYPE_F32 && false) return APE_ERR_INVALID_ARG;
-  const int bn = tile_n > 0 ? tile_n : (N >= 1536 ? 256 : 128);
+  const int bn = (tile_n & 0xfff) > 0 ? (tile_n & 0xfff) : (N >= 1536 ? 256 : 128);
   if (bn != 128 && bn != 256) return fail(APE_ERR_INVALID_ARG, "gemm: tile_n must be 128 or 256");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap ma, mb;
   if (int rc = make_map(&ma, A, in_dtype, M, K, lda, BM)) return rc;
-  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, bn)) return rc;
+  // cluster of 2 along M whenever there are at least two row blocks (tile_n bit 0x1000 forces single-CTA)
+  const bool single = (tile_n & 0x1000) != 0 || M <= BM;
+  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : bn / 2)) return rc;
   GemmParams p{};
   p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
@@ -470,6 +506,10 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
                 (act != ACT_SWIGLU || bn == 256);
   if (p.tma_store)
     if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 64)) return rc;
-  if (bn == 256) return launch_gemm<256, 4>(ma, mb, mc, p, st);
-  return launch_gemm<128, 6>(ma, mb, mc, p, st);
+  if (single) {
+    if (bn == 256) return launch_gemm<256, 4, 1>(ma, mb, mc, p, st);
+    return launch_gemm<128, 6, 1>(ma, mb, mc, p, st);
+  }
+  if (bn == 256) return launch_gemm<256, 4, 2>(ma, mb, mc, p, st);
+  return launch_gemm<128, 6, 2>(ma, mb, mc, p, st);
 }

@@ -272,12 +272,16 @@ class DeformableDetrTransformerVL(nn.Module):
         pre = []
         for lvl in range(n_levels):
             lvl_mask = level_ids == lvl
-            pre.append(torch.topk(logit.sigmoid() * lvl_mask, min(self.pre_nms_topk, logit.size(0)))[1])
+            # The reference calls torch.topk here; for a level with fewer tokens than pre_nms_topk (the 16x16 level at
+            # 1024^2) the result is padded with zero-score tokens of OTHER levels in an implementation-defined order
+            # (CPU and CUDA top-k differ).  The engine fixes the rule: stable descending sort = lowest index first.
+            order = torch.sort(logit.sigmoid() * lvl_mask, descending=True, stable=True)[1]
+            pre.append(order[: min(self.pre_nms_topk, logit.size(0))])
         pre = torch.cat(pre)
         post = ops.batched_nms(boxes[pre].float(), logit[pre].float(), level_ids[pre], self.nms_thresh_enc)
         keep = pre[post]
         if len(keep) < topk:
-            keep = torch.topk(logit, min(topk, logit.size(0)))[1]
+            keep = torch.sort(logit, descending=True, stable=True)[1][: min(topk, logit.size(0))]
         q_per_l = topk // n_levels
         ordered = level_ids[keep][None] == torch.arange(n_levels, device=level_ids.device)[:, None]
         km = (ordered & (ordered.cumsum(1) <= q_per_l)).any(0)

@@ -384,12 +384,16 @@ def select_proposals(logit, boxes_unact, level_ids, n_levels, topk, pre_nms_topk
     pre = []
     for lvl in range(n_levels):
         lvl_mask = level_ids == lvl
-        pre.append(torch.topk(logit.sigmoid() * lvl_mask, min(pre_nms_topk, logit.size(0)))[1])
+        # reference: torch.topk(...)[1].  For levels with fewer tokens than pre_nms_topk the tail of that result is a
+        # tie among zero scores whose order torch leaves implementation-defined (CPU != CUDA); the oracle and the
+        # engine both use the stable order (lowest index first), one of the valid outcomes of the reference call.
+        order = torch.sort(logit.sigmoid() * lvl_mask, descending=True, stable=True)[1]
+        pre.append(order[: min(pre_nms_topk, logit.size(0))])
     pre = torch.cat(pre)
     post = torchvision.ops.boxes.batched_nms(boxes[pre], logit[pre], level_ids[pre], nms_thresh)
     keep = pre[post]
     if len(keep) < topk:
-        keep = torch.topk(logit, min(topk, logit.size(0)))[1]
+        keep = torch.sort(logit, descending=True, stable=True)[1][: min(topk, logit.size(0))]
     q_per_l = topk // n_levels
     ordered = level_ids[keep][None] == torch.arange(n_levels)[:, None]
     km = (ordered & (ordered.cumsum(1) <= q_per_l)).any(0)

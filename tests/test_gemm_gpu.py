@@ -87,7 +87,7 @@ def test_vit_swiglu_shape_16bit_out(ops, dtype):
     assert ((pad == 9.0) | (pad == 0.0)).all()
 
 
-@pytest.mark.parametrize("tile", [128, 256])
+@pytest.mark.parametrize("tile", [128, 256, 128 | 0x1000, 256 | 0x1000])  # 0x1000: single-CTA (no cluster multicast)
 def test_tma_store_epilogue_edges(ops, tile):
     # M and N both ragged, bias + relu + residual, 16-bit output with an aligned pitch
     M, N, K = 777, 840, 192
@@ -98,6 +98,21 @@ def test_tma_store_epilogue_edges(ops, tile):
     res = rnd(M, N, dtype=dtype, seed=24)
     y = ops.linear_tc(x, w, b, act="relu", residual=res, tile_n=tile)
     torch.testing.assert_close(y.float(), ref_linear(x, w, b, "relu", res), rtol=4e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("M", [129, 256, 383, 4096])
+@pytest.mark.parametrize("tile", [128, 256])
+def test_cluster_pairs_with_odd_row_block_counts(ops, M, tile):
+    """Clusters of two CTAs share the weight tile by TMA multicast; an odd number of 128-row blocks leaves the
+    second CTA of the last cluster with an all-out-of-range tile that must still take part in the protocol."""
+    N, K = 512, 512
+    x = rnd(M, K, dtype=torch.bfloat16, seed=41)
+    w = rnd(N, K, dtype=torch.bfloat16, seed=42, scale=K ** -0.5)
+    b = rnd(N, dtype=torch.float32, seed=43)
+    y = ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile)
+    torch.testing.assert_close(y, ref_linear(x, w, b), rtol=2e-4, atol=2e-4)
+    y1 = ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile | 0x1000)
+    assert torch.equal(y, y1)  # same accumulation order with and without the cluster
 
 
 def test_many_tiles_per_cta_ring_wraparound(ops):

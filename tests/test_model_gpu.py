@@ -184,6 +184,11 @@ def test_ape_l_d_1024_matches_oracle_port_stagewise():
     # elements exceeded 2e-3 (max 4.4e-3) on B200, so the bound here is 1e-2 absolute on O(1) values
     torch.testing.assert_close(lo["memory"].cpu(), taps["memory"], rtol=1e-2, atol=1e-2)
     sel, want = model.transformer.last_topk_proposals.cpu(), taps["topk_proposals"]
+    # Stage-wise parity of the selection itself (bit-exact requirement): the engine's top-k / NMS / quota code on
+    # the ORACLE's encoder outputs must return exactly the oracle's indices.
+    geo = model._geometry((1, 3, 1024, 1024), [(1024, 768)], None)
+    stage = model.transformer.stage_select(taps["enc_outputs_class"].to(DEV), taps["enc_outputs_coord_unact"].to(DEV), geo)
+    assert torch.equal(stage.cpu(), want), "selection differs on identical inputs"
     # Selected proposals: identical except where upstream fp32 noise (see above) flips a near-tie of the top-k /
     # NMS ordering; report the agreement and require it to be near-total, then compare the heads on the queries
     # that both sides selected at the same slot.
@@ -191,7 +196,9 @@ def test_ape_l_d_1024_matches_oracle_port_stagewise():
     common = set(a) & set(b)
     frac = len(common) / len(b)
     print(f"proposal set agreement at full size: {frac:.4f} ({len(common)}/{len(b)})")
-    assert frac > 0.95, f"selected proposal sets differ ({frac:.3f} in common)"
+    # end to end the two sides see encoder outputs that differ by fp32 reduction-order noise (above); with untrained
+    # weights the proposal scores are nearly flat, so the discontinuous top-k / IoU>0.9 NMS flips a few percent
+    assert frac > 0.85, f"selected proposal sets differ ({frac:.3f} in common)"
     ia = torch.tensor([a.index(i) for i in sorted(common)])
     ib = torch.tensor([b.index(i) for i in sorted(common)])
     torch.testing.assert_close(lo["pred_logits"].cpu()[0][ia], taps["pred_logits"][0][ib], rtol=1e-2, atol=3e-2)
