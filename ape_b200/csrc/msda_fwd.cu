@@ -52,20 +52,29 @@ __host__ __device__ constexpr int threads_for(int lpr) { return lpr >= 4 ? 256 :
 // side of an integer for these ranges, and costs 3 instructions instead of a ~20-instruction idiv.
 __device__ __forceinline__ int fast_div(int i, float inv) { return __float2int_rz(((float)i + 0.5f) * inv); }
 
-// One sampling point -> 4 corner byte offsets + 4 weights.  Follows ms_deform_im2col_cuda.cuh:279-291
-// (in-range test) and :36-80 (corner validity, weights).  `x`,`y` are normalised locations.
-// Offsets are ALWAYS valid addresses (coordinates clamped into the level) and corners / samples the
-// reference skips get weight 0, so phase 2 needs no predicates.  The only observable difference:
-// a NaN/Inf texel next to the border is multiplied by 0 instead of being skipped (finite inputs:
-// identical results).
-__device__ __forceinline__ void make_sample(float x, float y, float a, int Hl, int Wl, int start,
-                                            int h, int H, int row_bytes, int4 &off, float4 &w) {
+// One sampling point -> one 16-byte record {corner(y0,x0) byte offset | flags, hh*a, lh*a, lw}.
+// Follows ms_deform_im2col_cuda.cuh:279-291 (in-range test) and :36-80 (corner validity, weights); `x`,`y` are
+// normalised locations.  Coordinates are clamped into the level so every offset is a valid address; corners or
+// samples the reference skips get weight 0 (the only observable difference: a NaN/Inf texel next to the border is
+// multiplied by 0 instead of being skipped — finite inputs give identical results).
+// flags (low 4 bits of the offset, which is a multiple of the >=16-byte row): 1 = x1 is a distinct texel,
+// 2 = y1 is a distinct texel, 4 = left corners valid, 8 = right corners valid.  The vertical validity and the
+// attention weight are folded into hh_a / lh_a; keeping lw in fp32 makes the 4 products identical to the
+// uncompressed form up to reassociation.  16 bytes per sample instead of 32 halves the shared memory a CTA pins,
+// which is L1 capacity returned to the gathered texels.
+struct __align__(16) Sample {
+  int off_flags;
+  float hh_a, lh_a, lw;
+};
+
+__device__ __forceinline__ Sample make_sample(float x, float y, float a, int Hl, int Wl, int start,
+                                              int h, int H, int row_bytes) {
   const float h_im = y * (float)Hl - 0.5f;
   const float w_im = x * (float)Wl - 0.5f;
   const bool in_range = h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl;
   const float hf = floorf(h_im), wf = floorf(w_im);
   const float lh = h_im - hf, lw = w_im - wf;
-  const float hh = 1.f - lh, hw = 1.f - lw;
+  const float hh = 1.f - lh;
   // saturating float->int conversions (NaN -> 0), then clamp into the level
   const int h_low = __float2int_rd(h_im), w_low = __float2int_rd(w_im);
   const bool hl_ok = in_range && h_low >= 0, hh_ok = in_range && h_low < Hl - 1;
@@ -73,61 +82,63 @@ __device__ __forceinline__ void make_sample(float x, float y, float a, int Hl, i
   const int hc = min(max(h_low, -1), Hl - 1), wc = min(max(w_low, -1), Wl - 1);
   const int y0 = max(hc, 0), y1 = min(hc + 1, Hl - 1);
   const int x0 = max(wc, 0), x1 = min(wc + 1, Wl - 1);
-  const int r0 = start + y0 * Wl, r1 = start + y1 * Wl;
-  off.x = ((r0 + x0) * H + h) * row_bytes;
-  off.y = ((r0 + x1) * H + h) * row_bytes;
-  off.z = ((r1 + x0) * H + h) * row_bytes;
-  off.w = ((r1 + x1) * H + h) * row_bytes;
-  w.x = (hl_ok && wl_ok) ? hh * hw * a : 0.f;
-  w.y = (hl_ok && wh_ok) ? hh * lw * a : 0.f;
-  w.z = (hh_ok && wl_ok) ? lh * hw * a : 0.f;
-  w.w = (hh_ok && wh_ok) ? lh * lw * a : 0.f;
+  Sample r;
+  r.off_flags = ((start + y0 * Wl + x0) * H + h) * row_bytes;
+  r.off_flags |= (x1 != x0 ? 1 : 0) | (y1 != y0 ? 2 : 0) | (wl_ok ? 4 : 0) | (wh_ok ? 8 : 0);
+  r.hh_a = hl_ok ? hh * a : 0.f;
+  r.lh_a = hh_ok ? lh * a : 0.f;
+  r.lw = in_range ? lw : 0.f;
+  return r;
 }
 
-// Phase 2: gather + accumulate + store for one lane.  The host guarantees LP % U == 0.
+// Phase 2: gather + accumulate + store for one lane.  The host guarantees P % U == 0.
+// s_dy[l] = byte distance between vertically adjacent texels of level l (W_l * H * row_bytes).
 template <typename T, int LPR, int U>
-__device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_off,
-                                            const float4 *s_w, int lps, int b, int q, int h) {
+__device__ __forceinline__ void gather_rows(const MsdaParams &p, const Sample *s_rec, const int *s_dy, int lps, int b,
+                                            int q, int h) {
   using E = Elem<T>;
   constexpr int VEC = E::kVec;
-  const int LP = p.L * p.P;
   const int r = threadIdx.x / LPR, c = threadIdx.x % LPR;
   if (q < 0 || q >= p.Q) return;
 
   const char *vb = reinterpret_cast<const char *>(p.value) + ((size_t)b * p.S * p.H * LPR + c) * 16;
-  const int4 *ro = s_off + r * lps;
-  const float4 *rw = s_w + r * lps;
+  const Sample *row = s_rec + r * lps;
+  const unsigned dxb = (unsigned)(p.H * LPR * 16);
 
   float acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
 #pragma unroll 1
-  for (int s0 = 0; s0 < LP; s0 += U) {
-    int4 o[U];
-    float4 w[U];
+  for (int l = 0; l < p.L; ++l) {
+    const unsigned dyb = (unsigned)s_dy[l];
+#pragma unroll 1
+    for (int pp = 0; pp < p.P; pp += U) {
+      Sample sm[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      o[u] = ro[s0 + u];
-      w[u] = rw[s0 + u];
-    }
-    uint4 v[U][4];
+      for (int u = 0; u < U; ++u) sm[u] = row[l * p.P + pp + u];
+      uint4 v[U][4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      v[u][0] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].x));
-      v[u][1] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].y));
-      v[u][2] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].z));
-      v[u][3] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + (unsigned)o[u].w));
-    }
+      for (int u = 0; u < U; ++u) {
+        const unsigned o0 = (unsigned)sm[u].off_flags & ~15u;
+        const unsigned ox = (sm[u].off_flags & 1) ? dxb : 0u, oy = (sm[u].off_flags & 2) ? dyb : 0u;
+        v[u][0] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + o0));
+        v[u][1] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + o0 + ox));
+        v[u][2] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + o0 + oy));
+        v[u][3] = ldg_nc_v4(reinterpret_cast<const uint4 *>(vb + o0 + oy + ox));
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float ww[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+      for (int u = 0; u < U; ++u) {
+        const float hw = (sm[u].off_flags & 4) ? 1.f - sm[u].lw : 0.f;
+        const float lw = (sm[u].off_flags & 8) ? sm[u].lw : 0.f;
+        const float ww[4] = {sm[u].hh_a * hw, sm[u].hh_a * lw, sm[u].lh_a * hw, sm[u].lh_a * lw};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float f[VEC];
-        E::unpack(v[u][k], f);
+        for (int k = 0; k < 4; ++k) {
+          float f[VEC];
+          E::unpack(v[u][k], f);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(ww[k], f[i], acc[i]);
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(ww[k], f[i], acc[i]);
+        }
       }
     }
   }
@@ -135,7 +146,7 @@ __device__ __forceinline__ void gather_rows(const MsdaParams &p, const int4 *s_o
   stg_stream_v4(ob, E::pack(acc));
 }
 
-// grid = (q_tiles * head_tiles, B); dynamic smem = R*lps*(16+16) bytes.
+// grid = (q_tiles * head_tiles, B); dynamic smem = R*lps*16 bytes.
 template <typename T, int LPR, int U>
 __global__ void __launch_bounds__(threads_for(LPR))
 msda_fwd_kernel(const MsdaParams p) {
@@ -144,17 +155,18 @@ msda_fwd_kernel(const MsdaParams p) {
   constexpr int R = NT / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_lvl[kMaxLevels * 3];
+  __shared__ int s_dy[kMaxLevels];
 
   const int LP = p.L * p.P;
   const int lps = LP | 1;  // odd stride (in 16 B units): conflict-free broadcast reads
-  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
-  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
+  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw);
 
   const int tid = threadIdx.x;
   if (tid < p.L) {
     s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
     s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
     s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+    s_dy[tid] = (int)p.shapes[tid * 2 + 1] * p.H * LPR * 16;
   }
   __syncthreads();
 
@@ -171,23 +183,20 @@ msda_fwd_kernel(const MsdaParams p) {
   for (int i = tid; i < R * LP; i += NT) {
     const int r = fast_div(i, inv_lp), s = i - r * LP;  // exact for i < 2^20
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    int4 off = make_int4(0, 0, 0, 0);
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    Sample rec = {0, 0.f, 0.f, 0.f};
     if (q < p.Q) {
       const int l = fast_div(s, inv_p);
       const size_t e = (((size_t)b * p.Q + q) * p.H + h) * LP + s;
       const float2 xy = E::load2(loc + 2 * e);
       const float a = E::load1(attn + e);
-      make_sample(xy.x, xy.y, a, s_lvl[l * 3], s_lvl[l * 3 + 1], s_lvl[l * 3 + 2], h, p.H, LPR * 16,
-                  off, w);
+      rec = make_sample(xy.x, xy.y, a, s_lvl[l * 3], s_lvl[l * 3 + 1], s_lvl[l * 3 + 2], h, p.H, LPR * 16);
     }
-    s_off[r * lps + s] = off;
-    s_w[r * lps + s] = w;
+    s_rec[r * lps + s] = rec;
   }
   __syncthreads();
   {
     const int r = tid / LPR;
-    gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
+    gather_rows<T, LPR, U>(p, s_rec, s_dy, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
   }
 }
 
@@ -202,19 +211,20 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   constexpr int R = NT / LPR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_lvl[kMaxLevels * 3];
+  __shared__ int s_dy[kMaxLevels];
   __shared__ float s_max[R], s_rinv[R];
 
   const int LP = p.L * p.P;
   const int lps = LP | 1;
-  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
-  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
-  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * (sizeof(int4) + sizeof(float4)));
+  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw);
+  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * sizeof(Sample));
 
   const int tid = threadIdx.x;
   if (tid < p.L) {
     s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
     s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
     s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+    s_dy[tid] = (int)p.shapes[tid * 2 + 1] * p.H * LPR * 16;
   }
   const int HT = 1 << p.ht_log2;
   const int QT = R >> p.ht_log2;
@@ -250,8 +260,7 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   for (int i = tid; i < R * LP; i += NT) {
     const int r = fast_div(i, inv_lp), s = i - r * LP;
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    int4 off = make_int4(0, 0, 0, 0);
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    Sample rec = {0, 0.f, 0.f, 0.f};
     if (q < p.Q) {
       const int l = fast_div(s, inv_p);
       const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1];
@@ -269,15 +278,14 @@ msda_fused_fwd_kernel(const MsdaParams p) {
         x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
         y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
       }
-      make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR * 16, off, w);
+      rec = make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR * 16);
     }
-    s_off[r * lps + s] = off;
-    s_w[r * lps + s] = w;
+    s_rec[r * lps + s] = rec;
   }
   __syncthreads();
   {
     const int r = tid / LPR;
-    gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
+    gather_rows<T, LPR, U>(p, s_rec, s_dy, lps, b, q0 + (r >> p.ht_log2), h0 + (r & (HT - 1)));
   }
 }
 
@@ -298,20 +306,21 @@ msda_fused_tiled_kernel(const MsdaParams p, int units_per_cta, int total_units) 
   static_assert(R % SW == 0 && TS % SH == 0, "tile geometry");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_lvl[kMaxLevels * 3];
+  __shared__ int s_dy[kMaxLevels];
   __shared__ int s_tiles[kMaxLevels + 1];
   __shared__ float s_max[R], s_rinv[R];
 
   const int LP = p.L * p.P;
   const int lps = LP | 1;
-  int4 *s_off = reinterpret_cast<int4 *>(smem_raw);
-  float4 *s_w = reinterpret_cast<float4 *>(smem_raw + (size_t)R * lps * sizeof(int4));
-  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * (sizeof(int4) + sizeof(float4)));
+  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw);
+  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * sizeof(Sample));
 
   const int tid = threadIdx.x;
   if (tid < p.L) {
     s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
     s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
     s_lvl[tid * 3 + 2] = (int)p.starts[tid];
+    s_dy[tid] = (int)p.shapes[tid * 2 + 1] * p.H * LPR * 16;
   }
   __syncthreads();
   if (tid == 0) {
@@ -369,8 +378,7 @@ msda_fused_tiled_kernel(const MsdaParams p, int units_per_cta, int total_units) 
       for (int i = tid; i < R * LP; i += NT) {
         const int r = fast_div(i, inv_lp), s = i - r * LP;
         const int qy = y0 + r / SW, qx = x0 + r % SW;
-        int4 off = make_int4(0, 0, 0, 0);
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        Sample rec = {0, 0.f, 0.f, 0.f};
         if (qy < Hl && qx < Wl) {
           const int ls = fast_div(s, inv_p);
           const int Hs = s_lvl[ls * 3], Ws = s_lvl[ls * 3 + 1];
@@ -386,16 +394,15 @@ msda_fused_tiled_kernel(const MsdaParams p, int units_per_cta, int total_units) 
             x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
             y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
           }
-          make_sample(x, y, a, Hs, Ws, s_lvl[ls * 3 + 2], h, p.H, LPR * 16, off, w);
+          rec = make_sample(x, y, a, Hs, Ws, s_lvl[ls * 3 + 2], h, p.H, LPR * 16);
         }
-        s_off[r * lps + s] = off;
-        s_w[r * lps + s] = w;
+        s_rec[r * lps + s] = rec;
       }
       __syncthreads();
       {
         const int r = tid / LPR;
         const int qy = y0 + r / SW, qx = x0 + r % SW;
-        gather_rows<T, LPR, U>(p, s_off, s_w, lps, b, (qy < Hl && qx < Wl) ? start + qy * Wl + qx : -1, h);
+        gather_rows<T, LPR, U>(p, s_rec, s_dy, lps, b, (qy < Hl && qx < Wl) ? start + qy * Wl + qx : -1, h);
       }
       __syncthreads();  // smem is rewritten by the next sub-tile
     }
@@ -427,13 +434,15 @@ msda_fwd_scalar_kernel(const MsdaParams p, int D, long long n) {
       for (int pt = 0; pt < p.P; ++pt) {
         const size_t e = (size_t)row * LP + l * p.P + pt;
         const float x = E::to_f(loc[2 * e]), y = E::to_f(loc[2 * e + 1]), a = E::to_f(attn[e]);
-        int4 off;
-        float4 w;
-        make_sample(x, y, a, Hl, Wl, st, h, p.H, 1, off, w);  // row_bytes=1 -> index of the (s,h) row
-        if (w.x != 0.f) acc = fmaf(w.x, E::to_f(vb[(size_t)off.x * D + c]), acc);
-        if (w.y != 0.f) acc = fmaf(w.y, E::to_f(vb[(size_t)off.y * D + c]), acc);
-        if (w.z != 0.f) acc = fmaf(w.z, E::to_f(vb[(size_t)off.z * D + c]), acc);
-        if (w.w != 0.f) acc = fmaf(w.w, E::to_f(vb[(size_t)off.w * D + c]), acc);
+        const Sample sm = make_sample(x, y, a, Hl, Wl, st, h, p.H, 16);  // offsets in units of 16 -> (s,h) row index * 16
+        const size_t r0 = (size_t)(((unsigned)sm.off_flags & ~15u) >> 4);
+        const size_t rx = (sm.off_flags & 1) ? (size_t)p.H : 0, ry = (sm.off_flags & 2) ? (size_t)Wl * p.H : 0;
+        const float hw = (sm.off_flags & 4) ? 1.f - sm.lw : 0.f, lw = (sm.off_flags & 8) ? sm.lw : 0.f;
+        const float w00 = sm.hh_a * hw, w01 = sm.hh_a * lw, w10 = sm.lh_a * hw, w11 = sm.lh_a * lw;
+        if (w00 != 0.f) acc = fmaf(w00, E::to_f(vb[r0 * D + c]), acc);
+        if (w01 != 0.f) acc = fmaf(w01, E::to_f(vb[(r0 + rx) * D + c]), acc);
+        if (w10 != 0.f) acc = fmaf(w10, E::to_f(vb[(r0 + ry) * D + c]), acc);
+        if (w11 != 0.f) acc = fmaf(w11, E::to_f(vb[(r0 + ry + rx) * D + c]), acc);
       }
     }
     out[idx] = E::from_f(acc);
@@ -453,7 +462,7 @@ template <typename T, int LPR, int U>
 int launch_plain(const MsdaParams &p, cudaStream_t st) {
   constexpr int NT = threads_for(LPR), R = NT / LPR;
   const int lps = (p.L * p.P) | 1;
-  const size_t smem = (size_t)R * lps * 32;
+  const size_t smem = (size_t)R * lps * 16;
   auto k = msda_fwd_kernel<T, LPR, U>;
   if (int rc = set_smem(k, smem)) return rc;
   const int QT = R >> p.ht_log2;
@@ -466,7 +475,7 @@ template <typename T, typename TO, int LPR, int U>
 int launch_fused(const MsdaParams &p, cudaStream_t st) {
   constexpr int NT = threads_for(LPR), R = NT / LPR;
   const int lps = (p.L * p.P) | 1;
-  const size_t smem = (size_t)R * lps * 36;
+  const size_t smem = (size_t)R * lps * 20;
   auto k = msda_fused_fwd_kernel<T, TO, LPR, U>;
   if (int rc = set_smem(k, smem)) return rc;
   const int QT = R >> p.ht_log2;
@@ -481,7 +490,7 @@ template <typename T, typename TO, int LPR, int U>
 int launch_fused_tiled(const MsdaParams &p, int total_tiles_per_head_image, cudaStream_t st) {
   constexpr int NT = threads_for(LPR), R = NT / LPR;
   const int lps = (p.L * p.P) | 1;
-  const size_t smem = (size_t)R * lps * 36;
+  const size_t smem = (size_t)R * lps * 20;
   auto k = msda_fused_tiled_kernel<T, TO, LPR, U>;
   if (int rc = set_smem(k, smem)) return rc;
   const int total_units = p.B * p.H * total_tiles_per_head_image;
@@ -508,8 +517,7 @@ int dispatch_lpr_plain(int lpr, const MsdaParams &p, cudaStream_t st) {
 
 template <typename T, typename TO>
 int dispatch_lpr_fused(int lpr, const MsdaParams &p, cudaStream_t st) {
-  const int LP = p.L * p.P;
-  if (LP % 2 != 0) {
+  if (p.P % 2 != 0) {
     switch (lpr) {
       case 2: return launch_fused<T, TO, 2, 1>(p, st);
       case 4: return launch_fused<T, TO, 4, 1>(p, st);
@@ -586,10 +594,10 @@ extern "C" int ape_msda_fwd_variant(const void *value, const int64_t *shapes, co
   const bool vec_ok = (row_bytes % 16 == 0) && is_pow2(lpr) && lpr <= 32 && L <= kMaxLevels;
   bool scalar = !vec_ok || (variant >= 0 && (variant & 0x1000));
   const int LP = L * P;
-  int ht = 0, unroll = (LP % 4 == 0) ? 4 : (LP % 2 == 0) ? 2 : 1;
+  int ht = 0, unroll = (P % 4 == 0) ? 4 : (P % 2 == 0) ? 2 : 1;
   if (!scalar) {
     const int R = threads_for(lpr) / lpr;
-    const size_t smem = (size_t)R * ((L * P) | 1) * 32;
+    const size_t smem = (size_t)R * ((L * P) | 1) * 16;
     if (smem > 200 * 1024) scalar = true;
     ht = default_ht(H, Q, R);
     if (variant >= 0) {
@@ -600,8 +608,8 @@ extern "C" int ape_msda_fwd_variant(const void *value, const int64_t *shapes, co
         ht = vh;
       }
       if (vu) {
-        if ((vu != 1 && vu != 2 && vu != 4) || LP % vu != 0)
-          return fail(APE_ERR_INVALID_ARG, "msda: unroll=%d must be 1, 2 or 4 and divide L*P=%d", vu, LP);
+        if ((vu != 1 && vu != 2 && vu != 4) || P % vu != 0)
+          return fail(APE_ERR_INVALID_ARG, "msda: unroll=%d must be 1, 2 or 4 and divide P=%d", vu, P);
         unroll = vu;
       }
     }
@@ -658,7 +666,7 @@ extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, cons
   if (row_bytes % 16 != 0 || !is_pow2(lpr) || L > kMaxLevels)
     return fail(APE_ERR_UNSUPPORTED, "msda_fused: D=%d dtype=%d L=%d not supported", D, dtype, L);
   const int R = threads_for(lpr) / lpr;
-  if ((size_t)R * ((L * P) | 1) * 36 > 200 * 1024)
+  if ((size_t)R * ((L * P) | 1) * 20 > 200 * 1024)
     return fail(APE_ERR_UNSUPPORTED, "msda_fused: L*P=%d too large for shared memory", L * P);
   p.ht_log2 = ilog2(default_ht(H, Q, R));
 #define APE_FUSED_DISPATCH(T)                                                           \
@@ -712,7 +720,7 @@ extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes,
   p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
   p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
 #define APE_TILED(T, TO, LPR)                                                              \
-  return (LP % 2 == 0) ? launch_fused_tiled<T, TO, LPR, 2>(p, tiles, st) : launch_fused_tiled<T, TO, LPR, 1>(p, tiles, st)
+  return (P % 2 == 0) ? launch_fused_tiled<T, TO, LPR, 2>(p, tiles, st) : launch_fused_tiled<T, TO, LPR, 1>(p, tiles, st)
   if (dtype == APE_DTYPE_F32) { APE_TILED(float, float, 8); }
   if (dtype == APE_DTYPE_F16) {
     if (offs_dtype == APE_DTYPE_F16) { APE_TILED(__half, __half, 4); }

@@ -187,6 +187,9 @@ class DeformableDetrTransformerVL(nn.Module):
         self.pre_nms_topk = pre_nms_topk
         self.nms_thresh_enc = nms_thresh_enc
         self.proposal_ambiguous = proposal_ambiguous
+        # spatially tiled persistent MSDA kernel for the encoder (ape_msda_fused_self_fwd); measured slower than the
+        # strip mapping on B200 at 1024^2 (0.49 vs 0.36 ms), kept selectable for tuning
+        self.tiled_encoder_msda = False
         self.embed_dim = encoder.embed_dim
         E = self.embed_dim
         self.level_embeds = nn.Parameter(torch.Tensor(num_feature_levels, E))
@@ -339,7 +342,8 @@ class DeformableDetrTransformerVL(nn.Module):
             query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
             query_pos=pos_flatten, query_key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
             spatial_shapes=geo["spatial_shapes"], reference_points=geo["reference_points"],
-            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"], host_shapes=geo["shapes"])
+            level_start_index=geo["level_start_index"], valid_ratios=geo["valid_ratios"],
+            host_shapes=geo["shapes"] if self.tiled_encoder_msda else None)
         # gen_encoder_output_proposals (:354-369): zero the memory of invalid anchors, project, normalise
         output_proposals = geo["output_proposals"]
         invalid = geo["proposal_invalid"]

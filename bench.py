@@ -282,6 +282,10 @@ def model_bench(args, rank, local_rank, world):
     events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
     model.use_cuda_graphs = graphs_on
     config["cuda_graphs"] = bool(graphs_on)
+    own_ms = {}
+    for (t, x, y) in events:
+        own_ms[t[0]] = own_ms.get(t[0], 0.0) + x.elapsed_time(y) / prof_steps
+    own_ms = {k: round(v, 3) for k, v in sorted(own_ms.items(), key=lambda kv: -kv[1])}
     enc = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] == t[2]]
     dec = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] != t[2]]
     # e2e: pinned host image in, detections out on the host (the model's public call does both)
@@ -330,6 +334,7 @@ def model_bench(args, rank, local_rank, world):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks,
             "stage_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+            "own_kernel_ms_per_step": own_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_model_arm(1, n_text, sd=model.state_dict())
