@@ -43,10 +43,13 @@ lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [
 
 lib.ape_layernorm.restype = _i
 lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp]
+lib.ape_layernorm_ex.restype = _i
+lib.ape_layernorm_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i64, _i,
+                                 _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]
 lib.ape_groupnorm_workspace_bytes.restype = _i64
 lib.ape_groupnorm_workspace_bytes.argtypes = [_i, _i, _i]
 lib.ape_groupnorm_nhwc.restype = _i
-lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _i, _vp]
+lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _i, _vp]
 lib.ape_rope_qk.restype = _i
 lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 
@@ -70,6 +73,7 @@ EXPORTS = (
     "ape_msda_fused_self_fwd",
     "ape_gemm_tn",
     "ape_layernorm",
+    "ape_layernorm_ex",
     "ape_rope_qk",
     "ape_groupnorm_workspace_bytes",
     "ape_groupnorm_nhwc",

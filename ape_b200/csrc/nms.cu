@@ -2,9 +2,9 @@
 //   the two-stage proposal selection   ape/modeling/ape_deta/deformable_transformer_vl.py:591-596
 //   the final class-aware NMS           ape/modeling/ape_deta/fast_rcnn.py:192 (detectron2 batched_nms)
 // Two launches: (1) upper-triangular IoU>thr bit matrix, 64x64 boxes per CTA; (2) one CTA scans the
-// sorted list in chunks of 64: a single thread resolves the 64x64 diagonal block in registers, then all
-// threads OR the rows of the boxes kept in that chunk into the suppression bitset (coalesced 8-byte
-// loads) — the serial dependency is 64 steps per chunk instead of one global round trip per box.
+// sorted list in chunks of 64: one warp resolves the 64x64 diagonal block in registers, then all threads OR
+// the rows of the boxes kept in that chunk into the suppression bitset out of shared memory (the rows of the
+// next chunk are prefetched with cp.async meanwhile) — the serial dependency is 64 register steps per chunk.
 // IoU arithmetic is written with explicit round-to-nearest intrinsics (no FMA contraction):
 //   inter / (area_a + area_b - inter) > thr, widths/heights clamped at 0, as torchvision's devIoU.
 #include "common.cuh"
@@ -42,9 +42,80 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__
   mask[(size_t)row * col_blocks + cb] = bits;
 }
 
-// single CTA; keep[i] = 1 iff sorted box i survives; *count = number kept.
-__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
-                                                       unsigned char *__restrict__ keep, int *__restrict__ count) {
+// single CTA, 1024 threads; keep[i] = 1 iff sorted box i survives; *count = number kept.
+// Per chunk of 64 boxes: (a) warp 0 resolves the 64x64 diagonal block with the rows in registers (lane i holds
+// rows i and i+32; the row broadcasts are shuffles that do not depend on the running bitset, so only a test +
+// predicated OR per box sits on the serial chain); (b) all threads OR the rows of the kept boxes into the
+// suppression bitset from SHARED memory — the chunk's rows were fetched with cp.async while the previous chunk
+// was being resolved (double buffer), so no global-memory latency sits between chunks.
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
+                                                        unsigned char *__restrict__ keep, int *__restrict__ count) {
+  extern __shared__ unsigned long long s_dyn[];
+  unsigned long long *removed = s_dyn;                      // col_blocks words
+  unsigned long long *rows[2] = {s_dyn + col_blocks, s_dyn + col_blocks + 64 * (size_t)col_blocks};  // [64][col_blocks] each
+  __shared__ unsigned long long s_keepbits;
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (int w = t; w < col_blocks; w += nt) removed[w] = 0;
+  auto prefetch = [&](int c, int buf) {
+    // rows base..base+63, words c..col_blocks-1 (word c = the diagonal block)
+    const int base = c * 64, nb = min(64, n - base), nw = col_blocks - c;
+    for (int i = t; i < nb * nw; i += nt) {
+      const int r = i / nw, w = c + (i - r * nw);
+      cp_async8(&rows[buf][r * col_blocks + w], mask + (size_t)(base + r) * col_blocks + w);
+    }
+    cp_async_commit();
+  };
+  prefetch(0, 0);
+  int total = 0;
+  for (int c = 0; c < col_blocks; ++c) {
+    const int buf = c & 1;
+    const int base = c * 64, nb = min(64, n - base);
+    cp_async_wait_all();
+    __syncthreads();  // chunk c's rows are in rows[buf]; removed[] of the previous chunk is complete
+    if (c + 1 < col_blocks) prefetch(c + 1, buf ^ 1);
+    if (t < 32) {
+      const unsigned long long r0 = (t < nb) ? rows[buf][t * col_blocks + c] : 0ull;
+      const unsigned long long r1 = (t + 32 < nb) ? rows[buf][(t + 32) * col_blocks + c] : 0ull;
+      unsigned long long rem = removed[c], kept = 0;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long row = __shfl_sync(0xffffffffu, i < 32 ? r0 : r1, i & 31);
+        if (i < nb && !((rem >> i) & 1ull)) {
+          kept |= 1ull << i;
+          rem |= row;  // diagonal block: bits j > i only
+        }
+      }
+      if (t == 0) s_keepbits = kept;
+      total += __popcll(kept);
+    }
+    __syncthreads();
+    const unsigned long long kept = s_keepbits;
+    if (t < nb) keep[base + t] = (unsigned char)((kept >> t) & 1ull);
+    // suppress later chunks: thread (g, wl) ORs rows g, g+8, .. of the chunk for word c+1+wl (+128, ..)
+    const int g = t >> 7, wl = t & 127;
+    for (int w = c + 1 + wl; w < col_blocks; w += 128) {
+      unsigned long long acc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = g + 8 * j;
+        if ((kept >> i) & 1ull) acc |= rows[buf][i * col_blocks + w];
+      }
+      if (acc) atomicOr(&removed[w], acc);
+    }
+  }
+  if (t == 0) *count = total;
+}
+
+// Fallback for very long lists (the double-buffered rows do not fit shared memory): same algorithm, rows read
+// straight from global memory.
+__global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
+                                                           unsigned char *__restrict__ keep, int *__restrict__ count) {
   extern __shared__ unsigned long long removed[];  // col_blocks words
   __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keepbits;
@@ -56,7 +127,6 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long 
   for (int c = 0; c < col_blocks; ++c) {
     const int base = c * 64;
     const int nb = min(64, n - base);
-    // stage the 64x64 diagonal block so the serial resolution below never waits on global memory
     if (t < nb) s_diag[t] = mask[(size_t)(base + t) * col_blocks + c];
     __syncthreads();
     if (t == 0) {
@@ -64,7 +134,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long 
       for (int i = 0; i < nb; ++i) {
         if (!((rem >> i) & 1ull)) {
           kept |= 1ull << i;
-          rem |= s_diag[i];  // diagonal block: bits j > i only
+          rem |= s_diag[i];
         }
       }
       s_keepbits = kept;
@@ -73,7 +143,6 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long 
     __syncthreads();
     const unsigned long long kept = s_keepbits;
     if (t < nb) keep[base + t] = (unsigned char)((kept >> t) & 1ull);
-    // suppress later chunks: OR the rows of every box kept in this chunk
     for (int w = c + 1 + t; w < col_blocks; w += blockDim.x) {
       unsigned long long acc = removed[w], k = kept;
       while (k) {
@@ -113,11 +182,20 @@ extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_thresh
   nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes_sorted), n, iou_threshold,
                                                reinterpret_cast<unsigned long long *>(workspace), cb);
   if (int rc = check_launch("nms_mask_kernel")) return rc;
-  const size_t smem = (size_t)cb * 8;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)cb * 8 * (1 + 2 * 64);
+  if (smem <= 200 * 1024) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    nms_scan_kernel<<<1, 1024, smem, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
+    return check_launch("nms_scan_kernel");
+  }
+  const size_t smem_big = (size_t)cb * 8;
+  if (smem_big > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
     if (e != cudaSuccess) return fail((int)e, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  nms_scan_kernel<<<1, 256, smem, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
+  nms_scan_big_kernel<<<1, 256, smem_big, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
   return check_launch("nms_scan_kernel");
 }

@@ -105,6 +105,116 @@ layernorm_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, lo
   }
 }
 
+// Extended row kernel for the deformable encoder (C <= 256 * MAXV):
+//   t  = LN(x; w, b, eps)                       (norms[1] of the previous layer, deformable_transformer_vl.py:36-54)
+//   t  = LN(t; w2, b2, eps2)       if w2        (layer_norm_v of the VisionLanguageFusion that follows, fuse_helper.py:224)
+//   y  = t + col_add[c]            if col_add   (gamma_v * delta_v: one vector per image for "name" prompts)
+//   y2 = y + row_add[row]          if y2        (query + query_pos, the operand of the sampling-offset / attention-weight GEMM)
+// so the activations make one trip through HBM where the module sequence makes four.
+template <typename TI, typename TO, int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_ex_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy, const float *__restrict__ w,
+                    const float *__restrict__ b, float eps, const float *__restrict__ w2, const float *__restrict__ b2,
+                    float eps2, const float *__restrict__ col_add, long long col_add_stride, int rows_per_image,
+                    const TO *__restrict__ row_add, long long ld_add, TO *__restrict__ y2, long long ldy2, int rows, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const TI *xr = x + (size_t)warp * ldx;
+  const int nvec = C >> 3;  // host guarantees C % 8 == 0
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      load8<TI>(xr + 8 * j, v[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    }
+  }
+  float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        sq += d * d;
+      }
+    }
+  float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      float ww[8], bb[8];
+      load8<float>(w + 8 * j, ww);
+      load8<float>(b + 8 * j, bb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[i][k] = (v[i][k] - mean) * rstd * ww[k] + bb[k];
+        sum += v[i][k];
+      }
+    }
+  }
+  if (w2) {
+    mean = warp_sum(sum) / (float)C;
+    sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[i][k] - mean;
+          sq += d * d;
+        }
+      }
+    rstd = rsqrtf(warp_sum(sq) / (float)C + eps2);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int j = lane + 32 * i;
+      if (j < nvec) {
+        float ww[8], bb[8];
+        load8<float>(w2 + 8 * j, ww);
+        load8<float>(b2 + 8 * j, bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] = (v[i][k] - mean) * rstd * ww[k] + bb[k];
+      }
+    }
+  }
+  const float *ca = col_add ? col_add + (size_t)(warp / rows_per_image) * col_add_stride : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      if (ca) {
+        float cc[8];
+        load8<float>(ca + 8 * j, cc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] += cc[k];
+      }
+      store8<TO>(y + (size_t)warp * ldy + 8 * j, v[i]);
+      if (y2) {
+        float a[8], o[8];
+        load8<TO>(row_add + (size_t)warp * ld_add + 8 * j, a);
+        // y2 is computed from the ROUNDED y so that it equals `y + row_add` evaluated on the stored tensors
+        float r[8];
+        if constexpr (sizeof(TO) == 4) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r[k] = v[i][k];
+        } else {
+          Elem<TO>::unpack(Elem<TO>::pack(v[i]), r);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = r[k] + a[k];
+        store8<TO>(y2 + (size_t)warp * ldy2 + 8 * j, o);
+      }
+    }
+  }
+}
+
 // Wide rows (C > 1024, e.g. the 2730-wide SwiGLU hidden): same contract, but the row is re-read from
 // L1/L2 for the variance and normalisation passes instead of being held in 128 registers per lane —
 // 8 resident warps per SM could not cover HBM latency.
@@ -218,6 +328,43 @@ extern "C" int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, c
   return fail(APE_ERR_UNSUPPORTED, "layernorm: dtype pair (%d -> %d) not supported", in_dtype, out_dtype);
 }
 
+extern "C" int ape_layernorm_ex(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
+                                float eps, const float *weight2, const float *bias2, float eps2, const float *col_add,
+                                int64_t col_add_stride, int rows_per_image, const void *row_add, int64_t ld_add, void *y2,
+                                int64_t ldy2, int rows, int C, int in_dtype, int out_dtype, void *stream) {
+  if (rows < 0 || C <= 0 || C > 1024 || C % 8 != 0) return fail(APE_ERR_INVALID_ARG, "layernorm_ex: rows=%d C=%d (C %% 8 == 0, C <= 1024)", rows, C);
+  if (ldx < C || ldy < C || (y2 && (ldy2 < C || ld_add < C)))
+    return fail(APE_ERR_INVALID_ARG, "layernorm_ex: row pitch smaller than C");
+  if (rows == 0) return APE_OK;
+  if (!x || !y || !weight || !bias || (weight2 && !bias2) || (y2 && !row_add) || (col_add && rows_per_image <= 0))
+    return fail(APE_ERR_NULL_PTR, "layernorm_ex: null pointer argument");
+  const int ie = dtype_size(in_dtype), oe = dtype_size(out_dtype);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y2) |
+                       reinterpret_cast<uintptr_t>(row_add) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(bias) |
+                       reinterpret_cast<uintptr_t>(weight2) | reinterpret_cast<uintptr_t>(bias2) | reinterpret_cast<uintptr_t>(col_add);
+  if ((ldx * ie) % 16 || (ldy * oe) % 16 || (ldy2 * oe) % 16 || (ld_add * oe) % 16 || (col_add_stride * 4) % 16 || (al & 15))
+    return fail(APE_ERR_INVALID_ARG, "layernorm_ex: rows / vectors must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (rows + 7) / 8;
+#define APE_LNX(TI, TO)                                                                                                   \
+  do {                                                                                                                    \
+    if (C <= 256)                                                                                                         \
+      ape::layernorm_ex_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
+          col_add, col_add_stride, rows_per_image > 0 ? rows_per_image : 1, (const TO *)row_add, ld_add, (TO *)y2, ldy2, rows, C);  \
+    else                                                                                                                  \
+      ape::layernorm_ex_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
+          col_add, col_add_stride, rows_per_image > 0 ? rows_per_image : 1, (const TO *)row_add, ld_add, (TO *)y2, ldy2, rows, C);  \
+    return check_launch("layernorm_ex_kernel");                                                                          \
+  } while (0)
+  if (in_dtype == APE_DTYPE_F16 && out_dtype == APE_DTYPE_F16) APE_LNX(__half, __half);
+  if (in_dtype == APE_DTYPE_BF16 && out_dtype == APE_DTYPE_BF16) APE_LNX(__nv_bfloat16, __nv_bfloat16);
+  if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_F32) APE_LNX(float, float);
+  if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_F16) APE_LNX(float, __half);
+  if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_BF16) APE_LNX(float, __nv_bfloat16);
+#undef APE_LNX
+  return fail(APE_ERR_UNSUPPORTED, "layernorm_ex: dtype pair (%d -> %d) not supported", in_dtype, out_dtype);
+}
+
 extern "C" int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_table, const int *pos_map,
                            int M, int C, int head_dim, int npos, int dtype, void *stream) {
   if (M < 0 || C <= 0 || head_dim <= 0 || head_dim % 8 != 0 || C % head_dim != 0 || npos <= 0)
@@ -280,31 +427,38 @@ gn_partial_kernel(const T *__restrict__ x, long long ldx, int rows_per_image, in
   }
 }
 
-// one thread per (b, group): fold strips and the C/G/8 vector columns of the group
+// one warp per (b, group): lanes stride over the strips (fixed assignment -> deterministic), fp64 fold
 __global__ void gn_finalize_kernel(const float *__restrict__ partial, int B, int strips, int vec_per_row, int vec_per_group,
                                    float count, float eps, float *__restrict__ stats /* [B, G, 2] mean, rstd */) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int G = vec_per_row / vec_per_group;
   if (idx >= B * G) return;
   const int b = idx / G, g = idx % G;
   double s = 0.0, ss = 0.0;
-  for (int st = 0; st < strips; ++st)
+  for (int st = lane; st < strips; st += 32)
     for (int v = 0; v < vec_per_group; ++v) {
-      const float *p = partial + (((size_t)b * strips + st) * vec_per_row + g * vec_per_group + v) * 2;
-      s += p[0];
-      ss += p[1];
+      const float2 p = *reinterpret_cast<const float2 *>(partial + (((size_t)b * strips + st) * vec_per_row + g * vec_per_group + v) * 2);
+      s += p.x;
+      ss += p.y;
     }
-  const double mean = s / count;
-  const double var = fmax(ss / count - mean * mean, 0.0);
-  stats[idx * 2] = (float)mean;
-  stats[idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    const double var = fmax(ss / count - mean * mean, 0.0);
+    stats[idx * 2] = (float)mean;
+    stats[idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy, const float *__restrict__ w,
-                const float *__restrict__ bias, const float *__restrict__ stats, int rows_per_image, long long total_rows,
-                int C, int vec_per_group) {
+gn_apply_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy, long long y_batch_stride,
+                const float *__restrict__ w, const float *__restrict__ bias, const float *__restrict__ stats, int rows_per_image,
+                long long total_rows, int C, int vec_per_group) {
   const int vec_per_row = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_rows * vec_per_row) return;
@@ -317,7 +471,7 @@ gn_apply_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, lon
   load8<TI>(x + (size_t)row * ldx + 8 * v, f);
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = (f[k] - mean) * rstd * __ldg(w + 8 * v + k) + __ldg(bias + 8 * v + k);
-  store8<TO>(y + (size_t)row * ldy + 8 * v, o);
+  store8<TO>(y + (size_t)b * y_batch_stride + (size_t)(row - (long long)b * rows_per_image) * ldy + 8 * v, o);
 }
 
 }  // namespace
@@ -328,15 +482,17 @@ extern "C" int64_t ape_groupnorm_workspace_bytes(int B, int rows_per_image, int 
   return ((int64_t)B * strips * (C / 8) * 2 + (int64_t)B * C) * 4;
 }
 
-extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
-                                  void *workspace, int B, int rows_per_image, int C, int groups, float eps, int in_dtype,
+extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, int64_t y_batch_stride,
+                                  const float *weight, const float *bias, void *workspace, int B, int rows_per_image, int C, int groups, float eps, int in_dtype,
                                   int out_dtype, void *stream) {
   using namespace ape;
   if (B < 0 || rows_per_image <= 0 || C <= 0 || groups <= 0 || C % groups != 0 || (C / groups) % 8 != 0 || 256 % (C / 8) != 0)
     return fail(APE_ERR_UNSUPPORTED, "groupnorm: C=%d groups=%d (channels per group must be a multiple of 8, C/8 must divide 256)", C, groups);
   if (B == 0) return APE_OK;
   if (!x || !y || !weight || !bias || !workspace) return fail(APE_ERR_NULL_PTR, "groupnorm: null pointer argument");
-  if ((ldx * dtype_size(in_dtype)) % 16 || (ldy * dtype_size(out_dtype)) % 16)
+  if (y_batch_stride == 0) y_batch_stride = (int64_t)rows_per_image * ldy;
+  if ((ldx * dtype_size(in_dtype)) % 16 || (ldy * dtype_size(out_dtype)) % 16 || (y_batch_stride * dtype_size(out_dtype)) % 16 ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(APE_ERR_INVALID_ARG, "groupnorm: rows must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int strips = (rows_per_image + kGnRowsPerCta - 1) / kGnRowsPerCta;
@@ -347,11 +503,11 @@ extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t l
   else if (in_dtype == APE_DTYPE_F16) gn_partial_kernel<__half><<<dim3(strips, B), 256, 0, st>>>((const __half *)x, ldx, rows_per_image, C, C / groups, partial);
   else gn_partial_kernel<__nv_bfloat16><<<dim3(strips, B), 256, 0, st>>>((const __nv_bfloat16 *)x, ldx, rows_per_image, C, C / groups, partial);
   if (int rc = check_launch("gn_partial_kernel")) return rc;
-  gn_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(partial, B, strips, vpr, vpg, (float)rows_per_image * (C / groups), eps, stats);
+  gn_finalize_kernel<<<(B * groups + 3) / 4, 128, 0, st>>>(partial, B, strips, vpr, vpg, (float)rows_per_image * (C / groups), eps, stats);
   if (int rc = check_launch("gn_finalize_kernel")) return rc;
   const long long total_rows = (long long)B * rows_per_image;
   const unsigned blocks = (unsigned)((total_rows * vpr + 255) / 256);
-#define APE_GN(TI, TO) gn_apply_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, stats, rows_per_image, total_rows, C, vpg)
+#define APE_GN(TI, TO) gn_apply_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, y_batch_stride, weight, bias, stats, rows_per_image, total_rows, C, vpg)
   if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_F32) APE_GN(float, float);
   else if (in_dtype == APE_DTYPE_F16 && out_dtype == APE_DTYPE_F16) APE_GN(__half, __half);
   else if (in_dtype == APE_DTYPE_BF16 && out_dtype == APE_DTYPE_BF16) APE_GN(__nv_bfloat16, __nv_bfloat16);

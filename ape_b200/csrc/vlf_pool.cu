@@ -6,8 +6,8 @@
 //     wl[s]  = clamp(w[s] - max_s(w), -5e4, 5e4)          (:99-108)
 //     p      = softmax_s(wl);   pooled[h,:] = sum_s p[s] * v_s
 // Three launches, v is read twice (16-bit), nothing of size S x 2048 is ever formed:
-//   (1) scores + per-CTA maxima, one warp per token;  (2) fold maxima (per head and global);
-//   (3) per-CTA partial sums of exp() and exp()*v over a strip of tokens, thread = channel.
+//   (1) scores + per-CTA maxima: ~300 CTAs each own a strip of tokens, one warp per token, qa in registers;
+//   (2) fold maxima (per head and global);  (3) per-CTA partial sums of exp() and exp()*v over the same strips.
 // The caller folds the [strips] partials (deterministic order) and applies the tiny projections.
 #include "common.cuh"
 
@@ -15,95 +15,76 @@ namespace ape {
 namespace {
 
 constexpr int kMaxHeads = 8;
-constexpr int kStrip = 256;  // tokens per CTA in the pooling pass
+constexpr int kMaxStrip = 512;  // tokens per CTA (both passes); bounds the exp() staging buffer
 
+__device__ __forceinline__ void load8f(const float *p, float *f) {
+  const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void load_row8(const T *p, float *f) {
+  if constexpr (sizeof(T) == 4) load8f(reinterpret_cast<const float *>(p), f);
+  else Elem<T>::unpack(*reinterpret_cast<const uint4 *>(p), f);
+}
+
+// Pass 1.  grid (nct, B), 256 threads; the CTA owns tokens [blockIdx.x*strip, +strip), one warp per token,
+// lane = 8 channels (C == 256), the 8x8 slice of qa a lane needs lives in registers.  The 8 per-head partial
+// dot products of a lane are reduced over the warp with a halving butterfly (9 shuffles instead of 40).
 template <typename T>
 __global__ void __launch_bounds__(256)
 vlf_scores_kernel(const T *__restrict__ v, const float *__restrict__ qa, const float *__restrict__ qc,
-                  float *__restrict__ scores, float *__restrict__ blockmax, int S, int C, int NH) {
-  // grid (ceil(S/8), B); 8 warps = 8 tokens per CTA; lane owns channels [8*lane + 256*i, +8)
-  extern __shared__ float s_qa[];  // NH * C
+                  float *__restrict__ scores, float *__restrict__ blockmax, int S, int NH, int strip) {
+  constexpr int C = 256;
   __shared__ float s_max[8][kMaxHeads];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NH * C; i += 256) s_qa[i] = qa[(size_t)b * NH * C + i];
-  __syncthreads();
-  const int s = blockIdx.x * 8 + warp;
-  float acc[kMaxHeads];
-#pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) acc[h] = 0.f;
-  if (s < S) {
-    const T *row = v + ((size_t)b * S + s) * C;
-    for (int c0 = lane * 8; c0 < C; c0 += 256) {
-      float f[8];
-      Elem<T>::unpack(*reinterpret_cast<const uint4 *>(row + c0), f);
-#pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h)
-        if (h < NH) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[h] = fmaf(f[k], s_qa[h * C + c0 + k], acc[h]);
-        }
-    }
-  }
+  float q[kMaxHeads][8];
 #pragma unroll
   for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < NH) load8f(qa + ((size_t)b * NH + h) * C + lane * 8, q[h]);
+    else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
-  }
-  if (lane == 0) {
-    for (int h = 0; h < NH; ++h) {
-      float t = -INFINITY;
-      if (s < S) {
-        t = acc[h] + qc[b * NH + h];
-        scores[((size_t)b * NH + h) * S + s] = t;
-      }
-      s_max[warp][h] = t;
+      for (int k = 0; k < 8; ++k) q[h][k] = 0.f;
     }
   }
-  __syncthreads();
-  if (threadIdx.x < NH) {
-    float m = s_max[0][threadIdx.x];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w][threadIdx.x]);
-    blockmax[((size_t)b * gridDim.x + blockIdx.x) * NH + threadIdx.x] = m;
-  }
-}
-// fp32 rows are 4 elements per 16 bytes: dedicated unpack-free variant
-template <>
-__global__ void __launch_bounds__(256)
-vlf_scores_kernel<float>(const float *__restrict__ v, const float *__restrict__ qa, const float *__restrict__ qc,
-                         float *__restrict__ scores, float *__restrict__ blockmax, int S, int C, int NH) {
-  extern __shared__ float s_qa[];
-  __shared__ float s_max[8][kMaxHeads];
-  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NH * C; i += 256) s_qa[i] = qa[(size_t)b * NH * C + i];
-  __syncthreads();
-  const int s = blockIdx.x * 8 + warp;
-  float acc[kMaxHeads];
+  // after the butterfly lane L holds head (L>>2)&7's total (see below); its bias:
+  const int myh = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const float myqc = myh < NH ? qc[b * NH + myh] : 0.f;
+  const int s0 = blockIdx.x * strip, s1 = min(S, s0 + strip);
+  float wmax = -INFINITY;
+  for (int s = s0 + warp; s < s1; s += 8) {
+    float f[8];
+    load_row8<T>(v + ((size_t)b * S + s) * C + lane * 8, f);
+    float a[kMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) acc[h] = 0.f;
-  if (s < S) {
-    const float *row = v + ((size_t)b * S + s) * C;
-    for (int c = lane; c < C; c += 32) {
-      const float f = row[c];
+    for (int h = 0; h < kMaxHeads; ++h) {
+      a[h] = 0.f;
 #pragma unroll
-      for (int h = 0; h < kMaxHeads; ++h)
-        if (h < NH) acc[h] = fmaf(f, s_qa[h * C + c], acc[h]);
+      for (int k = 0; k < 8; ++k) a[h] = fmaf(f[k], q[h][k], a[h]);
     }
-  }
+    // halving butterfly: bit 4 of the lane picks heads {0..3} / {4..7}, bit 3 the pair, bit 2 the head
+    float c4[4];
+    const bool hi16 = lane & 16;
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
-  }
-  if (lane == 0) {
-    for (int h = 0; h < NH; ++h) {
-      float t = -INFINITY;
-      if (s < S) {
-        t = acc[h] + qc[b * NH + h];
-        scores[((size_t)b * NH + h) * S + s] = t;
-      }
-      s_max[warp][h] = t;
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi16 ? a[i] : a[i + 4], keep = hi16 ? a[i + 4] : a[i];
+      c4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+    float c2[2];
+    const bool hi8 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi8 ? c4[i] : c4[i + 2], keep = hi8 ? c4[i + 2] : c4[i];
+      c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const bool hi4 = lane & 4;
+    float c1 = (hi4 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? c2[0] : c2[1], 4);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, 1);
+    const float t = c1 + myqc;
+    if ((lane & 3) == 0 && myh < NH) scores[((size_t)b * NH + myh) * S + s] = t;
+    wmax = fmaxf(wmax, t);
   }
+  if ((lane & 3) == 0) s_max[warp][myh] = wmax;
   __syncthreads();
   if (threadIdx.x < NH) {
     float m = s_max[0][threadIdx.x];
@@ -112,61 +93,107 @@ vlf_scores_kernel<float>(const float *__restrict__ v, const float *__restrict__ 
   }
 }
 
-// maxes[0] = global max over everything; maxes[1 + b*NH + h] = max over s of scores[b,h,:]
-__global__ void vlf_max_kernel(const float *__restrict__ blockmax, int B, int nblk, int NH, float *__restrict__ maxes) {
+// maxes[0] = global max over everything; maxes[1 + b*NH + h] = max over s of scores[b,h,:].  One CTA,
+// one warp per (b, h) pair (round-robin), lanes stride over the per-CTA maxima of pass 1.
+__global__ void __launch_bounds__(1024)
+vlf_max_kernel(const float *__restrict__ blockmax, int B, int nblk, int NH, float *__restrict__ maxes) {
   __shared__ float s_row[64];
-  const int t = threadIdx.x;
-  if (t < B * NH) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < B * NH; t += 32) {
     const int b = t / NH, h = t % NH;
     float m = -INFINITY;
-    for (int i = 0; i < nblk; ++i) m = fmaxf(m, blockmax[((size_t)b * nblk + i) * NH + h]);
-    maxes[1 + t] = m;
-    s_row[t] = m;
+    for (int i = lane; i < nblk; i += 32) m = fmaxf(m, blockmax[((size_t)b * nblk + i) * NH + h]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) {
+      maxes[1 + t] = m;
+      s_row[t] = m;
+    }
   }
   __syncthreads();
-  if (t == 0) {
+  if (threadIdx.x == 0) {
     float g = -INFINITY;
     for (int i = 0; i < B * NH; ++i) g = fmaxf(g, s_row[i]);
     maxes[0] = g;
   }
 }
 
-// grid (strips, B), blockDim = C (thread = channel).  partial[b, strip, h, 0..C-1] = sum_s e*v, [.., C] = sum_s e
+// Pass 2.  grid (nct, B), 256 threads, same strips as pass 1.  exp() of the strip's scores is staged in shared
+// memory, then one warp per token: lane = 8 channels, 8x8 fp32 accumulators; warps are folded through shared
+// memory in a fixed order.  partial[b, cta, h, 0..C-1] = sum_s e*v, [.., C] = sum_s e.
 template <typename T>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 vlf_pool_kernel(const T *__restrict__ v, const float *__restrict__ scores, const float *__restrict__ maxes,
-                float *__restrict__ partial, int S, int C, int NH, int stable_2d) {
-  __shared__ float s_e[kStrip][kMaxHeads];
-  const int b = blockIdx.y, strip = blockIdx.x, c = threadIdx.x;
-  const int s0 = strip * kStrip, n = min(kStrip, S - s0);
+                float *__restrict__ partial, int S, int NH, int strip, int stable_2d) {
+  constexpr int C = 256;
+  __shared__ __align__(16) float s_e[kMaxStrip][kMaxHeads];
+  __shared__ __align__(16) float s_red[8][C];
+  __shared__ float s_se[8][kMaxHeads];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = blockIdx.x * strip, n = min(strip, S - s0);
   const float gmax = stable_2d ? maxes[0] : 0.f;
-  for (int i = threadIdx.x; i < n * NH; i += blockDim.x) {
-    const int r = i / NH, h = i % NH;
-    const float t = scores[((size_t)b * NH + h) * S + s0 + r];
-    const float w = fminf(fmaxf(t - gmax, -50000.f), 50000.f);
-    const float rmax = fminf(fmaxf(maxes[1 + b * NH + h] - gmax, -50000.f), 50000.f);
-    s_e[r][h] = expf(fminf(fmaxf(w - rmax, -50000.f), 50000.f));
+  for (int i = threadIdx.x; i < n * kMaxHeads; i += 256) {
+    const int h = i / n, r = i - h * n;  // consecutive threads -> consecutive tokens of one head (coalesced)
+    float e = 0.f;
+    if (h < NH) {
+      const float t = scores[((size_t)b * NH + h) * S + s0 + r];
+      const float w = fminf(fmaxf(t - gmax, -50000.f), 50000.f);
+      const float rmax = fminf(fmaxf(maxes[1 + b * NH + h] - gmax, -50000.f), 50000.f);
+      e = expf(fminf(fmaxf(w - rmax, -50000.f), 50000.f));
+    }
+    s_e[r][h] = e;
   }
   __syncthreads();
-  float acc[kMaxHeads], se[kMaxHeads];
+  float acc[kMaxHeads][8], se[kMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kMaxHeads; ++h) acc[h] = se[h] = 0.f;
-  const T *col = v + ((size_t)b * S + s0) * C + c;
-  for (int r = 0; r < n; ++r) {
-    const float x = Elem<T>::to_f(col[(size_t)r * C]);
+  for (int h = 0; h < kMaxHeads; ++h) {
+    se[h] = 0.f;
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h)
-      if (h < NH) {
-        const float e = s_e[r][h];
-        acc[h] = fmaf(e, x, acc[h]);
-        se[h] += e;
+    for (int k = 0; k < 8; ++k) acc[h][k] = 0.f;
+  }
+  for (int r = warp; r < n; r += 8) {
+    float f[8], e[8];
+    load_row8<T>(v + ((size_t)b * S + s0 + r) * C + lane * 8, f);
+    load8f(&s_e[r][0], e);
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      se[h] += e[h];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[h][k] = fmaf(e[h], f[k], acc[h][k]);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) s_se[warp][h] = se[h];
+  }
+  float *dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * NH * (C + 1);
+#pragma unroll
+  for (int h = 0; h < kMaxHeads; ++h) {
+    if (h < NH) {  // CTA-uniform
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_red[warp][lane * 8 + k] = acc[h][k];
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+      dst[h * (C + 1) + threadIdx.x] = t;
+      if (threadIdx.x == 0) {
+        float u = 0.f;
+        for (int w = 0; w < 8; ++w) u += s_se[w][h];
+        dst[h * (C + 1) + C] = u;
       }
+    }
   }
-  float *dst = partial + ((size_t)b * gridDim.x + strip) * NH * (C + 1);
-  for (int h = 0; h < NH; ++h) {
-    dst[h * (C + 1) + c] = acc[h];
-    if (c == 0) dst[h * (C + 1) + C] = se[h];
-  }
+}
+
+int strips_for(int S, int *strip_out) {
+  int nct = 148 * 2;
+  int strip = (S + nct - 1) / nct;
+  if (strip > kMaxStrip) strip = kMaxStrip;
+  if (strip < 8) strip = 8;
+  *strip_out = strip;
+  return (S + strip - 1) / strip;
 }
 
 }  // namespace
@@ -175,33 +202,36 @@ vlf_pool_kernel(const T *__restrict__ v, const float *__restrict__ scores, const
 using namespace ape;
 
 extern "C" int64_t ape_vlf_pool_workspace_bytes(int B, int S, int C, int NH) {
-  const int64_t nblk = (S + 7) / 8, strips = (S + kStrip - 1) / kStrip;
-  return ((int64_t)B * NH * S + (int64_t)B * nblk * NH + 1 + (int64_t)B * NH + (int64_t)B * strips * NH * (C + 1)) * 4;
+  int strip;
+  const int64_t nct = strips_for(S, &strip);
+  return ((int64_t)B * NH * S + (int64_t)B * nct * NH + 1 + (int64_t)B * NH + (int64_t)B * nct * NH * (C + 1)) * 4;
 }
 
 extern "C" int ape_vlf_pool(const void *v, const float *qa, const float *qc, void *workspace, float **partial_out,
                             int *strips_out, int B, int S, int C, int NH, int stable_softmax_2d, int dtype, void *stream) {
-  if (B <= 0 || S <= 0 || C <= 0 || NH <= 0 || NH > kMaxHeads || C > 1024 || C % 32 != 0 || B * NH > 64 ||
-      (dtype != APE_DTYPE_F32 && C % 256 != 0))
-    return fail(APE_ERR_UNSUPPORTED, "vlf_pool: B=%d S=%d C=%d NH=%d not supported", B, S, C, NH);
+  if (B <= 0 || S <= 0 || NH <= 0 || NH > kMaxHeads || C != 256 || B * NH > 64 || B > 65535)
+    return fail(APE_ERR_UNSUPPORTED, "vlf_pool: B=%d S=%d C=%d NH=%d not supported (C must be 256, NH <= 8)", B, S, C, NH);
   if (!v || !qa || !qc || !workspace) return fail(APE_ERR_NULL_PTR, "vlf_pool: null pointer argument");
+  if ((reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(qa) & 15))
+    return fail(APE_ERR_INVALID_ARG, "vlf_pool: v / qa must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int nblk = (S + 7) / 8, strips = (S + kStrip - 1) / kStrip;
+  int strip;
+  const int nct = strips_for(S, &strip);
   float *scores = reinterpret_cast<float *>(workspace);
   float *blockmax = scores + (size_t)B * NH * S;
-  float *maxes = blockmax + (size_t)B * nblk * NH;
+  float *maxes = blockmax + (size_t)B * nct * NH;
   float *partial = maxes + 1 + (size_t)B * NH;
-  const size_t smem = (size_t)NH * C * 4;
-  if (dtype == APE_DTYPE_F32) vlf_scores_kernel<float><<<dim3(nblk, B), 256, smem, st>>>((const float *)v, qa, qc, scores, blockmax, S, C, NH);
-  else if (dtype == APE_DTYPE_F16) vlf_scores_kernel<__half><<<dim3(nblk, B), 256, smem, st>>>((const __half *)v, qa, qc, scores, blockmax, S, C, NH);
-  else vlf_scores_kernel<__nv_bfloat16><<<dim3(nblk, B), 256, smem, st>>>((const __nv_bfloat16 *)v, qa, qc, scores, blockmax, S, C, NH);
+  const dim3 grid(nct, B);
+  if (dtype == APE_DTYPE_F32) vlf_scores_kernel<float><<<grid, 256, 0, st>>>((const float *)v, qa, qc, scores, blockmax, S, NH, strip);
+  else if (dtype == APE_DTYPE_F16) vlf_scores_kernel<__half><<<grid, 256, 0, st>>>((const __half *)v, qa, qc, scores, blockmax, S, NH, strip);
+  else vlf_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, qa, qc, scores, blockmax, S, NH, strip);
   if (int rc = check_launch("vlf_scores_kernel")) return rc;
-  vlf_max_kernel<<<1, 64, 0, st>>>(blockmax, B, nblk, NH, maxes);
+  vlf_max_kernel<<<1, 1024, 0, st>>>(blockmax, B, nct, NH, maxes);
   if (int rc = check_launch("vlf_max_kernel")) return rc;
-  if (dtype == APE_DTYPE_F32) vlf_pool_kernel<float><<<dim3(strips, B), C, 0, st>>>((const float *)v, scores, maxes, partial, S, C, NH, stable_softmax_2d);
-  else if (dtype == APE_DTYPE_F16) vlf_pool_kernel<__half><<<dim3(strips, B), C, 0, st>>>((const __half *)v, scores, maxes, partial, S, C, NH, stable_softmax_2d);
-  else vlf_pool_kernel<__nv_bfloat16><<<dim3(strips, B), C, 0, st>>>((const __nv_bfloat16 *)v, scores, maxes, partial, S, C, NH, stable_softmax_2d);
+  if (dtype == APE_DTYPE_F32) vlf_pool_kernel<float><<<grid, 256, 0, st>>>((const float *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
+  else if (dtype == APE_DTYPE_F16) vlf_pool_kernel<__half><<<grid, 256, 0, st>>>((const __half *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
+  else vlf_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
   if (partial_out) *partial_out = partial;
-  if (strips_out) *strips_out = strips;
+  if (strips_out) *strips_out = nct;
   return check_launch("vlf_pool_kernel");
 }

@@ -48,6 +48,12 @@ class MLP(nn.Module):
         self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
 
     def forward(self, x):
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
+            from .. import ops  # tensor-core path: bias + ReLU in the GEMM epilogue, weights packed once
+
+            for i, layer in enumerate(self.layers):
+                x = ops.linear_module_tc(layer, x, act="relu" if i < self.num_layers - 1 else None)
+            return x
         for i, layer in enumerate(self.layers):
             x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
         return x

@@ -102,7 +102,9 @@ class MultiScaleDeformableAttention(nn.Module):
             value = query
         if identity is None:
             identity = query
-        if query_pos is not None:
+        if kwargs.get("query_with_pos") is not None:
+            query = kwargs["query_with_pos"]  # engine: `query + query_pos` already formed by the producing kernel
+        elif query_pos is not None:
             query = query + query_pos
         if not self.batch_first:
             query = query.permute(1, 0, 2)

@@ -101,37 +101,56 @@ class BiAttentionBlock(nn.Module):
             sum_s p[s,h] (W_vv,h v_s + b_vv,h) = W_vv,h (sum_s p[s,h] v_s) + b_vv,h — O(S*256*8) instead of
             three S x 256 x 2048 GEMMs (1.65 TFLOP per image over the six encoder layers).
         fp32 regardless of the engine dtype (tiny); differs from the literal op order by fp32 reassociation."""
+        dv, qa, qc = self.single_token_language_side(l)
+        dl = self.single_token_pool(v, qa, qc)
+        return dv.to(v.dtype), dl.to(l.dtype)
+
+    def single_token_language_side(self, l):
+        """Everything of the one-token case that depends on the language token only: delta_v [B,1,v_dim] and the
+        folded score operands qa [B,nh,v_dim], qc [B,nh] (scores[s,h] = v_s . qa[h] + qc[h])."""
         a = self.attn
         nh, hd = a.num_heads, a.head_dim
         with torch.autocast("cuda", enabled=False):
             lf = l.float()
-            B, S, _ = v.shape
+            B = lf.shape[0]
             k = F.linear(lf, a.l_proj.weight.float(), a.l_proj.bias.float()).view(B, nh, hd)
             val_l = F.linear(lf, a.values_l_proj.weight.float(), a.values_l_proj.bias.float())       # [B,1,E]
             dv = F.linear(val_l, a.out_v_proj.weight.float(), a.out_v_proj.bias.float())             # [B,1,v_dim]
             wq = a.v_proj.weight.float().view(nh, hd, -1)                                            # [nh,hd,v_dim]
             qa = torch.einsum("bhd,hdc->bhc", k, wq) * a.scale                                       # [B,nh,v_dim]
             qc = torch.einsum("bhd,hd->bh", k, a.v_proj.bias.float().view(nh, hd)) * a.scale         # [B,nh]
+        return dv, qa, qc
+
+    def single_token_pool(self, v, qa, qc, shift=None):
+        """delta_l [B,1,l_dim] from the vision tokens.  `shift` [B,1,v_dim] (fp32): the tensor passed as `v` is
+        v_true + shift (the engine hands over the already updated query = LN_v(x) + gamma_v * delta_v and avoids
+        materialising LN_v(x)); scores and the pooled vector are corrected exactly:
+        v_true.qa + qc = v.qa + (qc - shift.qa),  sum_s p_s v_true_s = sum_s p_s v_s - shift."""
+        a = self.attn
+        nh, hd = a.num_heads, a.head_dim
+        with torch.autocast("cuda", enabled=False):
+            B, S, _ = v.shape
+            if shift is not None:
+                qc = qc - torch.einsum("bc,bhc->bh", shift.reshape(B, -1).float(), qa)
             if v.is_cuda and nh <= 8 and a.clamp_min_for_underflow and a.clamp_max_for_overflow and \
-                    (v.shape[-1] % 256 == 0 or v.dtype == torch.float32) and v.shape[-1] % 32 == 0 and B * nh <= 64:
+                    v.shape[-1] == 256 and B * nh <= 64:
                 from .. import ops  # fused pooling kernels: v is read twice in its own dtype, nothing else of size S
 
                 pooled = ops.vlf_pool(v.contiguous(), qa, qc, a.stable_softmax_2d)
-                wvv = a.values_v_proj.weight.float().view(nh, hd, -1)
-                out_l = torch.einsum("bhc,hdc->bhd", pooled, wvv) + a.values_v_proj.bias.float().view(nh, hd)
-                dl = F.linear(out_l.reshape(B, 1, nh * hd), a.out_l_proj.weight.float(), a.out_l_proj.bias.float())
-                return dv.to(v.dtype), dl.to(l.dtype)
-            vf = v.float()
-            w = torch.einsum("bsc,bhc->bhs", vf, qa) + qc[..., None]                                 # [B,nh,S]
-            if a.stable_softmax_2d:
-                w = w - w.max()
-            w = a._clamp(w)
-            wl = a._clamp(w - w.max(dim=-1, keepdim=True)[0]).softmax(dim=-1)
-            pooled = torch.einsum("bhs,bsc->bhc", wl, vf)                                            # [B,nh,v_dim]
+            else:
+                vf = v.float()
+                w = torch.einsum("bsc,bhc->bhs", vf, qa) + qc[..., None]                             # [B,nh,S]
+                if a.stable_softmax_2d:
+                    w = w - w.max()
+                w = a._clamp(w)
+                wl = a._clamp(w - w.max(dim=-1, keepdim=True)[0]).softmax(dim=-1)
+                pooled = torch.einsum("bhs,bsc->bhc", wl, vf)                                        # [B,nh,v_dim]
+            if shift is not None:
+                pooled = pooled - shift.reshape(B, 1, -1).float()
             wvv = a.values_v_proj.weight.float().view(nh, hd, -1)
             out_l = torch.einsum("bhc,hdc->bhd", pooled, wvv) + a.values_v_proj.bias.float().view(nh, hd)
             dl = F.linear(out_l.reshape(B, 1, nh * hd), a.out_l_proj.weight.float(), a.out_l_proj.bias.float())
-        return dv.to(v.dtype), dl.to(l.dtype)
+        return dl
 
 
 class VisionLanguageFusion(nn.Module):

@@ -76,18 +76,28 @@ class ChannelMapper(nn.Module):
         first = inputs[self.in_features[0]]
         if first.is_cuda and first.dtype in (torch.float16, torch.bfloat16) and \
                 all(c.conv.kernel_size == (1, 1) and isinstance(c.norm, nn.GroupNorm) for c in self.convs):
-            # engine path: 1x1 conv = tcgen05 GEMM over tokens, GroupNorm kernel on the token-major layout
-            outs = []
-            for conv, f in zip(self.convs, self.in_features):
-                x = inputs[f]
-                B, C, H, W = x.shape
+            # engine path: 1x1 conv = tcgen05 GEMM over tokens, GroupNorm kernel on the token-major layout, written
+            # straight into its slice of the flattened [B, S, C] tensor the transformer consumes
+            # (deformable_transformer_vl.py:435-452 flattens + concatenates the levels): no concat copy.
+            xs = [inputs[f] for f in self.in_features]
+            B = first.shape[0]
+            hw = [int(x.shape[2]) * int(x.shape[3]) for x in xs]
+            Cout = self.convs[0].conv.out_channels
+            flat = torch.empty((B, sum(hw), Cout), dtype=first.dtype, device=first.device)
+            outs, start = [], 0
+            for conv, x, n in zip(self.convs, xs, hw):
+                _, C, H, W = x.shape
                 tok = x.permute(0, 2, 3, 1).reshape(B * H * W, C)  # free when x is channels_last (engine backbone)
                 w, b = ops.packed(conv.conv, tok.dtype)
                 y = ops.linear_tc(tok, w.view(w.shape[0], -1), b)
                 gw, gb = ops.packed(conv.norm, tok.dtype)
-                y = ops.groupnorm_nhwc(y.view(B, H * W, -1), gw, gb, conv.norm.num_groups, conv.norm.eps)
-                outs.append(y.view(B, H, W, -1).permute(0, 3, 1, 2))
+                dst = flat[:, start:start + n]
+                ops.groupnorm_nhwc(y.view(B, n, -1), gw, gb, conv.norm.num_groups, conv.norm.eps, out=dst)
+                outs.append(dst.view(B, H, W, Cout).permute(0, 3, 1, 2))
+                start += n
+            self.last_flat = flat
             return tuple(outs)
+        self.last_flat = None
         return tuple(self.convs[i](inputs[f]) for i, f in enumerate(self.in_features))
 
 
@@ -305,6 +315,9 @@ class DeformableDETRSegmVL(nn.Module):
                 features_l = self.model_language.forward_text(text_list, cache=cache)["last_hidden_state_eot"]
                 if cache:
                     self._text_cache[key] = features_l
+            if cache and features_l.device != self.device:  # keep cached vocabularies resident on the device
+                features_l = features_l.to(self.device)
+                self._text_cache[key] = features_l
             features_l = features_l.to(self.device).unsqueeze(0).repeat(bs, 1, 1)
             if self.name_prompt_fusion_text is not None and self.name_prompt_fusion_text[dataset_id]:
                 fusion = features_l
@@ -354,28 +367,36 @@ class DeformableDETRSegmVL(nn.Module):
         geo = self._geometry(images.shape, image_sizes, img_masks)
         graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
-            if graphs:
-                memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._graphed(
-                    ("encode", tuple(images.shape), tuple(image_sizes)), self._stage_encode, (images, fusion), (geo,))
+            if graphs and not self.profile_stages:
+                # encode -> select -> decode in ONE graph: the selection is written with static shapes and no host
+                # synchronisation (transformer.select_proposals), so nothing between the image upload and the final
+                # thresholding touches the host
+                (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
+                 init_reference, inter_references) = self._graphed(
+                    ("forward", prompt, tuple(images.shape), tuple(image_sizes), tuple(features_l.shape)),
+                    self._stage_all, (images, fusion, features_l), (geo, prompt))
+                self.transformer.last_topk_proposals = topk
+                mark("encode")
+                mark("select")
             else:
-                memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
-            mark("encode")
-            topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
-            self.transformer.last_topk_proposals = topk
-            mark("select")
-            if prompt == "name":
-                if fusion_out is not None:
-                    features_l = 1.0 * features_l + 0.0 * fusion_out.float()  # (:446)
-            else:
-                features_l = 0.0 * features_l + 1.0 * fusion_out.float()  # (:448)
-            if graphs:
-                # memory / output_memory / enc_coord are the encode graph's static outputs: constants of this graph
-                box_cls, box_pred, inter_states, init_reference, inter_references = self._graphed(
-                    ("decode", memory.data_ptr(), tuple(image_sizes), tuple(features_l.shape)), self._stage_decode,
-                    (topk, features_l), (memory, output_memory, enc_coord, geo))
-            else:
-                box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
-                    topk, features_l, memory, output_memory, enc_coord, geo)
+                if graphs:
+                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._graphed(
+                        ("encode", tuple(images.shape), tuple(image_sizes)), self._stage_encode, (images, fusion), (geo,))
+                else:
+                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+                mark("encode")
+                topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
+                self.transformer.last_topk_proposals = topk
+                mark("select")
+                features_l = self._mix_text(prompt, features_l, fusion_out)
+                if graphs:
+                    # memory / output_memory / enc_coord are the encode graph's static outputs: constants of this graph
+                    box_cls, box_pred, inter_states, init_reference, inter_references = self._graphed(
+                        ("decode", memory.data_ptr(), tuple(image_sizes), tuple(features_l.shape)), self._stage_decode,
+                        (topk, features_l), (memory, output_memory, enc_coord, geo))
+                else:
+                    box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
+                        topk, features_l, memory, output_memory, enc_coord, geo)
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
@@ -417,8 +438,26 @@ class DeformableDETRSegmVL(nn.Module):
     def _stage_encode(self, images, fusion, geo):
         features = self.backbone(images.to(self.engine_dtype))
         feats = self.neck({f: features[f] for f in self.neck.in_features})
-        memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(feats, geo, fusion)
+        memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(
+            feats, geo, fusion, feat_flatten=getattr(self.neck, "last_flat", None))
         return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats
+
+    @staticmethod
+    def _mix_text(prompt, features_l, fusion_out):
+        if prompt == "name":
+            if fusion_out is not None:
+                features_l = 1.0 * features_l + 0.0 * fusion_out.float()  # (:446)
+            return features_l
+        return 0.0 * features_l + 1.0 * fusion_out.float()  # (:448)
+
+    def _stage_all(self, images, fusion, features_l, geo, prompt):
+        memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+        topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
+        features_l = self._mix_text(prompt, features_l, fusion_out)
+        box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
+            topk, features_l, memory, output_memory, enc_coord, geo)
+        return (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
+                init_reference, inter_references)
 
     def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo):
         inter_states, init_reference, inter_references = self.transformer.stage_decode(

@@ -28,8 +28,27 @@ class _SelfAttention(nn.Module):
         self.embed_dim, self.num_heads = embed_dim, num_heads
         self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=0.0, batch_first=True)
 
+    def _packed(self, dtype):
+        w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
+        key = (dtype, w._version, b._version, w.data_ptr())
+        if getattr(self, "_pk", (None,))[0] != key:
+            E = self.embed_dim
+            with torch.no_grad():
+                self._pk = (key, w[: 2 * E].detach().to(dtype).contiguous(), b[: 2 * E].detach().float().contiguous(),
+                            w[2 * E:].detach().to(dtype).contiguous(), b[2 * E:].detach().float().contiguous())
+        return self._pk[1:]
+
     def forward(self, x, pos):
         E, nh = self.embed_dim, self.num_heads
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
+            # engine path: tcgen05 GEMMs for the in / out projections (residual in the epilogue)
+            wqk, bqk, wv, bv = self._packed(x.dtype)
+            B, N, _ = x.shape
+            qk = ops.linear_tc(x + pos.to(x.dtype), wqk, bqk).view(B, N, 2, nh, E // nh)
+            v = ops.linear_tc(x, wv, bv).view(B, N, nh, E // nh)
+            o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
+            o = o.transpose(1, 2).reshape(B, N, E)
+            return ops.linear_module_tc(self.attn.out_proj, o, residual=x.contiguous())
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
         qk = F.linear(x + pos, w[: 2 * E], b[: 2 * E])
         v = F.linear(x, w[2 * E:], b[2 * E:])
@@ -53,13 +72,16 @@ class _EncoderLayer(nn.Module):
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dim), nn.LayerNorm(embed_dim)])
 
     def forward(self, query, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index,
-                host_shapes=None):
+                host_shapes=None, query_with_pos=None, defer_last_norm=False):
         x = self.attentions[0](query, None, query, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
                                reference_points=reference_points, spatial_shapes=spatial_shapes,
-                               level_start_index=level_start_index, host_shapes=host_shapes)
+                               level_start_index=level_start_index, host_shapes=host_shapes,
+                               query_with_pos=query_with_pos)
         if x.dtype in (torch.float16, torch.bfloat16):  # engine path: libape_b200 LayerNorm kernel
             x = ops.layernorm_module(self.norms[0], x)
             x = self.ffns[0](x)
+            if defer_last_norm:  # the caller folds norms[1] into the kernel that consumes this layer's output
+                return x
             return ops.layernorm_module(self.norms[1], x)
         x = self.norms[0](x)
         x = self.ffns[0](x)
@@ -81,6 +103,16 @@ class _DecoderLayer(nn.Module):
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dim) for _ in range(3)])
 
     def forward(self, query, value, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+        if query.is_cuda and query.dtype in (torch.float16, torch.bfloat16) and value.dtype == query.dtype:
+            # engine path: every linear is a tcgen05 GEMM, norms are libape_b200 row kernels
+            x = self.attentions[0](query, query_pos)
+            x = ops.layernorm_module(self.norms[0], x)
+            x = self.attentions[1](x, None, value, None, query_pos=query_pos.to(x.dtype), key_padding_mask=key_padding_mask,
+                                   reference_points=reference_points, spatial_shapes=spatial_shapes,
+                                   level_start_index=level_start_index)
+            x = ops.layernorm_module(self.norms[1], x)
+            x = self.ffns[0](x)
+            return ops.layernorm_module(self.norms[2], x)
         x = self.attentions[0](query, query_pos)
         x = self.norms[0](x)
         x = self.attentions[1](x, None, value, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
@@ -109,26 +141,53 @@ class DeformableDetrTransformerEncoderVL(nn.Module):
         engine_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
         if engine_dtype is not None:
             query, query_pos = query.to(engine_dtype), query_pos.to(engine_dtype)
+            if query_l is not None and query_l.shape[1] == 1 and attention_mask_l is None and query.shape[-1] % 8 == 0 \
+                    and all(v is not None and not v.b_attn.attn.use_attention_mask_v for v in self.vl_layers):
+                return self._engine_single_token(query.contiguous(), query_pos.contiguous(), query_l,
+                                                 query_key_padding_mask, kwargs)
         for vl_layer, layer in zip(self.vl_layers, self.layers):
             if vl_layer is not None and query_l is not None:
-                if engine_dtype is not None and query_l.shape[1] == 1 and attention_mask_l is None:
-                    b = vl_layer.b_attn
-                    v = ops.layernorm_module(b.layer_norm_v, query)
-                    with torch.autocast("cuda", enabled=False):
-                        ln_l = b.layer_norm_l(query_l.float())
-                        dv, dl = b.single_token(v, ln_l)
-                        query = v + (b.gamma_v.float() * dv.float()).to(v.dtype)
-                        query_l = ln_l + b.gamma_l.float() * dl
-                else:
-                    query, query_l = vl_layer(query, query_l, attention_mask_v=query_key_padding_mask,
-                                              attention_mask_l=attention_mask_l)
-                    if engine_dtype is not None:
-                        query = query.to(engine_dtype)
+                query, query_l = vl_layer(query, query_l, attention_mask_v=query_key_padding_mask,
+                                          attention_mask_l=attention_mask_l)
+                if engine_dtype is not None:
+                    query = query.to(engine_dtype)
             query = layer(query, query_pos, query_key_padding_mask, kwargs["reference_points"],
                           kwargs["spatial_shapes"], kwargs["level_start_index"], kwargs.get("host_shapes"))
         if self.post_norm_layer is not None:
             query = self.post_norm_layer(query)
         return query, query_l
+
+    def _engine_single_token(self, x, query_pos, query_l, key_padding_mask, kwargs):
+        """Engine schedule of the encoder for "name" prompts (one language token).  Per layer:
+          tiny fp32 ops on the language token (delta_v, folded score operands)
+          -> ONE row kernel: [last norm of the previous layer] -> layer_norm_v -> + gamma_v*delta_v -> (query, query+pos)
+          -> pooling kernels over `query` (language-side update; fuse_helper.py:67-166 restructured)
+          -> deformable self-attention + FFN (tcgen05 GEMMs, fused gather), last norm deferred to the next layer.
+        Same functions as `vl_layer(...)` followed by `layer(...)`; the activations cross HBM once per row kernel."""
+        pending = None
+        for vl_layer, layer in zip(self.vl_layers, self.layers):
+            b = vl_layer.b_attn
+            with torch.autocast("cuda", enabled=False):
+                ln_l = b.layer_norm_l(query_l.float())
+                dv, qa, qc = b.single_token_language_side(ln_l)
+                shift = (b.gamma_v.float() * dv.float()).reshape(x.shape[0], -1).contiguous()  # [B, C]
+            vw, vb = ops.packed(b.layer_norm_v, x.dtype)
+            if pending is None:
+                query, qpos = ops.layernorm_ex(x, vw, vb, b.layer_norm_v.eps, col_add=shift, row_add=query_pos)
+            else:
+                query, qpos = ops.layernorm_ex(x, pending[0], pending[1], pending[2], weight2=vw, bias2=vb,
+                                               eps2=b.layer_norm_v.eps, col_add=shift, row_add=query_pos)
+            with torch.autocast("cuda", enabled=False):
+                dl = b.single_token_pool(query, qa, qc, shift=shift)
+                query_l = ln_l + b.gamma_l.float() * dl
+            x = layer(query, query_pos, key_padding_mask, kwargs["reference_points"], kwargs["spatial_shapes"],
+                      kwargs["level_start_index"], kwargs.get("host_shapes"), query_with_pos=qpos, defer_last_norm=True)
+            nw, nb = ops.packed(layer.norms[1], x.dtype)
+            pending = (nw, nb, layer.norms[1].eps)
+        x = ops.layernorm(x, pending[0], pending[1], eps=pending[2])
+        if self.post_norm_layer is not None:
+            x = self.post_norm_layer(x)
+        return x, query_l
 
 
 class DeformableDetrTransformerDecoderVL(nn.Module):
@@ -147,6 +206,9 @@ class DeformableDetrTransformerDecoderVL(nn.Module):
     def forward(self, query, key, value, query_pos=None, key_pos=None, attn_masks=None, query_key_padding_mask=None,
                 key_padding_mask=None, reference_points=None, valid_ratios=None, **kwargs):
         output = query
+        engine_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+        if engine_dtype is not None and value.dtype == engine_dtype:
+            output, query_pos = output.to(engine_dtype), query_pos.to(engine_dtype)
         intermediate, intermediate_ref = [], []
         for i, layer in enumerate(self.layers):
             if reference_points.shape[-1] == 4:
@@ -156,7 +218,7 @@ class DeformableDetrTransformerDecoderVL(nn.Module):
             output = layer(output, value, query_pos, key_padding_mask, ref_in, kwargs["spatial_shapes"],
                            kwargs["level_start_index"])
             if self.bbox_embed is not None:
-                tmp = self.bbox_embed[i](output)
+                tmp = self.bbox_embed[i](output).float()
                 if reference_points.shape[-1] == 4:
                     new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()
                 else:
@@ -269,30 +331,43 @@ class DeformableDetrTransformerVL(nn.Module):
         return torch.stack((pos[:, :, :, 0::2].sin(), pos[:, :, :, 1::2].cos()), dim=4).flatten(2)
 
     def select_proposals(self, logit, coord_unact, level_ids, n_levels):
-        """deformable_transformer_vl.py:569-625 for one image -> LongTensor[two_stage_num_proposals]."""
+        """deformable_transformer_vl.py:569-625 for one image -> LongTensor[min(two_stage_num_proposals, S)].
+
+        Same decisions as the reference's loop (per-level top-k -> class-aware NMS by level -> per-level quota ->
+        pad in score order), written with static shapes and no host synchronisation (masks + cumulative sums +
+        nonzero_static instead of boolean indexing), so the whole selection is CUDA-graph capturable."""
         topk = self.two_stage_num_proposals
+        S = logit.size(0)
+        fallback = torch.sort(logit, descending=True, stable=True)[1][: min(topk, S)]  # (:598-599)
+        if S < topk:
+            return fallback  # fewer tokens than queries: NMS can never keep `topk`, the reference takes this branch
+        dev = logit.device
         boxes = box_cxcywh_to_xyxy(coord_unact.sigmoid()).clamp(0, 1)
-        pre = []
-        for lvl in range(n_levels):
-            lvl_mask = level_ids == lvl
-            # The reference calls torch.topk here; for a level with fewer tokens than pre_nms_topk (the 16x16 level at
-            # 1024^2) the result is padded with zero-score tokens of OTHER levels in an implementation-defined order
-            # (CPU and CUDA top-k differ).  The engine fixes the rule: stable descending sort = lowest index first.
-            order = torch.sort(logit.sigmoid() * lvl_mask, descending=True, stable=True)[1]
-            pre.append(order[: min(self.pre_nms_topk, logit.size(0))])
-        pre = torch.cat(pre)
-        post = ops.batched_nms(boxes[pre].float(), logit[pre].float(), level_ids[pre], self.nms_thresh_enc)
-        keep = pre[post]
-        if len(keep) < topk:
-            keep = torch.sort(logit, descending=True, stable=True)[1][: min(topk, logit.size(0))]
+        lvls = torch.arange(n_levels, device=dev)
+        lvl_mask = level_ids[None] == lvls[:, None]                                           # [L,S]
+        # The reference calls torch.topk per level; for a level with fewer tokens than pre_nms_topk (the 16x16 level
+        # at 1024^2) the result is padded with zero-score tokens of OTHER levels in an implementation-defined order
+        # (CPU and CUDA top-k differ).  The engine fixes the rule: stable descending sort = lowest index first.
+        k = min(self.pre_nms_topk, S)
+        pre = torch.sort(logit.sigmoid()[None] * lvl_mask, dim=1, descending=True, stable=True)[1][:, :k].reshape(-1)
+        # detectron2 / torchvision batched_nms: coordinate-offset trick on boxes.float(), scores sorted descending
+        b = boxes[pre].float()
+        sc = logit[pre].float()
+        ids = level_ids[pre]
+        b = b + (ids.to(b) * (b.max() + 1))[:, None]  # offsets = idxs * (max_coordinate + 1)
+        order = sc.sort(0, descending=True)[1]
+        keep_mask, count = ops.nms_sorted_mask(b.index_select(0, order).contiguous(), self.nms_thresh_enc)
+        cand = pre[order]                       # candidates in NMS (descending score) order
+        kept = keep_mask.bool()                 # `keep = pre[post]` is cand[kept]
         q_per_l = topk // n_levels
-        ordered = level_ids[keep][None] == torch.arange(n_levels, device=level_ids.device)[:, None]
-        km = (ordered & (ordered.cumsum(1) <= q_per_l)).any(0)
-        if km.sum() < topk:
-            num_to_add = topk - km.sum()
-            pad = (~km).nonzero()[:num_to_add]
-            km[pad] = True
-        return keep[km]
+        per_lvl = (level_ids[cand][None] == lvls[:, None]) & kept[None]                       # [L,n]
+        km = (per_lvl & (per_lvl.cumsum(1) <= q_per_l)).any(0)
+        num_to_add = topk - km.sum()
+        extra = kept & ~km
+        km = km | (extra & (extra.cumsum(0) <= num_to_add))
+        sel = torch.nonzero_static(km, size=topk, fill_value=0)[:, 0]
+        picked = cand[sel]
+        return torch.where(count.to(torch.int64) < topk, fallback, picked)
 
     # -- staged forward ------------------------------------------------------------------------------
     # forward() = geometry() [pure function of the padded-image geometry, cacheable] -> stage_encode()
@@ -333,11 +408,20 @@ class DeformableDetrTransformerVL(nn.Module):
                     output_proposals=out, proposal_invalid=mask_flatten.unsqueeze(-1) | ~valid,
                     level_ids=torch.cat(level_ids), has_padding=bool(mask_flatten.any()))
 
-    def stage_encode(self, multi_level_feats, geo, query_l, attention_mask_l=None, mask_prompt_flatten=None):
-        feat_flatten = torch.cat([f.flatten(2).transpose(1, 2) for f in multi_level_feats], 1)
-        lvl_embed = torch.cat([self.level_embeds[i].view(1, 1, -1).expand(1, h * w, -1)
-                               for i, (h, w) in enumerate(geo["shapes"])], 1)
-        pos_flatten = geo["pos_flatten"] + lvl_embed
+    def stage_encode(self, multi_level_feats, geo, query_l, attention_mask_l=None, mask_prompt_flatten=None,
+                     feat_flatten=None):
+        """feat_flatten: optional [B,S,C] tensor that already holds the flattened levels (the engine neck writes its
+        outputs straight into it; `multi_level_feats` are then views of its slices)."""
+        if feat_flatten is None:
+            feat_flatten = torch.cat([f.flatten(2).transpose(1, 2) for f in multi_level_feats], 1)
+        engine_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
+        ck = ("pos_lvl", engine_dtype, self.level_embeds._version, self.level_embeds.data_ptr())
+        if geo.get("_pos_lvl_key") != ck:  # position embedding + level embedding: constant per geometry and weights
+            lvl_embed = torch.cat([self.level_embeds[i].view(1, 1, -1).expand(1, h * w, -1)
+                                   for i, (h, w) in enumerate(geo["shapes"])], 1)
+            geo["_pos_lvl"] = (geo["pos_flatten"] + lvl_embed.float()).to(engine_dtype).contiguous()
+            geo["_pos_lvl_key"] = ck
+        pos_flatten = geo["_pos_lvl"]
         memory, query_l = self.encoder(
             query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
             query_pos=pos_flatten, query_key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
@@ -350,9 +434,12 @@ class DeformableDetrTransformerVL(nn.Module):
         if mask_prompt_flatten is not None:
             output_proposals = output_proposals.masked_fill(~mask_prompt_flatten.unsqueeze(-1), float("inf"))
             invalid = invalid | ~mask_prompt_flatten.unsqueeze(-1)
+        nd = self.decoder.num_layers
+        if memory.is_cuda and memory.dtype in (torch.float16, torch.bfloat16):
+            output_memory, enc_cls, enc_coord = self._engine_proposal_heads(memory, invalid, output_proposals, nd)
+            return memory, query_l, output_memory, enc_cls, enc_coord
         output_memory = self.enc_output_norm(self.enc_output(memory.masked_fill(invalid, float(0))))
         output_proposals = output_proposals.to(output_memory.dtype)
-        nd = self.decoder.num_layers
         enc_cls = self.decoder.class_embed[nd](output_memory)
         enc_coord = self.decoder.bbox_embed[nd](output_memory) + output_proposals
         if self.proposal_ambiguous:
@@ -364,6 +451,57 @@ class DeformableDetrTransformerVL(nn.Module):
             enc_coord = torch.gather(coord_all, 1, idx.repeat(1, 1, 1, 4)).squeeze(1)
         return memory, query_l, output_memory, enc_cls, enc_coord
 
+    def _engine_proposal_heads(self, memory, invalid, output_proposals, nd):
+        """deformable_transformer_vl.py:354-369 + :503-533 on the tensor cores: enc_output -> LayerNorm, then the
+        class heads (Linear 256->1, main + ambiguous, stacked into one 8-row GEMM) and the box MLPs (first layers
+        of all heads stacked into one GEMM with a ReLU epilogue).  Logits and box deltas leave the last GEMMs in
+        fp32 (they feed top-k / NMS); the ambiguous-head argmax follows the reference."""
+        dt = memory.dtype
+        cls_mods = [self.decoder.class_embed[nd]] + (list(self.decoder.class_embed_ambiguous) if self.proposal_ambiguous else [])
+        box_mods = [self.decoder.bbox_embed[nd]] + (list(self.decoder.bbox_embed_ambiguous) if self.proposal_ambiguous else [])
+        params = [p for m in cls_mods + box_mods for p in m.parameters()]
+        key = (dt, tuple(p._version for p in params), params[0].data_ptr())
+        if getattr(self, "_heads_pk", (None,))[0] != key:
+            with torch.no_grad():
+                E = self.embed_dim
+                n = len(cls_mods)
+                wc = torch.zeros(8, E, device=memory.device, dtype=dt)
+                bc = torch.zeros(8, device=memory.device, dtype=torch.float32)
+                for j, m in enumerate(cls_mods):
+                    wc[j] = m.weight[0].to(dt)
+                    bc[j] = m.bias[0].float()
+                w0 = torch.cat([m.layers[0].weight for m in box_mods], 0).to(dt).contiguous()
+                b0 = torch.cat([m.layers[0].bias for m in box_mods], 0).float().contiguous()
+                rest = []
+                for m in box_mods:
+                    mids = [(l.weight.detach().to(dt).contiguous(), l.bias.detach().float().contiguous()) for l in m.layers[1:-1]]
+                    wl = torch.zeros(8, m.layers[-1].weight.shape[1], device=memory.device, dtype=dt)
+                    bl = torch.zeros(8, device=memory.device, dtype=torch.float32)
+                    wl[:4] = m.layers[-1].weight.to(dt)
+                    bl[:4] = m.layers[-1].bias.float()
+                    rest.append((mids, wl, bl))
+                self._heads_pk = (key, wc, bc, w0, b0, rest, n)
+        _, wc, bc, w0, b0, rest, n = self._heads_pk
+        om = ops.linear_module_tc(self.enc_output, memory.masked_fill(invalid, float(0)))
+        output_memory = ops.layernorm_module(self.enc_output_norm, om)
+        B, S, E = output_memory.shape
+        cls_all = ops.linear_tc(output_memory, wc, bc, out_dtype=torch.float32)[..., :n]      # [B,S,n] fp32
+        h0 = ops.linear_tc(output_memory, w0, b0, act="relu")                                  # [B,S,n*E]
+        props = output_proposals.float()
+        coords = []
+        for j, (mids, wl, bl) in enumerate(rest):
+            h = h0[..., j * E:(j + 1) * E]
+            for (w, b) in mids:
+                h = ops.linear_tc(h, w, b, act="relu")
+            coords.append(ops.linear_tc(h, wl, bl, out_dtype=torch.float32)[..., :4] + props)
+        if n == 1:
+            return output_memory, cls_all, coords[0]
+        idx = torch.argmax(cls_all, dim=-1, keepdim=True)                                      # [B,S,1]
+        enc_cls = torch.gather(cls_all, 2, idx)
+        coord_all = torch.stack(coords, dim=2)                                                 # [B,S,n,4]
+        enc_coord = torch.gather(coord_all, 2, idx.unsqueeze(-1).expand(-1, -1, 1, 4)).squeeze(2)
+        return output_memory, enc_cls, enc_coord
+
     def stage_select(self, enc_cls, enc_coord, geo):
         logit = enc_cls[..., 0].float()
         coord = enc_coord.float()
@@ -374,10 +512,16 @@ class DeformableDetrTransformerVL(nn.Module):
         c = memory.shape[-1]
         topk_unact = torch.gather(enc_coord.float(), 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).detach()
         reference = topk_unact.sigmoid()
-        pos_trans_out = self.pos_trans_norm(self.pos_trans(self.get_proposal_pos_embed(topk_unact).to(topk_unact.dtype)))
-        query_pos, query = torch.split(pos_trans_out, c, dim=2)
         topk_feats = torch.gather(output_memory, 1, topk_proposals.unsqueeze(-1).expand(-1, -1, c)).detach()
-        query = query + self.pix_trans_norm(self.pix_trans(topk_feats))
+        if memory.is_cuda and memory.dtype in (torch.float16, torch.bfloat16):
+            emb = self.get_proposal_pos_embed(topk_unact).to(memory.dtype)
+            pos_trans_out = ops.layernorm_module(self.pos_trans_norm, ops.linear_module_tc(self.pos_trans, emb))
+            query_pos, query = torch.split(pos_trans_out, c, dim=2)
+            query = query + ops.layernorm_module(self.pix_trans_norm, ops.linear_module_tc(self.pix_trans, topk_feats.to(memory.dtype)))
+        else:
+            pos_trans_out = self.pos_trans_norm(self.pos_trans(self.get_proposal_pos_embed(topk_unact).to(topk_unact.dtype)))
+            query_pos, query = torch.split(pos_trans_out, c, dim=2)
+            query = query + self.pix_trans_norm(self.pix_trans(topk_feats))
         inter_states, inter_references = self.decoder(
             query=query, key=None, value=memory, query_pos=query_pos,
             key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,

@@ -228,16 +228,53 @@ def layernorm(x, weight, bias, eps=1e-5, out_dtype=None, row_map=None, out=None)
     return out if x.dim() == 2 or out.shape[1] != C else out.view(*x.shape[:-1], C)
 
 
-def groupnorm_nhwc(x, weight, bias, groups, eps=1e-5, out_dtype=None):
-    """GroupNorm over token-major activations x [B, rows, C] (ape_groupnorm_nhwc); weight / bias fp32 [C]."""
+def layernorm_ex(x, weight, bias, eps, weight2=None, bias2=None, eps2=0.0, col_add=None, row_add=None, out_dtype=None):
+    """One pass over x [B, rows, C] (or [rows, C]) for LN -> optional second LN -> + col_add[image] -> (y, y + row_add)
+    (ape_layernorm_ex; the previous encoder layer's last norm, the fusion layer's layer_norm_v, gamma_v * delta_v and
+    `query + query_pos` in one kernel).  weights fp32 [C]; col_add fp32 [B, C]; row_add like x in the output dtype.
+    Returns (y, y2) with y2 None when row_add is None."""
+    C = x.shape[-1]
+    _require(x.is_cuda and x.is_contiguous(), "layernorm_ex: contiguous CUDA tensor")
+    x2 = x.view(-1, C)
+    rows = x2.shape[0]
+    rpi = x.shape[-2] if x.dim() == 3 else rows
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    y2 = None
+    if row_add is not None:
+        _require(row_add.dtype == out_dtype and row_add.is_contiguous() and row_add.numel() == x.numel(),
+                 "layernorm_ex: row_add must match x in the output dtype")
+        y2 = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    if col_add is not None:
+        col_add = col_add.reshape(-1, C)
+        _require(col_add.dtype == torch.float32 and col_add.is_contiguous() and col_add.shape[0] * rpi == rows,
+                 "layernorm_ex: col_add must be fp32 [images, C]")
+    for t in (weight, bias, weight2, bias2):
+        _require(t is None or (t.dtype == torch.float32 and t.is_contiguous()), "layernorm_ex: fp32 weights")
+    with torch.cuda.device(x.device), _timed(("layernorm_ex", rows, C, weight2 is not None, row_add is not None)):
+        rc = _lib.lib.ape_layernorm_ex(
+            x2.data_ptr(), C, y.data_ptr(), C, weight.data_ptr(), bias.data_ptr(), float(eps),
+            weight2.data_ptr() if weight2 is not None else None, bias2.data_ptr() if bias2 is not None else None, float(eps2),
+            col_add.data_ptr() if col_add is not None else None, C, int(rpi),
+            row_add.data_ptr() if row_add is not None else None, C, y2.data_ptr() if y2 is not None else None, C,
+            rows, C, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_layernorm_ex")
+    return y, y2
+
+
+def groupnorm_nhwc(x, weight, bias, groups, eps=1e-5, out_dtype=None, out=None):
+    """GroupNorm over token-major activations x [B, rows, C] (ape_groupnorm_nhwc); weight / bias fp32 [C].
+    out: optional [B, rows, C] view (unit channel stride, any batch stride) the result is written into."""
     _require(x.is_cuda and x.dim() == 3 and x.is_contiguous(), "groupnorm_nhwc: contiguous CUDA [B, rows, C]")
     B, rows, C = x.shape
-    out = torch.empty((B, rows, C), dtype=out_dtype or x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((B, rows, C), dtype=out_dtype or x.dtype, device=x.device)
+    _require(out.shape == x.shape and out.stride(2) == 1 and out.stride(1) == C, "groupnorm_nhwc: bad `out` view")
     ws = torch.empty((int(_lib.lib.ape_groupnorm_workspace_bytes(B, rows, C)),), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device), _timed(("groupnorm", B, rows, C)):
-        rc = _lib.lib.ape_groupnorm_nhwc(x.data_ptr(), C, out.data_ptr(), C, weight.data_ptr(), bias.data_ptr(),
-                                         ws.data_ptr(), B, rows, C, int(groups), float(eps), _lib.dtype_code(x.dtype),
-                                         _lib.dtype_code(out.dtype), _lib.current_stream_ptr())
+        rc = _lib.lib.ape_groupnorm_nhwc(x.data_ptr(), C, out.data_ptr(), C, out.stride(0) if B > 1 else 0, weight.data_ptr(),
+                                         bias.data_ptr(), ws.data_ptr(), B, rows, C, int(groups), float(eps),
+                                         _lib.dtype_code(x.dtype), _lib.dtype_code(out.dtype), _lib.current_stream_ptr())
     _lib.check(rc, "ape_groupnorm_nhwc")
     return out
 
@@ -275,6 +312,24 @@ def vlf_pool(v, qa, qc, stable_softmax_2d=True):
     return part[..., :C] / part[..., C:]
 
 
+def nms_sorted_mask(sorted_boxes, iou_threshold):
+    """Greedy NMS over boxes ALREADY sorted by descending score: uint8 keep mask [n] (static shape, no host
+    synchronisation: usable inside CUDA-graph capture) and the int32 [1] number of survivors."""
+    _require(sorted_boxes.is_cuda and sorted_boxes.dim() == 2 and sorted_boxes.shape[1] == 4 and
+             sorted_boxes.dtype == torch.float32 and sorted_boxes.is_contiguous(), "nms: boxes must be contiguous CUDA fp32 [n,4]")
+    n = sorted_boxes.shape[0]
+    keep = torch.empty((n,), dtype=torch.uint8, device=sorted_boxes.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=sorted_boxes.device)
+    if n == 0:
+        return keep, count
+    ws = torch.empty((int(_lib.lib.ape_nms_workspace_bytes(n)),), dtype=torch.uint8, device=sorted_boxes.device)
+    with torch.cuda.device(sorted_boxes.device), _timed(("nms", n)):
+        rc = _lib.lib.ape_nms_sorted(sorted_boxes.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
+                                     count.data_ptr(), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_nms_sorted")
+    return keep, count
+
+
 def nms(boxes, scores, iou_threshold):
     """torchvision.ops.nms replacement: indices of kept boxes, sorted by descending score."""
     _require(boxes.is_cuda and boxes.dim() == 2 and boxes.shape[1] == 4, "nms: boxes must be CUDA [n,4]")
@@ -282,14 +337,7 @@ def nms(boxes, scores, iou_threshold):
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
     order = scores.sort(0, descending=True)[1]  # same ordering call as torchvision's nms kernel wrapper
-    sb = boxes.float().index_select(0, order).contiguous()
-    ws = torch.empty((int(_lib.lib.ape_nms_workspace_bytes(n)),), dtype=torch.uint8, device=boxes.device)
-    keep = torch.empty((n,), dtype=torch.uint8, device=boxes.device)
-    count = torch.empty((1,), dtype=torch.int32, device=boxes.device)
-    with torch.cuda.device(boxes.device), _timed(("nms", n)):
-        rc = _lib.lib.ape_nms_sorted(sb.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
-                                     count.data_ptr(), _lib.current_stream_ptr())
-    _lib.check(rc, "ape_nms_sorted")
+    keep, _ = nms_sorted_mask(boxes.float().index_select(0, order).contiguous(), iou_threshold)
     return order[keep.bool()]
 
 

@@ -135,14 +135,29 @@ int ape_layernorm(const void *x, int64_t ldx, void *y, int64_t ldy, const float 
                   const int *row_map, int rows, int C, float eps, int in_dtype, int out_dtype, void *stream);
 
 /*
+ * Extended LayerNorm for the deformable encoder (C % 8 == 0, C <= 1024); one pass over the activations for
+ *   t = LN(x; weight, bias, eps)                 norms[1] of a detrex BaseTransformerLayer (deformable_transformer_vl.py:36-54)
+ *   t = LN(t; weight2, bias2, eps2)  if weight2  layer_norm_v of the next VisionLanguageFusion (fuse_helper.py:224)
+ *   y = t + col_add[image, :]        if col_add  gamma_v * delta_v of that fusion (one fp32 [C] vector per image for
+ *                                                "name" prompts; col_add_stride elements between images, rows_per_image rows each)
+ *   y2 = y + row_add[row, :]         if y2       query + query_pos (multi_scale_deform_attn.py:262-263); row_add / y2 in out_dtype
+ */
+int ape_layernorm_ex(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias, float eps,
+                     const float *weight2, const float *bias2, float eps2, const float *col_add, int64_t col_add_stride,
+                     int rows_per_image, const void *row_add, int64_t ld_add, void *y2, int64_t ldy2, int rows, int C,
+                     int in_dtype, int out_dtype, void *stream);
+
+/*
  * GroupNorm over token-major activations x [B, rows_per_image, C] (the neck's GroupNorm(32, 256) after each
  * 1x1 conv, configs/…1080k.py:42-55): statistics per (image, group) over all rows x C/groups channels, fp32,
- * deterministic.  workspace: ape_groupnorm_workspace_bytes(B, rows_per_image, C) bytes.
+ * deterministic.  y_batch_stride: elements between images of y (0 = rows_per_image * ldy), so the result can be
+ * written straight into its slice of the flattened multi-level feature tensor.
+ * workspace: ape_groupnorm_workspace_bytes(B, rows_per_image, C) bytes.
  */
 int64_t ape_groupnorm_workspace_bytes(int B, int rows_per_image, int C);
-int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, const float *weight, const float *bias,
-                       void *workspace, int B, int rows_per_image, int C, int groups, float eps, int in_dtype,
-                       int out_dtype, void *stream);
+int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t ldy, int64_t y_batch_stride, const float *weight,
+                       const float *bias, void *workspace, int B, int rows_per_image, int C, int groups, float eps,
+                       int in_dtype, int out_dtype, void *stream);
 
 /*
  * In-place 2-D rotary embedding on the q and k thirds of a fused qkv buffer [M, 3*C] (pitch ld):

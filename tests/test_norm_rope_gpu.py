@@ -86,3 +86,41 @@ def test_groupnorm_nhwc(ops, dtype, rows):
     tol = 2e-5 if dtype == torch.float32 else 4e-3
     torch.testing.assert_close(y.float(), want, rtol=tol, atol=tol)
     assert torch.equal(y, ops.groupnorm_nhwc(x, w, b, G, eps=1e-5))  # deterministic
+
+
+def test_groupnorm_writes_into_strided_slice(ops):
+    """The neck writes each level straight into its slice of the flattened [B, S, C] tensor."""
+    B, rows, C, G = 2, 300, 256, 32
+    x = torch.randn(B, rows, C, device=DEV).half()
+    w, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    flat = torch.full((B, 1000, C), 9.0, dtype=torch.float16, device=DEV)
+    ops.groupnorm_nhwc(x, w, b, G, out=flat[:, 200:500])
+    assert torch.equal(flat[:, 200:500], ops.groupnorm_nhwc(x, w, b, G))
+    assert (flat[:, :200] == 9).all() and (flat[:, 500:] == 9).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("second,col,row", [(False, False, False), (True, True, True), (False, True, True), (True, False, False)])
+@pytest.mark.parametrize("C", [256, 1024, 64])
+def test_layernorm_ex(ops, dtype, second, col, row, C):
+    """ape_layernorm_ex = LN -> [LN] -> [+ per-image vector] -> (y, [y + row_add]) against the op sequence in fp32."""
+    B, rows = 2, 333
+    g = torch.Generator().manual_seed(C + second)
+    x = (torch.randn(B, rows, C, generator=g) * 2 + 0.3).to(dtype).to(DEV)
+    w1, b1, w2, b2 = [(1 + 0.1 * torch.randn(C, generator=g)).to(DEV) if i % 2 == 0 else (0.1 * torch.randn(C, generator=g)).to(DEV)
+                      for i in range(4)]
+    ca = torch.randn(B, C, generator=g).to(DEV) if col else None
+    ra = torch.randn(B, rows, C, generator=g).to(dtype).to(DEV) if row else None
+    y, y2 = ops.layernorm_ex(x, w1, b1, 1e-5, weight2=w2 if second else None, bias2=b2 if second else None, eps2=1e-6,
+                             col_add=ca, row_add=ra)
+    t = F.layer_norm(x.float(), (C,), w1, b1, 1e-5)
+    if second:
+        t = F.layer_norm(t, (C,), w2, b2, 1e-6)
+    if col:
+        t = t + ca[:, None]
+    tol = {torch.float32: 2e-5, torch.float16: 4e-3, torch.bfloat16: 3e-2}[dtype]
+    torch.testing.assert_close(y.float(), t, rtol=tol, atol=tol)
+    if row:
+        assert torch.equal(y2, (y.float() + ra.float()).to(dtype))  # exactly `y + row_add` on the stored tensors
+    else:
+        assert y2 is None
