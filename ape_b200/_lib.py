@@ -61,6 +61,8 @@ lib.ape_nms_workspace_bytes.restype = _i64
 lib.ape_nms_workspace_bytes.argtypes = [_i]
 lib.ape_nms_sorted.restype = _i
 lib.ape_nms_sorted.argtypes = [_vp, _i, ctypes.c_float, _vp, _vp, _vp, _vp]
+lib.ape_nms_sorted_dev.restype = _i
+lib.ape_nms_sorted_dev.argtypes = [_vp, _i, _vp, ctypes.c_float, _vp, _vp, _vp, _vp]
 
 # every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = (
@@ -81,6 +83,7 @@ EXPORTS = (
     "ape_vlf_pool",
     "ape_nms_workspace_bytes",
     "ape_nms_sorted",
+    "ape_nms_sorted_dev",
 )
 
 

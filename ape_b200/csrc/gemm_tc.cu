@@ -35,6 +35,7 @@ struct GemmParams {
   int m_blocks, n_blocks, k_blocks;
   int out_dtype;  // APE_DTYPE_*
   int act;
+  int n_fastest;  // tile order: consecutive tiles walk the column blocks of one row group (A stays hot in L2)
   int tma_store;  // 16-bit output with 16-byte aligned rows: epilogue goes through smem + TMA store
   uint32_t idesc;
 };
@@ -295,7 +296,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = first; tile < num_tiles; tile += stride) {
-        const int m_blk = (tile % m_groups) * CL + rank, n_blk = tile / m_groups;
+        const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
+        const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
+        const int m_blk = mg * CL + rank;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
           tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
@@ -347,7 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint8_t *slab = s.c[warp - 2];
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = first; tile < num_tiles; tile += stride) {
-      const int m_blk = (tile % m_groups) * CL + rank, n_blk = tile / m_groups;
+      const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
+      const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
+      const int m_blk = mg * CL + rank;
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
       if (p.tma_store) {
@@ -384,6 +389,160 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x BN output tile.  CTA r loads its own
+// 128 rows of A and its own BN/2 rows of the weight tile; ONE thread of the leader CTA issues M=256 MMAs that read
+// both CTAs' shared memory and write both CTAs' tensor memory (CTA r holds rows 128r..128r+127 of the tile).
+// Per SM and k-block that is 32 KB written + 32 KB read from shared memory for 128x256x64 MACs — two thirds of
+// the single-CTA kernel's traffic, which ncu showed pinned at the shared-memory / L2->SM limits.
+//   full[stage]      leader only; expect_tx = both CTAs' bytes; every TMA of the pair completes on it
+//   empty[stage]     in each CTA; one multicast tcgen05.commit per k-block arrives on both
+//   tmem_full[acc]   in each CTA; multicast commit after the last k-block of a tile
+//   tmem_empty[acc]  leader only; 16 arrivals (8 epilogue warps of each CTA, the peer's arrive remotely)
+template <int BN, int STAGES>
+struct alignas(1024) PairSmem {
+  uint8_t a[STAGES][BM * BK * 2];
+  uint8_t b[STAGES][(BN / 2) * BK * 2];
+  uint8_t c[8][32 * 128];
+  uint64_t full[STAGES], empty[STAGES];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using Smem = PairSmem<BN, STAGES>;
+  Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr uint32_t CTA_STAGE_BYTES = (BM + BN / 2) * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t rank = tc::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_pairs = (p.m_blocks + 1) / 2;
+  const int num_tiles = m_pairs * p.n_blocks;
+  const int first = blockIdx.x / 2, stride = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&map_a);
+    tc::prefetch_tensormap(&map_b);
+    if (p.tma_store) tc::prefetch_tensormap(&map_c);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      tc::mbar_init(&s.full[i], 1);
+      tc::mbar_init(&s.empty[i], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s.tmem_full[i], 1);
+      tc::mbar_init(&s.tmem_empty[i], 16);
+    }
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
+  tc::cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  if (warp == 1) {
+    tc::tmem_alloc_pair(&s.tmem_base, TMEM_COLS);
+    tc::tmem_relinquish_pair();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = first; tile < num_tiles; tile += stride) {
+        const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_pairs;
+        const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
+        const int m_blk = mg * 2 + (int)rank;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          tc::mbar_wait(&s.empty[stage], phase ^ 1);
+          if (leader) tc::mbar_expect_tx(&s.full[stage], 2 * CTA_STAGE_BYTES);
+          const uint32_t full_leader = tc::mapa_u32(&s.full[stage], 0);
+          tc::tma_load_2d_pair(s.a[stage], &map_a, full_leader, kb * BK, m_blk * BM);
+          tc::tma_load_2d_pair(s.b[stage], &map_b, full_leader, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = first; tile < num_tiles; tile += stride) {
+        tc::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc::fence_after_sync();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          tc::mbar_wait(&s.full[stage], phase);
+          tc::fence_after_sync();
+          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(s.a[stage]));
+          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(s.b[stage]));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) tc::mma_f16_pair(tmem_d, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0);
+          tc::mma_commit_pair(&s.empty[stage], 3);  // both CTAs may refill this stage once the MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::mma_commit_pair(&s.tmem_full[acc], 3);  // accumulator complete -> both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    const int quad = warp % 4;
+    const int half = (warp - 2) / 4;
+    uint8_t *slab = s.c[warp - 2];
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = first; tile < num_tiles; tile += stride) {
+      const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_pairs;
+      const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
+      const int m_blk = mg * 2 + (int)rank;
+      tc::mbar_wait(&s.tmem_full[acc], acc_phase);
+      tc::fence_after_sync();
+      if (p.tma_store) {
+        if (p.out_dtype == APE_DTYPE_F16)
+          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+        else
+          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+      } else {
+        const int m = m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+          uint32_t r[32];
+          tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, r);
+          tc::tmem_ld_wait();
+          if (m < p.M) {
+            const int n0 = n_blk * BN + c * 32;
+            if (p.out_dtype == APE_DTYPE_F32) epilogue_chunk<float>(p, r, m, n0);
+            else if (p.out_dtype == APE_DTYPE_F16) epilogue_chunk<__half>(p, r, m, n0);
+            else epilogue_chunk<__nv_bfloat16>(p, r, m, n0);
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive_cluster(tc::mapa_u32(&s.tmem_empty[acc], 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.tma_store && lane == 0) tc::tma_store_wait_all();
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::cluster_sync_all();  // no CTA leaves (or frees tensor memory) while its peer can still touch it
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc_pair(tmem_base, TMEM_COLS);
   }
 }
 
@@ -443,6 +602,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
     attr_set = true;
   }
   p.n_blocks = (p.N + BN - 1) / BN;
+  p.n_fastest = p.n_blocks <= 8;  // few column blocks: keep the A rows of a group hot instead of re-reading A per column block
   const int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
   const int max_clusters = num_sms() / CL;
   const int clusters = groups < max_clusters ? groups : max_clusters;
@@ -461,6 +621,39 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, ma, mb, mc, p);
   if (e != cudaSuccess) return fail((int)e, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
+}
+
+template <int BN, int STAGES>
+int launch_gemm_pair(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mc, GemmParams &p, cudaStream_t st) {
+  using Smem = PairSmem<BN, STAGES>;
+  const size_t smem = sizeof(Smem) + 1024;
+  auto k = gemm_pair_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "gemm: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  p.n_blocks = (p.N + BN - 1) / BN;
+  p.n_fastest = p.n_blocks <= 8;
+  const int tiles = (p.m_blocks + 1) / 2 * p.n_blocks;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, ma, mb, mc, p);
+  if (e != cudaSuccess) return fail((int)e, "gemm_pair_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("gemm_pair_kernel");
 }
 
 }  // namespace
@@ -484,14 +677,19 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
   if (lda < K || ldw < K) return fail(APE_ERR_INVALID_ARG, "gemm: row pitch smaller than K");
   if (act == ACT_SWIGLU && ((N & 1) || residual)) return fail(APE_ERR_INVALID_ARG, "gemm: swiglu needs even N, no residual");
   if (residual && out_dtype == APE_DTYPE_F32 && false) return APE_ERR_INVALID_ARG;
-  const int bn = (tile_n & 0xfff) > 0 ? (tile_n & 0xfff) : (N >= 1536 ? 256 : 128);
+  const int bn = (tile_n & 0xfff) > 0 ? (tile_n & 0xfff) : (N > 128 ? 256 : 128);
   if (bn != 128 && bn != 256) return fail(APE_ERR_INVALID_ARG, "gemm: tile_n must be 128 or 256");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap ma, mb;
   if (int rc = make_map(&ma, A, in_dtype, M, K, lda, BM)) return rc;
   // cluster of 2 along M whenever there are at least two row blocks (tile_n bit 0x1000 forces single-CTA)
   const bool single = (tile_n & 0x1000) != 0 || M <= BM;
-  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : bn / 2)) return rc;
+  // kernel variant: default = cluster of 2 along M sharing the weight tile by TMA multicast (1-CTA MMA); 0x2000 = CTA-pair
+  // MMA (cta_group::2, 256 x bn tiles; measured equal or slower on B200 for these shapes, kept selectable);
+  // 0x8000 = cluster of 4 along M (weight tile split four ways)
+  const bool pair = !single && (tile_n & 0x2000) != 0;
+  const bool quad = !single && !pair && (tile_n & 0x8000) != 0 && M > 2 * BM;
+  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : quad ? bn / 4 : bn / 2)) return rc;
   GemmParams p{};
   p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
@@ -506,9 +704,18 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
                 (act != ACT_SWIGLU || bn == 256);
   if (p.tma_store)
     if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 64)) return rc;
+  if (pair) {
+    p.idesc = tc::make_idesc_f16(2 * BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
+    if (bn == 256) return launch_gemm_pair<256, 5>(ma, mb, mc, p, st);
+    return launch_gemm_pair<128, 6>(ma, mb, mc, p, st);
+  }
   if (single) {
     if (bn == 256) return launch_gemm<256, 4, 1>(ma, mb, mc, p, st);
     return launch_gemm<128, 6, 1>(ma, mb, mc, p, st);
+  }
+  if (quad) {
+    if (bn == 256) return launch_gemm<256, 4, 4>(ma, mb, mc, p, st);
+    return launch_gemm<128, 6, 4>(ma, mb, mc, p, st);
   }
   if (bn == 256) return launch_gemm<256, 4, 2>(ma, mb, mc, p, st);
   return launch_gemm<128, 6, 2>(ma, mb, mc, p, st);

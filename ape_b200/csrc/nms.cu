@@ -23,10 +23,12 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
 }
 
 // grid (col_blocks, row_blocks), 64 threads; mask[row * col_blocks + cb] bit j = IoU(row, cb*64+j) > thr, j > row
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__ boxes, int n, float thr,
-                                                      unsigned long long *__restrict__ mask, int col_blocks) {
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4 *__restrict__ boxes, int n, const int *__restrict__ n_dev,
+                                                      float thr, unsigned long long *__restrict__ mask, int col_blocks) {
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;  // lower triangle never read
+  if (n_dev) n = min(n, max(*n_dev, 0));  // only the first *n_dev boxes are real (static-shape callers)
+  if (cb * 64 >= n) return;
   __shared__ float4 cols[64];
   const int t = threadIdx.x;
   const int col = cb * 64 + t;
@@ -54,11 +56,13 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
-                                                        unsigned char *__restrict__ keep, int *__restrict__ count) {
+__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long *__restrict__ mask, int n, const int *__restrict__ n_dev,
+                                                        int pitch, unsigned char *__restrict__ keep, int *__restrict__ count) {
   extern __shared__ unsigned long long s_dyn[];
+  if (n_dev) n = min(n, max(*n_dev, 0));
+  const int col_blocks = (n + 63) / 64;  // active chunks; rows of `mask` are `pitch` words apart
   unsigned long long *removed = s_dyn;                      // col_blocks words
-  unsigned long long *rows[2] = {s_dyn + col_blocks, s_dyn + col_blocks + 64 * (size_t)col_blocks};  // [64][col_blocks] each
+  unsigned long long *rows[2] = {s_dyn + pitch, s_dyn + pitch + 64 * (size_t)pitch};  // [64][pitch] each
   __shared__ unsigned long long s_keepbits;
   const int t = threadIdx.x, nt = blockDim.x;
   for (int w = t; w < col_blocks; w += nt) removed[w] = 0;
@@ -67,11 +71,11 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
     const int base = c * 64, nb = min(64, n - base), nw = col_blocks - c;
     for (int i = t; i < nb * nw; i += nt) {
       const int r = i / nw, w = c + (i - r * nw);
-      cp_async8(&rows[buf][r * col_blocks + w], mask + (size_t)(base + r) * col_blocks + w);
+      cp_async8(&rows[buf][r * pitch + w], mask + (size_t)(base + r) * pitch + w);
     }
     cp_async_commit();
   };
-  prefetch(0, 0);
+  if (col_blocks > 0) prefetch(0, 0);
   int total = 0;
   for (int c = 0; c < col_blocks; ++c) {
     const int buf = c & 1;
@@ -80,8 +84,8 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
     __syncthreads();  // chunk c's rows are in rows[buf]; removed[] of the previous chunk is complete
     if (c + 1 < col_blocks) prefetch(c + 1, buf ^ 1);
     if (t < 32) {
-      const unsigned long long r0 = (t < nb) ? rows[buf][t * col_blocks + c] : 0ull;
-      const unsigned long long r1 = (t + 32 < nb) ? rows[buf][(t + 32) * col_blocks + c] : 0ull;
+      const unsigned long long r0 = (t < nb) ? rows[buf][t * pitch + c] : 0ull;
+      const unsigned long long r1 = (t + 32 < nb) ? rows[buf][(t + 32) * pitch + c] : 0ull;
       unsigned long long rem = removed[c], kept = 0;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = g + 8 * j;
-        if ((kept >> i) & 1ull) acc |= rows[buf][i * col_blocks + w];
+        if ((kept >> i) & 1ull) acc |= rows[buf][i * pitch + w];
       }
       if (acc) atomicOr(&removed[w], acc);
     }
@@ -114,9 +118,11 @@ __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned long long
 
 // Fallback for very long lists (the double-buffered rows do not fit shared memory): same algorithm, rows read
 // straight from global memory.
-__global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long long *__restrict__ mask, int n, int col_blocks,
-                                                           unsigned char *__restrict__ keep, int *__restrict__ count) {
+__global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long long *__restrict__ mask, int n, const int *__restrict__ n_dev,
+                                                           int pitch, unsigned char *__restrict__ keep, int *__restrict__ count) {
   extern __shared__ unsigned long long removed[];  // col_blocks words
+  if (n_dev) n = min(n, max(*n_dev, 0));
+  const int col_blocks = (n + 63) / 64;
   __shared__ unsigned long long s_diag[64];
   __shared__ unsigned long long s_keepbits;
   __shared__ int s_total;
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long l
   for (int c = 0; c < col_blocks; ++c) {
     const int base = c * 64;
     const int nb = min(64, n - base);
-    if (t < nb) s_diag[t] = mask[(size_t)(base + t) * col_blocks + c];
+    if (t < nb) s_diag[t] = mask[(size_t)(base + t) * pitch + c];
     __syncthreads();
     if (t == 0) {
       unsigned long long rem = removed[c], kept = 0;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long l
       while (k) {
         const int i = __ffsll((long long)k) - 1;
         k &= k - 1;
-        acc |= mask[(size_t)(base + i) * col_blocks + w];
+        acc |= mask[(size_t)(base + i) * pitch + w];
       }
       removed[w] = acc;
     }
@@ -167,8 +173,8 @@ extern "C" int64_t ape_nms_workspace_bytes(int n) {
   return (int64_t)n * cb * 8;
 }
 
-extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *workspace, uint8_t *keep,
-                              int *count, void *stream) {
+static int nms_launch(const float *boxes_sorted, int n, const int *n_dev, float iou_threshold, void *workspace, uint8_t *keep,
+                      int *count, void *stream) {
   if (n < 0) return fail(APE_ERR_INVALID_ARG, "nms: n=%d", n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (n == 0) {
@@ -179,7 +185,8 @@ extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_thresh
   if (reinterpret_cast<uintptr_t>(boxes_sorted) & 15) return fail(APE_ERR_INVALID_ARG, "nms: boxes must be 16-byte aligned");
   const int cb = (n + 63) / 64;
   if ((size_t)cb * 8 > 200 * 1024) return fail(APE_ERR_UNSUPPORTED, "nms: n=%d too large for the single-CTA scan", n);
-  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes_sorted), n, iou_threshold,
+  if (n_dev) cudaMemsetAsync(keep, 0, (size_t)n, st);  // entries past *n_dev are never visited
+  nms_mask_kernel<<<dim3(cb, cb), 64, 0, st>>>(reinterpret_cast<const float4 *>(boxes_sorted), n, n_dev, iou_threshold,
                                                reinterpret_cast<unsigned long long *>(workspace), cb);
   if (int rc = check_launch("nms_mask_kernel")) return rc;
   const size_t smem = (size_t)cb * 8 * (1 + 2 * 64);
@@ -188,7 +195,7 @@ extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_thresh
       cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail((int)e, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    nms_scan_kernel<<<1, 1024, smem, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
+    nms_scan_kernel<<<1, 1024, smem, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, n_dev, cb, keep, count);
     return check_launch("nms_scan_kernel");
   }
   const size_t smem_big = (size_t)cb * 8;
@@ -196,6 +203,17 @@ extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_thresh
     cudaError_t e = cudaFuncSetAttribute(nms_scan_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
     if (e != cudaSuccess) return fail((int)e, "nms: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
-  nms_scan_big_kernel<<<1, 256, smem_big, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, cb, keep, count);
+  nms_scan_big_kernel<<<1, 256, smem_big, st>>>(reinterpret_cast<const unsigned long long *>(workspace), n, n_dev, cb, keep, count);
   return check_launch("nms_scan_kernel");
+}
+
+extern "C" int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *workspace, uint8_t *keep,
+                              int *count, void *stream) {
+  return nms_launch(boxes_sorted, n, nullptr, iou_threshold, workspace, keep, count, stream);
+}
+
+extern "C" int ape_nms_sorted_dev(const float *boxes_sorted, int n_max, const int *n_dev, float iou_threshold, void *workspace,
+                                  uint8_t *keep, int *count, void *stream) {
+  if (!n_dev) return fail(APE_ERR_NULL_PTR, "nms: null n_dev");
+  return nms_launch(boxes_sorted, n_max, n_dev, iou_threshold, workspace, keep, count, stream);
 }

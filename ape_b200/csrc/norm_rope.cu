@@ -215,45 +215,78 @@ layernorm_ex_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y,
   }
 }
 
-// Wide rows (C > 1024, e.g. the 2730-wide SwiGLU hidden): same contract, but the row is re-read from
-// L1/L2 for the variance and normalisation passes instead of being held in 128 registers per lane —
-// 8 resident warps per SM could not cover HBM latency.
+// Wide rows (1024 < C <= 4096, e.g. the 2730-wide SwiGLU hidden): one CTA of 256 threads per row, each thread keeps
+// up to two 8-element vectors in registers, statistics through warp shuffles + 8 shared-memory partials; the row
+// makes exactly one trip in and one trip out.
+__device__ __forceinline__ float block_sum_256(float v, float *s_part) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // s_part may still be read from the previous reduction
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += s_part[i];
+  return t;
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 layernorm_wide_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy,
                       const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ row_map,
                       int rows, int C, float eps) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const TI *xr = x + (size_t)warp * ldx;
+  __shared__ float s_part[8];
+  const int row = blockIdx.x;
+  const bool wb_aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  const TI *xr = x + (size_t)row * ldx;
   const int nvec = (C + 7) >> 3;
+  float v[2][8];
   float sum = 0.f;
-  for (int j = lane; j < nvec; j += 32) {
-    float v[8];
-    load8<TI>(xr + 8 * j, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sum += (8 * j + k < C) ? v[k] : 0.f;
-  }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
-  for (int j = lane; j < nvec; j += 32) {
-    float v[8];
-    load8<TI>(xr + 8 * j, v);
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    if (j < nvec) {
+      load8<TI>(xr + 8 * j, v[i]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float d = (8 * j + k < C) ? v[k] - mean : 0.f;
-      sq += d * d;
+      for (int k = 0; k < 8; ++k) {
+        if (8 * j + k >= C) v[i][k] = 0.f;
+        sum += v[i][k];
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-  TO *yr = y + (size_t)(row_map ? row_map[warp] : warp) * ldy;
-  for (int j = lane; j < nvec; j += 32) {
-    float v[8], o[8];
-    load8<TI>(xr + 8 * j, v);
+  const float mean = block_sum_256(sum, s_part) / (float)C;
+  float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      o[k] = (8 * j + k < C) ? (v[k] - mean) * rstd * __ldg(w + 8 * j + k) + __ldg(b + 8 * j + k) : 0.f;
-    store8<TO>(yr + 8 * j, o);
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    if (j < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = (8 * j + k < C) ? v[i][k] - mean : 0.f;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum_256(sq, s_part) / (float)C + eps);
+  TO *yr = y + (size_t)(row_map ? row_map[row] : row) * ldy;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    if (j < nvec) {
+      float o[8];
+      if (8 * j + 8 <= C && wb_aligned) {
+        float ww[8], bb[8];
+        load8<float>(w + 8 * j, ww);
+        load8<float>(b + 8 * j, bb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v[i][k] - mean) * rstd * ww[k] + bb[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          o[k] = (8 * j + k < C) ? (v[i][k] - mean) * rstd * __ldg(w + 8 * j + k) + __ldg(b + 8 * j + k) : 0.f;
+      }
+      store8<TO>(yr + 8 * j, o);
+    }
   }
 }
 
@@ -287,12 +320,13 @@ template <typename TI, typename TO>
 int launch_ln(const void *x, long long ldx, void *y, long long ldy, const float *w, const float *b, const int *row_map,
               int rows, int C, float eps, cudaStream_t st) {
   const int blocks = (rows + 7) / 8;
-  if (C <= 1024 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0)
+  const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+  if (C <= 256 && aligned)
+    layernorm_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+  else if (C <= 1024 && aligned)
     layernorm_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
-  else if (x == y)  // in place: the single-read register variant is required
-    layernorm_kernel<TI, TO, 16><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
-  else
-    layernorm_wide_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+  else  // one CTA per row, row held in registers (also valid in place)
+    layernorm_wide_kernel<TI, TO><<<rows, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
   return check_launch("layernorm_kernel");
 }
 

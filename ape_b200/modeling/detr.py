@@ -243,6 +243,9 @@ class DeformableDETRSegmVL(nn.Module):
         self.profile_stages = False   # record CUDA-event stage times of the last forward in self.stage_ms
         self.use_cuda_graphs = False  # capture the static stages once per input geometry (16-bit engine mode)
         self._geo_cache, self._graph_cache = {}, {}
+        # static-shape final selection (one host sync per batch) for up to this many (query, class) pairs above the
+        # score threshold; more than that falls back to the dynamic path.  0 disables.
+        self.static_inference_cap = 8192
 
     # -- plumbing ----------------------------------------------------------------------------------
     @property
@@ -404,7 +407,11 @@ class DeformableDETRSegmVL(nn.Module):
             raise NotImplementedError("ape_b200: mask / semantic / panoptic heads are the next §8 rows; construct "
                                       "with test_mask_on=False, semantic_on=False, panoptic_on=False (boxes only)")
         mark("decode")
-        results = self.inference(box_cls, box_pred, image_sizes)
+        results = None
+        if do_postprocess and low and self.static_inference_cap > 0:
+            results = self._inference_static(box_cls, box_pred, image_sizes)  # CPU Instances, one host sync (None: overflow)
+        if results is None:
+            results = self.inference(box_cls, box_pred, image_sizes)
         if not do_postprocess:
             return results, None, None
         out = []
@@ -497,6 +504,54 @@ class DeformableDETRSegmVL(nn.Module):
             dst.copy_(src)
         graph.replay()
         return static_out
+
+    def _inference_static(self, box_cls, box_pred, image_sizes):
+        """`inference` (:759-810 + fast_rcnn.py:97-201) with static shapes: at most `static_inference_cap` (query, class)
+        pairs above the score threshold are compacted with nonzero_static (same row-major order as `.nonzero()`),
+        class-aware NMS runs on the padded list with the true count passed on the device, and the first top-k
+        survivors are packed into one tensor.  ONE device->host copy + synchronisation per batch instead of four
+        per image; if more pairs pass the threshold than the cap, returns None and the caller takes `inference`."""
+        cap, topk = int(self.static_inference_cap), int(self.test_topk_per_image)
+        if topk < 0:
+            return None
+        packs = []
+        for b, (h, w) in enumerate(image_sizes):
+            scores = box_cls[b].float().sigmoid()                                           # [Q, N] (bg column dropped again, :772)
+            xyxy = box_cxcywh_to_xyxy(box_pred[b].float())
+            boxes = torch.stack((xyxy[:, 0] * float(w), xyxy[:, 1] * float(h), xyxy[:, 2] * float(w), xyxy[:, 3] * float(h)), dim=-1)
+            valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)     # fast_rcnn.py:120-123
+            qmap = valid.cumsum(0) - 1                                                       # row index after the filter
+            boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
+                                 boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1)
+            mask = (scores > self.test_score_thresh) & valid[:, None]
+            n = mask.sum().to(torch.int32).reshape(1)
+            N = scores.shape[1]
+            flat = torch.nonzero_static(mask.flatten(), size=cap, fill_value=0)[:, 0]
+            slot_ok = torch.arange(cap, device=flat.device) < n
+            q, c = flat // N, flat % N
+            cb = boxes[q]
+            cs = torch.where(slot_ok, scores.flatten()[flat], scores.new_full((), float("-inf")))
+            # batched_nms: boxes + class * (max coordinate over the candidates + 1), scores sorted descending
+            mx = torch.where(slot_ok[:, None], cb, cb.new_full((), float("-inf"))).max()
+            nb = cb + (c.to(cb) * (mx + 1))[:, None]
+            order = cs.sort(0, descending=True)[1]
+            keep, _ = ops.nms_sorted_mask(nb.index_select(0, order).contiguous(), self.test_nms_thresh, n_valid=n)
+            pos = torch.nonzero_static(keep, size=topk, fill_value=0)[:, 0]
+            nk = keep.sum().clamp(max=topk).to(torch.float32)
+            sel = order[pos]
+            packs.append(torch.cat([cb[sel], cs[sel, None], c[sel, None].float(), qmap[q[sel], None].float(),
+                                    torch.stack([n[0].float(), nk]).expand(topk, 2)], dim=1))  # [topk, 9]
+        host = torch.stack(packs).to("cpu")  # the one synchronising copy
+        results = []
+        for b, (h, w) in enumerate(image_sizes):
+            p = host[b]
+            n, nk = int(p[0, 7].item()), int(p[0, 8].item())
+            if n > cap:
+                return None
+            p = p[:nk]
+            results.append(Instances((h, w), pred_boxes=Boxes(p[:, :4].contiguous()), scores=p[:, 4].contiguous(),
+                                     pred_classes=p[:, 5].to(torch.int64), query_index=p[:, 6].to(torch.int64)))
+        return results
 
     def inference(self, box_cls, box_pred, image_sizes):
         """:759-810 + fast_rcnn.py:40-95."""

@@ -312,9 +312,10 @@ def vlf_pool(v, qa, qc, stable_softmax_2d=True):
     return part[..., :C] / part[..., C:]
 
 
-def nms_sorted_mask(sorted_boxes, iou_threshold):
+def nms_sorted_mask(sorted_boxes, iou_threshold, n_valid=None):
     """Greedy NMS over boxes ALREADY sorted by descending score: uint8 keep mask [n] (static shape, no host
-    synchronisation: usable inside CUDA-graph capture) and the int32 [1] number of survivors."""
+    synchronisation: usable inside CUDA-graph capture) and the int32 [1] number of survivors.
+    n_valid: optional int32 [1] device tensor; only the first n_valid boxes are real (keep = 0 for the rest)."""
     _require(sorted_boxes.is_cuda and sorted_boxes.dim() == 2 and sorted_boxes.shape[1] == 4 and
              sorted_boxes.dtype == torch.float32 and sorted_boxes.is_contiguous(), "nms: boxes must be contiguous CUDA fp32 [n,4]")
     n = sorted_boxes.shape[0]
@@ -324,8 +325,13 @@ def nms_sorted_mask(sorted_boxes, iou_threshold):
         return keep, count
     ws = torch.empty((int(_lib.lib.ape_nms_workspace_bytes(n)),), dtype=torch.uint8, device=sorted_boxes.device)
     with torch.cuda.device(sorted_boxes.device), _timed(("nms", n)):
-        rc = _lib.lib.ape_nms_sorted(sorted_boxes.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
-                                     count.data_ptr(), _lib.current_stream_ptr())
+        if n_valid is None:
+            rc = _lib.lib.ape_nms_sorted(sorted_boxes.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
+                                         count.data_ptr(), _lib.current_stream_ptr())
+        else:
+            _require(n_valid.is_cuda and n_valid.dtype == torch.int32 and n_valid.numel() == 1, "nms: n_valid must be int32 [1]")
+            rc = _lib.lib.ape_nms_sorted_dev(sorted_boxes.data_ptr(), n, n_valid.data_ptr(), float(iou_threshold), ws.data_ptr(),
+                                             keep.data_ptr(), count.data_ptr(), _lib.current_stream_ptr())
     _lib.check(rc, "ape_nms_sorted")
     return keep, count
 

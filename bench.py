@@ -286,6 +286,14 @@ def model_bench(args, rank, local_rank, world):
     for (t, x, y) in events:
         own_ms[t[0]] = own_ms.get(t[0], 0.0) + x.elapsed_time(y) / prof_steps
     own_ms = {k: round(v, 3) for k, v in sorted(own_ms.items(), key=lambda kv: -kv[1])}
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):  # per-shape table for tuning (not part of the line)
+        detail = {}
+        for (t, x, y) in events:
+            d = detail.setdefault(" ".join(str(v) for v in t), [0.0, 0])
+            d[0] += x.elapsed_time(y) / prof_steps
+            d[1] += 1.0 / prof_steps
+        json.dump({k: [round(v[0], 4), round(v[1], 2)] for k, v in sorted(detail.items(), key=lambda kv: -kv[1][0])},
+                  open(os.path.join(ROOT, "gpurun_out", "own_kernel_detail.json"), "w"), indent=0)
     enc = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] == t[2]]
     dec = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] != t[2]]
     # e2e: pinned host image in, detections out on the host (the model's public call does both)

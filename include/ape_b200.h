@@ -187,6 +187,10 @@ int ape_vlf_pool(const void *v, const float *qa, const float *qc, void *workspac
 int64_t ape_nms_workspace_bytes(int n);
 int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *workspace, uint8_t *keep, int *count,
                    void *stream);
+/* Same, for static-shape callers (CUDA graphs): buffers are sized for n_max boxes, only the first min(n_max, *n_dev)
+ * (device int) are real; keep[i] = 0 for the rest.  workspace: ape_nms_workspace_bytes(n_max). */
+int ape_nms_sorted_dev(const float *boxes_sorted, int n_max, const int *n_dev, float iou_threshold, void *workspace,
+                       uint8_t *keep, int *count, void *stream);
 
 #ifdef __cplusplus
 }

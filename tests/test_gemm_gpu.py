@@ -87,7 +87,7 @@ def test_vit_swiglu_shape_16bit_out(ops, dtype):
     assert ((pad == 9.0) | (pad == 0.0)).all()
 
 
-@pytest.mark.parametrize("tile", [128, 256, 128 | 0x1000, 256 | 0x1000])  # 0x1000: single-CTA (no cluster multicast)
+@pytest.mark.parametrize("tile", [128, 256, 128 | 0x1000, 256 | 0x1000, 128 | 0x2000, 256 | 0x2000, 128 | 0x8000, 256 | 0x8000])  # default: cluster of 2 (multicast); 0x1000: single CTA; 0x2000: CTA-pair MMA; 0x8000: cluster of 4
 def test_tma_store_epilogue_edges(ops, tile):
     # M and N both ragged, bias + relu + residual, 16-bit output with an aligned pitch
     M, N, K = 777, 840, 192
@@ -100,7 +100,7 @@ def test_tma_store_epilogue_edges(ops, tile):
     torch.testing.assert_close(y.float(), ref_linear(x, w, b, "relu", res), rtol=4e-3, atol=4e-3)
 
 
-@pytest.mark.parametrize("M", [129, 256, 383, 4096])
+@pytest.mark.parametrize("M", [129, 256, 383, 640, 4096])
 @pytest.mark.parametrize("tile", [128, 256])
 def test_cluster_pairs_with_odd_row_block_counts(ops, M, tile):
     """Clusters of two CTAs share the weight tile by TMA multicast; an odd number of 128-row blocks leaves the
@@ -113,6 +113,8 @@ def test_cluster_pairs_with_odd_row_block_counts(ops, M, tile):
     torch.testing.assert_close(y, ref_linear(x, w, b), rtol=2e-4, atol=2e-4)
     y1 = ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile | 0x1000)
     assert torch.equal(y, y1)  # same accumulation order with and without the cluster
+    for flag in (0x2000, 0x8000):  # CTA-pair MMA (cta_group::2) and cluster of 4
+        assert torch.equal(y, ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile | flag))
 
 
 def test_many_tiles_per_cta_ring_wraparound(ops):
