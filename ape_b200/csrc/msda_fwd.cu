@@ -44,6 +44,7 @@ struct MsdaParams {
   int B, S, H, L, Q, P;
   int ht_log2;  // log2(heads per CTA)
   int ref_dim;  // fused: 2 or 4
+  int vec4;     // fused: P == 4 and offsets / logits rows allow 16 / 8-byte vector loads
 };
 
 __host__ __device__ constexpr int threads_for(int lpr) { return lpr >= 4 ? 256 : 64 * lpr; }
@@ -67,8 +68,8 @@ struct __align__(16) Sample {
   float hh_a, lh_a, lw;
 };
 
-__device__ __forceinline__ Sample make_sample(float x, float y, float a, int Hl, int Wl, int start,
-                                              int h, int H, int row_bytes) {
+// core of make_sample: corner (y0, x0) inside the level, flags and weights (off_flags holds the flags only)
+__device__ __forceinline__ Sample make_sample_xy(float x, float y, float a, int Hl, int Wl, int &y0, int &x0) {
   const float h_im = y * (float)Hl - 0.5f;
   const float w_im = x * (float)Wl - 0.5f;
   const bool in_range = h_im > -1.f && w_im > -1.f && h_im < (float)Hl && w_im < (float)Wl;
@@ -80,15 +81,47 @@ __device__ __forceinline__ Sample make_sample(float x, float y, float a, int Hl,
   const bool hl_ok = in_range && h_low >= 0, hh_ok = in_range && h_low < Hl - 1;
   const bool wl_ok = w_low >= 0, wh_ok = w_low < Wl - 1;
   const int hc = min(max(h_low, -1), Hl - 1), wc = min(max(w_low, -1), Wl - 1);
-  const int y0 = max(hc, 0), y1 = min(hc + 1, Hl - 1);
-  const int x0 = max(wc, 0), x1 = min(wc + 1, Wl - 1);
+  y0 = max(hc, 0);
+  x0 = max(wc, 0);
+  const int y1 = min(hc + 1, Hl - 1), x1 = min(wc + 1, Wl - 1);
   Sample r;
-  r.off_flags = ((start + y0 * Wl + x0) * H + h) * row_bytes;
-  r.off_flags |= (x1 != x0 ? 1 : 0) | (y1 != y0 ? 2 : 0) | (wl_ok ? 4 : 0) | (wh_ok ? 8 : 0);
+  r.off_flags = (x1 != x0 ? 1 : 0) | (y1 != y0 ? 2 : 0) | (wl_ok ? 4 : 0) | (wh_ok ? 8 : 0);
   r.hh_a = hl_ok ? hh * a : 0.f;
   r.lh_a = hh_ok ? lh * a : 0.f;
   r.lw = in_range ? lw : 0.f;
   return r;
+}
+
+__device__ __forceinline__ Sample make_sample(float x, float y, float a, int Hl, int Wl, int start,
+                                              int h, int H, int row_bytes) {
+  int y0, x0;
+  Sample r = make_sample_xy(x, y, a, Hl, Wl, y0, x0);
+  r.off_flags |= ((start + y0 * Wl + x0) * H + h) * row_bytes;
+  return r;
+}
+
+// 4 consecutive elements / 4 consecutive (x, y) pairs of the offsets / logits tensors as fp32 (one or two vector
+// loads instead of 4 / 8 scalar ones; the host checks the alignment and passes vec4 = true).
+template <typename TO>
+__device__ __forceinline__ void load4(const TO *p, float *f) {
+  if constexpr (sizeof(TO) == 4) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    float g[8];
+    Elem<TO>::unpack(make_uint4(v.x, v.y, 0u, 0u), g);
+    f[0] = g[0]; f[1] = g[1]; f[2] = g[2]; f[3] = g[3];
+  }
+}
+template <typename TO>
+__device__ __forceinline__ void load8(const TO *p, float *f) {
+  if constexpr (sizeof(TO) == 4) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    Elem<TO>::unpack(*reinterpret_cast<const uint4 *>(p), f);
+  }
 }
 
 // Phase 2: gather + accumulate + store for one lane.  The host guarantees P % U == 0.
@@ -238,12 +271,25 @@ msda_fused_fwd_kernel(const MsdaParams p) {
 
   // stage logits (coalesced), then one thread per row reduces max / sum(exp)
   const float inv_lp = 1.f / (float)LP, inv_p = 1.f / (float)p.P;
-  for (int i = tid; i < R * LP; i += NT) {
-    const int r = fast_div(i, inv_lp), s = i - r * LP;
-    const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    float v = 0.f;
-    if (q < p.Q) v = EO::load1(logits + ((size_t)b * p.Q + q) * p.logit_row_stride + (size_t)h * LP + s);
-    s_logit[r * lps + s] = v;
+  const bool vec4 = p.vec4 != 0;  // P == 4 and 8/16-byte aligned rows: one thread per (row, level), vector loads
+  if (vec4) {
+    const float inv_l = 1.f / (float)p.L;
+    for (int i = tid; i < R * p.L; i += NT) {
+      const int r = fast_div(i, inv_l), l = i - r * p.L;
+      const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (q < p.Q) load4<TO>(logits + ((size_t)b * p.Q + q) * p.logit_row_stride + h * LP + l * 4, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_logit[r * lps + l * 4 + k] = v[k];
+    }
+  } else {
+    for (int i = tid; i < R * LP; i += NT) {
+      const int r = fast_div(i, inv_lp), s = i - r * LP;
+      const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+      float v = 0.f;
+      if (q < p.Q) v = EO::load1(logits + ((size_t)b * p.Q + q) * p.logit_row_stride + (size_t)h * LP + s);
+      s_logit[r * lps + s] = v;
+    }
   }
   __syncthreads();
   if (tid < R) {
@@ -251,36 +297,70 @@ msda_fused_fwd_kernel(const MsdaParams p) {
     float m = row[0];
     for (int s = 1; s < LP; ++s) m = fmaxf(m, row[s]);
     float sum = 0.f;
-    for (int s = 0; s < LP; ++s) sum += expf(row[s] - m);
+    for (int s = 0; s < LP; ++s) sum += __expf(row[s] - m);
     s_max[tid] = m;
     s_rinv[tid] = 1.f / sum;
   }
   __syncthreads();
 
-  for (int i = tid; i < R * LP; i += NT) {
-    const int r = fast_div(i, inv_lp), s = i - r * LP;
-    const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    Sample rec = {0, 0.f, 0.f, 0.f};
-    if (q < p.Q) {
-      const int l = fast_div(s, inv_p);
-      const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1];
-      const size_t bq = (size_t)b * p.Q + q;
-      const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
-      const float a = expf(s_logit[r * lps + s] - s_max[r]) * s_rinv[r];
-      const float *rp = p.ref + (bq * p.L + l) * p.ref_dim;
-      float x, y;
-      if (p.ref_dim == 2) {
-        // multi_scale_deform_attn.py:298-303: ref + off / (W_l, H_l)
-        x = rp[0] + o.x / (float)Wl;
-        y = rp[1] + o.y / (float)Hl;
-      } else {
-        // multi_scale_deform_attn.py:304-311: ref_xy + off / P * ref_wh * 0.5
-        x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
-        y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
+  if (vec4) {
+    const float inv_l = 1.f / (float)p.L;
+    for (int i = tid; i < R * p.L; i += NT) {
+      const int r = fast_div(i, inv_l), l = i - r * p.L;
+      const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+      Sample *dst = s_rec + r * lps + l * 4;
+      if (q >= p.Q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[k] = Sample{0, 0.f, 0.f, 0.f};
+        continue;
       }
-      rec = make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR * 16);
+      const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1], start = s_lvl[l * 3 + 2];
+      const size_t bq = (size_t)b * p.Q + q;
+      float o[8];
+      load8<TO>(offs + bq * p.offs_row_stride + (h * LP + l * 4) * 2, o);
+      const float *rp = p.ref + (bq * p.L + l) * p.ref_dim;
+      const float mx = s_max[r], ri = s_rinv[r];
+      float sx, sy;  // loc = ref + off * (sx, sy)
+      if (p.ref_dim == 2) {  // multi_scale_deform_attn.py:298-303: ref + off / (W_l, H_l)
+        sx = 1.f / (float)Wl;
+        sy = 1.f / (float)Hl;
+      } else {               // :304-311: ref_xy + off / P * ref_wh * 0.5
+        sx = rp[2] * 0.125f;
+        sy = rp[3] * 0.125f;
+      }
+      const float rx = rp[0], ry = rp[1];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = __expf(s_logit[r * lps + l * 4 + k] - mx) * ri;
+        dst[k] = make_sample(fmaf(o[2 * k], sx, rx), fmaf(o[2 * k + 1], sy, ry), a, Hl, Wl, start, h, p.H, LPR * 16);
+      }
     }
-    s_rec[r * lps + s] = rec;
+  } else {
+    for (int i = tid; i < R * LP; i += NT) {
+      const int r = fast_div(i, inv_lp), s = i - r * LP;
+      const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
+      Sample rec = {0, 0.f, 0.f, 0.f};
+      if (q < p.Q) {
+        const int l = fast_div(s, inv_p);
+        const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1];
+        const size_t bq = (size_t)b * p.Q + q;
+        const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
+        const float a = __expf(s_logit[r * lps + s] - s_max[r]) * s_rinv[r];
+        const float *rp = p.ref + (bq * p.L + l) * p.ref_dim;
+        float x, y;
+        if (p.ref_dim == 2) {
+          // multi_scale_deform_attn.py:298-303: ref + off / (W_l, H_l)
+          x = rp[0] + o.x / (float)Wl;
+          y = rp[1] + o.y / (float)Hl;
+        } else {
+          // multi_scale_deform_attn.py:304-311: ref_xy + off / P * ref_wh * 0.5
+          x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
+          y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
+        }
+        rec = make_sample(x, y, a, Hl, Wl, s_lvl[l * 3 + 2], h, p.H, LPR * 16);
+      }
+      s_rec[r * lps + s] = rec;
+    }
   }
   __syncthreads();
   {
@@ -289,122 +369,224 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   }
 }
 
-// Fused, spatially tiled variant for self-attention over the feature pyramid itself (Q == S, query i IS
-// pixel i of the level structure — the encoder).  Same arithmetic as msda_fused_fwd_kernel; only the
-// work -> CTA mapping changes: a persistent CTA owns a contiguous run of 16x16-pixel super-tiles of one
-// (image, head, level) and walks each in 8x4 / 8x8 sub-tiles, so the texels its queries sample (own
-// neighbourhood at every level) stay resident in that SM's L1 instead of being re-fetched from L2 by
-// whichever SM happens to run the next strip of the raster order.
-template <typename T, typename TO, int LPR, int U>
-__global__ void __launch_bounds__(threads_for(LPR))
-msda_fused_tiled_kernel(const MsdaParams p, int units_per_cta, int total_units) {
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder kernel: self-attention over the feature pyramid itself (Q == S, query i IS pixel i of the level structure,
+// deformable_transformer_vl.py:69-121 -> multi_scale_deform_attn.py:283-348), 16-bit value.
+//
+// Why a separate kernel: the generic kernels gather 4 x 64-byte corner rows per sample through L1 — 55.9 M rows per
+// call at 1024^2 — and are bound by L1 wavefronts (one 128-byte line per 64-byte row) and L1 misses, not by HBM.
+// Here the pyramid is cut into REGIONS of 16x16 level-0 pixels; a region owns the 256 + 64 + 16 + 4 + 1 queries of
+// all levels that lie over it, and all of them sample around the same spot of every level.  A work unit =
+// (image, region, head):
+//   1. stage, per level, the window of value rows of this head around the region (halo kHalo pixels; 64 B per pixel,
+//      pixel-major, so the two x-corners of a sample are 128 contiguous bytes) into shared memory with cp.async;
+//   2. per sub-batch of 128 queries: softmax + sampling-location arithmetic -> 16-byte sample records whose offset
+//      points into the shared-memory window (or, for the rare sample that leaves the window, into global memory);
+//   3. gather: 8 lanes per query — lanes 0-3 own the 4 x 16 B chunks of the LEFT corner pixel, lanes 4-7 of the RIGHT
+//      one — so a quarter-warp reads 128 contiguous bytes per corner row: one conflict-free shared-memory
+//      wavefront instead of two L1 lines.  fp32 accumulation; the two halves are combined with one shuffle at the end.
+// Persistent CTAs (one per SM, 512 threads) stride over the units; the 8 heads of a region are adjacent units, i.e.
+// run at the same time on different SMs and share their L2 lines.  Same arithmetic per sample as the generic kernel
+// (make_sample); results differ from it only by fp32 summation order.
+constexpr int kRegion = 16;    // region edge in level-0 pixels
+constexpr int kHalo = 6;       // window halo in pixels of each level
+constexpr int kSelfLevels = 5; // 16 >> l must stay >= 1
+constexpr int kSub = 128;      // queries per sub-batch (bounds the record buffer)
+constexpr int kSelfThreads = 512;
+
+struct SelfGeom {  // host-computed, passed by value
+  int L, P, H;
+  int Hl[kSelfLevels], Wl[kSelfLevels], start[kSelfLevels];
+  int side[kSelfLevels];   // window edge (pixels) at level l
+  int woff[kSelfLevels + 1];  // window start in 16-byte units; [L] = total
+  int qcum[kSelfLevels + 1];  // queries of a region up to level l (exclusive prefix); [L] = total
+  int regions_x, regions_y;
+  int rec_off16, logit_off16, stat_off16;  // shared-memory layout (16-byte units)
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds_v4(unsigned addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// record: off_flags = (offset in 16-byte units) << 5 | global << 4 | flags (1: x1 distinct, 2: y1 distinct,
+// 4: left corners valid, 8: right corners valid); offset is relative to the shared-memory window base or,
+// with the global bit, to the value tensor of the image.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(kSelfThreads, 1)
+msda_self_kernel(const MsdaParams p, const SelfGeom g, int total_units) {
+  using E = Elem<T>;
   using EO = Elem<TO>;
-  constexpr int NT = threads_for(LPR);
-  constexpr int R = NT / LPR;
-  constexpr int SW = 8, SH = R / SW;  // sub-tile: 8 wide, 4 (fp32) or 8 (16-bit) rows of pixels
-  constexpr int TS = 16;              // super-tile edge in pixels
-  static_assert(R % SW == 0 && TS % SH == 0, "tile geometry");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_lvl[kMaxLevels * 3];
-  __shared__ int s_dy[kMaxLevels];
-  __shared__ int s_tiles[kMaxLevels + 1];
-  __shared__ float s_max[R], s_rinv[R];
-
-  const int LP = p.L * p.P;
-  const int lps = LP | 1;
-  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw);
-  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)R * lps * sizeof(Sample));
-
-  const int tid = threadIdx.x;
-  if (tid < p.L) {
-    s_lvl[tid * 3 + 0] = (int)p.shapes[tid * 2 + 0];
-    s_lvl[tid * 3 + 1] = (int)p.shapes[tid * 2 + 1];
-    s_lvl[tid * 3 + 2] = (int)p.starts[tid];
-    s_dy[tid] = (int)p.shapes[tid * 2 + 1] * p.H * LPR * 16;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int l = 0; l < p.L; ++l) {
-      s_tiles[l] = acc;
-      acc += ((s_lvl[l * 3] + TS - 1) / TS) * ((s_lvl[l * 3 + 1] + TS - 1) / TS);
-    }
-    s_tiles[p.L] = acc;
-  }
-  __syncthreads();
-  const int tiles = s_tiles[p.L];
-  const float inv_lp = 1.f / (float)LP, inv_p = 1.f / (float)p.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int LP = g.L * g.P, lps = LP | 1;
+  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw + (size_t)g.rec_off16 * 16);
+  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)g.logit_off16 * 16);
+  float *s_max = reinterpret_cast<float *>(smem_raw + (size_t)g.stat_off16 * 16);
+  float *s_rinv = s_max + kSub;
+  const unsigned win_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const int nq_total = g.qcum[g.L];
+  const int regions = g.regions_x * g.regions_y;
   const TO *offs = reinterpret_cast<const TO *>(p.loc);
   const TO *logits = reinterpret_cast<const TO *>(p.attn);
 
-  const int u_end = min(total_units, (int)(blockIdx.x + 1) * units_per_cta);
-  for (int u = blockIdx.x * units_per_cta; u < u_end; ++u) {
-    // unit -> (image, head, level, super-tile); tiles of one (image, head) are consecutive
-    const int b = u / (p.H * tiles);
-    const int rem = u - b * p.H * tiles;
-    const int h = rem / tiles, t = rem - h * tiles;
-    int l = 0;
-    while (l + 1 < p.L && t >= s_tiles[l + 1]) ++l;
-    const int Hl = s_lvl[l * 3], Wl = s_lvl[l * 3 + 1], start = s_lvl[l * 3 + 2];
-    const int txn = (Wl + TS - 1) / TS;
-    const int tl = t - s_tiles[l];
-    const int ty0 = (tl / txn) * TS, tx0 = (tl % txn) * TS;
-#pragma unroll 1
-    for (int sub = 0; sub < (TS / SH) * (TS / SW); ++sub) {
-      const int y0 = ty0 + (sub / (TS / SW)) * SH, x0 = tx0 + (sub % (TS / SW)) * SW;
-      if (y0 >= Hl || x0 >= Wl) continue;  // CTA-uniform
-      // stage logits (one 2*LP-byte run per query), then per-row softmax statistics
-      for (int i = tid; i < R * LP; i += NT) {
-        const int r = fast_div(i, inv_lp), s = i - r * LP;
-        const int qy = y0 + r / SW, qx = x0 + r % SW;
-        float v = 0.f;
-        if (qy < Hl && qx < Wl) {
-          const size_t bq = (size_t)b * p.Q + start + qy * Wl + qx;
-          v = EO::load1(logits + bq * p.logit_row_stride + (size_t)h * LP + s);
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    const int b = unit / (regions * g.H);
+    const int rem = unit - b * regions * g.H;
+    const int region = rem / g.H, h = rem - region * g.H;
+    const int X0 = (region % g.regions_x) * kRegion, Y0 = (region / g.regions_x) * kRegion;
+    const char *vimg = reinterpret_cast<const char *>(p.value) + (size_t)b * p.S * g.H * 64;
+
+    // ---- 1. stage the windows (all levels) of head h ------------------------------------------------------
+    __syncthreads();  // previous unit's gathers are done with the windows
+    for (int l = 0; l < g.L; ++l) {  // one thread per window pixel: 64 contiguous bytes = 4 cp.async
+      const int side = g.side[l], Hl = g.Hl[l], Wl = g.Wl[l];
+      const float inv_side = 1.f / (float)side;
+      const int wy_org = (Y0 >> l) - kHalo, wx_org = (X0 >> l) - kHalo;
+      unsigned char *wbase = smem_raw + (size_t)g.woff[l] * 16;
+      const char *lbase = vimg + ((size_t)g.start[l] * g.H + h) * 64;
+      for (int pix = tid; pix < side * side; pix += kSelfThreads) {
+        const int py = fast_div(pix, inv_side), px = pix - py * side;
+        const int y = wy_org + py, x = wx_org + px;
+        unsigned char *dst = wbase + pix * 64;
+        if (y >= 0 && y < Hl && x >= 0 && x < Wl) {
+          const char *src = lbase + (size_t)(y * Wl + x) * g.H * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) cp_async16(dst + c * 16, src + c * 16);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(dst + c * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        s_logit[r * lps + s] = v;
+      }
+    }
+
+    // ---- 2/3. sub-batches of queries ----------------------------------------------------------------------
+    for (int sub0 = 0; sub0 < nq_total; sub0 += kSub) {
+      const int nq = min(kSub, nq_total - sub0);
+      if (sub0 > 0) __syncthreads();  // records / logits of the previous sub-batch are no longer read
+      // one thread per (query, level): 4 logits / 4 (x, y) offsets per vector load (host guarantees P == 4)
+      const float inv_l = 1.f / (float)g.L;
+      for (int i = tid; i < nq * g.L; i += kSelfThreads) {
+        const int r = fast_div(i, inv_l), l = i - r * g.L;
+        const int j = sub0 + r;
+        int lq = 0;
+#pragma unroll
+        for (int k = 1; k < kSelfLevels; ++k) lq += (k < g.L && j >= g.qcum[k]) ? 1 : 0;
+        const int t = j - g.qcum[lq], sh = 4 - lq;  // region edge at level lq = 1 << sh
+        const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
+        const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
+        float v[4];
+        load4<TO>(logits + bq * p.logit_row_stride + h * LP + l * 4, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_logit[r * lps + l * 4 + k] = v[k];
       }
       __syncthreads();
-      if (tid < R) {
+      if (tid < nq) {
         const float *row = s_logit + tid * lps;
         float m = row[0];
         for (int s = 1; s < LP; ++s) m = fmaxf(m, row[s]);
         float sum = 0.f;
-        for (int s = 0; s < LP; ++s) sum += expf(row[s] - m);
+        for (int s = 0; s < LP; ++s) sum += __expf(row[s] - m);
         s_max[tid] = m;
         s_rinv[tid] = 1.f / sum;
       }
       __syncthreads();
-      for (int i = tid; i < R * LP; i += NT) {
-        const int r = fast_div(i, inv_lp), s = i - r * LP;
-        const int qy = y0 + r / SW, qx = x0 + r % SW;
-        Sample rec = {0, 0.f, 0.f, 0.f};
-        if (qy < Hl && qx < Wl) {
-          const int ls = fast_div(s, inv_p);
-          const int Hs = s_lvl[ls * 3], Ws = s_lvl[ls * 3 + 1];
-          const size_t bq = (size_t)b * p.Q + start + qy * Wl + qx;
-          const float2 o = EO::load2(offs + bq * p.offs_row_stride + ((size_t)h * LP + s) * 2);
-          const float a = expf(s_logit[r * lps + s] - s_max[r]) * s_rinv[r];
-          const float *rp = p.ref + (bq * p.L + ls) * p.ref_dim;
-          float x, y;
-          if (p.ref_dim == 2) {
-            x = rp[0] + o.x / (float)Ws;
-            y = rp[1] + o.y / (float)Hs;
-          } else {
-            x = rp[0] + o.x / (float)p.P * rp[2] * 0.5f;
-            y = rp[1] + o.y / (float)p.P * rp[3] * 0.5f;
-          }
-          rec = make_sample(x, y, a, Hs, Ws, s_lvl[ls * 3 + 2], h, p.H, LPR * 16);
+      for (int i = tid; i < nq * g.L; i += kSelfThreads) {
+        const int r = fast_div(i, inv_l), l = i - r * g.L;
+        const int j = sub0 + r;
+        int lq = 0;
+#pragma unroll
+        for (int k = 1; k < kSelfLevels; ++k) lq += (k < g.L && j >= g.qcum[k]) ? 1 : 0;
+        const int t = j - g.qcum[lq], sh = 4 - lq;
+        const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
+        const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
+        const int Hl = g.Hl[l], Wl = g.Wl[l], side = g.side[l];
+        float o[8];
+        load8<TO>(offs + bq * p.offs_row_stride + (h * LP + l * 4) * 2, o);
+        const float *rp = p.ref + (bq * g.L + l) * p.ref_dim;
+        const float mx = s_max[r], ri = s_rinv[r];
+        float sx, sy;
+        if (p.ref_dim == 2) {
+          sx = 1.f / (float)Wl;
+          sy = 1.f / (float)Hl;
+        } else {
+          sx = rp[2] * 0.125f;
+          sy = rp[3] * 0.125f;
         }
-        s_rec[r * lps + s] = rec;
+        const float rx = rp[0], ry = rp[1];
+        const int wy_org = (Y0 >> l) - kHalo, wx_org = (X0 >> l) - kHalo;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = __expf(s_logit[r * lps + l * 4 + k] - mx) * ri;
+          int y0, x0;
+          Sample rec = make_sample_xy(fmaf(o[2 * k], sx, rx), fmaf(o[2 * k + 1], sy, ry), a, Hl, Wl, y0, x0);
+          const int fl = rec.off_flags;
+          const int wy = y0 - wy_org, wx = x0 - wx_org;
+          if (wx >= 0 && wy >= 0 && wx + (fl & 1) < side && wy + ((fl >> 1) & 1) < side)
+            rec.off_flags = ((g.woff[l] + (wy * side + wx) * 4) << 5) | fl;                       // shared-memory window
+          else
+            rec.off_flags = ((((g.start[l] + y0 * Wl + x0) * g.H + h) * 4) << 5) | 16 | fl;       // global (16-byte units)
+          s_rec[r * lps + l * 4 + k] = rec;
+        }
       }
+      if (sub0 == 0) cp_async_wait_all_();  // windows landed (this thread's copies; the barrier covers the others')
       __syncthreads();
-      {
-        const int r = tid / LPR;
-        const int qy = y0 + r / SW, qx = x0 + r % SW;
-        gather_rows<T, LPR, U>(p, s_rec, s_dy, lps, b, (qy < Hl && qx < Wl) ? start + qy * Wl + qx : -1, h);
+
+      // ---- gather: 8 lanes per query ----
+      const int grp = lane >> 3, k = (lane >> 2) & 1, c = lane & 3;
+      for (int r0 = warp * 4; r0 < nq; r0 += (kSelfThreads / 32) * 4) {
+        const int rr = min(r0 + grp, nq - 1);
+        const bool active = r0 + grp < nq;
+        const Sample *row = s_rec + rr * lps;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 1
+        for (int l = 0; l < g.L; ++l) {
+          const unsigned dys = (unsigned)g.side[l] * 64u;              // window row pitch (bytes)
+          const unsigned dyg = (unsigned)g.Wl[l] * g.H * 64u;          // global row pitch (bytes)
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {  // P == 4 (host-checked)
+            const Sample sm = row[l * 4 + pp];
+            const unsigned f = (unsigned)sm.off_flags;
+            const unsigned dx = (f & 1u) & (unsigned)k, dy = (f >> 1) & 1u;
+            uint4 v0, v1;
+            if (!(f & 16u)) {
+              const unsigned a0 = win_base + ((f >> 5) << 4) + dx * 64u + c * 16u;
+              v0 = lds_v4(a0);
+              v1 = lds_v4(a0 + dy * dys);
+            } else {
+              const char *gp = vimg + ((size_t)(f >> 5) << 4) + dx * (unsigned)(g.H * 64) + c * 16;
+              v0 = ldg_nc_v4(reinterpret_cast<const uint4 *>(gp));
+              v1 = ldg_nc_v4(reinterpret_cast<const uint4 *>(gp + dy * dyg));
+            }
+            const float wx = k ? ((f & 8u) ? sm.lw : 0.f) : ((f & 4u) ? 1.f - sm.lw : 0.f);
+            const float w0 = sm.hh_a * wx, w1 = sm.lh_a * wx;
+            float f0[8], f1[8];
+            E::unpack(v0, f0);
+            E::unpack(v1, f1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w1, f1[i], fmaf(w0, f0[i], acc[i]));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+        if (active && k == 0) {
+          const int j = sub0 + rr;
+          int lq = 0;
+#pragma unroll
+          for (int kk = 1; kk < kSelfLevels; ++kk) lq += (kk < g.L && j >= g.qcum[kk]) ? 1 : 0;
+          const int t = j - g.qcum[lq], sh = 4 - lq;
+          const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
+          const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
+          stg_stream_v4(reinterpret_cast<uint4 *>(p.out) + (bq * g.H + h) * 4 + c, E::pack(acc));
+        }
       }
-      __syncthreads();  // smem is rewritten by the next sub-tile
     }
   }
 }
@@ -482,24 +664,6 @@ int launch_fused(const MsdaParams &p, cudaStream_t st) {
   dim3 grid((unsigned)(((p.Q + QT - 1) / QT) * (p.H >> p.ht_log2)), (unsigned)p.B);
   k<<<grid, NT, smem, st>>>(p);
   return check_launch("msda_fused_fwd_kernel");
-}
-
-// tile count of the level structure is only known on the device; bound it from S: every 16x16 super-tile
-// but the ragged edge ones holds 256 pixels, and a level adds at most (H/16 + W/16 + 1) ragged tiles.
-template <typename T, typename TO, int LPR, int U>
-int launch_fused_tiled(const MsdaParams &p, int total_tiles_per_head_image, cudaStream_t st) {
-  constexpr int NT = threads_for(LPR), R = NT / LPR;
-  const int lps = (p.L * p.P) | 1;
-  const size_t smem = (size_t)R * lps * 20;
-  auto k = msda_fused_tiled_kernel<T, TO, LPR, U>;
-  if (int rc = set_smem(k, smem)) return rc;
-  const int total_units = p.B * p.H * total_tiles_per_head_image;
-  int ctas = 148 * 4;
-  if (ctas > total_units) ctas = total_units;
-  const int per = (total_units + ctas - 1) / ctas;
-  ctas = (total_units + per - 1) / per;
-  k<<<ctas, NT, smem, st>>>(p, per, total_units);
-  return check_launch("msda_fused_tiled_kernel");
 }
 
 template <typename T, int U>
@@ -661,6 +825,11 @@ extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, cons
   p.value = value; p.shapes = shapes; p.starts = starts; p.loc = offsets; p.attn = logits; p.ref = ref;
   p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
   p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
+  {
+    const int eo = dtype_size(offs_dtype);
+    p.vec4 = P == 4 && (reinterpret_cast<uintptr_t>(offsets) & 15) == 0 && (offs_row_stride * eo) % 16 == 0 &&
+             (reinterpret_cast<uintptr_t>(logits) & (4 * eo - 1)) == 0 && (logit_row_stride * eo) % (4 * eo) == 0;
+  }
   const int row_bytes = D * dtype_size(dtype);
   const int lpr = row_bytes / 16;
   if (row_bytes % 16 != 0 || !is_pow2(lpr) || L > kMaxLevels)
@@ -683,8 +852,10 @@ extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, cons
 #undef APE_FUSED_DISPATCH
 }
 
-// Encoder self-attention variant: queries are the pixels of the level structure (Q == S).  Takes the level
-// shapes on the HOST as well (the caller built them; no device round trip) to size the persistent grid.
+// Encoder self-attention variant: queries are the pixels of the level structure (Q == S).  Takes the level shapes on
+// the HOST as well (the caller built them; no device round trip).  Geometries the region kernel does not cover
+// (32-bit value, more than 5 levels, level 0 not a multiple of 16 pixels, levels that are not exact halvings, head
+// dim * element size != 64 B) take the generic fused kernel: same results up to fp32 summation order.
 extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes, const int64_t *starts,
                                        const int *host_shapes, const void *offsets, int64_t offs_row_stride,
                                        const void *logits, int64_t logit_row_stride, const float *ref, int ref_dim,
@@ -697,21 +868,23 @@ extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes,
   if (offs_row_stride < (int64_t)H * L * P * 2 || logit_row_stride < (int64_t)H * L * P)
     return fail(APE_ERR_INVALID_ARG, "msda_self: row strides smaller than a row");
   long long total = 0;
-  int tiles = 0;
   for (int l = 0; l < L; ++l) {
     const int h = host_shapes[2 * l], w = host_shapes[2 * l + 1];
     if (h <= 0 || w <= 0) return fail(APE_ERR_INVALID_ARG, "msda_self: bad level shape");
     total += (long long)h * w;
-    tiles += ((h + 15) / 16) * ((w + 15) / 16);
   }
   if (total != S) return fail(APE_ERR_INVALID_ARG, "msda_self: level shapes do not sum to S=%d", S);
   if (B == 0 || S == 0) return APE_OK;
   if (!ref) return fail(APE_ERR_NULL_PTR, "msda_self: null reference_points");
-  const int row_bytes = D * dtype_size(dtype);
-  const int lpr = row_bytes / 16;
-  const int LP = L * P;
-  if ((lpr != 4 && lpr != 8) || L > kMaxLevels || (offs_dtype != dtype && offs_dtype != APE_DTYPE_F32))
-    // shapes outside the tuned encoder configuration take the generic fused kernel (same results)
+  const int eo = dtype_size(offs_dtype);
+  bool ok = dtype != APE_DTYPE_F32 && D * dtype_size(dtype) == 64 && L <= kSelfLevels && P == 4 &&
+            (reinterpret_cast<uintptr_t>(offsets) & 15) == 0 && (offs_row_stride * eo) % 16 == 0 &&
+            (reinterpret_cast<uintptr_t>(logits) & (4 * eo - 1)) == 0 && (logit_row_stride * eo) % (4 * eo) == 0 &&
+            (offs_dtype == dtype || offs_dtype == APE_DTYPE_F32) && host_shapes[0] % kRegion == 0 && host_shapes[1] % kRegion == 0 &&
+            (long long)S * H * 4 < (1LL << 26);
+  for (int l = 1; ok && l < L; ++l)
+    ok = host_shapes[2 * l] * (1 << l) == host_shapes[0] && host_shapes[2 * l + 1] * (1 << l) == host_shapes[1];
+  if (!ok)
     return ape_msda_fused_fwd(value, shapes, starts, offsets, offs_row_stride, logits, logit_row_stride, ref, ref_dim,
                               out, B, S, H, D, L, Q, P, dtype, offs_dtype, stream);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -719,14 +892,45 @@ extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes,
   p.value = value; p.shapes = shapes; p.starts = starts; p.loc = offsets; p.attn = logits; p.ref = ref;
   p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
   p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
-#define APE_TILED(T, TO, LPR)                                                              \
-  return (P % 2 == 0) ? launch_fused_tiled<T, TO, LPR, 2>(p, tiles, st) : launch_fused_tiled<T, TO, LPR, 1>(p, tiles, st)
-  if (dtype == APE_DTYPE_F32) { APE_TILED(float, float, 8); }
-  if (dtype == APE_DTYPE_F16) {
-    if (offs_dtype == APE_DTYPE_F16) { APE_TILED(__half, __half, 4); }
-    APE_TILED(__half, float, 4);
+  SelfGeom g{};
+  g.L = L; g.P = P; g.H = H;
+  int st_acc = 0, w16 = 0, qc = 0;
+  for (int l = 0; l < L; ++l) {
+    g.Hl[l] = host_shapes[2 * l]; g.Wl[l] = host_shapes[2 * l + 1]; g.start[l] = st_acc;
+    st_acc += g.Hl[l] * g.Wl[l];
+    g.side[l] = (kRegion >> l) + 2 * kHalo + 1;
+    g.woff[l] = w16; w16 += g.side[l] * g.side[l] * 4;
+    g.qcum[l] = qc; qc += (kRegion >> l) * (kRegion >> l);
   }
-  if (offs_dtype == APE_DTYPE_BF16) { APE_TILED(__nv_bfloat16, __nv_bfloat16, 4); }
-  APE_TILED(__nv_bfloat16, float, 4);
-#undef APE_TILED
+  g.woff[L] = w16; g.qcum[L] = qc;
+  g.regions_x = g.Wl[0] / kRegion; g.regions_y = g.Hl[0] / kRegion;
+  const int lps = (L * P) | 1;
+  g.rec_off16 = w16;
+  g.logit_off16 = g.rec_off16 + kSub * lps;
+  g.stat_off16 = g.logit_off16 + (kSub * lps * 4 + 15) / 16;
+  const size_t smem = (size_t)g.stat_off16 * 16 + 2 * kSub * 4;
+  if (smem > 227 * 1024)
+    return ape_msda_fused_fwd(value, shapes, starts, offsets, offs_row_stride, logits, logit_row_stride, ref, ref_dim,
+                              out, B, S, H, D, L, Q, P, dtype, offs_dtype, stream);
+  const long long units = (long long)B * g.regions_x * g.regions_y * H;
+  if (units >= (1LL << 31)) return fail(APE_ERR_UNSUPPORTED, "msda_self: too many work units");
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int ctas = (int)(units < sms ? units : sms);
+#define APE_SELF(T, TO)                                                                          \
+  do {                                                                                           \
+    auto k = msda_self_kernel<T, TO>;                                                            \
+    if (int rc = set_smem(k, smem)) return rc;                                                   \
+    k<<<ctas, kSelfThreads, smem, st>>>(p, g, (int)units);                                       \
+    return check_launch("msda_self_kernel");                                                     \
+  } while (0)
+  if (dtype == APE_DTYPE_F16) {
+    if (offs_dtype == APE_DTYPE_F16) APE_SELF(__half, __half);
+    APE_SELF(__half, float);
+  }
+  if (offs_dtype == APE_DTYPE_BF16) APE_SELF(__nv_bfloat16, __nv_bfloat16);
+  APE_SELF(__nv_bfloat16, float);
+#undef APE_SELF
 }

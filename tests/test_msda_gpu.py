@@ -229,23 +229,64 @@ def test_fused_entry_equals_unfused_composition(ape):
         torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("shapes", [[(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], [(16, 16), (8, 8)], [(33, 17)]])
-def test_tiled_self_attention_kernel_equals_generic_fused(ape, dtype, shapes):
-    """ape_msda_fused_self_fwd (spatially tiled persistent CTAs, encoder case Q == S) must reproduce
-    ape_msda_fused_fwd bit for bit: the per-row arithmetic is identical, only the work mapping differs."""
-    B, H, D, P = 2, 8, 32, 4
+def _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale):
+    """Queries = pixels; reference points = pixel centres (get_reference_points, deformable_transformer_vl.py:371-400);
+    offsets of a few pixels, as the sampling_offsets bias grid produces (multi_scale_deform_attn.py:195-207)."""
     L = len(shapes)
-    g = torch.Generator().manual_seed(17)
+    g = torch.Generator().manual_seed(seed)
     ss = torch.tensor(shapes)
     st = O.level_start_index(ss)
     S = int((ss[:, 0] * ss[:, 1]).sum())
     value = torch.randn(B, S, H, D, generator=g).to(DEV, dtype)
-    qo = torch.cat([torch.randn(B, S, H * L * P * 2, generator=g) * 3, torch.randn(B, S, H * L * P, generator=g)], -1).to(DEV, dtype)
-    n_off = H * L * P * 2
-    for ref_dim in (2, 4):
-        ref = torch.rand(B, S, L, ref_dim, generator=g).to(DEV)
+    offs = torch.randn(B, S, H * L * P * 2, generator=g) * off_scale
+    qo = torch.cat([offs, torch.randn(B, S, H * L * P, generator=g)], -1).to(DEV, dtype)
+    pts = []
+    for (h, w) in shapes:
+        ys, xs = torch.meshgrid((torch.arange(h) + 0.5) / h, (torch.arange(w) + 0.5) / w, indexing="ij")
+        pts.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+    ref = torch.cat(pts, 0)[None, :, None, :].expand(B, S, L, 2).contiguous().to(DEV)
+    return value, ss, st, qo, ref
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shapes", [[(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], [(16, 16), (8, 8)], [(33, 17)],
+                                    [(32, 48), (16, 24), (8, 12), (4, 6), (2, 3)], [(64, 32), (32, 16), (16, 8), (8, 4)]])
+def test_self_attention_kernel_equals_generic_fused(ape, dtype, shapes):
+    """ape_msda_fused_self_fwd (encoder case Q == S: region/window kernel for 16-bit values on exactly halving
+    pyramids, generic kernel otherwise) against ape_msda_fused_fwd: identical per-sample arithmetic, results equal up
+    to fp32 summation order (then rounded to the output dtype)."""
+    B, H, D, P = 2, 8, 32, 4
+    n_off = H * len(shapes) * P * 2
+    tol = {torch.float32: 1e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    for seed, off_scale in ((17, 3.0), (18, 8.0), (19, 0.5)):  # in-window, partly out-of-window (global path), tight
+        value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale)
         a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
         b = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P,
                                                  host_shapes=shapes)
-        assert torch.equal(a, b)
+        torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
+    # arbitrary (non pixel-centre) reference points and boxes: everything leaves the windows
+    g = torch.Generator().manual_seed(23)
+    for ref_dim in (2, 4):
+        r = torch.rand(B, value.shape[1], len(shapes), ref_dim, generator=g).to(DEV)
+        a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], r, P)
+        b = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], r, P,
+                                                 host_shapes=shapes)
+        torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
+
+
+def test_self_attention_kernel_full_size_vs_oracle(ape):
+    """APE-L_D 1024^2 encoder shape (S = 87 296), fp16: region kernel vs the C oracle on a random subset of queries."""
+    shapes = [(256, 256), (128, 128), (64, 64), (32, 32), (16, 16)]
+    B, H, D, P, L = 1, 8, 32, 4, 5
+    value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, torch.float16, 5, 2.5)
+    n_off = H * L * P * 2
+    got = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P,
+                                               host_shapes=shapes)
+    S = value.shape[1]
+    idx = torch.randperm(S, generator=torch.Generator().manual_seed(1))[:3000].sort()[0].to(DEV)
+    o6 = qo[0, idx, :n_off].float().view(1, -1, H, L, P, 2)
+    attn = qo[0, idx, n_off:].float().view(1, -1, H, L * P).softmax(-1).view(1, -1, H, L, P)
+    norm = torch.stack([ss[:, 1], ss[:, 0]], -1).to(DEV).float()
+    loc = ref[:, idx][:, :, None, :, None, :] + o6 / norm[None, None, None, :, None, :]
+    want = O.msda_c(value.float().cpu(), ss, st, loc.cpu().contiguous(), attn.cpu().contiguous())
+    torch.testing.assert_close(got[0, idx].float().cpu(), want[0], rtol=2e-3, atol=2e-3)
