@@ -131,8 +131,61 @@ def detector_postprocess(result: Instances, out_h, out_w):
                      b[:, 2].clamp(min=0, max=out_w), b[:, 3].clamp(min=0, max=out_h)), dim=-1)
     keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
     extra = {k: v[keep] for k, v in result.get_fields().items() if k not in ("pred_boxes", "scores", "pred_classes")}
+    if "pred_masks" in extra:  # ROIMasks(pred_masks[:, 0]).to_bitmasks(boxes, H, W, 0.5): paste into the rescaled boxes
+        extra["pred_masks"] = paste_masks_in_image(extra["pred_masks"][:, 0], b[keep], (out_h, out_w), 0.5)
     return Instances((out_h, out_w), pred_boxes=Boxes(b[keep]), scores=result.scores[keep],
                      pred_classes=result.pred_classes[keep], **extra)
+
+
+def bitmasks_crop_and_resize(masks, boxes, mask_size):
+    """detectron2 BitMasks.crop_and_resize: ROIAlign((S,S), scale 1, sampling_ratio 0, aligned=True) over the
+    boolean masks as float, then >= 0.5."""
+    from torchvision.ops import roi_align
+
+    batch_inds = torch.arange(len(boxes), device=masks.device).to(dtype=boxes.dtype)[:, None]
+    rois = torch.cat([batch_inds, boxes], dim=1)
+    out = roi_align(masks.to(torch.float32)[:, None], rois, (mask_size, mask_size), 1.0, 0, True).squeeze(1)
+    return out >= 0.5
+
+
+def paste_masks_in_image(masks, boxes, image_shape, threshold=0.5):
+    """detectron2.layers.mask_ops.paste_masks_in_image (`_do_paste_mask` with bilinear grid_sample, align_corners=False):
+    masks [N, S, S] (probabilities) pasted into boxes [N, 4] of an (H, W) image -> bool [N, H, W]."""
+    N = len(masks)
+    img_h, img_w = int(image_shape[0]), int(image_shape[1])
+    if N == 0:
+        return masks.new_empty((0, img_h, img_w), dtype=torch.bool)
+    out = torch.zeros((N, img_h, img_w), device=masks.device, dtype=torch.bool)
+    chunk = max(1, int((1 << 30) // (img_h * img_w * 4)))  # GPU_MEM_LIMIT of 1 GiB, as detectron2
+    for i0 in range(0, N, chunk):
+        m = masks[i0:i0 + chunk, None].float()
+        b = boxes[i0:i0 + chunk]
+        x0, y0, x1, y1 = torch.split(b, 1, dim=1)
+        img_y = torch.arange(0, img_h, device=masks.device, dtype=torch.float32) + 0.5
+        img_x = torch.arange(0, img_w, device=masks.device, dtype=torch.float32) + 0.5
+        img_y = (img_y - y0) / (y1 - y0) * 2 - 1
+        img_x = (img_x - x0) / (x1 - x0) * 2 - 1
+        gx = img_x[:, None, :].expand(len(b), img_h, img_w)
+        gy = img_y[:, :, None].expand(len(b), img_h, img_w)
+        grid = torch.stack([gx, gy], dim=3)
+        pasted = F.grid_sample(m, grid.to(m.dtype), align_corners=False)[:, 0]
+        out[i0:i0 + chunk] = pasted >= threshold
+    return out
+
+
+def sem_seg_postprocess(result, img_size, output_height, output_width):
+    """detectron2 sem_seg_postprocess: crop to the unpadded size, bilinear resize (align_corners=False)."""
+    result = result[:, : img_size[0], : img_size[1]].expand(1, -1, -1, -1)
+    return F.interpolate(result, size=(output_height, output_width), mode="bilinear", align_corners=False)[0]
+
+
+def get_stuff_score(box_cls, thing_classes, stuff_classes, entity):
+    """deformable_detr_segm_vl.py:1251-1271 (thing / stuff overlap case keeps all classes, as the clone there)."""
+    if entity == "thing+stuff" and stuff_classes and stuff_classes[0] == "things" and not set(thing_classes) & set(stuff_classes):
+        n = len(thing_classes)
+        s0, _ = box_cls[..., :n].min(dim=2, keepdim=True)
+        return torch.cat([s0, box_cls[..., n:]], dim=2)
+    return box_cls.clone()
 
 
 class _Criterion(nn.Module):
@@ -218,6 +271,11 @@ class DeformableDETRSegmVL(nn.Module):
 
         self.instance_on, self.semantic_on, self.panoptic_on = instance_on, semantic_on, panoptic_on
         self.test_mask_on = test_mask_on
+        self.semantic_post_nms = semantic_post_nms
+        self.stuff_prob_thing = stuff_prob_thing
+        # (thing_classes, stuff_classes) per dataset for the semantic branch; the reference reads them from detectron2's
+        # MetadataCatalog (deformable_detr.py:244-262).  None = "thing" entity over the dataset's vocabulary.
+        self.dataset_stuff = {}
         self.input_shapes, self.mask_in_features, self.mask_encode_level = input_shapes, mask_in_features, mask_encode_level
         hidden = transformer.embed_dim
         in_ch = input_shapes[mask_in_features[0]].channels
@@ -368,7 +426,8 @@ class DeformableDETRSegmVL(nn.Module):
         mark("preprocess")
         low = self.engine_dtype != torch.float32
         geo = self._geometry(images.shape, image_sizes, img_masks)
-        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
+        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1 and \
+            not (self.semantic_on or (self.instance_on and self.test_mask_on))  # mask tensors travel as attributes: eager
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
             if graphs and not self.profile_stages:
                 # encode -> select -> decode in ONE graph: the selection is written with static shapes and no host
@@ -403,21 +462,32 @@ class DeformableDETRSegmVL(nn.Module):
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
-        if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
-            raise NotImplementedError("ape_b200: mask / semantic / panoptic heads are the next §8 rows; construct "
-                                      "with test_mask_on=False, semantic_on=False, panoptic_on=False (boxes only)")
+        if self.panoptic_on:
+            raise NotImplementedError("ape_b200: panoptic merging (SURVEY.md 8f row 2); construct with panoptic_on=False")
+        need_masks = self.semantic_on or (self.instance_on and self.test_mask_on)
+        mask_pred = self.last_mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
+        self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
         results = None
-        if do_postprocess and low and self.static_inference_cap > 0:
+        if do_postprocess and low and self.static_inference_cap > 0 and not need_masks:
             results = self._inference_static(box_cls, box_pred, image_sizes)  # CPU Instances, one host sync (None: overflow)
         if results is None:
             results = self.inference(box_cls, box_pred, image_sizes)
+        padded_hw = tuple(images.shape[-2:])
+        if self.instance_on and self.test_mask_on:
+            for b, r in enumerate(results):  # (:588-603) masks of the kept queries only (bilinear resize is per channel)
+                m = F.interpolate(mask_pred[b, r.query_index][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0]
+                m = bitmasks_crop_and_resize(m.sigmoid() > 0.5, r.pred_boxes.tensor.to(m.device), 128)
+                r.pred_masks = m.unsqueeze(1).to(torch.float32)
         if not do_postprocess:
             return results, None, None
         out = []
         for r, inp, size in zip(results, batched_inputs, image_sizes):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
-            out.append({"instances": detector_postprocess(r, h, w).to("cpu")})
+            out.append({"instances": detector_postprocess(r, h, w).to("cpu")} if self.instance_on else {})
+        if self.semantic_on:
+            for o, sem in zip(out, self._semantic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
+                o["sem_seg"] = sem
         mark("inference")
         if marks is not None:
             torch.cuda.synchronize()
@@ -447,6 +517,9 @@ class DeformableDETRSegmVL(nn.Module):
         feats = self.neck({f: features[f] for f in self.neck.in_features})
         memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(
             feats, geo, fusion, feat_flatten=getattr(self.neck, "last_flat", None))
+        self._mask_features = None
+        if self.semantic_on or (self.instance_on and self.test_mask_on):
+            self._mask_features = self.maskdino_mask_features(memory, features, geo)
         return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats
 
     @staticmethod
@@ -476,6 +549,11 @@ class DeformableDETRSegmVL(nn.Module):
         with torch.autocast("cuda", enabled=False):
             box_cls = self.class_embed[lvl](inter_states[lvl], features_l.float())
             box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
+        self.last_mask_logits = None
+        if getattr(self, "_mask_features", None) is not None:
+            # (:507-517) only the last level's masks reach inference (the other levels are added times 0.0)
+            mf = self._mask_features
+            self.last_mask_logits = torch.einsum("bqc,bchw->bqhw", self.mask_embed(inter_states[lvl].to(mf.dtype)), mf)
         return box_cls, box_pred, inter_states, init_reference, inter_references
 
     def _graphed(self, key, fn, tensor_args, const_args):
@@ -504,6 +582,40 @@ class DeformableDETRSegmVL(nn.Module):
             dst.copy_(src)
         graph.replay()
         return static_out
+
+    def maskdino_mask_features(self, memory, features, geo):
+        """:728-750: p2 -> 1x1 conv + GroupNorm, + encoder memory of the mask_encode_level (bilinearly resized to p2),
+        3x3 conv + GroupNorm + ReLU, 1x1 conv -> [B, C, h, w]."""
+        lvl = self.mask_encode_level
+        shapes = geo["shapes"]
+        start = sum(h * w for h, w in shapes[:lvl])
+        h, w = shapes[lvl]
+        enc = memory[:, start:start + h * w].permute(0, 2, 1).reshape(memory.shape[0], -1, h, w)
+        x = self.lateral_conv(features[self.mask_in_features[0]])
+        x = x + F.interpolate(enc.to(x.dtype), size=x.shape[-2:], mode="bilinear", align_corners=False)
+        return self.mask_conv(self.output_conv(x))
+
+    def _semantic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs):
+        """Semantic branch (:628-666, `_postprocess_semantic` :875-918): class scores of the queries that survive the
+        detection NMS, softmax(sigmoid / 0.06) over classes, times the sigmoid masks at padded-image resolution."""
+        name = self.dataset_names[self.eval_dataset_id] if self.dataset_names else None
+        things, stuff, entity = self.dataset_stuff.get(name, (None, None, "thing"))
+        sem_cls = get_stuff_score(box_cls, things or [], stuff or [], entity)
+        outs = []
+        if self.semantic_post_nms:
+            keep = [r.query_index for r in self.inference(sem_cls, box_pred, image_sizes)]
+        else:
+            keep = [torch.arange(sem_cls.shape[1], device=sem_cls.device)] * sem_cls.shape[0]
+        for b, (qi, size, inp) in enumerate(zip(keep, image_sizes, batched_inputs)):
+            cls = F.softmax(sem_cls[b, qi].float().sigmoid() / 0.06, dim=-1)
+            m = F.interpolate(mask_pred[b, qi][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0].sigmoid()
+            result = torch.einsum("qc,qhw->chw", cls, m)  # stays on the GPU (the reference moves >1000 classes to the CPU, :896-898)
+            h, w = inp.get("height", size[0]), inp.get("width", size[1])
+            sem = sem_seg_postprocess(result, size, h, w)
+            if entity == "stuff" and stuff and stuff[0] == "things" and self.stuff_prob_thing > 0:
+                sem[0, ...] = math.log(self.stuff_prob_thing / (1 - self.stuff_prob_thing))
+            outs.append(sem)
+        return outs
 
     def _inference_static(self, box_cls, box_pred, image_sizes):
         """`inference` (:759-810 + fast_rcnn.py:97-201) with static shapes: at most `static_inference_cap` (query, class)

@@ -52,7 +52,7 @@ def randomize_degenerate_parameters(model, seed=1):
                 p.add_(torch.randn(p.shape, generator=g) * 0.02)
 
 
-def build_reference_model(spec, num_text=None, seed=0):
+def build_reference_model(spec, num_text=None, seed=0, test_mask_on=False, semantic_on=False):
     """-> (model_vision in eval mode, class-name list of length num_text)"""
     refshim.install()
     vit_mod = refshim.load("ape.modeling.backbone.vit_eva_clip")
@@ -98,9 +98,9 @@ def build_reference_model(spec, num_text=None, seed=0):
     meta = refshim.MetadataCatalog.get(f"fake_{spec['name']}_{n_text}")
     meta.thing_classes = names
     model = segm.DeformableDETRSegmVL(
-        instance_on=True, semantic_on=False, panoptic_on=False, input_shapes=shapes, mask_in_features=["p2"],
+        instance_on=True, semantic_on=semantic_on, panoptic_on=False, input_shapes=shapes, mask_in_features=["p2"],
         mask_encode_level=0, stuff_dataset_learn_thing=False, stuff_prob_thing=0.9, name_prompt_fusion_type="zero",
-        test_mask_on=False,
+        test_mask_on=test_mask_on,
         backbone=backbone, position_embedding=refshim.PositionEmbeddingSine(num_pos_feats=E // 2, temperature=10000,
                                                                            normalize=True, offset=-0.5),
         neck=neck, transformer=transformer, embed_dim=E, num_classes=spec["num_classes"],

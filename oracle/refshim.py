@@ -266,8 +266,58 @@ def detector_postprocess(results, output_height, output_width, mask_threshold=0.
     output_boxes.clip(results.image_size)
     results = results[output_boxes.nonempty()]
     if results.has("pred_masks"):
-        raise NotImplementedError("refshim: mask pasting is not restated yet")
+        # ROIMasks(results.pred_masks[:, 0]).to_bitmasks(boxes, H, W, mask_threshold) -> paste_masks_in_image
+        results.pred_masks = paste_masks_in_image(results.pred_masks[:, 0, :, :], results.pred_boxes.tensor,
+                                                  (output_height, output_width), threshold=mask_threshold)
     return results
+
+
+def _do_paste_mask(masks, boxes, img_h, img_w, skip_empty=True):
+    """detectron2/layers/mask_ops.py::_do_paste_mask (restated)."""
+    device = masks.device
+    if skip_empty:
+        x0_int, y0_int = torch.clamp(boxes.min(dim=0).values.floor()[:2] - 1, min=0).to(dtype=torch.int32)
+        x1_int = torch.clamp(boxes[:, 2].max().ceil() + 1, max=img_w).to(dtype=torch.int32)
+        y1_int = torch.clamp(boxes[:, 3].max().ceil() + 1, max=img_h).to(dtype=torch.int32)
+    else:
+        x0_int, y0_int = 0, 0
+        x1_int, y1_int = img_w, img_h
+    x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
+    N = masks.shape[0]
+    img_y = torch.arange(int(y0_int), int(y1_int), device=device, dtype=torch.float32) + 0.5
+    img_x = torch.arange(int(x0_int), int(x1_int), device=device, dtype=torch.float32) + 0.5
+    img_y = (img_y - y0) / (y1 - y0) * 2 - 1
+    img_x = (img_x - x0) / (x1 - x0) * 2 - 1
+    gx = img_x[:, None, :].expand(N, img_y.size(1), img_x.size(1))
+    gy = img_y[:, :, None].expand(N, img_y.size(1), img_x.size(1))
+    grid = torch.stack([gx, gy], dim=3)
+    if not masks.dtype.is_floating_point:
+        masks = masks.float()
+    img_masks = F.grid_sample(masks, grid.to(masks.dtype), align_corners=False)
+    if skip_empty:
+        return img_masks[:, 0], (slice(int(y0_int), int(y1_int)), slice(int(x0_int), int(x1_int)))
+    return img_masks[:, 0], ()
+
+
+def paste_masks_in_image(masks, boxes, image_shape, threshold=0.5):
+    """detectron2/layers/mask_ops.py::paste_masks_in_image (restated): CPU = one mask per chunk with skip_empty."""
+    N = len(masks)
+    img_h, img_w = int(image_shape[0]), int(image_shape[1])
+    if N == 0:
+        return masks.new_empty((0, img_h, img_w), dtype=torch.uint8)
+    device = boxes.device
+    num_chunks = N if device.type == "cpu" else max(1, int(math.ceil(N * img_h * img_w * 4 / 1024 ** 3)))
+    chunks = torch.chunk(torch.arange(N, device=device), num_chunks)
+    img_masks = torch.zeros(N, img_h, img_w, device=device, dtype=torch.bool if threshold >= 0 else torch.uint8)
+    for inds in chunks:
+        masks_chunk, spatial_inds = _do_paste_mask(masks[inds, None, :, :], boxes[inds], img_h, img_w,
+                                                   skip_empty=device.type == "cpu")
+        if threshold >= 0:
+            masks_chunk = (masks_chunk >= threshold).to(dtype=torch.bool)
+        else:
+            masks_chunk = (masks_chunk * 255).to(dtype=torch.uint8)
+        img_masks[(inds,) + spatial_inds] = masks_chunk
+    return img_masks
 
 
 def sem_seg_postprocess(result, img_size, output_height, output_width):

@@ -93,5 +93,48 @@ def main():
         print(cname, {k: tuple(v.shape) for k, v in rec.items() if k.startswith(("memory", "inter_states", "det", "topk"))})
 
 
+def main_masks():
+    """model_mini_masks.npz: the same MINI model with test_mask_on / semantic_on:
+    mask logits of the last decoder level, pasted instance masks (bit-packed) and the semantic map."""
+    spec = configs.MINI
+    model, names = ref_model.build_reference_model(spec, test_mask_on=True, semantic_on=True)
+    synth.fill_state_dict(model)
+    cap = {}
+    orig = model.maskdino_mask_features
+
+    def spy(*a, **k):
+        cap["mask_features"] = orig(*a, **k)
+        return cap["mask_features"]
+
+    model.maskdino_mask_features = spy
+    orig_interp = torch.nn.functional.interpolate
+    import ape.modeling.ape_deta.deformable_detr_segm_vl as segm  # the module object refshim loaded
+
+    def interp_spy(x, *a, **k):  # first 4-D call with num_queries channels is `mask_pred` (:563-566)
+        if x.dim() == 4 and x.shape[1] == spec["num_queries"] and "pred_masks" not in cap:
+            cap["pred_masks"] = x.clone()
+        return orig_interp(x, *a, **k)
+
+    segm.F.interpolate = interp_spy
+    sizes = [(48, 64, 96, 128)]
+    inputs = [{"image": synth.image(h, w, seed=i), "height": oh, "width": ow} for i, (h, w, oh, ow) in enumerate(sizes)]
+    try:
+        with torch.no_grad():
+            out = model(inputs)
+    finally:
+        segm.F.interpolate = orig_interp
+    inst = out[0]["instances"]
+    rec = {"mask_features": cap["mask_features"][:, ::8], "pred_masks": cap["pred_masks"],
+           "det0.boxes": inst.pred_boxes.tensor, "det0.scores": inst.scores, "det0.classes": inst.pred_classes,
+           "det0.masks_packed": torch.from_numpy(np.packbits(inst.pred_masks.numpy().astype(np.uint8), axis=-1)),
+           "det0.masks_shape": torch.tensor(inst.pred_masks.shape), "sem_seg": out[0]["sem_seg"]}
+    np.savez_compressed(os.path.join(HERE, "model_mini_masks.npz"), **{k: v.detach().cpu().numpy() for k, v in rec.items()})
+    print("masks", {k: tuple(v.shape) for k, v in rec.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "masks":
+        main_masks()
+    else:
+        main()
+        main_masks()

