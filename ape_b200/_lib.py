@@ -53,6 +53,8 @@ lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i
 lib.ape_rope_qk.restype = _i
 lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 
+lib.ape_attn_fwd.restype = _i
+lib.ape_attn_fwd.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
 lib.ape_vlf_pool_workspace_bytes.restype = _i64
 lib.ape_vlf_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
 lib.ape_vlf_pool.restype = _i
@@ -77,6 +79,7 @@ EXPORTS = (
     "ape_layernorm",
     "ape_layernorm_ex",
     "ape_rope_qk",
+    "ape_attn_fwd",
     "ape_groupnorm_workspace_bytes",
     "ape_groupnorm_nhwc",
     "ape_vlf_pool_workspace_bytes",

@@ -1,0 +1,317 @@
+// attn_fwd.cu — softmax attention core of the EVA-02 ViT blocks (Attention.forward, ape/modeling/backbone/
+// vit_eva_clip.py:218-319: q·k^T·scale -> softmax -> ·v, 16 heads x 64, window (N=1024) and global (N=4096) blocks)
+// on the 5th-gen tensor cores: flash-attention forward with tcgen05.mma, S and P·V accumulators in tensor memory,
+// Q/K/V tiles staged by TMA straight out of the fused [M, 3C] qkv buffer the qkv GEMM wrote (no head split copies).
+//
+// One CTA = 128 queries of one (sequence, head); it walks the keys in blocks of 64.  Roles (192 threads):
+//   warp 0      TMA producer : Q once, then K_j and V_j (64 x 64 each, 128-byte swizzle), each in its own single buffer
+//   warp 1      MMA issuer   : S_j = Q K_j^T (4 x tcgen05.mma 128x64x16, K-major operands) into TMEM columns 0..63;
+//                              O += P_j V_j (4 x tcgen05.mma 128x64x16, A = P from shared memory, B = V_j in its natural
+//                              [key][channel] layout = MN-major operand) accumulating in TMEM columns 64..127
+//   warps 2..5  softmax      : thread = query row (TMEM lane): tcgen05.ld S_j, exponentials in the exp2 domain relative
+//                              to a per-row reference maximum, P_j -> 16 bit -> 128B-swizzled shared memory.
+// O stays in tensor memory for the whole key loop.  The reference maximum is only moved when a row's maximum grows
+// by more than 2^8 (then the warp rescales its 32 rows of O in place with tcgen05.ld / tcgen05.st): P <= 256 fits the
+// 16-bit formats, and the common iteration touches S only.  That keeps the softmax threads under 85 registers, so
+// FOUR CTAs share an SM (49 KB shared memory, 128 TMEM columns each; the 512 CTAs of a ViT layer are one wave): while one CTA's rows are in the exponential
+// unit, the others' MMAs and loads proceed.  S_{j+1} is issued as soon as S_j has been read into registers.
+// Bound: for head dim 64 the 16 ex2/clk/SM of the SFU cap attention near half of the tensor peak (4 x 64 flops per
+// exponential); see DESIGN.md.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace ape {
+namespace {
+
+constexpr int QM = 128, KN = 64, HD = 64;
+constexpr int kAttnThreads = 192;
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+struct alignas(1024) AttnSmem {
+  uint8_t q[QM * HD * 2];   // 16 KB
+  uint8_t k[KN * HD * 2];   // 8 KB   (K and V are single buffers with their own barriers: K_{j+1} is fetched while
+  uint8_t v[KN * HD * 2];   // 8 KB    the softmax of block j runs, V_{j+1} while S_{j+1} is computed)
+  uint8_t p[QM * KN * 2];   // 16 KB
+  uint64_t q_full, k_full, k_empty, v_full, v_empty;
+  uint64_t s_full, s_empty, p_full, pv_done;
+  uint32_t tmem_base;
+};
+
+struct AttnParams {
+  void *out;
+  long long ldo;     // elements
+  int n;             // tokens per sequence (multiple of 128)
+  int heads, C;      // C = heads * 64
+  float scale_log2;  // softmax scale * log2(e)
+  uint32_t idesc_qk, idesc_pv;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads, 4)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem &s = *reinterpret_cast<AttnSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int row0 = seq * p.n;            // first token row of this sequence in the qkv buffer
+  const int nkv = p.n / KN;
+  constexpr uint32_t TMEM_COLS = 128;    // S (64 fp32 columns) | O (64)
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&map_qkv);
+    tc::mbar_init(&s.q_full, 1);
+    tc::mbar_init(&s.k_full, 1);
+    tc::mbar_init(&s.k_empty, 1);
+    tc::mbar_init(&s.v_full, 1);
+    tc::mbar_init(&s.v_empty, 1);
+    tc::mbar_init(&s.s_full, 1);
+    tc::mbar_init(&s.s_empty, 4);   // one arrival per softmax warp
+    tc::mbar_init(&s.p_full, 4);
+    tc::mbar_init(&s.pv_done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&s.tmem_base, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::mbar_expect_tx(&s.q_full, QM * HD * 2);
+      tc::tma_load_2d(s.q, &map_qkv, &s.q_full, head * HD, row0 + qblk * QM);                       // the box is 64 rows:
+      tc::tma_load_2d(s.q + KN * HD * 2, &map_qkv, &s.q_full, head * HD, row0 + qblk * QM + KN);    // two boxes per Q tile
+      for (int j = 0; j < nkv; ++j) {
+        tc::mbar_wait(&s.k_empty, (j & 1) ^ 1);  // S_{j-1} has been computed
+        tc::mbar_expect_tx(&s.k_full, KN * HD * 2);
+        tc::tma_load_2d(s.k, &map_qkv, &s.k_full, p.C + head * HD, row0 + j * KN);
+        tc::mbar_wait(&s.v_empty, (j & 1) ^ 1);  // O += P_{j-1} V_{j-1} has completed
+        tc::mbar_expect_tx(&s.v_full, KN * HD * 2);
+        tc::tma_load_2d(s.v, &map_qkv, &s.v_full, 2 * p.C + head * HD, row0 + j * KN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      tc::mbar_wait(&s.q_full, 0);
+      tc::fence_after_sync();
+      const uint64_t dq = tc::make_smem_desc_sw128(tc::smem_u32(s.q));
+      const uint64_t dk = tc::make_smem_desc_sw128(tc::smem_u32(s.k));
+      const uint64_t dv = tc::make_smem_desc_sw128(tc::smem_u32(s.v));
+      const uint64_t dp = tc::make_smem_desc_sw128(tc::smem_u32(s.p));
+      auto issue_qk = [&](int j) {
+        tc::mbar_wait(&s.k_full, j & 1);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc::mma_f16(tmem, dq + 2 * k, dk + 2 * k, p.idesc_qk, k != 0);
+        tc::mma_commit(&s.s_full);
+        tc::mma_commit(&s.k_empty);  // K_j may be replaced by K_{j+1}
+      };
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {  // S_{j+1} as soon as the softmax warps hold S_j in registers
+          tc::mbar_wait(&s.s_empty, j & 1);
+          issue_qk(j + 1);
+        }
+        tc::mbar_wait(&s.v_full, j & 1);
+        tc::mbar_wait(&s.p_full, j & 1);  // P_j is in shared memory (and O was rescaled if it had to be)
+        tc::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < KN / 16; ++k)  // A: +32 B per 16 keys inside the swizzle row; B (MN-major): +16 key rows = 2 KB
+          tc::mma_f16(tmem + 64, dp + 2 * k, dv + 128 * k, p.idesc_pv, (j | k) != 0);
+        tc::mma_commit(&s.pv_done);
+        tc::mma_commit(&s.v_empty);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax (warps 2..5; thread = query row) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    float m_ref = -INFINITY, l = 0.f;
+    uint8_t *prow = s.p + row * 128;
+    for (int j = 0; j < nkv; ++j) {
+      tc::mbar_wait(&s.s_full, j & 1);
+      tc::fence_after_sync();
+      // pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling); S is read from tensor
+      // memory twice instead of being held in 64 registers — 4 CTAs per SM need the threads under 85 registers
+      float m8[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = __uint_as_float(r[i]);
+          m8[i & 7] = (hh == 0 && i < 8) ? x : fmaxf(m8[i & 7], x);
+        }
+      }
+      const float mx = p.scale_log2 *
+          fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      // move the reference only when some row of this warp outgrew it by 2^8 (always on the first block)
+      const bool moved = __any_sync(0xffffffffu, mx > m_ref + kRescaleThreshold);
+      float alpha = 1.f;
+      if (moved) {
+        const float m_new = fmaxf(m_ref, mx);
+        alpha = ex2(m_ref - m_new);  // 0 on the first block (m_ref = -inf)
+        m_ref = m_new;
+        l *= alpha;
+      }
+      if (j > 0) {  // P_{j-1} has been consumed and O holds blocks 0..j-1
+        tc::mbar_wait(&s.pv_done, (j - 1) & 1);
+        tc::fence_after_sync();
+        if (moved) {  // warp-uniform: rescale this warp's 32 rows of O in place
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tc::tmem_ld_32x32b_x32(trow + 64 + 32 * hh, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st_32x32b_x32(trow + 64 + 32 * hh, o);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      // pass 2: exponentials -> 16 bit -> swizzled shared memory
+      float s8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
+        tc::tmem_ld_wait();
+        if (hh == 1) {  // S is in registers now: the tensor core may compute S_{j+1}
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&s.s_empty);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = ex2(fmaf(__uint_as_float(r[8 * c + i]), p.scale_log2, -m_ref));
+            s8[i] += e[i];
+          }
+          *reinterpret_cast<uint4 *>(prow + (((4 * hh + c) ^ (row & 7)) << 4)) = Elem<T>::pack(e);
+        }
+      }
+      l += ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+      tc::fence_proxy_async();  // P visible to the tensor core's (async proxy) reads
+      tc::fence_before_sync();  // ... and the O rescale ordered before the MMA that accumulates into it
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.p_full);
+    }
+    tc::mbar_wait(&s.pv_done, (nkv - 1) & 1);
+    tc::fence_after_sync();
+    const float inv = 1.f / l;
+    T *dst = reinterpret_cast<T *>(p.out) + (size_t)(row0 + qblk * QM + row) * p.ldo + head * HD;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tc::tmem_ld_32x32b_x32(trow + 64 + 32 * hh, o);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * c + i]) * inv;
+        *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = Elem<T>::pack(f);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn attn_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+}  // namespace ape
+
+using namespace ape;
+
+extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads,
+                            int head_dim, float scale, int dtype, void *stream) {
+  if (dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16) return fail(APE_ERR_INVALID_ARG, "attn: fp16 / bf16 only (dtype %d)", dtype);
+  if (head_dim != HD) return fail(APE_ERR_UNSUPPORTED, "attn: head_dim %d (only 64)", head_dim);
+  if (num_seq < 0 || n <= 0 || n % QM != 0 || heads <= 0 || heads > 65535 || num_seq > 65535)
+    return fail(APE_ERR_UNSUPPORTED, "attn: num_seq=%d n=%d heads=%d (n must be a multiple of 128)", num_seq, n, heads);
+  if (num_seq == 0) return APE_OK;
+  if (!qkv || !out) return fail(APE_ERR_NULL_PTR, "attn: null pointer argument");
+  const int C = heads * HD;
+  if (ld < 3 * C || ldo < C || (ld * 2) % 16 || (ldo * 2) % 16 || (reinterpret_cast<uintptr_t>(qkv) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(APE_ERR_INVALID_ARG, "attn: qkv [rows, >= 3*heads*64] / out [rows, >= heads*64] with 16-byte aligned rows");
+  EncodeTiledFn enc = attn_encoder();
+  if (!enc) return fail(APE_ERR_UNSUPPORTED, "attn: cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap map;
+  cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)((long long)num_seq * n)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)HD, (cuuint32_t)KN};  // 64 channels x 64 rows; Q takes two boxes
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&map, dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void *>(qkv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  AttnParams p{};
+  p.out = out; p.ldo = ldo; p.n = n; p.heads = heads; p.C = C;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int fmt = dtype == APE_DTYPE_BF16 ? 1 : 0;
+  p.idesc_qk = tc::make_idesc_f16(QM, KN, fmt);
+  p.idesc_pv = tc::make_idesc_f16(QM, HD, fmt) | (1u << 16);  // B (= V, [key][channel]) is MN-major
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(AttnSmem) + 1024;
+  dim3 grid((unsigned)(n / QM), (unsigned)heads, (unsigned)num_seq);
+  if (dtype == APE_DTYPE_F16) {
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      set = true;
+    }
+    attn_fwd_kernel<__half><<<grid, kAttnThreads, smem, st>>>(map, p);
+  } else {
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      set = true;
+    }
+    attn_fwd_kernel<__nv_bfloat16><<<grid, kAttnThreads, smem, st>>>(map, p);
+  }
+  return check_launch("attn_fwd_kernel");
+}

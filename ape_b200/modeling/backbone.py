@@ -178,6 +178,7 @@ class ViT(nn.Module):
             Block(embed_dim, num_heads, mlp_ratio, norm_layer, window_size if i in window_block_indexes else 0,
                   self.rope_win if i in window_block_indexes else self.rope_glb)
             for i in range(depth)])
+        self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
         self._out_feature_channels = {out_feature: embed_dim}
         self._out_feature_strides = {out_feature: patch_size}
         self._out_features = [out_feature]
@@ -301,10 +302,13 @@ class ViT(nn.Module):
             else:
                 ops.rope_qk_(qkv, rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
                 nb, n = B, g * g
-            q5 = qkv.view(nb, n, 3, heads, hd)
-            o = F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
-                                               q5[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
-            o = o.transpose(1, 2).reshape(M, C)
+            if self.engine_attention and ops.attention_supported(n, hd, qkv.dtype):
+                o = ops.attention_qkv(qkv, nb, n, heads, hd, blk.attn.scale)  # tcgen05 flash attention, no head-split copies
+            else:
+                q5 = qkv.view(nb, n, 3, heads, hd)
+                o = F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
+                                                   q5[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
+                o = o.transpose(1, 2).reshape(M, C)
             a = ops.layernorm(o, p["lnw"], p["lnb"], eps=1e-6)
             x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x)
             h = ops.layernorm(x, p["n2w"], p["n2b"], eps=1e-6)

@@ -168,6 +168,17 @@ int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_
                 int C, int head_dim, int npos, int dtype, void *stream);
 
 /*
+ * Softmax attention core of the ViT blocks (Attention.forward, ape/modeling/backbone/vit_eva_clip.py:218-319, the
+ * part xformers / F.scaled_dot_product_attention computes there): out = softmax(q k^T * scale) v per (sequence, head),
+ * flash-attention style on tcgen05 tensor cores.  qkv [num_seq * n, >= 3*heads*64] (pitch ld elements): columns
+ * [0,C) = q, [C,2C) = k, [2C,3C) = v with C = heads*64, head h at columns h*64 (the layout the fused qkv GEMM writes,
+ * RoPE already applied); sequence s owns rows [s*n, (s+1)*n).  out [num_seq * n, >= C] (pitch ldo).  fp16 or bf16,
+ * head_dim 64, n a multiple of 128; fp32 softmax statistics and accumulation.
+ */
+int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads, int head_dim,
+                 float scale, int dtype, void *stream);
+
+/*
  * Language-side attention pooling of VisionLanguageFusion for a single language token ("name" prompts):
  * softmax over the S vision tokens of scores t[s,h] = v_s . qa[h] + qc[h] (with the reference's global-max shift
  * and +-5e4 clamps, fuse_helper.py:88-110) and the p-weighted sum of v.  v [B,S,C] dtype; qa [B,NH,C], qc [B,NH] fp32.

@@ -1,0 +1,49 @@
+"""GPU: the tcgen05 flash-attention kernel (ape_attn_fwd) against a plain PyTorch fp32 reference of the same op
+(softmax(q k^T * scale) v per head) on the same 16-bit inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import ape_b200
+
+    return ape_b200.ops
+
+
+def ref_attention(qkv, num_seq, n, heads, hd, scale):
+    q, k, v = qkv.float().view(num_seq, n, 3, heads, hd).permute(2, 0, 3, 1, 4)  # [3][s, h, n, d]
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(num_seq * n, heads * hd)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("num_seq,n,heads", [(1, 128, 1), (2, 256, 3), (4, 1024, 16), (1, 4096, 16)])
+def test_attention_matches_fp32_reference(ops, dtype, tol, num_seq, n, heads):
+    hd = 64
+    g = torch.Generator().manual_seed(n + heads)
+    qkv = torch.randn(num_seq * n, 3 * heads * hd, generator=g).to(DEV, dtype)
+    scale = hd ** -0.5
+    got = ops.attention_qkv(qkv, num_seq, n, heads, hd, scale)
+    want = ref_attention(qkv, num_seq, n, heads, hd, scale)
+    torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
+
+
+def test_attention_large_logits_and_pitch(ops):
+    """Peaked softmax (scores of +-40) and a qkv buffer with a padded row pitch."""
+    num_seq, n, heads, hd = 2, 384, 2, 64
+    g = torch.Generator().manual_seed(3)
+    buf = torch.zeros(num_seq * n, 3 * heads * hd + 64, dtype=torch.float16, device=DEV)
+    qkv = buf[:, : 3 * heads * hd]
+    qkv.copy_((torch.randn(num_seq * n, 3 * heads * hd, generator=g) * 3).to(DEV))
+    got = ops.attention_qkv(qkv, num_seq, n, heads, hd, 0.5)
+    want = ref_attention(qkv, num_seq, n, heads, hd, 0.5)
+    torch.testing.assert_close(got.float(), want, rtol=4e-3, atol=4e-3)
+
+
+def test_attention_rejects_unsupported(ops):
+    with pytest.raises(RuntimeError):
+        ops.attention_qkv(torch.zeros(100, 192, dtype=torch.float16, device=DEV), 1, 100, 1, 64, 1.0)  # n % 128 != 0
