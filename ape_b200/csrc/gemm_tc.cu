@@ -36,6 +36,11 @@ struct GemmParams {
   int out_dtype;  // APE_DTYPE_*
   int act;
   int n_fastest;  // tile order: consecutive tiles walk the column blocks of one row group (A stays hot in L2)
+  // optional 2-D rotary embedding on output columns [0, rope_cols) (q and k thirds of a fused qkv projection;
+  // VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346), applied after the bias in fp32: 64-channel heads
+  const float *rope_cos, *rope_sin;  // [npos, 64]
+  const int *rope_pos;               // [M] row -> position, or nullptr: row % rope_npos
+  int rope_cols, rope_npos;
   int tma_store;  // 16-bit output with 16-byte aligned rows: epilogue goes through smem + TMA store
   uint32_t idesc;
 };
@@ -137,6 +142,20 @@ __device__ __forceinline__ void finish64(const GemmParams &p, float *v, int m, i
 #pragma unroll
       for (int i = 0; i < 64; ++i)
         if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+    }
+  }
+  if (p.rope_cos != nullptr && n0 < p.rope_cols && m < p.M) {  // this 64-column chunk is one head of q or k
+    const int pos = p.rope_pos ? __ldg(p.rope_pos + m) : m % p.rope_npos;
+    const float4 *c4 = reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64);
+    const float4 *s4 = reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 c = __ldg(c4 + i), sn = __ldg(s4 + i);
+      const float t0 = v[4 * i], t1 = v[4 * i + 1], t2 = v[4 * i + 2], t3 = v[4 * i + 3];
+      v[4 * i] = t0 * c.x - t1 * sn.x;       // rotate_half pairs (2i, 2i+1) -> (-t[2i+1], t[2i])
+      v[4 * i + 1] = t1 * c.y + t0 * sn.y;
+      v[4 * i + 2] = t2 * c.z - t3 * sn.z;
+      v[4 * i + 3] = t3 * c.w + t2 * sn.w;
     }
   }
   if (p.act == ACT_RELU || p.act == ACT_GELU) {
@@ -661,9 +680,15 @@ int launch_gemm_pair(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
 
 using namespace ape;
 
-extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
-                           const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
-                           int out_dtype, int act, int tile_n, void *stream) {
+struct RopeArgs {
+  const float *cos, *sin;
+  const int *pos;
+  int cols, npos;
+};
+
+static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
+                     const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
+                     int out_dtype, int act, int tile_n, const RopeArgs *rope, void *stream) {
   if (in_dtype != APE_DTYPE_F16 && in_dtype != APE_DTYPE_BF16)
     return fail(APE_ERR_INVALID_ARG, "gemm: operands must be fp16 or bf16 (got dtype %d)", in_dtype);
   if (out_dtype != APE_DTYPE_F32 && out_dtype != APE_DTYPE_F16 && out_dtype != APE_DTYPE_BF16)
@@ -704,6 +729,11 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
                 (act != ACT_SWIGLU || bn == 256);
   if (p.tma_store)
     if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 64)) return rc;
+  if (rope) {
+    if (!p.tma_store || act != ACT_NONE || rope->cols % 64 != 0 || rope->cols > N || rope->npos <= 0 || !rope->cos || !rope->sin)
+      return fail(APE_ERR_INVALID_ARG, "gemm+rope: needs a 16-bit aligned output, no activation, rope_cols a multiple of 64 <= N");
+    p.rope_cos = rope->cos; p.rope_sin = rope->sin; p.rope_pos = rope->pos; p.rope_cols = rope->cols; p.rope_npos = rope->npos;
+  }
   if (pair) {
     p.idesc = tc::make_idesc_f16(2 * BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
     if (bn == 256) return launch_gemm_pair<256, 5>(ma, mb, mc, p, st);
@@ -719,4 +749,21 @@ extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ld
   }
   if (bn == 256) return launch_gemm<256, 4, 2>(ma, mb, mc, p, st);
   return launch_gemm<128, 6, 2>(ma, mb, mc, p, st);
+}
+
+extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
+                           const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
+                           int out_dtype, int act, int tile_n, void *stream) {
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr, stream);
+}
+
+extern "C" int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
+                                const float *bias, int M, int N, int K, int in_dtype, int out_dtype, const float *cos_table,
+                                const float *sin_table, const int *pos_map, int npos, int head_dim, int rope_cols,
+                                int tile_n, void *stream) {
+  if (head_dim != 64) return fail(APE_ERR_UNSUPPORTED, "gemm+rope: head_dim %d (only 64)", head_dim);
+  if ((reinterpret_cast<uintptr_t>(cos_table) | reinterpret_cast<uintptr_t>(sin_table)) & 15)
+    return fail(APE_ERR_INVALID_ARG, "gemm+rope: cos / sin tables must be 16-byte aligned");
+  RopeArgs r{cos_table, sin_table, pos_map, rope_cols, npos};
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, nullptr, 0, M, N, K, in_dtype, out_dtype, ACT_NONE, tile_n, &r, stream);
 }

@@ -80,6 +80,7 @@ class BiAttentionBlock(nn.Module):
                                          clamp_min_for_underflow, clamp_max_for_overflow, use_attention_mask_v)
         self.gamma_v = nn.Parameter(init_values * torch.ones(v_dim))
         self.gamma_l = nn.Parameter(init_values * torch.ones(l_dim))
+        self.fold_language_side = True  # one-token case: fold the small projection chains into two GEMVs (CUDA)
 
     def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
         # fuse_helper.py:221-232 — note the residual is added to the *normalised* v / l
@@ -105,11 +106,50 @@ class BiAttentionBlock(nn.Module):
         dl = self.single_token_pool(v, qa, qc)
         return dv.to(v.dtype), dl.to(l.dtype)
 
+    def _folded_language_maps(self):
+        """The one-token case is affine in the language token on both sides, so the chains of small projections are
+        folded once per set of weights (fp64, stored fp32):
+          [qa | qc | delta_v] = ln_l @ G^T + g0     (l_proj -> per-head v_proj^T; l_proj -> v_proj bias; values_l_proj -> out_v_proj)
+          delta_l             = pooled @ E^T + e0   (values_v_proj per head -> out_l_proj)
+        One GEMV each per layer instead of ~25 small kernels; results differ from the op-by-op order by fp32 rounding."""
+        a = self.attn
+        params = [a.l_proj.weight, a.l_proj.bias, a.v_proj.weight, a.v_proj.bias, a.values_l_proj.weight, a.values_l_proj.bias,
+                  a.out_v_proj.weight, a.out_v_proj.bias, a.values_v_proj.weight, a.values_v_proj.bias, a.out_l_proj.weight,
+                  a.out_l_proj.bias]
+        key = tuple((t._version, t.data_ptr()) for t in params)
+        if getattr(self, "_folded", (None,))[0] != key:
+            nh, hd = a.num_heads, a.head_dim
+            with torch.no_grad():
+                d = lambda t: t.detach().double()
+                wl, bl = d(a.l_proj.weight).view(nh, hd, -1), d(a.l_proj.bias).view(nh, hd)           # [nh,hd,L]
+                wq, bq = d(a.v_proj.weight).view(nh, hd, -1), d(a.v_proj.bias).view(nh, hd)           # [nh,hd,C]
+                A = torch.einsum("hdc,hdj->hcj", wq, wl) * a.scale                                    # [nh,C,L]
+                a0 = torch.einsum("hdc,hd->hc", wq, bl) * a.scale
+                Cm = torch.einsum("hd,hdj->hj", bq, wl) * a.scale                                     # [nh,L]
+                c0 = torch.einsum("hd,hd->h", bq, bl) * a.scale
+                D = d(a.out_v_proj.weight) @ d(a.values_l_proj.weight)                                # [C,L]
+                d0 = d(a.out_v_proj.weight) @ d(a.values_l_proj.bias) + d(a.out_v_proj.bias)
+                G = torch.cat([A.reshape(-1, A.shape[-1]), Cm, D], 0).float().contiguous()
+                g0 = torch.cat([a0.reshape(-1), c0, d0], 0).float().contiguous()
+                wvv, bvv = d(a.values_v_proj.weight).view(nh, hd, -1), d(a.values_v_proj.bias)        # [nh,hd,C]
+                wol = d(a.out_l_proj.weight).view(-1, nh, hd)                                         # [L,nh,hd]
+                E = torch.einsum("jhd,hdc->jhc", wol, wvv).reshape(wol.shape[0], -1).float().contiguous()
+                e0 = (d(a.out_l_proj.weight) @ bvv + d(a.out_l_proj.bias)).float().contiguous()
+            self._folded = (key, G, g0, E, e0)
+        return self._folded[1:]
+
     def single_token_language_side(self, l):
         """Everything of the one-token case that depends on the language token only: delta_v [B,1,v_dim] and the
         folded score operands qa [B,nh,v_dim], qc [B,nh] (scores[s,h] = v_s . qa[h] + qc[h])."""
         a = self.attn
         nh, hd = a.num_heads, a.head_dim
+        if l.is_cuda and self.fold_language_side:
+            with torch.autocast("cuda", enabled=False):
+                G, g0, _, _ = self._folded_language_maps()
+                B = l.shape[0]
+                y = F.linear(l.float().reshape(B, -1), G, g0)
+                C = a.v_proj.weight.shape[1]
+                return y[:, nh * C + nh:].reshape(B, 1, C), y[:, : nh * C].reshape(B, nh, C), y[:, nh * C: nh * C + nh]
         with torch.autocast("cuda", enabled=False):
             lf = l.float()
             B = lf.shape[0]
@@ -147,6 +187,9 @@ class BiAttentionBlock(nn.Module):
                 pooled = torch.einsum("bhs,bsc->bhc", wl, vf)                                        # [B,nh,v_dim]
             if shift is not None:
                 pooled = pooled - shift.reshape(B, 1, -1).float()
+            if v.is_cuda and self.fold_language_side:
+                _, _, E, e0 = self._folded_language_maps()
+                return F.linear(pooled.reshape(B, 1, -1), E, e0)
             wvv = a.values_v_proj.weight.float().view(nh, hd, -1)
             out_l = torch.einsum("bhc,hdc->bhd", pooled, wvv) + a.values_v_proj.bias.float().view(nh, hd)
             dl = F.linear(out_l.reshape(B, 1, nh * hd), a.out_l_proj.weight.float(), a.out_l_proj.bias.float())

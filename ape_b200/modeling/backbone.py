@@ -178,6 +178,7 @@ class ViT(nn.Module):
             Block(embed_dim, num_heads, mlp_ratio, norm_layer, window_size if i in window_block_indexes else 0,
                   self.rope_win if i in window_block_indexes else self.rope_glb)
             for i in range(depth)])
+        self.fused_rope = False
         self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
         self._out_feature_channels = {out_feature: embed_dim}
         self._out_feature_strides = {out_feature: patch_size}
@@ -295,12 +296,22 @@ class ViT(nn.Module):
         hbuf2 = torch.empty((M, hid_p), dtype=dtype, device=dev)
         for blk, p in zip(self.blocks, pk["blocks"]):
             h = ops.layernorm(x, p["n1w"], p["n1b"], eps=1e-6)
-            qkv = ops.linear_tc(h, p["wqkv"], p["bqkv"])
+            # RoPE in the qkv GEMM epilogue (ape_gemm_tn_rope) is available but OFF: measured +26 us per qkv GEMM (the 8
+            # epilogue warps wait on the cos/sin rows) against 8.7 us for the separate ape_rope_qk pass
+            fused_rope = self.fused_rope and hd == 64 and C % 8 == 0
             if blk.window_size > 0:
-                ops.rope_qk_(qkv, rope_win[0], rope_win[1], C, hd)  # position = index inside the window
+                if fused_rope:
+                    qkv = ops.linear_rope_tc(h, p["wqkv"], p["bqkv"], rope_win[0], rope_win[1], C, hd)
+                else:
+                    qkv = ops.linear_tc(h, p["wqkv"], p["bqkv"])
+                    ops.rope_qk_(qkv, rope_win[0], rope_win[1], C, hd)  # position = index inside the window
                 nb, n = B * nw * nw, w * w
             else:
-                ops.rope_qk_(qkv, rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
+                if fused_rope:
+                    qkv = ops.linear_rope_tc(h, p["wqkv"], p["bqkv"], rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
+                else:
+                    qkv = ops.linear_tc(h, p["wqkv"], p["bqkv"])
+                    ops.rope_qk_(qkv, rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
                 nb, n = B, g * g
             if self.engine_attention and ops.attention_supported(n, hd, qkv.dtype):
                 o = ops.attention_qkv(qkv, nb, n, heads, hd, blk.attn.scale)  # tcgen05 flash attention, no head-split copies

@@ -182,6 +182,28 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
     return out.view(*x.shape[:-1], n_out) if ret_view else out
 
 
+def linear_rope_tc(x, weight, bias, cos, sin, num_channels, head_dim, pos_map=None):
+    """Fused qkv projection + 2-D RoPE on the q and k thirds (ape_gemm_tn_rope): x [M, K] @ weight[3C, K]^T + bias with the
+    rotary embedding applied in the GEMM epilogue (fp32, before the single rounding).  Returns [M, 3C]."""
+    _require(x.is_cuda and x.dim() == 2 and x.dtype == weight.dtype and x.dtype in (torch.float16, torch.bfloat16),
+             "linear_rope_tc: 2-D fp16/bf16 CUDA operands")
+    M, K = x.shape
+    N = weight.shape[0]
+    _require(weight.shape[1] == K and x.stride(1) == 1 and weight.stride(1) == 1 and x.stride(0) % 8 == 0 and
+             weight.stride(0) % 8 == 0, "linear_rope_tc: bad operand layout")
+    _require(cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape[1] == head_dim,
+             "linear_rope_tc: cos/sin must be contiguous fp32 [npos, head_dim]")
+    out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
+        rc = _lib.lib.ape_gemm_tn_rope(x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), N,
+                                       bias.data_ptr() if bias is not None else None, M, N, K, _lib.dtype_code(x.dtype),
+                                       _lib.dtype_code(x.dtype), cos.data_ptr(), sin.data_ptr(),
+                                       pos_map.data_ptr() if pos_map is not None else None, cos.shape[0], int(head_dim),
+                                       2 * int(num_channels), 0, _lib.current_stream_ptr())
+    _lib.check(rc, "ape_gemm_tn_rope")
+    return out
+
+
 def packed(module, dtype, extra=None):
     """(weight in `dtype`, fp32 bias) of an nn.Linear / nn.LayerNorm-like module, cached on the module and
     refreshed when its parameters change (load_state_dict, .to()).  LayerNorm weights stay fp32."""

@@ -126,6 +126,16 @@ int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C,
                 int tile_n, void *stream);
 
 /*
+ * ape_gemm_tn with the 2-D rotary embedding of the ViT (VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346) fused into
+ * the epilogue: C = A W^T + bias, then t' = t*cos + rotate_half(t)*sin on output columns [0, rope_cols) — the q and k
+ * thirds of the fused qkv projection (vit_eva_clip.py:225-262) — in fp32 before the single rounding to the 16-bit
+ * output.  cos/sin fp32 [npos, 64]; row m uses position pos_map[m] (int32, device) or m % npos when NULL; head_dim 64.
+ */
+int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
+                     int M, int N, int K, int in_dtype, int out_dtype, const float *cos_table, const float *sin_table,
+                     const int *pos_map, int npos, int head_dim, int rope_cols, int tile_n, void *stream);
+
+/*
  * LayerNorm over the last dimension (nn.LayerNorm / inner_attn_ln / ffn_ln of vit_eva_clip.py:505-523,266,130;
  * norms of the detrex transformer layers).  fp32 statistics; x [rows, C] pitch ldx (in_dtype), y pitch ldy
  * (out_dtype); weight/bias fp32 [C].  Pitches must cover C rounded up to 8 elements; padding elements

@@ -145,3 +145,30 @@ def test_rejects_bad_arguments(ops):
         ops.linear_tc(x, x)  # fp32 operands are not a tensor-core format here
     with pytest.raises(RuntimeError):
         ops.linear_tc(x.cpu().half(), x.cpu().half())  # no CPU path
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("use_map", [False, True])
+def test_qkv_projection_with_fused_rope(ops, dtype, tol, use_map):
+    """ape_gemm_tn_rope = ape_gemm_tn followed by the 2-D rotary embedding on the q and k thirds (the separate
+    ape_rope_qk kernel and the reference formula, utils_eva02.py:248-252,346), single rounding."""
+    M, C, heads, hd, K, npos = 640, 256, 4, 64, 192, 160
+    x = rnd(M, K, dtype=dtype, seed=51)
+    w = rnd(3 * C, K, dtype=dtype, seed=52, scale=K ** -0.5)
+    b = rnd(3 * C, dtype=torch.float32, seed=53)
+    g = torch.Generator().manual_seed(54)
+    ang = torch.randn(npos, hd, generator=g)
+    cos, sin = ang.cos().to(DEV), ang.sin().to(DEV)
+    pos = torch.randint(0, npos, (M,), generator=g).to(torch.int32).to(DEV) if use_map else None
+    got = ops.linear_rope_tc(x, w, b, cos, sin, C, hd, pos_map=pos)
+    y = ref_linear(x, w, b)
+    pidx = pos.long() if use_map else torch.arange(M, device=DEV) % npos
+
+    def rope(t):
+        t = t.view(M, heads, hd)
+        pr = t.reshape(M, heads, hd // 2, 2)
+        rot = torch.stack((-pr[..., 1], pr[..., 0]), -1).flatten(-2)
+        return (t * cos[pidx][:, None] + rot * sin[pidx][:, None]).reshape(M, C)
+
+    want = torch.cat([rope(y[:, :C]), rope(y[:, C:2 * C]), y[:, 2 * C:]], 1)
+    torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
