@@ -210,9 +210,17 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
         const int n0 = n_blk * BN + c0 + hh * 64;
         // bias only (activation is the gate below)
         if (p.bias != nullptr) {
+          if (n0 + 64 <= p.N) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+            for (int i = 0; i < 16; ++i) {
+              const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
+              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+          }
         }
         float o[32];
 #pragma unroll

@@ -180,8 +180,9 @@ def model_bench(args, rank, local_rank, world):
     config = {"workload": "APE-L_D detection forward, 1024x1024 image, 1203-name vocabulary, boxes only, batch 1 per GPU",
               "weights": "random init of the real architecture (380 M params)", "text": "seeded synthetic features (text tower out of path)",
               "l2": "per-step working set (weights 1.5 GB fp32 + activations) >> 126 MB L2",
-              "dense_ops": "ViT linears/LayerNorm/RoPE + ms_deform_attn = libape_b200 kernels (tcgen05 GEMM); attention, convs, "
-                           "encoder/decoder linears, top-k/NMS = torch library kernels this round",
+              "dense_ops": "libape_b200 kernels: every linear of the ViT / pyramid / neck / encoder / decoder / heads (tcgen05 GEMM), ViT "
+                           "attention (tcgen05 flash attention), LayerNorm / RoPE / GroupNorm, fused ms_deform_attn, VLF pooling, NMS; "
+                           "library: four 3x3 convolutions (cuDNN), decoder self-attention over 900 queries (SDPA), sort, small elementwise glue",
               "parallelism": f"dp{args.gpus} (one image per GPU; one NCCL gather of packed detections per step when N>1)"}
     if args.impl == "reference":
         if rank != 0:
