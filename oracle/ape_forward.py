@@ -543,10 +543,45 @@ def build_text_inputs(text_feats, spec, phrase, batch, bank_reset=False):
     return fl, fl
 
 
-def forward(images, out_sizes, text_feats, sd, spec, phrase=False, taps=None, bank_reset=False):
-    """Whole detection forward (boxes only).  images: list of CHW float RGB 0..255;
-    out_sizes: list of (height, width) the detections are rescaled to; text_feats [N_t, lang_dim].
-    Returns list of dicts(boxes, scores, classes, query_index) + the tap dict."""
+# ------------------------------------------------------------------------------------------------
+# mask head, instance-mask post-processing, semantic branch (deformable_detr_segm_vl.py:728-750, :507-517,
+# :563-603, :628-666, :875-918; detectron2 BitMasks.crop_and_resize / paste_masks_in_image / sem_seg_postprocess)
+# ------------------------------------------------------------------------------------------------
+def mask_features(memory, p2, shapes, sd):
+    """maskdino_mask_features (:728-750), mask_encode_level 0, GroupNorm(32) convs without bias."""
+    h, w = shapes[0]
+    enc = memory[:, : h * w].permute(0, 2, 1).reshape(memory.shape[0], -1, h, w)
+    x = F.group_norm(F.conv2d(p2, sd["lateral_conv.weight"]), 32, sd["lateral_conv.norm.weight"], sd["lateral_conv.norm.bias"])
+    x = x + F.interpolate(enc, size=x.shape[-2:], mode="bilinear", align_corners=False)
+    x = F.relu(F.group_norm(F.conv2d(x, sd["output_conv.weight"], padding=1), 32, sd["output_conv.norm.weight"],
+                            sd["output_conv.norm.bias"]))
+    return F.conv2d(x, sd["mask_conv.weight"])
+
+
+def crop_and_resize(masks, boxes, size):
+    """detectron2 BitMasks.crop_and_resize: ROIAlign(size, scale 1, sampling_ratio 0, aligned) on the float mask, >= 0.5."""
+    rois = torch.cat([torch.arange(len(boxes), dtype=boxes.dtype)[:, None], boxes], dim=1)
+    return torchvision.ops.roi_align(masks.to(torch.float32)[:, None], rois, (size, size), 1.0, 0, True).squeeze(1) >= 0.5
+
+
+def paste_masks(masks, boxes, out_h, out_w, threshold=0.5):
+    """detectron2 paste_masks_in_image (bilinear grid_sample, align_corners=False), whole image per mask."""
+    out = torch.zeros(len(masks), out_h, out_w, dtype=torch.bool)
+    for i in range(len(masks)):
+        x0, y0, x1, y1 = boxes[i]
+        iy = (torch.arange(out_h, dtype=torch.float32) + 0.5 - y0) / (y1 - y0) * 2 - 1
+        ix = (torch.arange(out_w, dtype=torch.float32) + 0.5 - x0) / (x1 - x0) * 2 - 1
+        grid = torch.stack([ix[None, :].expand(out_h, out_w), iy[:, None].expand(out_h, out_w)], dim=2)[None]
+        out[i] = F.grid_sample(masks[i][None, None].float(), grid, align_corners=False)[0, 0] >= threshold
+    return out
+
+
+def forward(images, out_sizes, text_feats, sd, spec, phrase=False, taps=None, bank_reset=False, masks_on=False,
+            semantic_on=False):
+    """Whole detection forward.  images: list of CHW float RGB 0..255; out_sizes: list of (height, width) the
+    detections are rescaled to; text_feats [N_t, lang_dim].  masks_on / semantic_on: the reference's test_mask_on /
+    semantic_on branches ("thing" entity).  Returns list of dicts(boxes, scores, classes, query_index[, masks, sem_seg])
+    + the tap dict."""
     taps = {} if taps is None else taps
     with torch.no_grad():
         batch, img_masks, sizes = preprocess(images, spec)
@@ -571,13 +606,30 @@ def forward(images, out_sizes, text_feats, sd, spec, phrase=False, taps=None, ba
         logits = vl_align(hs, fl, sd, f"class_embed.{nd - 1}")
         coord = (mlp(hs, sd, f"bbox_embed.{nd - 1}", 3) + inverse_sigmoid(reference)).sigmoid()
         taps["pred_logits"], taps["pred_boxes"] = logits, coord
+        mask_pred = None
+        if masks_on or semantic_on:
+            shapes = [tuple(f.shape[-2:]) for f in ml]
+            mf = mask_features(tr["memory"], pyr["p2"], shapes, sd)
+            mask_pred = torch.einsum("bqc,bchw->bqhw", mlp(hs, sd, "mask_embed", 3), mf)  # last level only (:517)
+            taps["mask_features"], taps["pred_masks"] = mf, mask_pred
+        padded = tuple(batch.shape[-2:])
         results = []
         for b in range(len(images)):
             scores = torch.cat((logits[b].sigmoid(), torch.zeros(logits.shape[1], 1)), dim=1)
             h, w = sizes[b]
             boxes = box_cxcywh_to_xyxy(coord[b]) * torch.tensor([w, h, w, h], dtype=torch.float32)
-            bx, sc, cl, qi = fast_rcnn_inference_single(boxes, scores, (h, w), spec["test_score_thresh"],
-                                                        spec["test_nms_thresh"], spec["test_topk"])
-            bx, keep = detector_postprocess(bx, (h, w), out_sizes[b][0], out_sizes[b][1])
-            results.append(dict(boxes=bx[keep], scores=sc[keep], classes=cl[keep], query_index=qi[keep]))
+            bx0, sc, cl, qi = fast_rcnn_inference_single(boxes, scores, (h, w), spec["test_score_thresh"],
+                                                         spec["test_nms_thresh"], spec["test_topk"])
+            bx, keep = detector_postprocess(bx0, (h, w), out_sizes[b][0], out_sizes[b][1])
+            r = dict(boxes=bx[keep], scores=sc[keep], classes=cl[keep], query_index=qi[keep])
+            if masks_on:  # (:588-603) + detector_postprocess
+                m = F.interpolate(mask_pred[b, qi][None], size=padded, mode="bilinear", align_corners=False)[0]
+                m128 = crop_and_resize(m.sigmoid() > 0.5, bx0, 128).to(torch.float32)
+                r["masks"] = paste_masks(m128[keep], bx[keep], out_sizes[b][0], out_sizes[b][1])
+            if semantic_on:  # (:628-666, :875-918), semantic_post_nms with the detector's own thresholds
+                cls = F.softmax(logits[b, qi].sigmoid() / 0.06, dim=-1)
+                m = F.interpolate(mask_pred[b, qi][None], size=padded, mode="bilinear", align_corners=False)[0].sigmoid()
+                sem = torch.einsum("qc,qhw->chw", cls, m)[:, :h, :w].expand(1, -1, -1, -1)
+                r["sem_seg"] = F.interpolate(sem, size=tuple(out_sizes[b]), mode="bilinear", align_corners=False)[0]
+            results.append(r)
     return results, taps

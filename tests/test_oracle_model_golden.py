@@ -64,3 +64,21 @@ def test_port_matches_reference_golden(case, sd):
         assert torch.equal(r["classes"], g[f"det{b}.classes"])  # bit-exact: kept (query, class) pairs
         torch.testing.assert_close(r["scores"], g[f"det{b}.scores"], rtol=1e-3, atol=1e-5)
         torch.testing.assert_close(r["boxes"], g[f"det{b}.boxes"], rtol=1e-3, atol=1e-2)
+
+
+def test_port_masks_and_semantic_match_reference_golden(sd):
+    """SURVEY.md 8(a) rows a17 / a19 / a20 of the port against the reference's own outputs (model_mini_masks.npz)."""
+    import numpy as np
+
+    spec = configs.MINI
+    g = load_golden("model_mini_masks.npz")
+    text = synth.text_features(8192, spec["lang_dim"])[: spec["num_classes"]]
+    res, taps = AF.forward([synth.image(48, 64, seed=0)], [(96, 128)], text, sd, spec, masks_on=True, semantic_on=True)
+    torch.testing.assert_close(taps["mask_features"][:, ::8], g["mask_features"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(taps["pred_masks"], g["pred_masks"], rtol=1e-3, atol=1e-3)
+    r = res[0]
+    assert torch.equal(r["classes"], g["det0.classes"])
+    want = torch.from_numpy(np.unpackbits(g["det0.masks_packed"].numpy(), axis=-1)).bool()[..., : int(g["det0.masks_shape"][2])]
+    assert r["masks"].shape == want.shape
+    assert (r["masks"] != want).float().mean().item() < 1e-3
+    torch.testing.assert_close(r["sem_seg"], g["sem_seg"], rtol=1e-3, atol=1e-3)
