@@ -154,16 +154,15 @@ def cpu_model_arm(steps, n_text=1203, sd=None):
     spec["test_score_thresh"] = 0.1
     text = synthetic.text_features(8192, spec["lang_dim"])[:n_text]
     if sd is None:
+        # reference arm: same synthetic weights; the score calibration of the GPU arm (one more whole forward, ~2 min of
+        # host time) is skipped — thresholding / NMS of a few hundred candidates is < 0.1 % of the CPU time of a forward
         m = build_model(spec, num_text=n_text)  # parameter container only; the port is functional over its state_dict
         synthetic.fill_state_dict(m)
         sd = m.state_dict()
-        _, taps = AF.forward([synthetic.image(1024, 1024, seed=99)], [(1024, 1024)], text, sd, spec)
-        kth = torch.topk(taps["pred_logits"].flatten(), 500).values[-1]
-        sd[f"class_embed.{spec['dec_layers'] - 1}.bias0"].add_(math.log(0.1 / 0.9) - kth)
     else:
         sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     img = torch.randint(0, 256, (3, 1024, 1024), generator=torch.Generator().manual_seed(0)).to(torch.float32)
-    n = max(1, min(steps, 2))
+    n = 1  # one whole-image forward is ~2 minutes of host time on the B200 box: a bounded sample by construction
     t0 = time.perf_counter()
     for _ in range(n):
         res, _ = AF.forward([img], [(1024, 1024)], text, sd, spec)
