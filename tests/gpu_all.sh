@@ -1,0 +1,9 @@
+#!/bin/bash
+# Everything that needs a B200, in the order used during development (run through gpurun):
+#   bash tests/gpu_all.sh            tests + smoke + bench + per-kernel profile
+set -u
+mkdir -p gpurun_out
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+echo "== gpu tests"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -6
+echo "== bench"; timeout 900 python bench.py --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench.json | cut -c1-300
+echo "== per-kernel profile (CUPTI under graph replay)"; timeout 300 python tests/profile_step.py --out gpurun_out/kernels_step.json 2>&1 | grep -v Warn | head -20
