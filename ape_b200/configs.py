@@ -37,6 +37,19 @@ APE_L_D_1536 = copy.deepcopy(APE_L_D)
 APE_L_D_1536["name"] = "APE-L_D-1536"
 APE_L_D_1536["backbone"].update(img_size=1536, square_pad=1536)         # configs/common/backbone/vitl_eva02_clip_1536.py
 
+# APE-Ti (BASELINE.json configs[0]): configs/common/backbone/vitt_eva02.py:10-41 (ape/modeling/backbone/vit_eva02.py:
+# packed-SwiGLU "w12", fused qkv, no sub-LN, 14x14 windows over a 64x64 token grid padded to 70x70) under the same
+# deformable transformer as APE-L_D (…/ape_deta_vitt_eva02_vlf_lsj1024_cp_16x4_1080k.py:19-176).
+APE_TI = copy.deepcopy(APE_L_D)
+APE_TI["name"] = "APE-Ti"
+APE_TI["backbone"] = dict(
+    variant="eva02",                                                   # vit_eva02.py: swiglu=True, naiveswiglu=False, subln=False
+    img_size=1024, patch_size=16, embed_dim=192, depth=12, num_heads=3,
+    window_size=14, mlp_ratio=4 * 2 / 3, window_block_indexes=[0, 1, 3, 4, 6, 7, 9, 10],
+    pretrain_img_size=224, pt_hw_seq_len=16,
+    out_channels=256, scale_factors=(4.0, 2.0, 1.0, 0.5), square_pad=1024,
+)
+
 MINI = dict(
     name="MINI",
     backbone=dict(

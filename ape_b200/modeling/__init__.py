@@ -32,7 +32,9 @@ def build_model(spec, num_text=None):
               num_heads=b["num_heads"], drop_path_rate=0.0, window_size=b["window_size"], mlp_ratio=b["mlp_ratio"],
               qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), window_block_indexes=b["window_block_indexes"],
               residual_block_indexes=[], use_rel_pos=True, out_feature="last_feat", use_act_checkpoint=False,
-              xattn=False, rope=True, pt_hw_seq_len=b["pt_hw_seq_len"], intp_freq=True, naiveswiglu=True, subln=True,
+              xattn=False, rope=True, pt_hw_seq_len=b["pt_hw_seq_len"], intp_freq=True,
+              naiveswiglu=b.get("variant", "eva_clip") == "eva_clip", subln=b.get("variant", "eva_clip") == "eva_clip",
+              swiglu=b.get("variant", "eva_clip") == "eva02",
               pretrain_img_size=b["pretrain_img_size"], pretrain_use_cls_token=True)
     backbone = SimpleFeaturePyramid(net=net, in_feature="last_feat", out_channels=b["out_channels"],
                                     scale_factors=b["scale_factors"], top_block=LastLevelMaxPool(), norm="LN",

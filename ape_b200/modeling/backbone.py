@@ -99,18 +99,40 @@ class SwiGLU(nn.Module):
         return self.w3(self.ffn_ln(F.silu(self.w1(x)) * self.w2(x)))
 
 
+class PackedSwiGLU(nn.Module):
+    """vit_eva02.py `xops_SwiGLU` (:41-160): w1 and w2 stacked in one `w12` Linear, no inner LayerNorm."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.w12 = nn.Linear(in_features, 2 * hidden_features)
+        self.w3 = nn.Linear(hidden_features, in_features)
+
+    def forward(self, x):
+        w1, w2 = torch.unbind(self.w12.weight.view(2, self.w12.weight.shape[0] // 2, -1), dim=0)
+        b1, b2 = torch.unbind(self.w12.bias.view(2, -1), dim=0)
+        return self.w3(F.silu(F.linear(x, w1, b1)) * F.linear(x, w2, b2))
+
+
 class Attention(nn.Module):
-    def __init__(self, dim, num_heads, rope, norm_layer):
+    """subln=True: vit_eva_clip.py:135-319 (separate q/k/v projections + inner_attn_ln, APE-L);
+    subln=False: vit_eva02.py `Attention` (fused `qkv` projection, no inner norm, APE-Ti)."""
+
+    def __init__(self, dim, num_heads, rope, norm_layer, subln=True):
         super().__init__()
         self.num_heads = num_heads
         head_dim = dim // num_heads
         self.scale = head_dim ** -0.5
-        self.q_proj = nn.Linear(dim, dim, bias=False)
-        self.k_proj = nn.Linear(dim, dim, bias=False)
-        self.v_proj = nn.Linear(dim, dim, bias=False)
+        self.subln = subln
+        if subln:
+            self.q_proj = nn.Linear(dim, dim, bias=False)
+            self.k_proj = nn.Linear(dim, dim, bias=False)
+            self.v_proj = nn.Linear(dim, dim, bias=False)
+        else:
+            self.qkv = nn.Linear(dim, dim * 3, bias=False)
         self.q_bias = nn.Parameter(torch.zeros(dim))
         self.v_bias = nn.Parameter(torch.zeros(dim))
-        self.inner_attn_ln = norm_layer(dim)
+        if subln:
+            self.inner_attn_ln = norm_layer(dim)
         self.proj = nn.Linear(dim, dim)
         self.rope = rope
 
@@ -118,26 +140,33 @@ class Attention(nn.Module):
         B, H, W, C = x.shape
         N = H * W
         x = x.reshape(B, N, C)
-        q = F.linear(x, self.q_proj.weight, self.q_bias)
-        k = F.linear(x, self.k_proj.weight, None)
-        v = F.linear(x, self.v_proj.weight, self.v_bias)
-        q = q.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
-        k = k.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
-        v = v.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
+        if self.subln:
+            q = F.linear(x, self.q_proj.weight, self.q_bias)
+            k = F.linear(x, self.k_proj.weight, None)
+            v = F.linear(x, self.v_proj.weight, self.v_bias)
+            q = q.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
+            k = k.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
+            v = v.reshape(B, N, self.num_heads, -1).permute(0, 2, 1, 3)
+        else:
+            bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias), self.v_bias))
+            qkv = F.linear(x, self.qkv.weight, bias).reshape(B, N, 3, self.num_heads, -1).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0], qkv[1], qkv[2]
         q = self.rope(q).type_as(v)
         k = self.rope(k).type_as(v)
         o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, scale=self.scale)
         o = o.permute(0, 2, 1, 3).reshape(B, N, -1)
-        return self.proj(self.inner_attn_ln(o)).view(B, H, W, C)
+        if self.subln:
+            o = self.inner_attn_ln(o)
+        return self.proj(o).view(B, H, W, C)
 
 
 class Block(nn.Module):
-    def __init__(self, dim, num_heads, mlp_ratio, norm_layer, window_size, rope):
+    def __init__(self, dim, num_heads, mlp_ratio, norm_layer, window_size, rope, subln=True, packed_swiglu=False):
         super().__init__()
         self.norm1 = norm_layer(dim)
-        self.attn = Attention(dim, num_heads, rope, norm_layer)
+        self.attn = Attention(dim, num_heads, rope, norm_layer, subln=subln)
         self.norm2 = norm_layer(dim)
-        self.mlp = SwiGLU(dim, int(dim * mlp_ratio), norm_layer)
+        self.mlp = PackedSwiGLU(dim, int(dim * mlp_ratio)) if packed_swiglu else SwiGLU(dim, int(dim * mlp_ratio), norm_layer)
         self.window_size = window_size
 
     def forward(self, x):
@@ -160,12 +189,15 @@ class ViT(nn.Module):
                  rope=False, postnorm=False, pt_hw_seq_len=16, intp_freq=False, naiveswiglu=False, subln=False,
                  window_size=0, window_block_indexes=(), residual_block_indexes=(), use_act_checkpoint=False,
                  pretrain_img_size=224, pretrain_use_cls_token=True, out_feature="last_feat", xattn=False,
-                 frozen_stages=-1):
+                 frozen_stages=-1, swiglu=False):
         super().__init__()
-        if not (rope and naiveswiglu and subln and qkv_bias and use_abs_pos and intp_freq) or postnorm or init_values \
+        variant_l = naiveswiglu and subln and not swiglu        # vit_eva_clip.py (APE-L_*: sub-LN, naive SwiGLU)
+        variant_ti = swiglu and not naiveswiglu and not subln   # vit_eva02.py   (APE-Ti: packed SwiGLU, fused qkv)
+        if not (rope and (variant_l or variant_ti) and qkv_bias and use_abs_pos and intp_freq) or postnorm or init_values \
                 or len(residual_block_indexes) or qk_scale is not None:
-            raise NotImplementedError("ape_b200.ViT implements the EVA-02 configuration APE uses "
-                                      "(rope, naiveswiglu, subln, qkv_bias, abs pos, intp_freq; pre-norm)")
+            raise NotImplementedError("ape_b200.ViT implements the two EVA-02 configurations APE uses "
+                                      "(rope, qkv_bias, abs pos, intp_freq, pre-norm; naiveswiglu + subln, or packed swiglu)")
+        self._variant_l = variant_l
         self.pretrain_use_cls_token = pretrain_use_cls_token
         self.patch_embed = PatchEmbed((patch_size, patch_size), (patch_size, patch_size), in_chans=in_chans,
                                       embed_dim=embed_dim)
@@ -176,7 +208,7 @@ class ViT(nn.Module):
         self.rope_glb = VisionRotaryEmbeddingFast(half, pt_hw_seq_len, img_size // patch_size)
         self.blocks = nn.ModuleList([
             Block(embed_dim, num_heads, mlp_ratio, norm_layer, window_size if i in window_block_indexes else 0,
-                  self.rope_win if i in window_block_indexes else self.rope_glb)
+                  self.rope_win if i in window_block_indexes else self.rope_glb, subln=variant_l, packed_swiglu=variant_ti)
             for i in range(depth)])
         self.fused_rope = False
         self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
@@ -218,6 +250,8 @@ class ViT(nn.Module):
     # patch embedding and one at the end instead of two copies per block.
     # ---------------------------------------------------------------------------------------------
     def _engine_ok(self, x):
+        if not self._variant_l:  # the tensor-core token path is written for the APE-L block layout
+            return False
         ws = next((b.window_size for b in self.blocks if b.window_size > 0), 0)
         g = x.shape[-1] // self.patch_embed.proj.kernel_size[0]
         return x.shape[-1] == x.shape[-2] and (ws == 0 or g % ws == 0)

@@ -110,19 +110,26 @@ def vit_attention(x, sd, p, num_heads, rope):
     B, H, W, C = x.shape
     N = H * W
     x = x.reshape(B, N, C)
-    q = F.linear(x, sd[p + ".q_proj.weight"], sd[p + ".q_bias"])
-    k = F.linear(x, sd[p + ".k_proj.weight"], None)
-    v = F.linear(x, sd[p + ".v_proj.weight"], sd[p + ".v_bias"])
-    q = q.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
-    k = k.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
-    v = v.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
+    fused = p + ".qkv.weight" in sd  # vit_eva02.py Attention (APE-Ti): one qkv projection, no inner LayerNorm
+    if fused:
+        bias = torch.cat((sd[p + ".q_bias"], torch.zeros_like(sd[p + ".v_bias"]), sd[p + ".v_bias"]))
+        qkv = F.linear(x, sd[p + ".qkv.weight"], bias).reshape(B, N, 3, num_heads, -1).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+    else:
+        q = F.linear(x, sd[p + ".q_proj.weight"], sd[p + ".q_bias"])
+        k = F.linear(x, sd[p + ".k_proj.weight"], None)
+        v = F.linear(x, sd[p + ".v_proj.weight"], sd[p + ".v_bias"])
+        q = q.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
+        k = k.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
+        v = v.reshape(B, N, num_heads, -1).permute(0, 2, 1, 3)
     cos, sin = rope
     q = q * cos + rotate_half(q) * sin
     k = k * cos + rotate_half(k) * sin
     scale = q.shape[-1] ** -0.5
     o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, scale=scale)
     o = o.permute(0, 2, 1, 3).reshape(B, N, -1)
-    o = _ln(o, sd, p + ".inner_attn_ln", 1e-6)
+    if not fused:
+        o = _ln(o, sd, p + ".inner_attn_ln", 1e-6)
     o = _lin(o, sd, p + ".proj")
     return o.view(B, H, W, C)
 
@@ -139,6 +146,11 @@ def vit_block(x, sd, p, num_heads, window_size, rope):
         x = window_unpartition(x, window_size, pad_hw, (H, W))
     x = shortcut + x
     y = _ln(x, sd, p + ".norm2", 1e-6)
+    if p + ".mlp.w12.weight" in sd:  # packed SwiGLU without inner norm (vit_eva02.py xops_SwiGLU, APE-Ti)
+        w12, b12 = sd[p + ".mlp.w12.weight"], sd[p + ".mlp.w12.bias"]
+        hid = w12.shape[0] // 2
+        hidden = F.silu(F.linear(y, w12[:hid], b12[:hid])) * F.linear(y, w12[hid:], b12[hid:])
+        return x + _lin(hidden, sd, p + ".mlp.w3")
     # SwiGLU (vit_eva_clip.py:125-132)
     hidden = F.silu(_lin(y, sd, p + ".mlp.w1")) * _lin(y, sd, p + ".mlp.w2")
     hidden = _ln(hidden, sd, p + ".mlp.ffn_ln", 1e-6)

@@ -55,7 +55,8 @@ def randomize_degenerate_parameters(model, seed=1):
 def build_reference_model(spec, num_text=None, seed=0, test_mask_on=False, semantic_on=False):
     """-> (model_vision in eval mode, class-name list of length num_text)"""
     refshim.install()
-    vit_mod = refshim.load("ape.modeling.backbone.vit_eva_clip")
+    ti = spec["backbone"].get("variant", "eva_clip") == "eva02"
+    vit_mod = refshim.load("ape.modeling.backbone.vit_eva02" if ti else "ape.modeling.backbone.vit_eva_clip")
     tr = refshim.load("ape.modeling.ape_deta.deformable_transformer_vl")
     segm = refshim.load("ape.modeling.ape_deta.deformable_detr_segm_vl")
     from ape.layers import VisionLanguageFusion  # noqa  (reference class, via refshim)
@@ -67,8 +68,8 @@ def build_reference_model(spec, num_text=None, seed=0, test_mask_on=False, seman
         num_heads=b["num_heads"], drop_path_rate=0.0, window_size=b["window_size"], mlp_ratio=b["mlp_ratio"],
         qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), window_block_indexes=b["window_block_indexes"],
         residual_block_indexes=[], use_rel_pos=True, out_feature="last_feat", use_act_checkpoint=False, xattn=False,
-        rope=True, pt_hw_seq_len=b["pt_hw_seq_len"], intp_freq=True, naiveswiglu=True, subln=True,
-        pretrain_img_size=b["pretrain_img_size"], pretrain_use_cls_token=True)
+        rope=True, pt_hw_seq_len=b["pt_hw_seq_len"], intp_freq=True, naiveswiglu=not ti, subln=not ti,
+        pretrain_img_size=b["pretrain_img_size"], pretrain_use_cls_token=True, **({"swiglu": True} if ti else {}))
     backbone = vit_mod.SimpleFeaturePyramid(
         net=net, in_feature="last_feat", out_channels=b["out_channels"], scale_factors=b["scale_factors"],
         top_block=refshim.LastLevelMaxPool(), norm="LN", square_pad=b["square_pad"])

@@ -132,8 +132,50 @@ def main_masks():
     print("masks", {k: tuple(v.shape) for k, v in rec.items()})
 
 
+def main_ti():
+    """model_ti_1024.npz — BASELINE.json configs[0]: APE-Ti (vit_eva02.py backbone), one image padded to 1024^2,
+    80-name vocabulary, "name" prompt, pytorch_attn=True / SDPA-math on CPU.  The image is 768 x 1024 so that a
+    quarter of the square is padding (masks, valid ratios).  Per-token tensors are stored sub-sampled."""
+    import time
+
+    spec = configs.APE_TI
+    n_text = 80
+    model, names = ref_model.build_reference_model(spec, num_text=n_text)
+    synth.fill_state_dict(model)
+    model.test_score_thresh = 0.0
+    cap = {}
+    model.backbone.register_forward_hook(lambda m, i, o: cap.__setitem__("backbone", o))
+    model.transformer.register_forward_hook(lambda m, i, o: cap.__setitem__("transformer", o))
+    gathered = []
+    orig_gather = torch.gather
+
+    def spy(inp, dim, index, *a, **k):
+        if index.dim() == 3 and index.shape[-1] == 4 and index.shape[1] == spec["num_queries"]:
+            gathered.append(index[..., 0].clone())
+        return orig_gather(inp, dim, index, *a, **k)
+
+    torch.gather = spy
+    t0 = time.time()
+    try:
+        with torch.no_grad():
+            out = model([{"image": synth.image(768, 1024, seed=11), "height": 384, "width": 512}])
+    finally:
+        torch.gather = orig_gather
+    print(f"reference APE-Ti forward on CPU: {time.time() - t0:.1f} s")
+    (inter_states, init_reference, inter_references, enc_cls, enc_coord_unact, anchors, memory, feats_l) = cap["transformer"]
+    inst = out[0]["instances"]
+    rec = {f"backbone.{k}": v[:, ::16, ::4, ::4] for k, v in cap["backbone"].items()}
+    rec.update(memory=memory[:, ::128], enc_outputs_class=enc_cls[:, ::16], topk_proposals=gathered[0],
+               init_reference=init_reference, inter_states_last=inter_states[-1][:, ::3], inter_references_last=inter_references[-1],
+               **{"det0.boxes": inst.pred_boxes.tensor, "det0.scores": inst.scores, "det0.classes": inst.pred_classes})
+    np.savez_compressed(os.path.join(HERE, "model_ti_1024.npz"), **{k: v.detach().cpu().numpy() for k, v in rec.items()})
+    print("ti", {k: tuple(v.shape) for k, v in rec.items()})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "masks":
+    if len(sys.argv) > 1 and sys.argv[1] == "ti":
+        main_ti()
+    elif len(sys.argv) > 1 and sys.argv[1] == "masks":
         main_masks()
     else:
         main()

@@ -256,3 +256,33 @@ def test_ape_l_d_1024_matches_oracle_port_stagewise():
     assert abs(len(inst) - len(res[0]["scores"])) <= 3
     k = min(20, len(inst), len(res[0]["scores"]))
     torch.testing.assert_close(inst.scores[:k], res[0]["scores"][:k], rtol=2e-2, atol=1e-3)
+
+
+@pytest.mark.slow
+def test_ape_ti_1024_matches_reference_golden():
+    """BASELINE.json configs[0] on the engine: APE-Ti (vit_eva02.py backbone on the fp32 library path, engine kernels
+    for deformable attention / NMS), one 768 x 1024 image padded to 1024^2, 80 names, against tensors recorded from the
+    reference model on the CPU (tests/golden/model_ti_1024.npz)."""
+    spec = configs.APE_TI
+    g = load_golden("model_ti_1024.npz")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from ape_b200.modeling import build_model
+
+    model = build_model(spec, num_text=80)
+    synth.fill_state_dict(model)
+    model = model.to(DEV)
+    out = model([{"image": synth.image(768, 1024, seed=11), "height": 384, "width": 512}])
+    lo = model.last_outputs
+    for k in ("p2", "p4", "p6"):
+        torch.testing.assert_close(lo["features"][k][:, ::16, ::4, ::4].cpu(), g[f"backbone.{k}"], rtol=2e-3, atol=2e-3)
+    # fp32 on both sides, different reduction orders over 6 encoder layers (cf. the APE-L_D full-size test)
+    torch.testing.assert_close(lo["memory"][:, ::128].cpu(), g["memory"], rtol=1e-2, atol=1e-2)
+    sel, want = model.transformer.last_topk_proposals.cpu()[0].tolist(), g["topk_proposals"][0].tolist()
+    frac = len(set(sel) & set(want)) / len(want)
+    print(f"APE-Ti proposal set agreement with the reference: {frac:.4f}")
+    assert frac > 0.85
+    inst = out[0]["instances"]
+    assert abs(len(inst) - len(g["det0.scores"])) <= 3
+    k = min(20, len(inst))
+    torch.testing.assert_close(inst.scores[:k], g["det0.scores"][:k], rtol=2e-2, atol=1e-3)
