@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define APE_ABI_VERSION 1
+#define APE_ABI_VERSION 2
 
 /* element types accepted by the kernels (value of the `dtype` argument) */
 #define APE_DTYPE_F32 0
