@@ -27,6 +27,11 @@ class BiMultiHeadAttention(nn.Module):
         self.clamp_min_for_underflow = clamp_min_for_underflow
         self.clamp_max_for_overflow = clamp_max_for_overflow
         self.use_attention_mask_v = use_attention_mask_v
+        # Phrase prompts at scale (BASELINE.json configs[3]: S = 196 416 vision tokens x 5 000 phrases x 8 heads) would
+        # materialise 31 GB of fp32 scores several times over.  Above this many score bytes the two softmaxes are
+        # evaluated as two streaming attention calls (no S x N_t tensor) — identical mathematics as long as the +-5e4
+        # clamps cannot bind, which is checked from the operand norms first.
+        self.stream_threshold_bytes = 1 << 30
         for m in (self.v_proj, self.l_proj, self.values_v_proj, self.values_l_proj, self.out_v_proj, self.out_l_proj):
             nn.init.xavier_uniform_(m.weight)
             m.bias.data.fill_(0)
@@ -50,6 +55,19 @@ class BiMultiHeadAttention(nn.Module):
         k = heads(self.l_proj(l))
         val_v = heads(self.values_v_proj(v))
         val_l = heads(self.values_l_proj(l))
+        src_len = k.shape[1]
+        masked = attention_mask_l is not None or (attention_mask_v is not None and self.use_attention_mask_v)
+        if not masked and bsz * nh * tgt_len * src_len * 4 > self.stream_threshold_bytes:
+            # |score| <= |q_s| |k_t|: if that bound stays inside the clamps, every shift in fuse_helper.py:88-108
+            # (global max, row max) is a softmax-invariant translation and both clamps are identities
+            bound = q.float().norm(dim=-1).max() * k.float().norm(dim=-1).max()
+            if float(bound) < 25000.0:
+                q4, k4 = q.view(bsz, nh, tgt_len, hd), k.view(bsz, nh, src_len, hd)
+                out_v = F.scaled_dot_product_attention(q4, k4, val_l.view(bsz, nh, src_len, hd), scale=1.0)   # softmax over phrases
+                out_l = F.scaled_dot_product_attention(k4, q4, val_v.view(bsz, nh, tgt_len, hd), scale=1.0)   # softmax over pixels
+                out_v = out_v.transpose(1, 2).reshape(bsz, tgt_len, self.embed_dim)
+                out_l = out_l.transpose(1, 2).reshape(bsz, src_len, self.embed_dim)
+                return self.out_v_proj(out_v), self.out_l_proj(out_l)
         w = torch.bmm(q, k.transpose(1, 2))
         if self.stable_softmax_2d:
             w = w - w.max()
