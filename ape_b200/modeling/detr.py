@@ -9,9 +9,9 @@ ape/modeling/ape_deta/ape_deta.py:20-40 (`SomeThing`).  Same constructor keyword
 "instances" out, results on CPU), same parameter names incl. the shared `class_embed` /
 `bbox_embed` aliases under `transformer.decoder`.
 
-Scope: inference of box detections for "name" and "phrase"/"text" prompts.
-Training, mask / semantic / panoptic post-processing and mask prompts raise NotImplementedError
-(next rows of §8f) — loudly, never silently."""
+Scope: inference (boxes, instance masks, semantic maps) for "name", "phrase" / "text" and "expression"
+prompts.  Training, panoptic merging and mask prompts raise NotImplementedError (next rows of §8f) — loudly, never
+silently."""
 import copy
 import math
 from typing import Dict, List
@@ -347,12 +347,19 @@ class DeformableDETRSegmVL(nn.Module):
             prompt = batched_inputs[0]["prompt"]
         else:
             prompt = "name"
-        if prompt == "expression":
-            raise NotImplementedError("ape_b200: expression prompts (SURVEY.md §8f)")
-        self.test_topk_per_image = self.select_box_nums_for_evaluation
+        if prompt == "expression":  # (:184-193) referring expressions: one box per image, texts from `expressions`
+            for x in batched_inputs:
+                if not isinstance(x["expressions"], list):
+                    x["expressions"] = [x["expressions"]]
+                assert all(isinstance(xx, str) and len(xx) > 0 for xx in x["expressions"])
+            self.test_topk_per_image = 1
+        else:
+            self.test_topk_per_image = self.select_box_nums_for_evaluation
         if self.select_box_nums_for_evaluation_list is not None:
             self.test_topk_per_image = self.select_box_nums_for_evaluation_list[dataset_id]
         text_list = None
+        if prompt == "expression":
+            text_list = [xx for x in batched_inputs for xx in x["expressions"]]  # (:289-290)
         if prompt == "text":
             texts = [x["text_prompt"] for x in batched_inputs]
             text_list = [x.strip() for x in ",".join(texts).split(",")]
@@ -387,9 +394,9 @@ class DeformableDETRSegmVL(nn.Module):
             else:
                 fusion = None
             return prompt, features_l, fusion
-        # phrase (:292-337)
+        # phrase / expression (:284-337)
         if not text_list:
-            raise NotImplementedError("ape_b200: phrase prompts need `text_prompt` at inference")
+            raise NotImplementedError("ape_b200: phrase prompts need `text_prompt` (or `expressions`) at inference")
         features_l = self.model_language.forward_text(text_list)["last_hidden_state_eot"].to(self.device)
         if self.text_feature_bank and not self.text_feature_bank_reset and 0 <= dataset_id < len(self.dataset_names):
             n = self.criterion[dataset_id].num_classes

@@ -589,11 +589,12 @@ def paste_masks(masks, boxes, out_h, out_w, threshold=0.5):
 
 
 def forward(images, out_sizes, text_feats, sd, spec, phrase=False, taps=None, bank_reset=False, masks_on=False,
-            semantic_on=False):
+            semantic_on=False, topk=None):
     """Whole detection forward.  images: list of CHW float RGB 0..255; out_sizes: list of (height, width) the
     detections are rescaled to; text_feats [N_t, lang_dim].  masks_on / semantic_on: the reference's test_mask_on /
-    semantic_on branches ("thing" entity).  Returns list of dicts(boxes, scores, classes, query_index[, masks, sem_seg])
-    + the tap dict."""
+    semantic_on branches ("thing" entity).  topk: detections kept per image (default spec["test_topk"]; 1 for
+    "expression" prompts, deformable_detr_segm_vl.py:184-193, which otherwise follow the phrase path).
+    Returns list of dicts(boxes, scores, classes, query_index[, masks, sem_seg]) + the tap dict."""
     taps = {} if taps is None else taps
     with torch.no_grad():
         batch, img_masks, sizes = preprocess(images, spec)
@@ -631,7 +632,7 @@ def forward(images, out_sizes, text_feats, sd, spec, phrase=False, taps=None, ba
             h, w = sizes[b]
             boxes = box_cxcywh_to_xyxy(coord[b]) * torch.tensor([w, h, w, h], dtype=torch.float32)
             bx0, sc, cl, qi = fast_rcnn_inference_single(boxes, scores, (h, w), spec["test_score_thresh"],
-                                                         spec["test_nms_thresh"], spec["test_topk"])
+                                                         spec["test_nms_thresh"], spec["test_topk"] if topk is None else topk)
             bx, keep = detector_postprocess(bx0, (h, w), out_sizes[b][0], out_sizes[b][1])
             r = dict(boxes=bx[keep], scores=sc[keep], classes=cl[keep], query_index=qi[keep])
             if masks_on:  # (:588-603) + detector_postprocess

@@ -22,10 +22,12 @@ CASES = {
     "single": ([(48, 64, 96, 128)], None),
     "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
     "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
+    # referring expressions (prompt "expression": texts from `expressions`, one box per image; :184-193, :289-290)
+    "expression": ([(64, 56, 128, 112)], ["the red apple on the left", "a dog"]),
 }
 
 
-def main():
+def main(only=None):
     spec = configs.MINI
     model, names = ref_model.build_reference_model(spec)
     synth.fill_state_dict(model)
@@ -44,10 +46,15 @@ def main():
         layer.register_forward_hook(hook(f"vlf{i}"))
 
     for cname, (sizes, text) in CASES.items():
+        if only and cname != only:
+            continue
         inputs = []
         for i, (h, w, oh, ow) in enumerate(sizes):
             d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
-            if text is not None:
+            if isinstance(text, list):
+                d["prompt"] = "expression"
+                d["expressions"] = list(text)
+            elif text is not None:
                 d["prompt"] = "text"
                 d["text_prompt"] = text
             inputs.append(d)
@@ -173,7 +180,9 @@ def main_ti():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "ti":
+    if len(sys.argv) > 1 and sys.argv[1] in CASES:
+        main(only=sys.argv[1])
+    elif len(sys.argv) > 1 and sys.argv[1] == "ti":
         main_ti()
     elif len(sys.argv) > 1 and sys.argv[1] == "masks":
         main_masks()

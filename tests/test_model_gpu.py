@@ -17,6 +17,7 @@ CASES = {
     "single": ([(48, 64, 96, 128)], None),
     "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
     "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
+    "expression": ([(64, 56, 128, 112)], ["the red apple on the left", "a dog"]),
 }
 
 
@@ -45,7 +46,9 @@ def test_mini_matches_reference_golden(case, mini):
     inputs = []
     for i, (h, w, oh, ow) in enumerate(sizes):
         d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
-        if text:
+        if isinstance(text, list):
+            d.update(prompt="expression", expressions=list(text))
+        elif text:
             d.update(prompt="text", text_prompt=text)
         inputs.append(d)
     out = model(inputs)

@@ -14,6 +14,7 @@ CASES = {
     "single": ([(48, 64, 96, 128)], None),
     "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
     "phrase": ([(64, 48, 64, 48)], 3),
+    "expression": ([(64, 56, 128, 112)], 2),  # two referring expressions, one box kept per image
 }
 
 
@@ -41,7 +42,7 @@ def test_port_matches_reference_golden(case, sd):
     outs = [(oh, ow) for (_, _, oh, ow) in sizes]
     n_text = n_phrase if n_phrase else spec["num_classes"]
     text = synth.text_features(8192, spec["lang_dim"])[:n_text]
-    res, taps = AF.forward(images, outs, text, sd, spec, phrase=bool(n_phrase))
+    res, taps = AF.forward(images, outs, text, sd, spec, phrase=bool(n_phrase), topk=1 if case == "expression" else None)
     tol = dict(rtol=2e-4, atol=2e-4)
     for k in ("p2", "p3", "p4", "p5", "p6"):
         torch.testing.assert_close(taps[f"backbone.{k}"][:, ::4], g[f"backbone.{k}"], **tol)
