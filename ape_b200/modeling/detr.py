@@ -9,9 +9,8 @@ ape/modeling/ape_deta/ape_deta.py:20-40 (`SomeThing`).  Same constructor keyword
 "instances" out, results on CPU), same parameter names incl. the shared `class_embed` /
 `bbox_embed` aliases under `transformer.decoder`.
 
-Scope: inference (boxes, instance masks, semantic maps) for "name", "phrase" / "text" and "expression"
-prompts.  Training, panoptic merging and mask prompts raise NotImplementedError (next rows of §8f) — loudly, never
-silently."""
+Scope: inference (boxes, instance masks, semantic and panoptic maps) for "name", "phrase" / "text" and
+"expression" prompts.  Training and mask prompts raise NotImplementedError (next rows of §8f) — loudly, never silently."""
 import copy
 import math
 from typing import Dict, List
@@ -272,6 +271,9 @@ class DeformableDETRSegmVL(nn.Module):
         self.instance_on, self.semantic_on, self.panoptic_on = instance_on, semantic_on, panoptic_on
         self.test_mask_on = test_mask_on
         self.semantic_post_nms = semantic_post_nms
+        self.panoptic_post_nms = panoptic_post_nms
+        self.panoptic_configs = panoptic_configs if panoptic_configs is not None else {
+            "prob": 0.1, "pano_temp": 0.06, "transform_eval": True, "object_mask_threshold": 0.01, "overlap_threshold": 0.4}
         self.stuff_prob_thing = stuff_prob_thing
         # (thing_classes, stuff_classes) per dataset for the semantic branch; the reference reads them from detectron2's
         # MetadataCatalog (deformable_detr.py:244-262).  None = "thing" entity over the dataset's vocabulary.
@@ -434,7 +436,7 @@ class DeformableDETRSegmVL(nn.Module):
         low = self.engine_dtype != torch.float32
         geo = self._geometry(images.shape, image_sizes, img_masks)
         graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1 and \
-            not (self.semantic_on or (self.instance_on and self.test_mask_on))  # mask tensors travel as attributes: eager
+            not (self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on))  # mask tensors travel as attributes: eager
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
             if graphs and not self.profile_stages:
                 # encode -> select -> decode in ONE graph: the selection is written with static shapes and no host
@@ -469,9 +471,7 @@ class DeformableDETRSegmVL(nn.Module):
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
-        if self.panoptic_on:
-            raise NotImplementedError("ape_b200: panoptic merging (SURVEY.md 8f row 2); construct with panoptic_on=False")
-        need_masks = self.semantic_on or (self.instance_on and self.test_mask_on)
+        need_masks = self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)
         mask_pred = self.last_mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
@@ -495,6 +495,9 @@ class DeformableDETRSegmVL(nn.Module):
         if self.semantic_on:
             for o, sem in zip(out, self._semantic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
                 o["sem_seg"] = sem
+        if self.panoptic_on:
+            for o, pan in zip(out, self._panoptic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
+                o["panoptic_seg"] = pan
         mark("inference")
         if marks is not None:
             torch.cuda.synchronize()
@@ -525,7 +528,7 @@ class DeformableDETRSegmVL(nn.Module):
         memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(
             feats, geo, fusion, feat_flatten=getattr(self.neck, "last_flat", None))
         self._mask_features = None
-        if self.semantic_on or (self.instance_on and self.test_mask_on):
+        if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
             self._mask_features = self.maskdino_mask_features(memory, features, geo)
         return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats
 
@@ -622,6 +625,30 @@ class DeformableDETRSegmVL(nn.Module):
             if entity == "stuff" and stuff and stuff[0] == "things" and self.stuff_prob_thing > 0:
                 sem[0, ...] = math.log(self.stuff_prob_thing / (1 - self.stuff_prob_thing))
             outs.append(sem)
+        return outs
+
+    def _panoptic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs):
+        """Panoptic branch (:671-696): queries that survive the detection NMS, merged by
+        `postprocess.postprocess_panoptic` (the reference's `_postprocess_panoptic`, :919-998, without its per-segment
+        host round trips).  Needs the thing / stuff split of the evaluated dataset in `self.dataset_stuff`."""
+        from .postprocess import postprocess_panoptic
+
+        name = self.dataset_names[self.eval_dataset_id] if self.dataset_names else None
+        if name not in self.dataset_stuff:
+            raise RuntimeError(f"ape_b200: panoptic_on needs model.dataset_stuff[{name!r}] = (thing_classes, stuff_classes, entity)")
+        things, stuff, _ = self.dataset_stuff[name]
+        things, stuff = list(things or []), list(stuff or [])
+        thing_ids = range(len(things))  # contiguous ids of the thing classes (metadata.thing_dataset_id_to_contiguous_id.values())
+        if self.panoptic_post_nms:
+            keep = [r.query_index for r in self.inference(box_cls, box_pred, image_sizes)]
+        else:
+            keep = [torch.arange(box_cls.shape[1], device=box_cls.device)] * box_cls.shape[0]
+        outs = []
+        for b, (qi, size, inp) in enumerate(zip(keep, image_sizes, batched_inputs)):
+            m = F.interpolate(mask_pred[b, qi][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0]
+            h, w = inp.get("height", size[0]), inp.get("width", size[1])
+            outs.append(postprocess_panoptic(box_cls[b, qi].float(), m, size, h, w, thing_ids, len(things),
+                                             bool(stuff) and stuff[0] == "things", self.panoptic_configs))
         return outs
 
     def _inference_static(self, box_cls, box_pred, image_sizes):
