@@ -41,6 +41,8 @@ lib.ape_msda_fused_self_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64
 lib.ape_gemm_tn.restype = _i
 lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
 
+lib.ape_gemm_tn_ex.restype = _i
+lib.ape_gemm_tn_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 8 + [_vp]
 lib.ape_gemm_tn_rope.restype = _i
 lib.ape_gemm_tn_rope.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
 
@@ -79,6 +81,7 @@ EXPORTS = (
     "ape_msda_fused_fwd",
     "ape_msda_fused_self_fwd",
     "ape_gemm_tn",
+    "ape_gemm_tn_ex",
     "ape_gemm_tn_rope",
     "ape_layernorm",
     "ape_layernorm_ex",

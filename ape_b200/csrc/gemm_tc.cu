@@ -24,7 +24,7 @@ namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SWIGLU = 3, ACT_CLAMP = 4 };
 
 struct GemmParams {
   void *C;
@@ -34,6 +34,7 @@ struct GemmParams {
   int M, N, K;
   int m_blocks, n_blocks, k_blocks;
   int out_dtype;  // APE_DTYPE_*
+  int res_dtype;  // APE_DTYPE_* of `residual` (fp32-output GEMMs may add a 16-bit residual and vice versa)
   int act;
   int n_fastest;  // tile order: consecutive tiles walk the column blocks of one row group (A stays hot in L2)
   // optional 2-D rotary embedding on output columns [0, rope_cols) (q and k thirds of a fused qkv projection;
@@ -60,7 +61,46 @@ constexpr int kThreads = 320;
 __device__ __forceinline__ float act_fn(float x, int act) {
   if (act == ACT_RELU) return fmaxf(x, 0.f);
   if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (act == ACT_CLAMP) return fminf(fmaxf(x, -50000.f), 50000.f);  // vision_language_align.py:49-51
   return x;
+}
+
+// 32 accumulator columns of one row += residual[m, n0 .. n0+31] read in its own dtype (fp32 or 16-bit).
+__device__ __forceinline__ void add_residual32(const GemmParams &p, float *v, int m, int n0) {
+  if (p.res_dtype == APE_DTYPE_F32) {
+    const float *res = reinterpret_cast<const float *>(p.residual) + (size_t)m * p.ldr + n0;
+    if (n0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(res) + i);
+        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += __ldg(res + i);
+    }
+  } else {
+    const uint16_t *res = reinterpret_cast<const uint16_t *>(p.residual) + (size_t)m * p.ldr + n0;
+    const bool half = p.res_dtype == APE_DTYPE_F16;
+    if (n0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f[8];
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(res) + i);
+        if (half) Elem<__half>::unpack(u, f); else Elem<__nv_bfloat16>::unpack(u, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[8 * i + k] += f[k];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) {
+          const uint16_t u = __ldg(res + i);
+          v[i] += half ? __half2float(__ushort_as_half(u)) : __uint_as_float((uint32_t)u << 16);
+        }
+    }
+  }
 }
 
 template <typename TO>
@@ -120,10 +160,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = act_fn(v[i], p.act);
-  if (p.residual != nullptr) {
-    const TO *res = reinterpret_cast<const TO *>(p.residual) + (size_t)m * p.ldr + n0;
-    for (int i = 0; i < nvalid; ++i) v[i] += Elem<TO>::to_f(res[i]);
-  }
+  if (p.residual != nullptr) add_residual32(p, v, m, n0);
   store_row<TO>(C + (size_t)m * p.ldc + n0, v, nvalid);
 }
 
@@ -158,25 +195,13 @@ __device__ __forceinline__ void finish64(const GemmParams &p, float *v, int m, i
       v[4 * i + 3] = t3 * c.w + t2 * sn.w;
     }
   }
-  if (p.act == ACT_RELU || p.act == ACT_GELU) {
+  if (p.act == ACT_RELU || p.act == ACT_GELU || p.act == ACT_CLAMP) {
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = act_fn(v[i], p.act);
   }
   if (p.residual != nullptr && m < p.M) {
-    const TO *res = reinterpret_cast<const TO *>(p.residual) + (size_t)m * p.ldr + n0;
-    if (n0 + 64 <= p.N && (reinterpret_cast<uintptr_t>(res) & 15) == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float f[8];
-        Elem<TO>::unpack(__ldg(reinterpret_cast<const uint4 *>(res) + i), f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[8 * i + k] += f[k];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 64; ++i)
-        if (n0 + i < p.N) v[i] += Elem<TO>::to_f(res[i]);
-    }
+    add_residual32(p, v, m, n0);
+    if (n0 + 32 < p.N) add_residual32(p, v + 32, m, n0 + 32);
   }
 }
 
@@ -260,6 +285,61 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<uint4 *>(my_row + ((j ^ (lane & 7)) << 4)) = Elem<TO>::pack(v + 8 * j);
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_store_2d(map_c, slab, n0, row0);
+      tc::tma_store_commit();
+    }
+  }
+}
+
+// fp32 output: the warp's (32 rows) x (BN/2 columns) part of a tile in steps of 32 columns = one 128-byte-swizzled slab
+// (32 rows x 128 B) per TMA store.  Used for the residual stream (sum kept in fp32 between the 16-bit GEMMs) and for
+// logits that feed top-k / NMS.
+template <int BN>
+__device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab,
+                                                 uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk) {
+  const int row0 = m_blk * BM + quad * 32;
+  const int m = row0 + lane;
+  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16);
+  uint8_t *my_row = slab + lane * 128;
+  constexpr int HALF = BN / 2;
+#pragma unroll 1
+  for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 32) {
+    const int n0 = n_blk * BN + c0;
+    if (n0 >= p.N) break;
+    uint32_t r[32];
+    tc::tmem_ld_32x32b_x32(trow + c0, r);
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (p.bias != nullptr) {
+      if (n0 + 32 <= p.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
+          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+      }
+    }
+    if (p.act == ACT_RELU || p.act == ACT_GELU || p.act == ACT_CLAMP) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = act_fn(v[i], p.act);
+    }
+    if (p.residual != nullptr && m < p.M) add_residual32(p, v, m, n0);
+    if (lane == 0) tc::tma_store_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4 *>(my_row + ((j ^ (lane & 7)) << 4)) =
+          make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                     __float_as_uint(v[4 * j + 3]));
     tc::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -383,7 +463,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
       if (p.tma_store) {
-        if (p.out_dtype == APE_DTYPE_F16)
+        if (p.out_dtype == APE_DTYPE_F32)
+          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+        else if (p.out_dtype == APE_DTYPE_F16)
           epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
         else
           epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
@@ -537,7 +619,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
       if (p.tma_store) {
-        if (p.out_dtype == APE_DTYPE_F16)
+        if (p.out_dtype == APE_DTYPE_F32)
+          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+        else if (p.out_dtype == APE_DTYPE_F16)
           epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
         else
           epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
@@ -596,10 +680,11 @@ int make_map(CUtensorMap *map, const void *base, int dtype, long long rows, long
   EncodeTiledFn enc = get_encoder();
   if (!enc) return fail(APE_ERR_UNSUPPORTED, "gemm: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (dtype == APE_DTYPE_F32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  CUresult r = enc(map, dtype == APE_DTYPE_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                        : dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -695,13 +780,15 @@ struct RopeArgs {
 };
 
 static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
-                     const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
+                     const float *bias, const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype,
                      int out_dtype, int act, int tile_n, const RopeArgs *rope, void *stream) {
+  if (residual && res_dtype != APE_DTYPE_F32 && res_dtype != APE_DTYPE_F16 && res_dtype != APE_DTYPE_BF16)
+    return fail(APE_ERR_INVALID_ARG, "gemm: bad res_dtype %d", res_dtype);
   if (in_dtype != APE_DTYPE_F16 && in_dtype != APE_DTYPE_BF16)
     return fail(APE_ERR_INVALID_ARG, "gemm: operands must be fp16 or bf16 (got dtype %d)", in_dtype);
   if (out_dtype != APE_DTYPE_F32 && out_dtype != APE_DTYPE_F16 && out_dtype != APE_DTYPE_BF16)
     return fail(APE_ERR_INVALID_ARG, "gemm: bad out_dtype %d", out_dtype);
-  if (act < 0 || act > ACT_SWIGLU) return fail(APE_ERR_INVALID_ARG, "gemm: bad activation %d", act);
+  if (act < 0 || act > ACT_CLAMP) return fail(APE_ERR_INVALID_ARG, "gemm: bad activation %d", act);
   if (M < 0 || N <= 0 || K <= 0) return fail(APE_ERR_INVALID_ARG, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
   if (M == 0) return APE_OK;
   if (!A || !W || !C) return fail(APE_ERR_NULL_PTR, "gemm: null pointer argument");
@@ -709,14 +796,15 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
     return fail(APE_ERR_INVALID_ARG, "gemm: A/W base and row pitch must be 16-byte aligned (TMA)");
   if (lda < K || ldw < K) return fail(APE_ERR_INVALID_ARG, "gemm: row pitch smaller than K");
   if (act == ACT_SWIGLU && ((N & 1) || residual)) return fail(APE_ERR_INVALID_ARG, "gemm: swiglu needs even N, no residual");
-  if (residual && out_dtype == APE_DTYPE_F32 && false) return APE_ERR_INVALID_ARG;
   const int bn = (tile_n & 0xfff) > 0 ? (tile_n & 0xfff) : (N > 128 ? 256 : 128);
   if (bn != 128 && bn != 256) return fail(APE_ERR_INVALID_ARG, "gemm: tile_n must be 128 or 256");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap ma, mb;
   if (int rc = make_map(&ma, A, in_dtype, M, K, lda, BM)) return rc;
   // cluster of 2 along M whenever there are at least two row blocks (tile_n bit 0x1000 forces single-CTA)
-  const bool single = (tile_n & 0x1000) != 0 || M <= BM;
+  // default variant per shape from the measured sweep (profiles/r01_gemm_sweep.txt): the multicast cluster only wins when
+  // the K loop is long (K >= 2048: w3, FFN2); bit 0x4000 forces it, bit 0x1000 forces the single-CTA kernel
+  const bool single = (tile_n & 0x1000) != 0 || M <= BM || (K < 2048 && (tile_n & 0xE000) == 0);
   // kernel variant: default = cluster of 2 along M sharing the weight tile by TMA multicast (1-CTA MMA); 0x2000 = CTA-pair
   // MMA (cta_group::2, 256 x bn tiles; measured equal or slower on B200 for these shapes, kept selectable);
   // 0x8000 = cluster of 4 along M (weight tile split four ways)
@@ -728,17 +816,18 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   p.M = M; p.N = N; p.K = K;
   p.m_blocks = (M + BM - 1) / BM;
   p.k_blocks = (K + BK - 1) / BK;
-  p.out_dtype = out_dtype; p.act = act;
+  p.out_dtype = out_dtype; p.act = act; p.res_dtype = res_dtype;
   p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
   // 16-bit outputs with 16-byte aligned rows leave through shared memory + TMA stores
   const int n_out = act == ACT_SWIGLU ? N / 2 : N;
   CUtensorMap mc = ma;
-  p.tma_store = out_dtype != APE_DTYPE_F32 && (ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
-                (act != ACT_SWIGLU || bn == 256);
-  if (p.tma_store)
-    if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 64)) return rc;
+  const int oe = out_dtype == APE_DTYPE_F32 ? 4 : 2;
+  p.tma_store = (ldc * oe) % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                (act != ACT_SWIGLU || (bn == 256 && oe == 2)) && (oe == 2 || n_out >= 32);
+  if (p.tma_store)  // one slab = 32 rows x 128 bytes
+    if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 128 / oe)) return rc;
   if (rope) {
-    if (!p.tma_store || act != ACT_NONE || rope->cols % 64 != 0 || rope->cols > N || rope->npos <= 0 || !rope->cos || !rope->sin)
+    if (!p.tma_store || oe != 2 || act != ACT_NONE || rope->cols % 64 != 0 || rope->cols > N || rope->npos <= 0 || !rope->cos || !rope->sin)
       return fail(APE_ERR_INVALID_ARG, "gemm+rope: needs a 16-bit aligned output, no activation, rope_cols a multiple of 64 <= N");
     p.rope_cos = rope->cos; p.rope_sin = rope->sin; p.rope_pos = rope->pos; p.rope_cols = rope->cols; p.rope_npos = rope->npos;
   }
@@ -762,7 +851,15 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
 extern "C" int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
                            const float *bias, const void *residual, int64_t ldr, int M, int N, int K, int in_dtype,
                            int out_dtype, int act, int tile_n, void *stream) {
-  return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr, stream);
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, out_dtype, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr,
+                   stream);
+}
+
+extern "C" int ape_gemm_tn_ex(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
+                              const float *bias, const void *residual, int64_t ldr, int res_dtype, int M, int N, int K,
+                              int in_dtype, int out_dtype, int act, int tile_n, void *stream) {
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, res_dtype, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr,
+                   stream);
 }
 
 extern "C" int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
@@ -773,5 +870,5 @@ extern "C" int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64
   if ((reinterpret_cast<uintptr_t>(cos_table) | reinterpret_cast<uintptr_t>(sin_table)) & 15)
     return fail(APE_ERR_INVALID_ARG, "gemm+rope: cos / sin tables must be 16-byte aligned");
   RopeArgs r{cos_table, sin_table, pos_map, rope_cols, npos};
-  return gemm_impl(A, lda, W, ldw, C, ldc, bias, nullptr, 0, M, N, K, in_dtype, out_dtype, ACT_NONE, tile_n, &r, stream);
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, nullptr, 0, out_dtype, M, N, K, in_dtype, out_dtype, ACT_NONE, tile_n, &r, stream);
 }

@@ -47,12 +47,13 @@ class MLP(nn.Module):
         h = [hidden_dim] * (num_layers - 1)
         self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
 
-    def forward(self, x):
+    def forward(self, x, out_dtype=None):
         if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
             from .. import ops  # tensor-core path: bias + ReLU in the GEMM epilogue, weights packed once
 
             for i, layer in enumerate(self.layers):
-                x = ops.linear_module_tc(layer, x, act="relu" if i < self.num_layers - 1 else None)
+                last = i == self.num_layers - 1
+                x = ops.linear_module_tc(layer, x, act=None if last else "relu", out_dtype=out_dtype if last else None)
             return x
         for i, layer in enumerate(self.layers):
             x = F.relu(layer(x)) if i < self.num_layers - 1 else layer(x)
@@ -70,12 +71,13 @@ class FFN(nn.Module):
             nn.Dropout(0.0),
         )
 
-    def forward(self, x):
+    def forward(self, x, out_dtype=None):
         if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
             from .. import ops  # tensor-core path: ReLU and the residual add live in the GEMM epilogues
 
             h = ops.linear_module_tc(self.layers[0][0], x, act="relu")
-            return ops.linear_module_tc(self.layers[1], h, residual=x.contiguous())
+            # out_dtype float32: the sum x + ffn(x) leaves the epilogue unrounded (it feeds a LayerNorm)
+            return ops.linear_module_tc(self.layers[1], h, residual=x.contiguous(), out_dtype=out_dtype)
         return x + self.layers[1](F.relu(self.layers[0][0](x)))
 
 

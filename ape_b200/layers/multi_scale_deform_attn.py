@@ -135,8 +135,10 @@ class MultiScaleDeformableAttention(nn.Module):
             value, spatial_shapes, level_start_index, qo[..., :n_off], qo[..., n_off:],
             reference_points.to(torch.float32).contiguous(), self.num_points,
             host_shapes=kwargs.get("host_shapes"))
-        if engine and self.batch_first and identity.dtype == output.dtype:
-            return ops.linear_module_tc(self.output_proj, output, residual=identity.contiguous())
+        if engine and self.batch_first and identity.dtype in (output.dtype, torch.float32):
+            # `sum_dtype=torch.float32` (engine layers): identity + output_proj(...) leaves the epilogue as fp32
+            return ops.linear_module_tc(self.output_proj, output, residual=identity.contiguous(),
+                                        out_dtype=kwargs.get("sum_dtype"))
         output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)

@@ -298,7 +298,7 @@ class ViT(nn.Module):
         w = ws if ws else g
         ids = torch.arange(g * g, device=device).view(nw, w, nw, w).permute(0, 2, 1, 3).reshape(-1)  # window-major -> raster
         pos = get_abs_pos(self.pos_embed.detach().float(), self.pretrain_use_cls_token, (g, g)).reshape(g * g, -1)
-        geo = dict(ids=ids, pos=pos[ids].to(dtype).repeat(B, 1).contiguous(),
+        geo = dict(ids=ids, pos=pos[ids].float().repeat(B, 1).contiguous(),  # fp32: first value of the residual stream
                    glb_map=ids.to(torch.int32).repeat(B).contiguous(), inv=torch.argsort(ids))
         self._geom[k] = geo
         return geo
@@ -321,7 +321,9 @@ class ViT(nn.Module):
         w = ws if ws else g
         # patch embedding as a GEMM over window-major im2col rows; abs-pos added as the epilogue residual
         cols = img.view(B, 3, nw, w, ps, nw, w, ps).permute(0, 2, 5, 3, 6, 1, 4, 7).reshape(B * g * g, 3 * ps * ps)
-        x = ops.linear_tc(cols, pk["patch_w"], pk["patch_b"], residual=geo["pos"])
+        # The residual stream `x` stays fp32 for all 24 blocks (only GEMM / attention operands and LayerNorm outputs are
+        # 16-bit): every branch output is added in the GEMM epilogue to the fp32 stream and written back as fp32.
+        x = ops.linear_tc(cols, pk["patch_w"], pk["patch_b"], residual=geo["pos"], out_dtype=torch.float32)
         M = x.shape[0]
         rope_win = (self.rope_win.freqs_cos.float().contiguous(), self.rope_win.freqs_sin.float().contiguous())
         rope_glb = (self.rope_glb.freqs_cos.float().contiguous(), self.rope_glb.freqs_sin.float().contiguous())
@@ -329,7 +331,7 @@ class ViT(nn.Module):
         hbuf = torch.empty((M, hid_p), dtype=dtype, device=dev)
         hbuf2 = torch.empty((M, hid_p), dtype=dtype, device=dev)
         for blk, p in zip(self.blocks, pk["blocks"]):
-            h = ops.layernorm(x, p["n1w"], p["n1b"], eps=1e-6)
+            h = ops.layernorm(x, p["n1w"], p["n1b"], eps=1e-6, out_dtype=dtype)
             # RoPE in the qkv GEMM epilogue (ape_gemm_tn_rope) is available but OFF: measured +26 us per qkv GEMM (the 8
             # epilogue warps wait on the cos/sin rows) against 8.7 us for the separate ape_rope_qk pass
             fused_rope = self.fused_rope and hd == 64 and C % 8 == 0
@@ -355,13 +357,13 @@ class ViT(nn.Module):
                                                    q5[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
                 o = o.transpose(1, 2).reshape(M, C)
             a = ops.layernorm(o, p["lnw"], p["lnb"], eps=1e-6)
-            x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x)
-            h = ops.layernorm(x, p["n2w"], p["n2b"], eps=1e-6)
+            x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x, out_dtype=torch.float32)
+            h = ops.layernorm(x, p["n2w"], p["n2b"], eps=1e-6, out_dtype=dtype)
             ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]])
             ops.layernorm(hbuf[:, :p["hid"]], p["fw"], p["fb"], eps=1e-6, out=hbuf2[:, :p["hid"]])
-            x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x)
-        # back to raster order: [B, g, g, C] tokens (NHWC memory)
-        return x.view(B, g * g, C)[:, geo["inv"]].view(B, g, g, C)
+            x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x, out_dtype=torch.float32)
+        # back to raster order: [B, g, g, C] tokens (NHWC memory), 16-bit operand of the pyramid GEMMs
+        return x.to(dtype).view(B, g * g, C)[:, geo["inv"]].view(B, g, g, C)
 
 
 def _convT_as_gemm(ct, dtype):

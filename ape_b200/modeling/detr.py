@@ -552,13 +552,19 @@ class DeformableDETRSegmVL(nn.Module):
     def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo):
         inter_states, init_reference, inter_references = self.transformer.stage_decode(
             memory, output_memory, enc_coord, topk, geo)
+        states16 = inter_states  # decoder outputs are LayerNorm outputs in the engine dtype
         inter_states, init_reference, inter_references = inter_states.float(), init_reference.float(), inter_references.float()
         # only the last decoder level feeds inference (:514-523); levels 0..n-2 are aux outputs
         lvl = inter_states.shape[0] - 1
         reference = init_reference if lvl == 0 else inter_references[lvl - 1]
         with torch.autocast("cuda", enabled=False):
-            box_cls = self.class_embed[lvl](inter_states[lvl], features_l.float())
-            box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
+            if states16.dtype in (torch.float16, torch.bfloat16):
+                # engine: query x text logits and the box MLP on the tensor cores (fp32 accumulation, fp32 outputs)
+                box_cls = self.class_embed[lvl](states16[lvl], features_l.float())
+                box_pred = (self.bbox_embed[lvl](states16[lvl], out_dtype=torch.float32) + inverse_sigmoid(reference)).sigmoid()
+            else:
+                box_cls = self.class_embed[lvl](inter_states[lvl], features_l.float())
+                box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
         self.last_mask_logits = None
         if getattr(self, "_mask_features", None) is not None:
             # (:507-517) only the last level's masks reach inference (the other levels are added times 0.0)

@@ -48,7 +48,7 @@ class _SelfAttention(nn.Module):
             v = ops.linear_tc(x, wv, bv).view(B, N, nh, E // nh)
             o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
             o = o.transpose(1, 2).reshape(B, N, E)
-            return ops.linear_module_tc(self.attn.out_proj, o, residual=x.contiguous())
+            return ops.linear_module_tc(self.attn.out_proj, o, residual=x.contiguous(), out_dtype=torch.float32)
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
         qk = F.linear(x + pos, w[: 2 * E], b[: 2 * E])
         v = F.linear(x, w[2 * E:], b[2 * E:])
@@ -76,13 +76,16 @@ class _EncoderLayer(nn.Module):
         x = self.attentions[0](query, None, query, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
                                reference_points=reference_points, spatial_shapes=spatial_shapes,
                                level_start_index=level_start_index, host_shapes=host_shapes,
-                               query_with_pos=query_with_pos)
-        if x.dtype in (torch.float16, torch.bfloat16):  # engine path: libape_b200 LayerNorm kernel
-            x = ops.layernorm_module(self.norms[0], x)
-            x = self.ffns[0](x)
+                               query_with_pos=query_with_pos,
+                               sum_dtype=torch.float32 if query.dtype != torch.float32 else None)
+        if query.dtype in (torch.float16, torch.bfloat16):
+            # engine path: the two residual sums (query + attention, x + ffn) are fp32 tensors written by the GEMM epilogues;
+            # the LayerNorm kernels read them and emit the 16-bit operands of the next GEMMs
+            x = ops.layernorm_module(self.norms[0], x, out_dtype=query.dtype)
+            x = self.ffns[0](x, out_dtype=torch.float32)
             if defer_last_norm:  # the caller folds norms[1] into the kernel that consumes this layer's output
                 return x
-            return ops.layernorm_module(self.norms[1], x)
+            return ops.layernorm_module(self.norms[1], x, out_dtype=query.dtype)
         x = self.norms[0](x)
         x = self.ffns[0](x)
         return self.norms[1](x)
@@ -105,14 +108,15 @@ class _DecoderLayer(nn.Module):
     def forward(self, query, value, query_pos, key_padding_mask, reference_points, spatial_shapes, level_start_index):
         if query.is_cuda and query.dtype in (torch.float16, torch.bfloat16) and value.dtype == query.dtype:
             # engine path: every linear is a tcgen05 GEMM, norms are libape_b200 row kernels
+            dt = query.dtype  # residual sums in fp32 (GEMM epilogues), LayerNorm outputs / GEMM operands in dt
             x = self.attentions[0](query, query_pos)
-            x = ops.layernorm_module(self.norms[0], x)
-            x = self.attentions[1](x, None, value, None, query_pos=query_pos.to(x.dtype), key_padding_mask=key_padding_mask,
+            x = ops.layernorm_module(self.norms[0], x, out_dtype=dt)
+            x = self.attentions[1](x, None, value, None, query_pos=query_pos.to(dt), key_padding_mask=key_padding_mask,
                                    reference_points=reference_points, spatial_shapes=spatial_shapes,
-                                   level_start_index=level_start_index)
-            x = ops.layernorm_module(self.norms[1], x)
-            x = self.ffns[0](x)
-            return ops.layernorm_module(self.norms[2], x)
+                                   level_start_index=level_start_index, sum_dtype=torch.float32)
+            x = ops.layernorm_module(self.norms[1], x, out_dtype=dt)
+            x = self.ffns[0](x, out_dtype=torch.float32)
+            return ops.layernorm_module(self.norms[2], x, out_dtype=dt)
         x = self.attentions[0](query, query_pos)
         x = self.norms[0](x)
         x = self.attentions[1](x, None, value, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
@@ -165,26 +169,27 @@ class DeformableDetrTransformerEncoderVL(nn.Module):
           -> deformable self-attention + FFN (tcgen05 GEMMs, fused gather), last norm deferred to the next layer.
         Same functions as `vl_layer(...)` followed by `layer(...)`; the activations cross HBM once per row kernel."""
         pending = None
+        dt = x.dtype
         for vl_layer, layer in zip(self.vl_layers, self.layers):
             b = vl_layer.b_attn
             with torch.autocast("cuda", enabled=False):
                 ln_l = b.layer_norm_l(query_l.float())
                 dv, qa, qc = b.single_token_language_side(ln_l)
                 shift = (b.gamma_v.float() * dv.float()).reshape(x.shape[0], -1).contiguous()  # [B, C]
-            vw, vb = ops.packed(b.layer_norm_v, x.dtype)
+            vw, vb = ops.packed(b.layer_norm_v, dt)
             if pending is None:
-                query, qpos = ops.layernorm_ex(x, vw, vb, b.layer_norm_v.eps, col_add=shift, row_add=query_pos)
-            else:
+                query, qpos = ops.layernorm_ex(x, vw, vb, b.layer_norm_v.eps, col_add=shift, row_add=query_pos, out_dtype=dt)
+            else:  # x is the previous layer's fp32 sum (x + ffn(x))
                 query, qpos = ops.layernorm_ex(x, pending[0], pending[1], pending[2], weight2=vw, bias2=vb,
-                                               eps2=b.layer_norm_v.eps, col_add=shift, row_add=query_pos)
+                                               eps2=b.layer_norm_v.eps, col_add=shift, row_add=query_pos, out_dtype=dt)
             with torch.autocast("cuda", enabled=False):
                 dl = b.single_token_pool(query, qa, qc, shift=shift)
                 query_l = ln_l + b.gamma_l.float() * dl
             x = layer(query, query_pos, key_padding_mask, kwargs["reference_points"], kwargs["spatial_shapes"],
                       kwargs["level_start_index"], kwargs.get("host_shapes"), query_with_pos=qpos, defer_last_norm=True)
-            nw, nb = ops.packed(layer.norms[1], x.dtype)
+            nw, nb = ops.packed(layer.norms[1], dt)
             pending = (nw, nb, layer.norms[1].eps)
-        x = ops.layernorm(x, pending[0], pending[1], eps=pending[2])
+        x = ops.layernorm(x, pending[0], pending[1], eps=pending[2], out_dtype=dt)
         if self.post_norm_layer is not None:
             x = self.post_norm_layer(x)
         return x, query_l
@@ -218,7 +223,7 @@ class DeformableDetrTransformerDecoderVL(nn.Module):
             output = layer(output, value, query_pos, key_padding_mask, ref_in, kwargs["spatial_shapes"],
                            kwargs["level_start_index"])
             if self.bbox_embed is not None:
-                tmp = self.bbox_embed[i](output).float()
+                tmp = self.bbox_embed[i](output, out_dtype=torch.float32).float()
                 if reference_points.shape[-1] == 4:
                     new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()
                 else:

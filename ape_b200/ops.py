@@ -138,14 +138,14 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
     return out
 
 
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu": 3}
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu": 3, "clamp": 4}
 
 
 def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0, out=None):
     """act(x @ weight.T + bias) (+ residual) on the tcgen05 tensor cores (ape_gemm_tn).
 
     x [..., K] and weight [N, K] fp16/bf16 with unit inner stride; bias fp32 [N] (or None); residual
-    [..., N] of the output dtype.  act="swiglu": weight rows are interleaved (gate_j, up_j) pairs and the
+    [..., N] fp32 / fp16 / bf16 (any of them with any output dtype: fp32 sums over 16-bit operands).  act="swiglu": weight rows are interleaved (gate_j, up_j) pairs and the
     result has N/2 columns."""
     _require(x.is_cuda and weight.is_cuda, "linear_tc: CUDA tensors only")
     _require(x.dtype == weight.dtype and x.dtype in (torch.float16, torch.bfloat16), "linear_tc: fp16/bf16 operands")
@@ -166,18 +166,18 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
         _require(out.dim() == 2 and out.shape == (M, n_out) and out.stride(1) == 1 and out.is_cuda, "linear_tc: bad `out`")
         out_dtype = out.dtype
         ret_view = False
-    res_ptr, ldr = None, 0
+    res_ptr, ldr, res_dt = None, 0, 0
     if residual is not None:
         r2 = residual.reshape(-1, n_out)
-        _require(r2.dtype == out_dtype and r2.stride(1) == 1, "linear_tc: residual must match the output dtype")
-        res_ptr, ldr = r2.data_ptr(), r2.stride(0)
+        _require(r2.stride(1) == 1 and r2.is_cuda, "linear_tc: residual needs unit inner stride")
+        res_ptr, ldr, res_dt = r2.data_ptr(), r2.stride(0), _lib.dtype_code(r2.dtype)
     if bias is not None:
         _require(bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N, "linear_tc: bias must be fp32 [N]")
     with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
-        rc = _lib.lib.ape_gemm_tn(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
-                                  out.stride(0), bias.data_ptr() if bias is not None else None, res_ptr, ldr,
-                                  M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
-                                  _lib.current_stream_ptr())
+        rc = _lib.lib.ape_gemm_tn_ex(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
+                                     out.stride(0), bias.data_ptr() if bias is not None else None, res_ptr, ldr, res_dt,
+                                     M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
+                                     _lib.current_stream_ptr())
     _lib.check(rc, "ape_gemm_tn")
     return out.view(*x.shape[:-1], n_out) if ret_view else out
 
@@ -226,7 +226,7 @@ def linear_module_tc(module, x, act=None, residual=None, out_dtype=None):
 
 
 def layernorm_module(module, x, out_dtype=None):
-    w, b = packed(module, x.dtype)
+    w, b = packed(module, torch.float32)
     return layernorm(x, w, b, eps=module.eps, out_dtype=out_dtype)
 
 

@@ -72,3 +72,28 @@ def image(h, w, seed=0):
 def text_features(n, dim, seed=2):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(n, dim, generator=g)
+
+
+def suppress_invalid_anchor_logits(module, target=-math.log(99.0)):
+    """Shift the biases of the two-stage proposal class heads so that INVALID anchors (padding / border tokens: their
+    memory is zeroed before `enc_output`, deformable_transformer_vl.py:354-366, so they all share one constant logit)
+    score at the 0.01 prior, as with trained weights.  With purely random heads that constant lands among the top
+    scores by chance (1.32 for the APE-L_D names), the per-level top-k fills up with identical degenerate proposals and
+    the reference falls into its `nms proposals < topk` branch.  A pure function of the state_dict: the reference-side
+    golden generator, the oracle port and the engine all apply it after `fill_state_dict`."""
+    sd = module.state_dict()
+    w, b = sd["transformer.enc_output.weight"], sd["transformer.enc_output.bias"]
+    nw, nb = sd["transformer.enc_output_norm.weight"], sd["transformer.enc_output_norm.bias"]
+    const = torch.nn.functional.layer_norm(b.float()[None], (b.numel(),), nw.float(), nb.float(), 1e-5)[0]
+    heads = sorted(k[: -len(".weight")] for k in sd if k.endswith(".weight") and sd[k].dim() == 2 and sd[k].shape[0] == 1
+                   and k.startswith("transformer.decoder.class_embed"))
+    seen = set()
+    with torch.no_grad():
+        for h in heads:
+            hb = sd[h + ".bias"]
+            if hb.data_ptr() in seen:
+                continue
+            seen.add(hb.data_ptr())
+            logit = (sd[h + ".weight"].float() @ const.to(sd[h + ".weight"].device) + hb.float())[0]
+            hb.add_((target - logit).to(hb.dtype))
+    return sd

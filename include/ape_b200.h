@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define APE_ABI_VERSION 2
+#define APE_ABI_VERSION 3
 
 /* element types accepted by the kernels (value of the `dtype` argument) */
 #define APE_DTYPE_F32 0
@@ -118,12 +118,21 @@ int ape_msda_fused_self_fwd(const void *value, const int64_t *spatial_shapes, co
  * A [M,K] and W [N,K] (nn.Linear weight layout) are fp16 or bf16 (in_dtype), K contiguous, row pitches
  * lda / ldw in elements (16-byte aligned rows).  fp32 accumulation in tensor memory.
  * bias: fp32 [N] or NULL.  residual: [M,N] of out_dtype with pitch ldr, or NULL.
- * act: 0 none, 1 ReLU, 2 GELU(erf), 3 SwiGLU over interleaved (gate, up) column pairs -> C is [M, N/2].
- * out_dtype: APE_DTYPE_* of C (pitch ldc elements).  tile_n: 0 = auto, or 128 / 256.
+ * act: 0 none, 1 ReLU, 2 GELU(erf), 3 SwiGLU over interleaved (gate, up) column pairs -> C is [M, N/2],
+ *      4 clamp to +-50000 (VisionLanguageAlign, vision_language_align.py:49-51).
+ * out_dtype: APE_DTYPE_* of C (pitch ldc elements).  tile_n: 0 = auto, or 128 / 256 (| 0x1000 single CTA, 0x4000 cluster of
+ * two CTAs sharing the weight tile by TMA multicast, 0x2000 CTA-pair MMA, 0x8000 cluster of four).
  */
 int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
                 const void *residual, int64_t ldr, int M, int N, int K, int in_dtype, int out_dtype, int act,
                 int tile_n, void *stream);
+
+/* ape_gemm_tn with the residual in its own element type (res_dtype): the engine keeps the residual stream / pre-LayerNorm
+ * sums in fp32 (out_dtype F32) while GEMM operands and LayerNorm outputs are 16-bit, so e.g. a 16-bit residual is added
+ * into an fp32 output (encoder: query + output_proj(...)) or an fp32 residual into an fp32 output (ViT: x + proj(...)). */
+int ape_gemm_tn_ex(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
+                   const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype, int out_dtype,
+                   int act, int tile_n, void *stream);
 
 /*
  * ape_gemm_tn with the 2-D rotary embedding of the ViT (VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346) fused into

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(built):
 def test_abi_version(built):
     import ape_b200
 
-    assert ape_b200._lib.lib.ape_abi_version() == 2
+    assert ape_b200._lib.lib.ape_abi_version() == 3
     assert ape_b200._lib.lib.ape_last_error() == b""
 
 
