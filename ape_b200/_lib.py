@@ -13,63 +13,92 @@ LIB_PATH = os.path.join(_HERE, "libape_b200.so")
 APE_DTYPE_F32, APE_DTYPE_F16, APE_DTYPE_BF16 = 0, 1, 2
 _DTYPE_CODE = {torch.float32: APE_DTYPE_F32, torch.float16: APE_DTYPE_F16, torch.bfloat16: APE_DTYPE_BF16}
 
-if not os.path.exists(LIB_PATH):
+# APE_B200_CONTAINER_ONLY=1: import the package for its parameter containers / configs only (bench.py's CPU reference arm
+# builds the reference-named state_dict this way) WITHOUT mapping the native library; every kernel entry point then raises.
+CONTAINER_ONLY = os.environ.get("APE_B200_CONTAINER_ONLY") == "1"
+
+
+class _NotLoaded:
+    def __getattr__(self, name):
+        raise RuntimeError(f"libape_b200.so is not loaded (APE_B200_CONTAINER_ONLY=1): `{name}` is unavailable; "
+                           "ape_b200 has no CPU / PyTorch fallback")
+
+
+if CONTAINER_ONLY:
+    lib = _NotLoaded()
+elif not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} not found: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
         "ape_b200 has no CPU / PyTorch fallback."
     )
-
-lib = ctypes.CDLL(LIB_PATH)
+else:
+    lib = ctypes.CDLL(LIB_PATH)
 
 _vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
 
-lib.ape_abi_version.restype = _i
-lib.ape_abi_version.argtypes = []
-lib.ape_last_error.restype = ctypes.c_char_p
-lib.ape_last_error.argtypes = []
-lib.ape_launch_count.restype = ctypes.c_uint64
-lib.ape_launch_count.argtypes = []
-lib.ape_msda_fwd.restype = _i
-lib.ape_msda_fwd.argtypes = [_vp] * 6 + [_i] * 8 + [_vp]
-lib.ape_msda_fwd_variant.restype = _i
-lib.ape_msda_fwd_variant.argtypes = [_vp] * 6 + [_i] * 9 + [_vp]
-lib.ape_msda_fused_fwd.restype = _i
-lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
 
-lib.ape_msda_fused_self_fwd.restype = _i
-lib.ape_msda_fused_self_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 8 + [_vp]
-lib.ape_gemm_tn.restype = _i
-lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
+def _declare(lib):
 
-lib.ape_gemm_tn_ex.restype = _i
-lib.ape_gemm_tn_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 8 + [_vp]
-lib.ape_gemm_tn_rope.restype = _i
-lib.ape_gemm_tn_rope.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.ape_abi_version.restype = _i
+    lib.ape_abi_version.argtypes = []
+    lib.ape_last_error.restype = ctypes.c_char_p
+    lib.ape_last_error.argtypes = []
+    lib.ape_launch_count.restype = ctypes.c_uint64
+    lib.ape_launch_count.argtypes = []
+    lib.ape_msda_fwd.restype = _i
+    lib.ape_msda_fwd.argtypes = [_vp] * 6 + [_i] * 8 + [_vp]
+    lib.ape_msda_fwd_variant.restype = _i
+    lib.ape_msda_fwd_variant.argtypes = [_vp] * 6 + [_i] * 9 + [_vp]
+    lib.ape_msda_fused_fwd.restype = _i
+    lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
 
-lib.ape_layernorm.restype = _i
-lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp]
-lib.ape_layernorm_ex.restype = _i
-lib.ape_layernorm_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i64, _i,
-                                 _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]
-lib.ape_groupnorm_workspace_bytes.restype = _i64
-lib.ape_groupnorm_workspace_bytes.argtypes = [_i, _i, _i]
-lib.ape_groupnorm_nhwc.restype = _i
-lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _i, _vp]
-lib.ape_rope_qk.restype = _i
-lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+    lib.ape_msda_pair_values.restype = _i
+    lib.ape_msda_pair_values.argtypes = [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+    lib.ape_msda_pair_supported.restype = _i
+    lib.ape_msda_pair_supported.argtypes = [_vp, _i, _i, _i, _i, _i]
+    lib.ape_msda_pair_fused_fwd.restype = _i
+    lib.ape_msda_pair_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 10 + [_vp]
+    lib.ape_gemm_tn.restype = _i
+    lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
 
-lib.ape_attn_fwd.restype = _i
-lib.ape_attn_fwd.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
-lib.ape_vlf_pool_workspace_bytes.restype = _i64
-lib.ape_vlf_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
-lib.ape_vlf_pool.restype = _i
-lib.ape_vlf_pool.argtypes = [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i)] + [_i] * 6 + [_vp]
-lib.ape_nms_workspace_bytes.restype = _i64
-lib.ape_nms_workspace_bytes.argtypes = [_i]
-lib.ape_nms_sorted.restype = _i
-lib.ape_nms_sorted.argtypes = [_vp, _i, ctypes.c_float, _vp, _vp, _vp, _vp]
-lib.ape_nms_sorted_dev.restype = _i
-lib.ape_nms_sorted_dev.argtypes = [_vp, _i, _vp, ctypes.c_float, _vp, _vp, _vp, _vp]
+    lib.ape_gemm_tn_ex.restype = _i
+    lib.ape_gemm_tn_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 8 + [_vp]
+    lib.ape_gemm_tn_rope.restype = _i
+    lib.ape_gemm_tn_rope.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+
+    lib.ape_layernorm.restype = _i
+    lib.ape_layernorm.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, ctypes.c_float, _i, _i, _vp]
+    lib.ape_layernorm_ex.restype = _i
+    lib.ape_layernorm_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp, ctypes.c_float, _vp, _vp, ctypes.c_float, _vp, _i64, _i,
+                                     _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]
+    lib.ape_groupnorm_workspace_bytes.restype = _i64
+    lib.ape_groupnorm_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.ape_groupnorm_nhwc.restype = _i
+    lib.ape_groupnorm_nhwc.argtypes = [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _i, _i, _vp]
+    lib.ape_rope_qk.restype = _i
+    lib.ape_rope_qk.argtypes = [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+
+    lib.ape_attn_fwd.restype = _i
+    lib.ape_attn_fwd.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
+    lib.ape_vlf_pool_workspace_bytes.restype = _i64
+    lib.ape_vlf_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.ape_vlf_pool.restype = _i
+    lib.ape_vlf_pool.argtypes = [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_i)] + [_i] * 6 + [_vp]
+    lib.ape_nms_workspace_bytes.restype = _i64
+    lib.ape_nms_workspace_bytes.argtypes = [_i]
+    lib.ape_nms_sorted.restype = _i
+    lib.ape_nms_sorted.argtypes = [_vp, _i, ctypes.c_float, _vp, _vp, _vp, _vp]
+    lib.ape_nms_sorted_dev.restype = _i
+    lib.ape_nms_sorted_dev.argtypes = [_vp, _i, _vp, ctypes.c_float, _vp, _vp, _vp, _vp]
+    lib.ape_nms_classwise_workspace_bytes.restype = _i64
+    lib.ape_nms_classwise_workspace_bytes.argtypes = [_i]
+    lib.ape_nms_classwise.restype = _i
+    lib.ape_nms_classwise.argtypes = [_vp, _vp, _i64, _vp, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]
+
+
+
+if not CONTAINER_ONLY:
+    _declare(lib)
 
 # every symbol include/ape_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = (
@@ -79,7 +108,9 @@ EXPORTS = (
     "ape_msda_fwd",
     "ape_msda_fwd_variant",
     "ape_msda_fused_fwd",
-    "ape_msda_fused_self_fwd",
+    "ape_msda_pair_values",
+    "ape_msda_pair_supported",
+    "ape_msda_pair_fused_fwd",
     "ape_gemm_tn",
     "ape_gemm_tn_ex",
     "ape_gemm_tn_rope",
@@ -94,6 +125,8 @@ EXPORTS = (
     "ape_nms_workspace_bytes",
     "ape_nms_sorted",
     "ape_nms_sorted_dev",
+    "ape_nms_classwise_workspace_bytes",
+    "ape_nms_classwise",
 )
 
 

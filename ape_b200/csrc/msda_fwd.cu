@@ -369,228 +369,6 @@ msda_fused_fwd_kernel(const MsdaParams p) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Encoder kernel: self-attention over the feature pyramid itself (Q == S, query i IS pixel i of the level structure,
-// deformable_transformer_vl.py:69-121 -> multi_scale_deform_attn.py:283-348), 16-bit value.
-//
-// Why a separate kernel: the generic kernels gather 4 x 64-byte corner rows per sample through L1 — 55.9 M rows per
-// call at 1024^2 — and are bound by L1 wavefronts (one 128-byte line per 64-byte row) and L1 misses, not by HBM.
-// Here the pyramid is cut into REGIONS of 16x16 level-0 pixels; a region owns the 256 + 64 + 16 + 4 + 1 queries of
-// all levels that lie over it, and all of them sample around the same spot of every level.  A work unit =
-// (image, region, head):
-//   1. stage, per level, the window of value rows of this head around the region (halo kHalo pixels; 64 B per pixel,
-//      pixel-major, so the two x-corners of a sample are 128 contiguous bytes) into shared memory with cp.async;
-//   2. per sub-batch of 128 queries: softmax + sampling-location arithmetic -> 16-byte sample records whose offset
-//      points into the shared-memory window (or, for the rare sample that leaves the window, into global memory);
-//   3. gather: 8 lanes per query — lanes 0-3 own the 4 x 16 B chunks of the LEFT corner pixel, lanes 4-7 of the RIGHT
-//      one — so a quarter-warp reads 128 contiguous bytes per corner row: one conflict-free shared-memory
-//      wavefront instead of two L1 lines.  fp32 accumulation; the two halves are combined with one shuffle at the end.
-// Persistent CTAs (one per SM, 512 threads) stride over the units; the 8 heads of a region are adjacent units, i.e.
-// run at the same time on different SMs and share their L2 lines.  Same arithmetic per sample as the generic kernel
-// (make_sample); results differ from it only by fp32 summation order.
-constexpr int kRegion = 16;    // region edge in level-0 pixels
-constexpr int kHalo = 6;       // window halo in pixels of each level
-constexpr int kSelfLevels = 5; // 16 >> l must stay >= 1
-constexpr int kSub = 128;      // queries per sub-batch (bounds the record buffer)
-constexpr int kSelfThreads = 512;
-
-struct SelfGeom {  // host-computed, passed by value
-  int L, P, H;
-  int Hl[kSelfLevels], Wl[kSelfLevels], start[kSelfLevels];
-  int side[kSelfLevels];   // window edge (pixels) at level l
-  int woff[kSelfLevels + 1];  // window start in 16-byte units; [L] = total
-  int qcum[kSelfLevels + 1];  // queries of a region up to level l (exclusive prefix); [L] = total
-  int regions_x, regions_y;
-  int rec_off16, logit_off16, stat_off16;  // shared-memory layout (16-byte units)
-};
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ uint4 lds_v4(unsigned addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-  return r;
-}
-
-// record: off_flags = (offset in 16-byte units) << 5 | global << 4 | flags (1: x1 distinct, 2: y1 distinct,
-// 4: left corners valid, 8: right corners valid); offset is relative to the shared-memory window base or,
-// with the global bit, to the value tensor of the image.
-template <typename T, typename TO>
-__global__ void __launch_bounds__(kSelfThreads, 1)
-msda_self_kernel(const MsdaParams p, const SelfGeom g, int total_units) {
-  using E = Elem<T>;
-  using EO = Elem<TO>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int LP = g.L * g.P, lps = LP | 1;
-  Sample *s_rec = reinterpret_cast<Sample *>(smem_raw + (size_t)g.rec_off16 * 16);
-  float *s_logit = reinterpret_cast<float *>(smem_raw + (size_t)g.logit_off16 * 16);
-  float *s_max = reinterpret_cast<float *>(smem_raw + (size_t)g.stat_off16 * 16);
-  float *s_rinv = s_max + kSub;
-  const unsigned win_base = (unsigned)__cvta_generic_to_shared(smem_raw);
-  const int nq_total = g.qcum[g.L];
-  const int regions = g.regions_x * g.regions_y;
-  const TO *offs = reinterpret_cast<const TO *>(p.loc);
-  const TO *logits = reinterpret_cast<const TO *>(p.attn);
-
-  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-    const int b = unit / (regions * g.H);
-    const int rem = unit - b * regions * g.H;
-    const int region = rem / g.H, h = rem - region * g.H;
-    const int X0 = (region % g.regions_x) * kRegion, Y0 = (region / g.regions_x) * kRegion;
-    const char *vimg = reinterpret_cast<const char *>(p.value) + (size_t)b * p.S * g.H * 64;
-
-    // ---- 1. stage the windows (all levels) of head h ------------------------------------------------------
-    __syncthreads();  // previous unit's gathers are done with the windows
-    for (int l = 0; l < g.L; ++l) {  // one thread per window pixel: 64 contiguous bytes = 4 cp.async
-      const int side = g.side[l], Hl = g.Hl[l], Wl = g.Wl[l];
-      const float inv_side = 1.f / (float)side;
-      const int wy_org = (Y0 >> l) - kHalo, wx_org = (X0 >> l) - kHalo;
-      unsigned char *wbase = smem_raw + (size_t)g.woff[l] * 16;
-      const char *lbase = vimg + ((size_t)g.start[l] * g.H + h) * 64;
-      for (int pix = tid; pix < side * side; pix += kSelfThreads) {
-        const int py = fast_div(pix, inv_side), px = pix - py * side;
-        const int y = wy_org + py, x = wx_org + px;
-        unsigned char *dst = wbase + pix * 64;
-        if (y >= 0 && y < Hl && x >= 0 && x < Wl) {
-          const char *src = lbase + (size_t)(y * Wl + x) * g.H * 64;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) cp_async16(dst + c * 16, src + c * 16);
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(dst + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-    }
-
-    // ---- 2/3. sub-batches of queries ----------------------------------------------------------------------
-    for (int sub0 = 0; sub0 < nq_total; sub0 += kSub) {
-      const int nq = min(kSub, nq_total - sub0);
-      if (sub0 > 0) __syncthreads();  // records / logits of the previous sub-batch are no longer read
-      // one thread per (query, level): 4 logits / 4 (x, y) offsets per vector load (host guarantees P == 4)
-      const float inv_l = 1.f / (float)g.L;
-      for (int i = tid; i < nq * g.L; i += kSelfThreads) {
-        const int r = fast_div(i, inv_l), l = i - r * g.L;
-        const int j = sub0 + r;
-        int lq = 0;
-#pragma unroll
-        for (int k = 1; k < kSelfLevels; ++k) lq += (k < g.L && j >= g.qcum[k]) ? 1 : 0;
-        const int t = j - g.qcum[lq], sh = 4 - lq;  // region edge at level lq = 1 << sh
-        const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
-        const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
-        float v[4];
-        load4<TO>(logits + bq * p.logit_row_stride + h * LP + l * 4, v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_logit[r * lps + l * 4 + k] = v[k];
-      }
-      __syncthreads();
-      if (tid < nq) {
-        const float *row = s_logit + tid * lps;
-        float m = row[0];
-        for (int s = 1; s < LP; ++s) m = fmaxf(m, row[s]);
-        float sum = 0.f;
-        for (int s = 0; s < LP; ++s) sum += __expf(row[s] - m);
-        s_max[tid] = m;
-        s_rinv[tid] = 1.f / sum;
-      }
-      __syncthreads();
-      for (int i = tid; i < nq * g.L; i += kSelfThreads) {
-        const int r = fast_div(i, inv_l), l = i - r * g.L;
-        const int j = sub0 + r;
-        int lq = 0;
-#pragma unroll
-        for (int k = 1; k < kSelfLevels; ++k) lq += (k < g.L && j >= g.qcum[k]) ? 1 : 0;
-        const int t = j - g.qcum[lq], sh = 4 - lq;
-        const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
-        const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
-        const int Hl = g.Hl[l], Wl = g.Wl[l], side = g.side[l];
-        float o[8];
-        load8<TO>(offs + bq * p.offs_row_stride + (h * LP + l * 4) * 2, o);
-        const float *rp = p.ref + (bq * g.L + l) * p.ref_dim;
-        const float mx = s_max[r], ri = s_rinv[r];
-        float sx, sy;
-        if (p.ref_dim == 2) {
-          sx = 1.f / (float)Wl;
-          sy = 1.f / (float)Hl;
-        } else {
-          sx = rp[2] * 0.125f;
-          sy = rp[3] * 0.125f;
-        }
-        const float rx = rp[0], ry = rp[1];
-        const int wy_org = (Y0 >> l) - kHalo, wx_org = (X0 >> l) - kHalo;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = __expf(s_logit[r * lps + l * 4 + k] - mx) * ri;
-          int y0, x0;
-          Sample rec = make_sample_xy(fmaf(o[2 * k], sx, rx), fmaf(o[2 * k + 1], sy, ry), a, Hl, Wl, y0, x0);
-          const int fl = rec.off_flags;
-          const int wy = y0 - wy_org, wx = x0 - wx_org;
-          if (wx >= 0 && wy >= 0 && wx + (fl & 1) < side && wy + ((fl >> 1) & 1) < side)
-            rec.off_flags = ((g.woff[l] + (wy * side + wx) * 4) << 5) | fl;                       // shared-memory window
-          else
-            rec.off_flags = ((((g.start[l] + y0 * Wl + x0) * g.H + h) * 4) << 5) | 16 | fl;       // global (16-byte units)
-          s_rec[r * lps + l * 4 + k] = rec;
-        }
-      }
-      if (sub0 == 0) cp_async_wait_all_();  // windows landed (this thread's copies; the barrier covers the others')
-      __syncthreads();
-
-      // ---- gather: 8 lanes per query ----
-      const int grp = lane >> 3, k = (lane >> 2) & 1, c = lane & 3;
-      for (int r0 = warp * 4; r0 < nq; r0 += (kSelfThreads / 32) * 4) {
-        const int rr = min(r0 + grp, nq - 1);
-        const bool active = r0 + grp < nq;
-        const Sample *row = s_rec + rr * lps;
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 1
-        for (int l = 0; l < g.L; ++l) {
-          const unsigned dys = (unsigned)g.side[l] * 64u;              // window row pitch (bytes)
-          const unsigned dyg = (unsigned)g.Wl[l] * g.H * 64u;          // global row pitch (bytes)
-#pragma unroll
-          for (int pp = 0; pp < 4; ++pp) {  // P == 4 (host-checked)
-            const Sample sm = row[l * 4 + pp];
-            const unsigned f = (unsigned)sm.off_flags;
-            const unsigned dx = (f & 1u) & (unsigned)k, dy = (f >> 1) & 1u;
-            uint4 v0, v1;
-            if (!(f & 16u)) {
-              const unsigned a0 = win_base + ((f >> 5) << 4) + dx * 64u + c * 16u;
-              v0 = lds_v4(a0);
-              v1 = lds_v4(a0 + dy * dys);
-            } else {
-              const char *gp = vimg + ((size_t)(f >> 5) << 4) + dx * (unsigned)(g.H * 64) + c * 16;
-              v0 = ldg_nc_v4(reinterpret_cast<const uint4 *>(gp));
-              v1 = ldg_nc_v4(reinterpret_cast<const uint4 *>(gp + dy * dyg));
-            }
-            const float wx = k ? ((f & 8u) ? sm.lw : 0.f) : ((f & 4u) ? 1.f - sm.lw : 0.f);
-            const float w0 = sm.hh_a * wx, w1 = sm.lh_a * wx;
-            float f0[8], f1[8];
-            E::unpack(v0, f0);
-            E::unpack(v1, f1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(w1, f1[i], fmaf(w0, f0[i], acc[i]));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
-        if (active && k == 0) {
-          const int j = sub0 + rr;
-          int lq = 0;
-#pragma unroll
-          for (int kk = 1; kk < kSelfLevels; ++kk) lq += (kk < g.L && j >= g.qcum[kk]) ? 1 : 0;
-          const int t = j - g.qcum[lq], sh = 4 - lq;
-          const int qy = (Y0 >> lq) + (t >> sh), qx = (X0 >> lq) + (t & ((1 << sh) - 1));
-          const size_t bq = (size_t)b * p.Q + g.start[lq] + qy * g.Wl[lq] + qx;
-          stg_stream_v4(reinterpret_cast<uint4 *>(p.out) + (bq * g.H + h) * 4 + c, E::pack(acc));
-        }
-      }
-    }
-  }
-}
-
 // Scalar fallback for shapes the vector path does not cover (D*sizeof(T) not a power-of-two
 // multiple of 16 B, L > 16, or tiles that do not fit shared memory).  One thread per output
 // scalar, fp32 accumulation.  Correctness path only.
@@ -850,87 +628,4 @@ extern "C" int ape_msda_fused_fwd(const void *value, const int64_t *shapes, cons
     default: APE_FUSED_DISPATCH(__nv_bfloat16)
   }
 #undef APE_FUSED_DISPATCH
-}
-
-// Encoder self-attention variant: queries are the pixels of the level structure (Q == S).  Takes the level shapes on
-// the HOST as well (the caller built them; no device round trip).  Geometries the region kernel does not cover
-// (32-bit value, more than 5 levels, level 0 not a multiple of 16 pixels, levels that are not exact halvings, head
-// dim * element size != 64 B) take the generic fused kernel: same results up to fp32 summation order.
-extern "C" int ape_msda_fused_self_fwd(const void *value, const int64_t *shapes, const int64_t *starts,
-                                       const int *host_shapes, const void *offsets, int64_t offs_row_stride,
-                                       const void *logits, int64_t logit_row_stride, const float *ref, int ref_dim,
-                                       void *out, int B, int S, int H, int D, int L, int P, int dtype, int offs_dtype,
-                                       void *stream) {
-  const int Q = S;
-  if (int rc = validate(value, shapes, starts, offsets, logits, out, B, S, H, D, L, Q, P, dtype)) return rc;
-  if (!host_shapes) return fail(APE_ERR_NULL_PTR, "msda_self: null host_shapes");
-  if (ref_dim != 2 && ref_dim != 4) return fail(APE_ERR_INVALID_ARG, "msda_self: ref_dim must be 2 or 4");
-  if (offs_row_stride < (int64_t)H * L * P * 2 || logit_row_stride < (int64_t)H * L * P)
-    return fail(APE_ERR_INVALID_ARG, "msda_self: row strides smaller than a row");
-  long long total = 0;
-  for (int l = 0; l < L; ++l) {
-    const int h = host_shapes[2 * l], w = host_shapes[2 * l + 1];
-    if (h <= 0 || w <= 0) return fail(APE_ERR_INVALID_ARG, "msda_self: bad level shape");
-    total += (long long)h * w;
-  }
-  if (total != S) return fail(APE_ERR_INVALID_ARG, "msda_self: level shapes do not sum to S=%d", S);
-  if (B == 0 || S == 0) return APE_OK;
-  if (!ref) return fail(APE_ERR_NULL_PTR, "msda_self: null reference_points");
-  const int eo = dtype_size(offs_dtype);
-  bool ok = dtype != APE_DTYPE_F32 && D * dtype_size(dtype) == 64 && L <= kSelfLevels && P == 4 &&
-            (reinterpret_cast<uintptr_t>(offsets) & 15) == 0 && (offs_row_stride * eo) % 16 == 0 &&
-            (reinterpret_cast<uintptr_t>(logits) & (4 * eo - 1)) == 0 && (logit_row_stride * eo) % (4 * eo) == 0 &&
-            (offs_dtype == dtype || offs_dtype == APE_DTYPE_F32) && host_shapes[0] % kRegion == 0 && host_shapes[1] % kRegion == 0 &&
-            (long long)S * H * 4 < (1LL << 26);
-  for (int l = 1; ok && l < L; ++l)
-    ok = host_shapes[2 * l] * (1 << l) == host_shapes[0] && host_shapes[2 * l + 1] * (1 << l) == host_shapes[1];
-  if (!ok)
-    return ape_msda_fused_fwd(value, shapes, starts, offsets, offs_row_stride, logits, logit_row_stride, ref, ref_dim,
-                              out, B, S, H, D, L, Q, P, dtype, offs_dtype, stream);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MsdaParams p{};
-  p.value = value; p.shapes = shapes; p.starts = starts; p.loc = offsets; p.attn = logits; p.ref = ref;
-  p.out = out; p.offs_row_stride = offs_row_stride; p.logit_row_stride = logit_row_stride;
-  p.B = B; p.S = S; p.H = H; p.L = L; p.Q = Q; p.P = P; p.ref_dim = ref_dim;
-  SelfGeom g{};
-  g.L = L; g.P = P; g.H = H;
-  int st_acc = 0, w16 = 0, qc = 0;
-  for (int l = 0; l < L; ++l) {
-    g.Hl[l] = host_shapes[2 * l]; g.Wl[l] = host_shapes[2 * l + 1]; g.start[l] = st_acc;
-    st_acc += g.Hl[l] * g.Wl[l];
-    g.side[l] = (kRegion >> l) + 2 * kHalo + 1;
-    g.woff[l] = w16; w16 += g.side[l] * g.side[l] * 4;
-    g.qcum[l] = qc; qc += (kRegion >> l) * (kRegion >> l);
-  }
-  g.woff[L] = w16; g.qcum[L] = qc;
-  g.regions_x = g.Wl[0] / kRegion; g.regions_y = g.Hl[0] / kRegion;
-  const int lps = (L * P) | 1;
-  g.rec_off16 = w16;
-  g.logit_off16 = g.rec_off16 + kSub * lps;
-  g.stat_off16 = g.logit_off16 + (kSub * lps * 4 + 15) / 16;
-  const size_t smem = (size_t)g.stat_off16 * 16 + 2 * kSub * 4;
-  if (smem > 227 * 1024)
-    return ape_msda_fused_fwd(value, shapes, starts, offsets, offs_row_stride, logits, logit_row_stride, ref, ref_dim,
-                              out, B, S, H, D, L, Q, P, dtype, offs_dtype, stream);
-  const long long units = (long long)B * g.regions_x * g.regions_y * H;
-  if (units >= (1LL << 31)) return fail(APE_ERR_UNSUPPORTED, "msda_self: too many work units");
-  int sms = 0, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
-  const int ctas = (int)(units < sms ? units : sms);
-#define APE_SELF(T, TO)                                                                          \
-  do {                                                                                           \
-    auto k = msda_self_kernel<T, TO>;                                                            \
-    if (int rc = set_smem(k, smem)) return rc;                                                   \
-    k<<<ctas, kSelfThreads, smem, st>>>(p, g, (int)units);                                       \
-    return check_launch("msda_self_kernel");                                                     \
-  } while (0)
-  if (dtype == APE_DTYPE_F16) {
-    if (offs_dtype == APE_DTYPE_F16) APE_SELF(__half, __half);
-    APE_SELF(__half, float);
-  }
-  if (offs_dtype == APE_DTYPE_BF16) APE_SELF(__nv_bfloat16, __nv_bfloat16);
-  APE_SELF(__nv_bfloat16, float);
-#undef APE_SELF
 }

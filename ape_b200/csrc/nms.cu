@@ -163,6 +163,102 @@ __global__ void __launch_bounds__(256) nms_scan_big_kernel(const unsigned long l
   if (t == 0) *count = s_total;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Class-aware NMS for the open-vocabulary head when (almost) every (query, class) pair is a candidate
+// (test_score_thresh = 0.0 with 900 queries x 1203 names = 1.08 M pairs: fast_rcnn.py:129-192 -> batched_nms, which
+// torchvision runs class by class above 25 000 boxes on CUDA, `_batched_nms_vanilla`).  Every class sees the SAME Q boxes
+// (boxes are per query), so one Q x Q IoU bit matrix serves all classes; the per-class work is "sort the queries by this
+// class's score, greedy scan with the shared matrix".  Kernel 1 builds the matrix (one ballot per 32 pairs); kernel 2 is
+// persistent: the matrix lives in shared memory, one WARP owns a class: compaction of the candidates (score > thresh),
+// bitonic sort of 64-bit (score, index) keys in shared memory, scan with the suppression bitset in registers (lane w
+// = word w), result written class-major: out[c][q] = score if (q, c) survives else -inf.
+__global__ void __launch_bounds__(256) cw_mask_kernel(const float4 *__restrict__ boxes, int Q, int W, float thr,
+                                                      unsigned *__restrict__ mask) {
+  const int task = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (task >= Q * W) return;
+  const int i = task / W, w = task - i * W;
+  const int j = w * 32 + lane;
+  bool bit = false;
+  if (j < Q && j != i) bit = iou_gt(boxes[i], boxes[j], thr);
+  const unsigned bits = __ballot_sync(0xffffffffu, bit);
+  if (lane == 0) mask[task] = bits;
+}
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+  const unsigned u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+constexpr int kCwWarps = 8, kCwMaxQ = 1024;
+
+__global__ void __launch_bounds__(kCwWarps * 32) cw_scan_kernel(const unsigned *__restrict__ mask, const float *__restrict__ scores,
+                                                                long long ld, const unsigned char *__restrict__ row_valid, int Q,
+                                                                int N, int W, float score_thresh, float *__restrict__ out) {
+  extern __shared__ unsigned long long s_cw[];
+  unsigned long long *keys = s_cw + (size_t)(threadIdx.x >> 5) * kCwMaxQ;           // this warp's sort buffer
+  unsigned *s_mask = reinterpret_cast<unsigned *>(s_cw + (size_t)kCwWarps * kCwMaxQ);  // [Q][W]
+  for (int i = threadIdx.x; i < Q * W; i += blockDim.x) s_mask[i] = mask[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const float ninf = __int_as_float(0xff800000);
+  for (int c = blockIdx.x * kCwWarps + warp; c < N; c += gridDim.x * kCwWarps) {
+    // 1. candidates of this class, compacted (order irrelevant: the keys are sorted next)
+    int n = 0;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const int q = q0 + lane;
+      float sc = 0.f;
+      bool cand = false;
+      if (q < Q && (!row_valid || row_valid[q])) {
+        sc = scores[(size_t)q * ld + c];
+        cand = sc > score_thresh;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      if (cand) keys[n + __popc(m & lt)] = ((unsigned long long)ordered_bits(sc) << 32) | (unsigned)(0xffffffffu - (unsigned)q);
+      n += __popc(m);
+    }
+    int np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    for (int i = n + lane; i < np2; i += 32) keys[i] = 0ull;
+    __syncwarp();
+    // 2. bitonic sort, descending: higher score first, ties -> lower query index first
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = lane; t < (np2 >> 1); t += 32) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // element with bit j clear
+          const int p = i | j;
+          const unsigned long long a = keys[i], b = keys[p];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[p] = a; }
+        }
+        __syncwarp();
+      }
+    }
+    // 3. greedy scan: `removed` / `kept` bitsets live in registers, lane w = word w
+    unsigned removed = 0, kept = 0;
+    unsigned long long key = n > 0 ? keys[0] : 0ull;
+    for (int i = 0; i < n; ++i) {
+      const unsigned long long next = (i + 1 < n) ? keys[i + 1] : 0ull;  // independent of the chain below
+      const unsigned q = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+      const unsigned r = __shfl_sync(0xffffffffu, removed, q >> 5);
+      if (!((r >> (q & 31)) & 1u)) {  // warp-uniform
+        if (lane == (int)(q >> 5)) kept |= 1u << (q & 31);
+        if (lane < W) removed |= s_mask[q * W + lane];
+      }
+      key = next;
+    }
+    // 4. class-major output row
+    float *orow = out + (size_t)c * Q;
+    for (int q0 = 0; q0 < Q; q0 += 32) {
+      const unsigned kb = __shfl_sync(0xffffffffu, kept, q0 >> 5);
+      const int q = q0 + lane;
+      if (q < Q) orow[q] = ((kb >> lane) & 1u) ? scores[(size_t)q * ld + c] : ninf;
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 }  // namespace ape
 
@@ -216,4 +312,35 @@ extern "C" int ape_nms_sorted_dev(const float *boxes_sorted, int n_max, const in
                                   uint8_t *keep, int *count, void *stream) {
   if (!n_dev) return fail(APE_ERR_NULL_PTR, "nms: null n_dev");
   return nms_launch(boxes_sorted, n_max, n_dev, iou_threshold, workspace, keep, count, stream);
+}
+
+extern "C" int64_t ape_nms_classwise_workspace_bytes(int Q) { return (int64_t)Q * ((Q + 31) / 32) * 4; }
+
+extern "C" int ape_nms_classwise(const float *boxes, const float *scores, int64_t ld_scores, const uint8_t *row_valid, int Q,
+                                 int N, float score_thresh, float iou_threshold, void *workspace, float *out, void *stream) {
+  if (Q < 0 || N < 0 || Q > kCwMaxQ) return fail(APE_ERR_UNSUPPORTED, "nms_classwise: Q=%d N=%d (Q <= %d)", Q, N, kCwMaxQ);
+  if (Q == 0 || N == 0) return APE_OK;
+  if (!boxes || !scores || !workspace || !out) return fail(APE_ERR_NULL_PTR, "nms_classwise: null pointer argument");
+  if (reinterpret_cast<uintptr_t>(boxes) & 15) return fail(APE_ERR_INVALID_ARG, "nms_classwise: boxes must be 16-byte aligned");
+  if (ld_scores < N) return fail(APE_ERR_INVALID_ARG, "nms_classwise: ld_scores < N");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int W = (Q + 31) / 32;
+  cw_mask_kernel<<<(Q * W + 7) / 8, 256, 0, st>>>(reinterpret_cast<const float4 *>(boxes), Q, W, iou_threshold,
+                                                  reinterpret_cast<unsigned *>(workspace));
+  if (int rc = check_launch("cw_mask_kernel")) return rc;
+  const size_t smem = (size_t)kCwWarps * kCwMaxQ * 8 + (size_t)Q * W * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(cw_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return fail((int)e, "nms_classwise: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int ctas = min(sms, (N + kCwWarps - 1) / kCwWarps);
+  cw_scan_kernel<<<ctas, kCwWarps * 32, smem, st>>>(reinterpret_cast<const unsigned *>(workspace), scores, ld_scores, row_valid, Q,
+                                                    N, W, score_thresh, out);
+  return check_launch("cw_scan_kernel");
 }

@@ -52,6 +52,8 @@ class MultiScaleDeformableAttention(nn.Module):
         self.output_proj = nn.Linear(embed_dim, embed_dim)
         # accepted for config compatibility; this engine has exactly one (CUDA) path
         self.pytorch_attn = pytorch_attn
+        # engine: calls with at least this many queries (the encoder) gather from the pair layout (csrc/msda_pair.cu)
+        self.pair_layout_min_queries = 2048
         self._qcat = None
         self.init_weights()
 
@@ -127,14 +129,22 @@ class MultiScaleDeformableAttention(nn.Module):
         else:
             value = self.value_proj(value)
             qo = F.linear(query, wq, bq)  # [B,Q, H*L*P*2 + H*L*P]
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], float(0))
-        value = value.view(bs, num_value, self.num_heads, -1).contiguous()
         n_off = self.num_heads * self.num_levels * self.num_points * 2
-        output = ops.ms_deform_attn_fused_forward(
-            value, spatial_shapes, level_start_index, qo[..., :n_off], qo[..., n_off:],
-            reference_points.to(torch.float32).contiguous(), self.num_points,
-            host_shapes=kwargs.get("host_shapes"))
+        ref32 = reference_points.to(torch.float32).contiguous()
+        host_shapes = kwargs.get("host_shapes")
+        head_dim = self.embed_dim // self.num_heads
+        if engine and host_shapes is not None and num_query >= self.pair_layout_min_queries and \
+                ops.msda_pair_supported(host_shapes, self.num_heads, head_dim, self.num_points, value.dtype):
+            # many queries: pair layout (token s | token s+1 in one 128-byte line) + 16-bit corner blend
+            value2 = ops.msda_pair_values(value, self.num_heads, token_mask=key_padding_mask)
+            output = ops.ms_deform_attn_pair_fused_forward(value2, spatial_shapes, level_start_index, host_shapes,
+                                                           qo[..., :n_off], qo[..., n_off:], ref32, self.num_points)
+        else:
+            if key_padding_mask is not None:
+                value = value.masked_fill(key_padding_mask[..., None], float(0))
+            value = value.view(bs, num_value, self.num_heads, -1).contiguous()
+            output = ops.ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, qo[..., :n_off], qo[..., n_off:],
+                                                      ref32, self.num_points)
         if engine and self.batch_first and identity.dtype in (output.dtype, torch.float32):
             # `sum_dtype=torch.float32` (engine layers): identity + output_proj(...) leaves the epilogue as fp32
             return ops.linear_module_tc(self.output_proj, output, residual=identity.contiguous(),

@@ -113,7 +113,10 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
     filter_inds = filter_mask.nonzero()
     boxes = boxes[filter_inds[:, 0]]
     scores = scores[filter_mask]
-    keep = ops.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
+    if boxes.is_cuda:
+        keep = ops.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
+    else:  # host tensors (fp32 parity runs without a GPU): the library the reference itself calls
+        keep = torchvision.ops.batched_nms(boxes.float(), scores, filter_inds[:, 1], nms_thresh)
     if topk_per_image >= 0:
         keep = keep[:topk_per_image]
     boxes, scores, filter_inds = boxes[keep], scores[keep], filter_inds[keep]
@@ -302,7 +305,10 @@ class DeformableDETRSegmVL(nn.Module):
         self.engine_dtype = torch.float32
         self.profile_stages = False   # record CUDA-event stage times of the last forward in self.stage_ms
         self.use_cuda_graphs = False  # capture the static stages once per input geometry (16-bit engine mode)
-        self._geo_cache, self._graph_cache = {}, {}
+        import collections
+
+        self._geo_cache, self._graph_cache = {}, collections.OrderedDict()
+        self.graph_cache_size = 8  # captured graphs kept (LRU)
         # static-shape final selection (one host sync per batch) for up to this many (query, class) pairs above the
         # score threshold; more than that falls back to the dynamic path.  0 disables.
         self.static_inference_cap = 8192
@@ -476,8 +482,8 @@ class DeformableDETRSegmVL(nn.Module):
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
         results = None
-        if do_postprocess and low and self.static_inference_cap > 0 and not need_masks:
-            results = self._inference_static(box_cls, box_pred, image_sizes)  # CPU Instances, one host sync (None: overflow)
+        if do_postprocess and box_cls.is_cuda and self.static_inference_cap > 0 and not need_masks:
+            results = self._inference_static(box_cls, box_pred, image_sizes)  # CPU Instances, one host sync
         if results is None:
             results = self.inference(box_cls, box_pred, image_sizes)
         padded_hw = tuple(images.shape[-2:])
@@ -576,8 +582,15 @@ class DeformableDETRSegmVL(nn.Module):
         """Run fn(*tensor_args, *const_args) through a CUDA graph captured once per key: inputs are copied into
         static buffers, the replay reuses the captured launch sequence (about 2 000 kernel launches per image
         otherwise dominate the wall clock).  Outputs are static buffers, valid until the next replay of `key`."""
+        key = (key, self.engine_dtype)
         entry = self._graph_cache.get(key)
+        if entry is not None:
+            self._graph_cache.move_to_end(key)
         if entry is None:
+            # bounded cache: every distinct (h, w) inside the square pad is its own graph (masks / valid ratios are baked in),
+            # each with a private memory pool; evict the least recently used together with its geometry
+            while len(self._graph_cache) >= self.graph_cache_size:
+                self._graph_cache.popitem(last=False)
             static_in = [t.clone() for t in tensor_args]
             # autocast's weight-cast cache must be off while capturing: cached casts would be freed when the
             # autocast region ends while the graph still reads them
@@ -591,9 +604,9 @@ class DeformableDETRSegmVL(nn.Module):
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     static_out = fn(*static_in, *const_args)
-            entry = (graph, static_in, static_out)
+            entry = (graph, static_in, static_out, const_args)  # const_args: the graph owns the geometry tensors it reads
             self._graph_cache[key] = entry
-        graph, static_in, static_out = entry
+        graph, static_in, static_out = entry[:3]
         for dst, src in zip(static_in, tensor_args):
             dst.copy_(src)
         graph.replay()
@@ -658,55 +671,81 @@ class DeformableDETRSegmVL(nn.Module):
         return outs
 
     def _inference_static(self, box_cls, box_pred, image_sizes):
-        """`inference` (:759-810 + fast_rcnn.py:97-201) with static shapes: at most `static_inference_cap` (query, class)
-        pairs above the score threshold are compacted with nonzero_static (same row-major order as `.nonzero()`),
-        class-aware NMS runs on the padded list with the true count passed on the device, and the first top-k
-        survivors are packed into one tensor.  ONE device->host copy + synchronisation per batch instead of four
-        per image; if more pairs pass the threshold than the cap, returns None and the caller takes `inference`."""
+        """`inference` (:759-810 + fast_rcnn.py:97-201) with static shapes and ONE device->host copy + synchronisation per
+        batch instead of four per image.  Two device paths, chosen by the number n of (query, class) pairs above the score
+        threshold (as torchvision's batched_nms switches strategy by size):
+          n <= static_inference_cap: pairs compacted with nonzero_static (same row-major order as `.nonzero()`), class-aware
+             NMS with the coordinate-offset trick on the padded list (true count passed on the device), first top-k kept;
+          n  > static_inference_cap (test_score_thresh 0.0 with a 1203-name vocabulary: 1.08 M pairs): per-class NMS over the
+             shared per-query boxes (`ops.nms_classwise`, torchvision's `_batched_nms_vanilla` semantics), top-k of the
+             surviving scores.  Memory is bounded by Q^2 bits whatever the vocabulary size."""
         cap, topk = int(self.static_inference_cap), int(self.test_topk_per_image)
-        if topk < 0:
+        if topk < 0 or box_cls.shape[1] > 1024:
             return None
-        packs = []
-        for b, (h, w) in enumerate(image_sizes):
-            scores = box_cls[b].float().sigmoid()                                           # [Q, N] (bg column dropped again, :772)
-            xyxy = box_cxcywh_to_xyxy(box_pred[b].float())
-            boxes = torch.stack((xyxy[:, 0] * float(w), xyxy[:, 1] * float(h), xyxy[:, 2] * float(w), xyxy[:, 3] * float(h)), dim=-1)
-            valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)     # fast_rcnn.py:120-123
-            qmap = valid.cumsum(0) - 1                                                       # row index after the filter
-            boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
-                                 boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1)
-            mask = (scores > self.test_score_thresh) & valid[:, None]
-            n = mask.sum().to(torch.int32).reshape(1)
-            N = scores.shape[1]
-            flat = torch.nonzero_static(mask.flatten(), size=cap, fill_value=0)[:, 0]
-            slot_ok = torch.arange(cap, device=flat.device) < n
-            q, c = flat // N, flat % N
-            cb = boxes[q]
-            cs = torch.where(slot_ok, scores.flatten()[flat], scores.new_full((), float("-inf")))
-            # batched_nms: boxes + class * (max coordinate over the candidates + 1), scores sorted descending
-            mx = torch.where(slot_ok[:, None], cb, cb.new_full((), float("-inf"))).max()
-            nb = cb + (c.to(cb) * (mx + 1))[:, None]
-            order = cs.sort(0, descending=True)[1]
-            keep, _ = ops.nms_sorted_mask(nb.index_select(0, order).contiguous(), self.test_nms_thresh, n_valid=n)
-            pos = torch.nonzero_static(keep, size=topk, fill_value=0)[:, 0]
-            nk = keep.sum().clamp(max=topk).to(torch.float32)
-            sel = order[pos]
-            packs.append(torch.cat([cb[sel], cs[sel, None], c[sel, None].float(), qmap[q[sel], None].float(),
-                                    torch.stack([n[0].float(), nk]).expand(topk, 2)], dim=1))  # [topk, 9]
-        host = torch.stack(packs).to("cpu")  # the one synchronising copy
+        classwise = bool(getattr(self, "_static_overflowed", False))
+        for attempt in range(2):
+            packs = []
+            for b, (h, w) in enumerate(image_sizes):
+                scores = box_cls[b].float().sigmoid().contiguous()                              # [Q, N] (bg column dropped again, :772)
+                xyxy = box_cxcywh_to_xyxy(box_pred[b].float())
+                boxes = torch.stack((xyxy[:, 0] * float(w), xyxy[:, 1] * float(h), xyxy[:, 2] * float(w), xyxy[:, 3] * float(h)), dim=-1)
+                valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)     # fast_rcnn.py:120-123
+                qmap = valid.cumsum(0) - 1                                                       # row index after the filter
+                boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
+                                     boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1).contiguous()
+                mask = (scores > self.test_score_thresh) & valid[:, None]
+                n = mask.sum().to(torch.int32).reshape(1)
+                Q, N = scores.shape
+                if classwise:
+                    k = min(topk, Q * N)
+                    surv = ops.nms_classwise(boxes, scores, self.test_score_thresh, self.test_nms_thresh,
+                                             row_valid=valid.to(torch.uint8))                   # [N, Q], -inf = gone
+                    topv, topi = torch.topk(surv.flatten(), k)                                  # descending score
+                    c, q = topi // Q, topi % Q
+                    nk = torch.isfinite(topv).sum().to(torch.float32)
+                    pack = torch.cat([boxes[q], topv[:, None], c[:, None].float(), qmap[q, None].float(),
+                                      torch.stack([n[0].float(), nk]).expand(k, 2)], dim=1)
+                    if k < topk:
+                        pack = torch.cat([pack, pack.new_zeros(topk - k, 9)], 0)
+                    packs.append(pack)
+                    continue
+                flat = torch.nonzero_static(mask.flatten(), size=cap, fill_value=0)[:, 0]
+                slot_ok = torch.arange(cap, device=flat.device) < n
+                q, c = flat // N, flat % N
+                cb = boxes[q]
+                cs = torch.where(slot_ok, scores.flatten()[flat], scores.new_full((), float("-inf")))
+                # batched_nms: boxes + class * (max coordinate over the candidates + 1), scores sorted descending
+                mx = torch.where(slot_ok[:, None], cb, cb.new_full((), float("-inf"))).max()
+                nb = cb + (c.to(cb) * (mx + 1))[:, None]
+                order = cs.sort(0, descending=True)[1]
+                keep, _ = ops.nms_sorted_mask(nb.index_select(0, order).contiguous(), self.test_nms_thresh, n_valid=n)
+                pos = torch.nonzero_static(keep, size=topk, fill_value=0)[:, 0]
+                nk = keep.sum().clamp(max=topk).to(torch.float32)
+                sel = order[pos]
+                packs.append(torch.cat([cb[sel], cs[sel, None], c[sel, None].float(), qmap[q[sel], None].float(),
+                                        torch.stack([n[0].float(), nk]).expand(topk, 2)], dim=1))  # [topk, 9]
+            host = torch.stack(packs).to("cpu")  # the one synchronising copy
+            over = any(int(host[b, 0, 7].item()) > cap for b in range(len(image_sizes)))
+            if over == classwise:
+                break
+            classwise = over  # wrong path for this batch: run the other one (and start with it next time)
+        self._static_overflowed = classwise
         results = []
         for b, (h, w) in enumerate(image_sizes):
             p = host[b]
-            n, nk = int(p[0, 7].item()), int(p[0, 8].item())
-            if n > cap:
-                return None
+            nk = int(p[0, 8].item())
             p = p[:nk]
             results.append(Instances((h, w), pred_boxes=Boxes(p[:, :4].contiguous()), scores=p[:, 4].contiguous(),
                                      pred_classes=p[:, 5].to(torch.int64), query_index=p[:, 6].to(torch.int64)))
         return results
 
     def inference(self, box_cls, box_pred, image_sizes):
-        """:759-810 + fast_rcnn.py:40-95."""
+        """:759-810 + fast_rcnn.py:40-95.  CUDA: the static-shape selection above (device results; bounded memory for any
+        vocabulary size); CPU: the literal per-image sequence."""
+        if box_cls.is_cuda and self.static_inference_cap > 0:
+            res = self._inference_static(box_cls, box_pred, image_sizes)
+            if res is not None:
+                return [r.to(box_cls.device) for r in res]
         results = []
         zeros = torch.zeros((box_cls.size(1), 1), device=box_cls.device, dtype=box_cls.dtype)
         for b, (h, w) in enumerate(image_sizes):

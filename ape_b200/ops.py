@@ -11,8 +11,6 @@ import torch
 
 from . import _lib
 
-_DISABLE_TILED = False  # tests / sweeps flip this to compare the two encoder kernels
-
 _NS = "ape"
 
 # bench.py sets this to a list to collect (tag, start_event, end_event) around every launch of the
@@ -94,7 +92,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets,
-                                 attention_logits, reference_points, num_points, host_shapes=None):
+                                 attention_logits, reference_points, num_points):
     """Fused tail of MultiScaleDeformableAttention.forward (multi_scale_deform_attn.py:283-348).
 
     value [B,S,H,D]; sampling_offsets [B,Q,>=H*L*P*2] and attention_logits [B,Q,>=H*L*P] are the
@@ -105,26 +103,8 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
     Q = sampling_offsets.shape[1]
     P = int(num_points)
     _require(value.is_cuda and value.is_contiguous(), "value must be a contiguous CUDA tensor")
-    _require(sampling_offsets.dtype == attention_logits.dtype, "offsets/logits dtype mismatch")
-    _require(sampling_offsets.stride(-1) == 1 and attention_logits.stride(-1) == 1, "unit inner stride required")
-    _require(sampling_offsets.stride(0) == Q * sampling_offsets.stride(1), "offsets batch stride")
-    _require(attention_logits.stride(0) == Q * attention_logits.stride(1), "logits batch stride")
-    ref = reference_points
-    _require(ref.dtype == torch.float32 and ref.is_contiguous(), "reference_points must be contiguous fp32")
-    _require(ref.shape[:3] == (B, Q, L), "reference_points must be [B,Q,L,2|4]")
+    ref = _check_fused(sampling_offsets, attention_logits, reference_points, B, Q, L)
     out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
-    if host_shapes is not None and Q == S and not _DISABLE_TILED:
-        # self-attention over the pyramid (encoder): spatially tiled persistent kernel
-        hs = (ctypes.c_int * (2 * L))(*[int(v) for hw in host_shapes for v in hw])
-        with torch.cuda.device(value.device), _timed(("msda_fused", B, S, Q, L, P, value.element_size(),
-                                                      sampling_offsets.element_size())):
-            rc = _lib.lib.ape_msda_fused_self_fwd(
-                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs,
-                sampling_offsets.data_ptr(), sampling_offsets.stride(1), attention_logits.data_ptr(),
-                attention_logits.stride(1), ref.data_ptr(), ref.shape[-1], out.data_ptr(), B, S, H, D, L, P,
-                _lib.dtype_code(value.dtype), _lib.dtype_code(sampling_offsets.dtype), _lib.current_stream_ptr())
-        _lib.check(rc, "ape_msda_fused_self_fwd")
-        return out
     with torch.cuda.device(value.device), _timed(("msda_fused", B, S, Q, L, P, value.element_size(),
                                                   sampling_offsets.element_size())):
         rc = _lib.lib.ape_msda_fused_fwd(
@@ -135,6 +115,67 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
             B, S, H, D, L, Q, P, _lib.dtype_code(value.dtype), _lib.dtype_code(sampling_offsets.dtype),
             _lib.current_stream_ptr())
     _lib.check(rc, "ape_msda_fused_fwd")
+    return out
+
+
+def _check_fused(sampling_offsets, attention_logits, reference_points, B, Q, L):
+    _require(sampling_offsets.dtype == attention_logits.dtype, "offsets/logits dtype mismatch")
+    _require(sampling_offsets.stride(-1) == 1 and attention_logits.stride(-1) == 1, "unit inner stride required")
+    _require(sampling_offsets.stride(0) == Q * sampling_offsets.stride(1), "offsets batch stride")
+    _require(attention_logits.stride(0) == Q * attention_logits.stride(1), "logits batch stride")
+    ref = reference_points
+    _require(ref.dtype == torch.float32 and ref.is_contiguous(), "reference_points must be contiguous fp32")
+    _require(ref.shape[:3] == (B, Q, L), "reference_points must be [B,Q,L,2|4]")
+    return ref
+
+
+def msda_pair_supported(host_shapes, H, D, P, dtype):
+    """True when the pair-layout kernel covers this geometry (16-bit value, D = 32, P = 4, L <= 8, levels >= 2 wide)."""
+    if dtype not in (torch.float16, torch.bfloat16):
+        return False
+    L = len(host_shapes)
+    hs = (ctypes.c_int * (2 * L))(*[int(v) for hw in host_shapes for v in hw])
+    return bool(_lib.lib.ape_msda_pair_supported(hs, L, int(H), int(D), int(P), _lib.dtype_code(dtype)))
+
+
+def msda_pair_values(value, num_heads, token_mask=None):
+    """value [B,S,H*32] (16-bit, unit inner stride, uniform row pitch) -> pair layout [B,S,H,2,32] (ape_msda_pair_values):
+    entry (s, h) = channels of token s then of token s+1.  token_mask [B,S] bool: masked tokens are written as zeros."""
+    _require(value.is_cuda and value.dim() == 3 and value.stride(2) == 1 and value.stride(0) == value.shape[1] * value.stride(1),
+             "msda_pair_values: CUDA [B,S,C] with uniform row pitch")
+    B, S, C = value.shape
+    H = int(num_heads)
+    out = torch.empty((B, S, H, 2, C // H), dtype=value.dtype, device=value.device)
+    mptr = None
+    if token_mask is not None:
+        token_mask = token_mask.to(torch.uint8).contiguous()
+        _require(token_mask.numel() == B * S, "msda_pair_values: token_mask must be [B,S]")
+        mptr = token_mask.data_ptr()
+    with torch.cuda.device(value.device), _timed(("msda_pair_values", B, S, C)):
+        rc = _lib.lib.ape_msda_pair_values(value.data_ptr(), value.stride(1), out.data_ptr(), mptr, B, S, H, C // H,
+                                           _lib.dtype_code(value.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_msda_pair_values")
+    return out
+
+
+def ms_deform_attn_pair_fused_forward(value2, spatial_shapes, level_start_index, host_shapes, sampling_offsets,
+                                      attention_logits, reference_points, num_points, heads_per_cta=0):
+    """ms_deform_attn_fused_forward over the pair layout (ape_msda_pair_fused_fwd).  value2 [B,S,H,2,32]."""
+    B, S, H, two, D = value2.shape
+    L = spatial_shapes.shape[0]
+    Q = sampling_offsets.shape[1]
+    _require(value2.is_cuda and value2.is_contiguous() and two == 2, "value2 must be a contiguous CUDA [B,S,H,2,D] tensor")
+    ref = _check_fused(sampling_offsets, attention_logits, reference_points, B, Q, L)
+    hs = (ctypes.c_int * (2 * L))(*[int(v) for hw in host_shapes for v in hw])
+    out = torch.empty((B, Q, H * D), dtype=value2.dtype, device=value2.device)
+    with torch.cuda.device(value2.device), _timed(("msda_fused", B, S, Q, L, int(num_points), value2.element_size(),
+                                                   sampling_offsets.element_size())):
+        rc = _lib.lib.ape_msda_pair_fused_fwd(
+            value2.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs,
+            sampling_offsets.data_ptr(), sampling_offsets.stride(1), attention_logits.data_ptr(),
+            attention_logits.stride(1), ref.data_ptr(), ref.shape[-1], out.data_ptr(), B, S, H, D, L, Q, int(num_points),
+            _lib.dtype_code(value2.dtype), _lib.dtype_code(sampling_offsets.dtype), int(heads_per_cta), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_msda_pair_fused_fwd")
     return out
 
 
@@ -376,6 +417,29 @@ def nms_sorted_mask(sorted_boxes, iou_threshold, n_valid=None):
     return keep, count
 
 
+def nms_classwise(boxes, scores, score_thresh, iou_threshold, row_valid=None):
+    """Class-aware NMS over ALL (query, class) pairs with score > score_thresh (ape_nms_classwise): boxes [Q,4] fp32 xyxy,
+    scores [Q,N] fp32.  Returns fp32 [N,Q] (class-major): the score where the pair survives, -inf elsewhere.  Static
+    shapes, no host synchronisation.  Bounded memory: Q*Q/8 bytes of workspace whatever N is (the dense n x n bit matrix of
+    `nms_sorted_mask` would need terabytes for the 1.08 M pairs of a 1203-name vocabulary at threshold 0)."""
+    _require(boxes.is_cuda and boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.dim() == 2 and boxes.shape[1] == 4,
+             "nms_classwise: boxes must be contiguous CUDA fp32 [Q,4]")
+    _require(scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.stride(1) == 1 and
+             scores.shape[0] == boxes.shape[0], "nms_classwise: scores must be CUDA fp32 [Q,N]")
+    Q, N = scores.shape
+    _require(Q <= 1024, f"nms_classwise: at most 1024 queries (got {Q})")
+    out = torch.empty((N, Q), dtype=torch.float32, device=scores.device)
+    ws = torch.empty((max(1, int(_lib.lib.ape_nms_classwise_workspace_bytes(Q))),), dtype=torch.uint8, device=scores.device)
+    if row_valid is not None:
+        _require(row_valid.dtype == torch.uint8 and row_valid.is_contiguous() and row_valid.numel() == Q, "nms_classwise: row_valid uint8 [Q]")
+    with torch.cuda.device(scores.device), _timed(("nms_classwise", Q, N)):
+        rc = _lib.lib.ape_nms_classwise(boxes.data_ptr(), scores.data_ptr(), scores.stride(0),
+                                        row_valid.data_ptr() if row_valid is not None else None, Q, N, float(score_thresh),
+                                        float(iou_threshold), ws.data_ptr(), out.data_ptr(), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_nms_classwise")
+    return out
+
+
 def nms(boxes, scores, iou_threshold):
     """torchvision.ops.nms replacement: indices of kept boxes, sorted by descending score."""
     _require(boxes.is_cuda and boxes.dim() == 2 and boxes.shape[1] == 4, "nms: boxes must be CUDA [n,4]")
@@ -391,6 +455,9 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     """detectron2 / torchvision batched_nms (coordinate-offset trick, boxes.float()) on ape_nms_sorted."""
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    if boxes.shape[0] > 32768:  # n x n/64 x 8 bytes of IoU bits: 134 MB at the limit
+        raise RuntimeError(f"ape_b200.ops.batched_nms: {boxes.shape[0]} candidates need a dense IoU bit matrix of "
+                           f"{boxes.shape[0] ** 2 // 8 / 2 ** 30:.1f} GiB; use ops.nms_classwise (per-class NMS over shared boxes)")
     boxes = boxes.float()
     max_coordinate = boxes.max()
     offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))

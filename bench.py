@@ -143,61 +143,170 @@ def fused_msda_bytes(B, S, Q, L, e, eo):
     return e * B * S * H * D + eo * B * Q * H * L * P * 3 + 4 * B * Q * L * 2 + e * B * Q * H * D + 24 * L
 
 
-def cpu_model_arm(steps, n_text=1203, sd=None):
-    """Reference arm for the ape_l_d workload: the oracle's CPU port of the reference forward
-    (oracle/ape_forward.py; /root/reference itself cannot travel to the GPU box), fp32, all host threads.
-    `sd`: state_dict of the already calibrated engine model (same weights as the GPU arm); when None the
-    same synthetic weights are built (without the score calibration, see below)."""
+BENCH_SCORE_THRESH = 0.0123  # ~500 of the 1.08 M (query, class) scores of the synthetic-weight model pass (golden image: 500 at 0.012292)
+
+
+def bench_spec():
     import copy
 
-    from ape_b200 import configs, synthetic
+    from ape_b200 import configs
+
+    spec = copy.deepcopy(configs.APE_L_D)
+    spec["test_score_thresh"] = BENCH_SCORE_THRESH
+    return spec
+
+
+def bench_weights(model):
+    """Synthetic weights shared by BOTH arms: a pure function of parameter names and shapes (ape_b200/synthetic.py), then the
+    proposal-head bias shift that makes invalid anchors score at the prior (as with trained weights)."""
+    from ape_b200 import synthetic
+
+    synthetic.fill_state_dict(model)
+    synthetic.suppress_invalid_anchor_logits(model)
+    return model
+
+
+def cpu_model_arm(steps, warmup, n_text=1203, sd=None, seed=0):
+    """Reference arm for the ape_l_d workload: the oracle's CPU port of the reference forward
+    (oracle/ape_forward.py; /root/reference itself cannot travel to the GPU box), fp32, up to 32 host threads.
+    One whole-image forward is ~25 s of host time on the B200 box, so the arm runs at most 1 warm-up and 3 timed
+    forwards and DECLARES what it ran.  Same spec, same weights, same threshold, same image generator as the GPU arm."""
+    from ape_b200 import synthetic
     from ape_b200.modeling import build_model
     from oracle import ape_forward as AF
 
     cores = host_threads()
     torch.set_num_threads(cores)
-    spec = copy.deepcopy(configs.APE_L_D)
-    spec["test_score_thresh"] = 0.1
+    spec = bench_spec()
     text = synthetic.text_features(8192, spec["lang_dim"])[:n_text]
     if sd is None:
-        # reference arm: same synthetic weights; the score calibration of the GPU arm (one more whole forward, ~2 min of
-        # host time) is skipped — thresholding / NMS of a few hundred candidates is < 0.1 % of the CPU time of a forward
-        m = build_model(spec, num_text=n_text)  # parameter container only; the port is functional over its state_dict
-        synthetic.fill_state_dict(m)
+        m = bench_weights(build_model(spec, num_text=n_text))  # parameter container only; the port is functional over its state_dict
         sd = m.state_dict()
     else:
         sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
-    img = torch.randint(0, 256, (3, 1024, 1024), generator=torch.Generator().manual_seed(0)).to(torch.float32)
-    n = 1  # one whole-image forward is ~2 minutes of host time on the B200 box: a bounded sample by construction
+    img = torch.randint(0, 256, (3, 1024, 1024), generator=torch.Generator().manual_seed(seed)).to(torch.float32)
+    w = 1 if warmup > 0 else 0
+    for _ in range(w):
+        AF.forward([img], [(1024, 1024)], text, sd, spec)
+    n = max(1, min(steps, 3))
     t0 = time.perf_counter()
     for _ in range(n):
         res, _ = AF.forward([img], [(1024, 1024)], text, sd, spec)
     dt = (time.perf_counter() - t0) / n
-    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{n} whole-image forward(s) of the oracle port (APE-L_D 1024^2, {n_text} names, fp32), "
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port", "steps_run": n, "warmup_run": w,
+            "sample": f"{n} whole-image forward(s) after {w} warm-up of the oracle port (APE-L_D 1024^2, {n_text} names, fp32), "
                       f"{cores} threads of {os.cpu_count()} host cores",
             "ms_per_step": dt * 1e3, "detections": int(res[0]["scores"].numel())}
 
 
-def model_bench(args, rank, local_rank, world):
-    from ape_b200 import configs
 
+def msda_microbench(dev, quick=False):
+    """BASELINE.json config 5 inside the driver-run record: ms_deform_attn forward on 4-level (128^2..16^2) and the
+    model's 5-level pyramids, Q in {300, 900, S}, fp32 / fp16 / bf16, L2 flushed before every timed launch, median of 7:
+    the drop-in operator (ape_msda_fwd), the engine's fused kernels (generic and pair layout, incl. the pairing pass) and —
+    when oracle/_ref/libref_msda.so travelled with the repo — the REFERENCE's own CUDA kernel recompiled for sm_100a on
+    identical tensors (measurement only: the 'kernel to beat'; never on the product path)."""
+    from ape_b200 import ops
+
+    ref_cuda = None
+    try:
+        from oracle import msda as O
+
+        if O.have_ref_cuda():
+            ref_cuda = O.ref_cuda
+    except Exception:  # noqa: BLE001
+        ref_cuda = None
+    peak, _ = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def med(fn, iters=7):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    L4 = [(128, 128), (64, 64), (32, 32), (16, 16)]
+    cases = [("L4_q300", L4, 300), ("L4_q900", L4, 900), ("L4_qS", L4, None), ("L5_1024_q900", L5_1024, 900),
+             ("L5_1024_qS", L5_1024, None)]
+    if quick:
+        cases = [cases[1], cases[4]]
+    rows = []
+    for name, shapes, Q in cases:
+        ss = torch.tensor(shapes, dtype=torch.int64)
+        areas = ss[:, 0] * ss[:, 1]
+        st = torch.cat([areas.new_zeros(1), areas.cumsum(0)[:-1]])
+        S, L = int(areas.sum()), len(shapes)
+        q = S if Q is None else Q
+        g = torch.Generator().manual_seed(3)
+        value = torch.randn(1, S, H, D, generator=g)
+        loc = torch.rand(1, q, H, L, P, 2, generator=g)
+        logits = torch.randn(1, q, H, L * P, generator=g)
+        attn = logits.softmax(-1).view(1, q, H, L, P)
+        ssd, std = ss.to(dev), st.to(dev)
+        for dname, dt, e in (("f32", torch.float32, 4), ("f16", torch.float16, 2), ("bf16", torch.bfloat16, 2)):
+            v, lo, at = (t.to(dev, dt) for t in (value, loc, attn))
+            nb = msda_bytes(1, S, q, L, e)
+            r = {"case": name, "dtype": dname, "S": S, "Q": q, "L": L, "alg_MB": round(nb / 1e6, 2)}
+            t = med(lambda: ops.ms_deform_attn_forward(v, ssd, std, lo, at, 64))
+            r["op_ms"], r["op_frac_hbm"] = round(t, 4), round(nb / t / 1e6 / peak, 4)
+            if ref_cuda is not None and dt != torch.bfloat16:
+                t = med(lambda: ref_cuda(v, ssd, std, lo, at))
+                r["reference_kernel_ms"] = round(t, 4)
+                r["speedup_vs_reference_kernel"] = round(t / r["op_ms"], 2)
+            if dt != torch.float32:
+                # engine form: raw offsets (reference point 0, so loc = off / (W,H)) + logits, as the module calls it
+                norm = torch.tensor([[w_, h_] for h_, w_ in shapes], dtype=torch.float32)
+                offs = (loc * norm[None, None, None, :, None, :]).reshape(1, q, -1)
+                qo = torch.cat([offs, logits.reshape(1, q, -1)], -1).to(dev, dt)
+                n_off = H * L * P * 2
+                ref0 = torch.zeros(1, q, L, 2, device=dev)
+                fb = fused_msda_bytes(1, S, q, L, e, e)
+                t = med(lambda: ops.ms_deform_attn_fused_forward(v, ssd, std, qo[..., :n_off], qo[..., n_off:], ref0, P))
+                r["fused_ms"], r["fused_frac_hbm"] = round(t, 4), round(fb / t / 1e6 / peak, 4)
+                if ops.msda_pair_supported(shapes, H, D, P, dt):
+                    v3 = v.view(1, S, H * D)
+                    t = med(lambda: ops.ms_deform_attn_pair_fused_forward(ops.msda_pair_values(v3, H), ssd, std, shapes,
+                                                                          qo[..., :n_off], qo[..., n_off:], ref0, P))
+                    r["pair_ms_incl_pairing"], r["pair_frac_hbm"] = round(t, 4), round(fb / t / 1e6 / peak, 4)
+                    v2 = ops.msda_pair_values(v3, H)
+                    t = med(lambda: ops.ms_deform_attn_pair_fused_forward(v2, ssd, std, shapes, qo[..., :n_off], qo[..., n_off:], ref0, P))
+                    r["pair_gather_only_ms"] = round(t, 4)
+            rows.append(r)
+            del v, lo, at
+    return {"peak_GBps": peak, "flush": "256 MiB memset before every timed launch", "reference_kernel": ref_cuda is not None,
+            "rows": rows}
+
+
+def model_bench(args, rank, local_rank, world):
     n_text = 1203
+    # identical in both arms (the driver compares it): nothing below depends on which implementation runs
     config = {"workload": "APE-L_D detection forward, 1024x1024 image, 1203-name vocabulary, boxes only, batch 1 per GPU",
-              "weights": "random init of the real architecture (380 M params)", "text": "seeded synthetic features (text tower out of path)",
-              "l2": "per-step working set (weights 1.5 GB fp32 + activations) >> 126 MB L2",
-              "dense_ops": "libape_b200 kernels: every linear of the ViT / pyramid / neck / encoder / decoder / heads (tcgen05 GEMM), ViT "
-                           "attention (tcgen05 flash attention), LayerNorm / RoPE / GroupNorm, fused ms_deform_attn, VLF pooling, NMS; "
-                           "library: four 3x3 convolutions (cuDNN), decoder self-attention over 900 queries (SDPA), sort, small elementwise glue",
+              "weights": "random init of the real architecture (380 M params): ape_b200/synthetic.py, invalid anchors at the 0.01 prior",
+              "text": "seeded synthetic features (text tower out of path)",
+              "l2": "per-step working set (weights 0.75 GB 16-bit + activations) >> 126 MB L2",
+              "selection": f"test_score_thresh {BENCH_SCORE_THRESH} (~500 of 1.08M scores pass with these weights; README recipe: 0.1 "
+                           "with trained weights); NMS 0.7; top-300",
               "parallelism": f"dp{args.gpus} (one image per GPU; one NCCL gather of packed detections per step when N>1)"}
     if args.impl == "reference":
         if rank != 0:
             return
-        cb = cpu_model_arm(args.steps, n_text)
+        os.environ["APE_B200_CONTAINER_ONLY"] = "1"  # parameter containers only: libape_b200.so is not mapped in this arm
+        cb = cpu_model_arm(args.steps, args.warmup, n_text)
         print(json.dumps({"impl": "reference", "metric": "images_per_sec", "value": cb["value"], "unit": "images/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                          "n_gpus": args.gpus, "steps": cb["steps_run"], "warmup": cb["warmup_run"],
+                          "requested": {"steps": args.steps, "warmup": args.warmup},
+                          "ms_per_step": cb["ms_per_step"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": config,
+                          "data": "synthetic", "config": config, "detections_per_image": cb["detections"],
                           "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                           "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -216,21 +325,9 @@ def model_bench(args, rank, local_rank, world):
     from ape_b200 import synthetic
 
     tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
-    model = build_model(configs.APE_L_D, num_text=n_text)
-    synthetic.fill_state_dict(model)  # non-degenerate random weights (nothing the reference zero-inits stays 0)
-    model.test_score_thresh = 0.1     # SURVEY.md 8(d) config 2 (README recipe --confidence-threshold 0.1)
-    model = model.to(dev)
+    model = bench_weights(build_model(bench_spec(), num_text=n_text)).to(dev)
     model.engine_dtype = tdt  # parameters stay fp32; 16-bit = tensor-core engine path
     model.use_cuda_graphs = tdt != torch.float32 and not args.no_graphs
-    # Untrained weights put every score near the 0.01 prior, so nothing would reach the 0.1 threshold and
-    # the selection stage would be skipped.  Shift the classifier bias once so that ~500 of the 1.08 M
-    # (query, class) scores pass, as with a trained detector; identical for every step.
-    model([{"image": synthetic.image(1024, 1024, seed=99), "height": 1024, "width": 1024}])
-    lg = model.last_outputs["pred_logits"].float().flatten()
-    kth = torch.topk(lg, 500).values[-1]
-    with torch.no_grad():
-        model.class_embed[len(model.class_embed) - 2].bias0.add_((math.log(0.1 / 0.9) - kth).to(model.class_embed[0].bias0.dtype))
-    config["selection"] = "test_score_thresh 0.1, bias calibrated so ~500 of 1.08M scores pass; NMS 0.7; top-300"
     g = torch.Generator().manual_seed(rank)
     NIMG = 4
     host_imgs = [torch.randint(0, 256, (3, 1024, 1024), generator=g).to(torch.float32).pin_memory() for _ in range(NIMG)]
@@ -294,7 +391,8 @@ def model_bench(args, rank, local_rank, world):
     launches = (ape_b200._lib.launch_count() - n0) // prof_steps * args.steps
     events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
     model.use_cuda_graphs = graphs_on
-    config["cuda_graphs"] = bool(graphs_on)
+    engine = {"cuda_graphs": bool(graphs_on), "engine_dtype": args.dtype,
+              "residual_stream": "fp32 (GEMM epilogues write fp32 sums; operands and LayerNorm outputs 16-bit)"}
     own_ms = {}
     for (t, x, y) in events:
         own_ms[t[0]] = own_ms.get(t[0], 0.0) + x.elapsed_time(y) / prof_steps
@@ -314,6 +412,7 @@ def model_bench(args, rank, local_rank, world):
     attn_flops = sum(4.0 * t[1] * t[3] * t[2] * t[2] * 64 for (t, x, y) in events if t[0] == "attention") / prof_steps
     attn_ms = sum(x.elapsed_time(y) for (t, x, y) in events if t[0] == "attention") / prof_steps
     enc = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] == t[2]]
+    pairing_ms = sum(x.elapsed_time(y) for (t, x, y) in events if t[0] == "msda_pair_values") / max(1, len(enc))
     dec = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "msda_fused" and t[3] != t[2]]
     # e2e: pinned host image in, detections out on the host (the model's public call does both)
     e2e_steps = max(3, min(args.steps, 10))
@@ -335,7 +434,7 @@ def model_bench(args, rank, local_rank, world):
         peak, peak_src = peaks()
         tag, _ = enc[0]
         _, B, S, Q, L, _, e, eo = tag
-        enc_ms = sum(x for _, x in enc) / len(enc)
+        enc_ms = sum(x for _, x in enc) / len(enc) + pairing_ms  # one logical op = pairing pass + gather kernel
         nbytes = fused_msda_bytes(B, S, Q, L, e, eo)
         achieved = nbytes / (enc_ms * 1e-3) / 1e9
         traffic = None
@@ -349,9 +448,10 @@ def model_bench(args, rank, local_rank, world):
             "metric": "images_per_sec", "value": world * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
-            "config": config,
+            "config": config, "engine": engine,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "msda_fused_fwd_kernel (encoder, Q=S)",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "msda_pair_fused_kernel + msda_pair_values_kernel (encoder, Q=S)" if pairing_ms > 0
+                         else "msda_fused_fwd_kernel (encoder, Q=S)", "pairing_pass_ms": pairing_ms,
                          "algorithmic_bytes_per_launch": nbytes, "launch_ms": enc_ms,
                          "launches_per_step": len(enc) / prof_steps,
                          "share_of_step": enc_ms * len(enc) / prof_steps / ms_per_step,
@@ -380,8 +480,10 @@ def model_bench(args, rank, local_rank, world):
             line["roofline_attention"] = {"bound": "tensor", "achieved": a, "peak": tpeak, "unit": "TFLOP/s", "frac": a / tpeak,
                                           "peak_source": tpeak_src, "kernel": "attn_fwd_kernel (24 ViT blocks)",
                                           "flops_per_step": attn_flops, "ms_per_step": attn_ms}
+        if world == 1 and not args.no_microbench:
+            line["msda_microbench"] = msda_microbench(dev, quick=args.quick_microbench)
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_model_arm(1, n_text, sd=model.state_dict())
+            cb = cpu_model_arm(1, 0, n_text, sd=model.state_dict(), seed=rank)
             line["detections_per_image"] = {"engine": len(inst), "cpu_port": cb["detections"]}
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
@@ -398,6 +500,8 @@ def main():
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true", help="skip the config-5 ms_deform_attn microbench keys")
+    ap.add_argument("--quick-microbench", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="disable CUDA-graph capture of the static stages")
     args = ap.parse_args()
 

@@ -101,14 +101,23 @@ int ape_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const i
                        void *stream);
 
 /*
- * ape_msda_fused_fwd for self-attention over the feature pyramid itself (the encoder: Q == S, query i is pixel i
- * of the level structure).  Identical results; the work is tiled spatially (16x16-pixel super-tiles walked by
- * persistent CTAs) so sampled texels are re-used out of L1.  host_shapes: int32 [L,2] (H_l, W_l) on the HOST.
+ * Second-generation fused kernel for calls with many queries (the encoder: Q = S = 87 296 at 1024^2), 16-bit value, D = 32,
+ * P = 4.  `value2` is the PAIR layout [B][S][H][2][D]: entry (s, h) = channels of token s followed by those of token s+1, one
+ * aligned 128-byte line, so a bilinear sample costs two full L1 lines instead of four half-used ones; the four corners of
+ * the P points of one level are blended with packed 16-bit FMAs, levels are summed in fp32 (the reference's half kernel
+ * accumulates everything in half, ms_deform_im2col_cuda.cuh:270,290).  Same sampling semantics as ape_msda_fused_fwd.
+ *   ape_msda_pair_values     value [B,S,H*D] (row pitch ld elements) -> value2; token_mask [B*S] bytes or NULL zeroes masked
+ *                            tokens (key_padding_mask, multi_scale_deform_attn.py:286-287)
+ *   ape_msda_pair_supported  1 if the geometry is covered (host_shapes int32 [L,2] on the HOST: every level >= 2 wide)
+ *   ape_msda_pair_fused_fwd  heads_per_cta: 0 = auto (1 for Q >= 128: a CTA's 32 rows are consecutive queries of one head)
  */
-int ape_msda_fused_self_fwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start,
+int ape_msda_pair_values(const void *value, int64_t ld, void *value2, const uint8_t *token_mask, int B, int S, int H, int D,
+                         int dtype, void *stream);
+int ape_msda_pair_supported(const int *host_shapes, int L, int H, int D, int P, int dtype);
+int ape_msda_pair_fused_fwd(const void *value2, const int64_t *spatial_shapes, const int64_t *level_start,
                             const int *host_shapes, const void *offsets, int64_t offs_row_stride, const void *logits,
-                            int64_t logit_row_stride, const float *ref, int ref_dim, void *out, int B, int S, int H,
-                            int D, int L, int P, int dtype, int offs_dtype, void *stream);
+                            int64_t logit_row_stride, const float *ref, int ref_dim, void *out, int B, int S, int H, int D,
+                            int L, int Q, int P, int dtype, int offs_dtype, int heads_per_cta, void *stream);
 
 /*
  * Tensor-core linear layer: C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), tcgen05 / TMA / TMEM.
@@ -221,6 +230,19 @@ int ape_nms_sorted(const float *boxes_sorted, int n, float iou_threshold, void *
  * (device int) are real; keep[i] = 0 for the rest.  workspace: ape_nms_workspace_bytes(n_max). */
 int ape_nms_sorted_dev(const float *boxes_sorted, int n_max, const int *n_dev, float iou_threshold, void *workspace,
                        uint8_t *keep, int *count, void *stream);
+
+/*
+ * Class-aware NMS when (almost) every (query, class) pair is a candidate (test_score_thresh 0.0: 900 queries x 1203 names;
+ * fast_rcnn.py:129-192 -> batched_nms, class by class as torchvision's _batched_nms_vanilla).  All classes share the Q
+ * per-query boxes, so one Q x Q IoU bit matrix serves every class; one warp sorts and scans one class.
+ * boxes [Q,4] fp32 xyxy (16-byte aligned), scores [Q,N] fp32 (row pitch ld_scores), row_valid [Q] bytes or NULL,
+ * candidates = valid rows with score > score_thresh.  out [N,Q] fp32 CLASS-major: the score where (q, c) survives, -inf
+ * elsewhere (a top-k over it yields the detections in descending score order).  Q <= 1024.
+ * workspace: ape_nms_classwise_workspace_bytes(Q).
+ */
+int64_t ape_nms_classwise_workspace_bytes(int Q);
+int ape_nms_classwise(const float *boxes, const float *scores, int64_t ld_scores, const uint8_t *row_valid, int Q, int N,
+                      float score_thresh, float iou_threshold, void *workspace, float *out, void *stream);
 
 #ifdef __cplusplus
 }

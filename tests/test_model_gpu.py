@@ -107,24 +107,37 @@ def test_mini_masks_and_semantic_match_reference_golden(mini):
 
 
 def test_masks_engine_fp16_mode_close_to_fp32(mini):
-    """fp16 engine mode of the mask / semantic rows against the fp32 mode of the same model."""
+    """fp16 engine mode of the mask / semantic rows (a17 / a19 / a20) against the fp32 mode of the same model (which is pinned
+    to the reference golden above): mask logits of the proposals both modes selected, the semantic map and the instance masks."""
     model, _ = mini
     inp = [{"image": synth.image(56, 64, seed=2), "height": 112, "width": 128}]
     model.test_mask_on, model.semantic_on = True, True
     try:
         ref = model(inp)
         ref_logits = model.last_outputs["pred_masks"].float().clone()
+        ref_sel = model.transformer.last_topk_proposals[0].tolist()
         model.engine_dtype = torch.float16
         got = model(inp)
         got_logits = model.last_outputs["pred_masks"].float()
+        got_sel = model.transformer.last_topk_proposals[0].tolist()
     finally:
         model.engine_dtype = torch.float32
         model.test_mask_on, model.semantic_on = False, False
-    # selected proposals may differ between precisions; compare the mask logits of queries chosen identically
-    torch.testing.assert_close(got[0]["sem_seg"].shape, ref[0]["sem_seg"].shape)
-    assert got_logits.shape == ref_logits.shape
-    assert torch.isfinite(got_logits).all() and torch.isfinite(got[0]["sem_seg"]).all()
-    assert got[0]["instances"].pred_masks.dtype == torch.bool
+    assert got_logits.shape == ref_logits.shape and got[0]["sem_seg"].shape == ref[0]["sem_seg"].shape
+    common = sorted(set(ref_sel) & set(got_sel))
+    assert len(common) >= 0.8 * len(ref_sel), "the two precisions selected mostly different proposals"
+    ia = torch.tensor([got_sel.index(i) for i in common], device=got_logits.device)
+    ib = torch.tensor([ref_sel.index(i) for i in common], device=got_logits.device)
+    a, b = got_logits[0, ia], ref_logits[0, ib]
+    rms = b.pow(2).mean().sqrt().item()
+    err = (a - b).abs().max().item()
+    print(f"mask logits fp16 engine vs fp32: max|err| {err:.3e} on rms {rms:.3e} ({len(common)}/{len(ref_sel)} common proposals)")
+    assert err < 3e-2 * max(rms, 1.0)
+    sem_err = (got[0]["sem_seg"].float() - ref[0]["sem_seg"].float()).abs().max().item()
+    print(f"sem_seg fp16 engine vs fp32: max|err| {sem_err:.3e}")
+    assert sem_err < 5e-2
+    gi, ri = got[0]["instances"], ref[0]["instances"]
+    assert gi.pred_masks.dtype == torch.bool and abs(len(gi) - len(ri)) <= max(2, len(ri) // 5)
 
 
 def test_mini_matches_oracle_port(mini):

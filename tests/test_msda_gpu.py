@@ -248,40 +248,70 @@ def _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale):
     return value, ss, st, qo, ref
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, mask=None, hpc=0):
+    B, S = value.shape[:2]
+    v2 = ape.ops.msda_pair_values(value.view(B, S, -1), H, token_mask=mask)
+    return ape.ops.ms_deform_attn_pair_fused_forward(v2, ss.to(DEV), st.to(DEV), shapes, qo[..., :n_off], qo[..., n_off:], ref, P,
+                                                     heads_per_cta=hpc)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shapes", [[(40, 56), (20, 28), (10, 14), (5, 7), (3, 4)], [(16, 16), (8, 8)], [(33, 17)],
-                                    [(32, 48), (16, 24), (8, 12), (4, 6), (2, 3)], [(64, 32), (32, 16), (16, 8), (8, 4)]])
-def test_self_attention_kernel_equals_generic_fused(ape, dtype, shapes):
-    """ape_msda_fused_self_fwd (encoder case Q == S: region/window kernel for 16-bit values on exactly halving
-    pyramids, generic kernel otherwise) against ape_msda_fused_fwd: identical per-sample arithmetic, results equal up
-    to fp32 summation order (then rounded to the output dtype)."""
+                                    [(32, 48), (16, 24), (8, 12), (4, 6), (2, 3)], [(64, 32), (32, 16), (16, 8), (8, 4)],
+                                    [(7, 2), (1, 2)]])
+def test_pair_kernel_equals_generic_fused(ape, dtype, shapes):
+    """ape_msda_pair_fused_fwd (pair layout, 16-bit corner blend per level, fp32 across levels) against ape_msda_fused_fwd
+    (fp32 blend) on encoder-like calls: same sampling semantics incl. every border case; the difference is the 16-bit
+    rounding of the per-level partial sums (bounded below by the rounding of the 16-bit output itself)."""
     B, H, D, P = 2, 8, 32, 4
     n_off = H * len(shapes) * P * 2
-    tol = {torch.float32: 1e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
-    for seed, off_scale in ((17, 3.0), (18, 8.0), (19, 0.5)):  # in-window, partly out-of-window (global path), tight
+    tol = {torch.float16: 4e-3, torch.bfloat16: 3e-2}[dtype]
+    assert ape.ops.msda_pair_supported(shapes, H, D, P, dtype)
+    for seed, off_scale in ((17, 3.0), (18, 8.0), (19, 0.5), (20, 40.0)):  # (20: most samples out of range / on borders)
         value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale)
         a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
-        b = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P,
-                                                 host_shapes=shapes)
-        torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
-    # arbitrary (non pixel-centre) reference points and boxes: everything leaves the windows
+        for hpc in (0, 8):
+            b = _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, hpc=hpc)
+            torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
+    # arbitrary (non pixel-centre) reference points and boxes, fp32 offsets / logits, a token mask
     g = torch.Generator().manual_seed(23)
+    S = value.shape[1]
+    mask = (torch.rand(B, S, generator=g) < 0.2).to(DEV)
     for ref_dim in (2, 4):
-        r = torch.rand(B, value.shape[1], len(shapes), ref_dim, generator=g).to(DEV)
-        a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], r, P)
-        b = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], r, P,
-                                                 host_shapes=shapes)
+        r = torch.rand(B, S, len(shapes), ref_dim, generator=g).to(DEV)
+        vm = value.masked_fill(mask[:, :, None, None], 0.0)
+        a = ape.ops.ms_deform_attn_fused_forward(vm, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], r, P)
+        b = _pair_run(ape, value, ss, st, shapes, qo, n_off, r, P, H, mask=mask)
         torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
+        qf = qo.float()
+        c = _pair_run(ape, value, ss, st, shapes, qf, n_off, r, P, H, mask=mask)
+        torch.testing.assert_close(c.float(), a.float(), rtol=tol, atol=tol)
 
 
-def test_self_attention_kernel_full_size_vs_oracle(ape):
-    """APE-L_D 1024^2 encoder shape (S = 87 296), fp16: region kernel vs the C oracle on a random subset of queries."""
+def test_pair_kernel_propagates_no_nan_from_out_of_range_locations(ape):
+    """NaN / Inf sampling offsets are out of range in the reference (weight exactly 0): they must not poison the sum."""
+    shapes = [(16, 16), (8, 8)]
+    B, H, D, P = 1, 8, 32, 4
+    n_off = H * len(shapes) * P * 2
+    value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, torch.float16, 3, 2.0)
+    qo = qo.clone()
+    qo[0, ::7, 0] = float("nan")
+    qo[0, ::5, 3] = float("inf")
+    a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
+    b = _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H)
+    assert torch.isfinite(b).all() and torch.isfinite(a).all()
+    torch.testing.assert_close(b.float(), a.float(), rtol=4e-3, atol=4e-3)
+
+
+def test_pair_kernel_full_size_vs_oracle(ape):
+    """APE-L_D 1024^2 encoder shape (S = 87 296), fp16: pair kernel vs the C oracle (double accumulation) on a random subset
+    of queries; prints the error of both the fp32-blend kernel and the pair kernel."""
     shapes = [(256, 256), (128, 128), (64, 64), (32, 32), (16, 16)]
     B, H, D, P, L = 1, 8, 32, 4, 5
     value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, torch.float16, 5, 2.5)
     n_off = H * L * P * 2
-    got = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P,
-                                               host_shapes=shapes)
+    got = _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H)
+    gen = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
     S = value.shape[1]
     idx = torch.randperm(S, generator=torch.Generator().manual_seed(1))[:3000].sort()[0].to(DEV)
     o6 = qo[0, idx, :n_off].float().view(1, -1, H, L, P, 2)
@@ -289,4 +319,9 @@ def test_self_attention_kernel_full_size_vs_oracle(ape):
     norm = torch.stack([ss[:, 1], ss[:, 0]], -1).to(DEV).float()
     loc = ref[:, idx][:, :, None, :, None, :] + o6 / norm[None, None, None, :, None, :]
     want = O.msda_c(value.float().cpu(), ss, st, loc.cpu().contiguous(), attn.cpu().contiguous())
-    torch.testing.assert_close(got[0, idx].float().cpu(), want[0], rtol=2e-3, atol=2e-3)
+    e_pair = (got[0, idx].float().cpu() - want[0]).abs()
+    e_gen = (gen[0, idx].float().cpu() - want[0]).abs()
+    rms = want.pow(2).mean().sqrt().item()
+    print(f"\nfull-size fp16 MSDA vs C oracle (rms {rms:.3f}): fp32-blend kernel max {e_gen.max():.2e} mean {e_gen.mean():.2e}; "
+          f"pair kernel max {e_pair.max():.2e} mean {e_pair.mean():.2e}")
+    torch.testing.assert_close(got[0, idx].float().cpu(), want[0], rtol=3e-3, atol=3e-3)
