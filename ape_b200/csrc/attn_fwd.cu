@@ -41,6 +41,7 @@ struct AttnParams {
   void *out;
   long long ldo;     // elements
   int n;             // tokens per sequence (multiple of 128)
+  int n_valid;       // keys >= n_valid of every sequence are masked out (rows padded up to n; n_valid <= n)
   int heads, C;      // C = heads * 64
   float scale_log2;  // softmax scale * log2(e)
   uint32_t idesc_qk, idesc_pv;
@@ -60,7 +61,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int row0 = seq * p.n;            // first token row of this sequence in the qkv buffer
-  const int nkv = p.n / KN;
+  const int nkv = (p.n_valid + KN - 1) / KN;  // key blocks that hold at least one real key
   constexpr uint32_t TMEM_COLS = 128;    // S (64 fp32 columns) | O (64)
 
   if (warp == 0 && lane == 0) {
@@ -148,11 +149,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       // pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling); S is read from tensor
       // memory twice instead of being held in 64 registers — 4 CTAs per SM need the threads under 85 registers
       float m8[8];
+      const int kvalid = p.n_valid - j * KN;  // real keys in this block (>= 1; < 64 only in the last block of a padded sequence)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[32];
         tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
         tc::tmem_ld_wait();
+        if (kvalid < KN) {  // warp-uniform: padded keys score -inf
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * hh + i >= kvalid) r[i] = 0xff800000u;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float x = __uint_as_float(r[i]);
@@ -199,6 +206,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&s.s_empty);
+        }
+        if (kvalid < KN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * hh + i >= kvalid) r[i] = 0xff800000u;  // ex2(-inf) = 0: no weight on padded keys
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -264,8 +276,17 @@ EncodeTiledFn attn_encoder() {
 
 using namespace ape;
 
+extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
+                               int head_dim, float scale, int dtype, void *stream);
+
 extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads,
                             int head_dim, float scale, int dtype, void *stream) {
+  return ape_attn_fwd_ex(qkv, ld, out, ldo, num_seq, n, n, heads, head_dim, scale, dtype, stream);
+}
+
+extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
+                               int head_dim, float scale, int dtype, void *stream) {
+  if (n_valid <= 0 || n_valid > n) return fail(APE_ERR_INVALID_ARG, "attn: n_valid=%d must be in [1, n=%d]", n_valid, n);
   if (dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16) return fail(APE_ERR_INVALID_ARG, "attn: fp16 / bf16 only (dtype %d)", dtype);
   if (head_dim != HD) return fail(APE_ERR_UNSUPPORTED, "attn: head_dim %d (only 64)", head_dim);
   if (num_seq < 0 || n <= 0 || n % QM != 0 || heads <= 0 || heads > 65535 || num_seq > 65535)
@@ -288,7 +309,7 @@ extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
   AttnParams p{};
-  p.out = out; p.ldo = ldo; p.n = n; p.heads = heads; p.C = C;
+  p.out = out; p.ldo = ldo; p.n = n; p.n_valid = n_valid; p.heads = heads; p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int fmt = dtype == APE_DTYPE_BF16 ? 1 : 0;
   p.idesc_qk = tc::make_idesc_f16(QM, KN, fmt);

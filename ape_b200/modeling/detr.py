@@ -441,26 +441,27 @@ class DeformableDETRSegmVL(nn.Module):
         mark("preprocess")
         low = self.engine_dtype != torch.float32
         geo = self._geometry(images.shape, image_sizes, img_masks)
-        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1 and \
-            not (self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on))  # mask tensors travel as attributes: eager
+        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
+        need_masks = self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
             if graphs and not self.profile_stages:
                 # encode -> select -> decode in ONE graph: the selection is written with static shapes and no host
                 # synchronisation (transformer.select_proposals), so nothing between the image upload and the final
                 # thresholding touches the host
                 (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
-                 init_reference, inter_references) = self._graphed(
-                    ("forward", prompt, tuple(images.shape), tuple(image_sizes), tuple(features_l.shape)),
+                 init_reference, inter_references, mask_logits) = self._graphed(
+                    ("forward", prompt, tuple(images.shape), tuple(image_sizes), tuple(features_l.shape), need_masks),
                     self._stage_all, (images, fusion, features_l), (geo, prompt))
                 self.transformer.last_topk_proposals = topk
                 mark("encode")
                 mark("select")
             else:
                 if graphs:
-                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._graphed(
-                        ("encode", tuple(images.shape), tuple(image_sizes)), self._stage_encode, (images, fusion), (geo,))
+                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features = self._graphed(
+                        ("encode", tuple(images.shape), tuple(image_sizes), need_masks), self._stage_encode, (images, fusion), (geo,))
                 else:
-                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+                    memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features = \
+                        self._stage_encode(images, fusion, geo)
                 mark("encode")
                 topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
                 self.transformer.last_topk_proposals = topk
@@ -468,17 +469,16 @@ class DeformableDETRSegmVL(nn.Module):
                 features_l = self._mix_text(prompt, features_l, fusion_out)
                 if graphs:
                     # memory / output_memory / enc_coord are the encode graph's static outputs: constants of this graph
-                    box_cls, box_pred, inter_states, init_reference, inter_references = self._graphed(
-                        ("decode", memory.data_ptr(), tuple(image_sizes), tuple(features_l.shape)), self._stage_decode,
-                        (topk, features_l), (memory, output_memory, enc_coord, geo))
+                    box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits = self._graphed(
+                        ("decode", memory.data_ptr(), tuple(image_sizes), tuple(features_l.shape), need_masks), self._stage_decode,
+                        (topk, features_l), (memory, output_memory, enc_coord, geo, mask_features))
                 else:
-                    box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
-                        topk, features_l, memory, output_memory, enc_coord, geo)
+                    box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits = self._stage_decode(
+                        topk, features_l, memory, output_memory, enc_coord, geo, mask_features)
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
-        need_masks = self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)
-        mask_pred = self.last_mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
+        mask_pred = mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
         results = None
@@ -533,10 +533,10 @@ class DeformableDETRSegmVL(nn.Module):
         feats = self.neck({f: features[f] for f in self.neck.in_features})
         memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(
             feats, geo, fusion, feat_flatten=getattr(self.neck, "last_flat", None))
-        self._mask_features = None
+        mask_features = None
         if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
-            self._mask_features = self.maskdino_mask_features(memory, features, geo)
-        return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats
+            mask_features = self.maskdino_mask_features(memory, features, geo)
+        return memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features
 
     @staticmethod
     def _mix_text(prompt, features_l, fusion_out):
@@ -547,15 +547,15 @@ class DeformableDETRSegmVL(nn.Module):
         return 0.0 * features_l + 1.0 * fusion_out.float()  # (:448)
 
     def _stage_all(self, images, fusion, features_l, geo, prompt):
-        memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats = self._stage_encode(images, fusion, geo)
+        memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features = self._stage_encode(images, fusion, geo)
         topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
         features_l = self._mix_text(prompt, features_l, fusion_out)
-        box_cls, box_pred, inter_states, init_reference, inter_references = self._stage_decode(
-            topk, features_l, memory, output_memory, enc_coord, geo)
+        box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits = self._stage_decode(
+            topk, features_l, memory, output_memory, enc_coord, geo, mask_features)
         return (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
-                init_reference, inter_references)
+                init_reference, inter_references, mask_logits)
 
-    def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo):
+    def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo, mask_features=None):
         inter_states, init_reference, inter_references = self.transformer.stage_decode(
             memory, output_memory, enc_coord, topk, geo)
         states16 = inter_states  # decoder outputs are LayerNorm outputs in the engine dtype
@@ -571,12 +571,21 @@ class DeformableDETRSegmVL(nn.Module):
             else:
                 box_cls = self.class_embed[lvl](inter_states[lvl], features_l.float())
                 box_pred = (self.bbox_embed[lvl](inter_states[lvl]) + inverse_sigmoid(reference)).sigmoid()
-        self.last_mask_logits = None
-        if getattr(self, "_mask_features", None) is not None:
+        mask_logits = None
+        if mask_features is not None:
             # (:507-517) only the last level's masks reach inference (the other levels are added times 0.0)
-            mf = self._mask_features
-            self.last_mask_logits = torch.einsum("bqc,bchw->bqhw", self.mask_embed(inter_states[lvl].to(mf.dtype)), mf)
-        return box_cls, box_pred, inter_states, init_reference, inter_references
+            mf = mask_features
+            if states16.dtype in (torch.float16, torch.bfloat16) and mf.dtype == states16.dtype and mf.shape[1] % 8 == 0:
+                # engine: einsum("bqc,bchw->bqhw") = one tcgen05 GEMM per image over the token-major mask features
+                # (fp32 accumulation, fp32 logits: their sign decides the mask)
+                B, C, mh, mw = mf.shape
+                tok = mf.permute(0, 2, 3, 1).reshape(B, mh * mw, C)  # free: the engine's mask features are channels_last
+                emb = self.mask_embed(states16[lvl])
+                mask_logits = torch.stack([ops.linear_tc(emb[b].contiguous(), tok[b], out_dtype=torch.float32)
+                                           for b in range(B)]).view(B, -1, mh, mw)
+            else:
+                mask_logits = torch.einsum("bqc,bchw->bqhw", self.mask_embed(inter_states[lvl].to(mf.dtype)), mf)
+        return box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits
 
     def _graphed(self, key, fn, tensor_args, const_args):
         """Run fn(*tensor_args, *const_args) through a CUDA graph captured once per key: inputs are copied into
@@ -619,6 +628,34 @@ class DeformableDETRSegmVL(nn.Module):
         shapes = geo["shapes"]
         start = sum(h * w for h, w in shapes[:lvl])
         h, w = shapes[lvl]
+        p2 = features[self.mask_in_features[0]]
+        if memory.is_cuda and memory.dtype in (torch.float16, torch.bfloat16) and p2.dtype == memory.dtype \
+                and isinstance(self.lateral_conv.norm, nn.GroupNorm) and p2.shape[1] % 8 == 0:
+            # engine: token-major throughout; the two 1x1 convolutions are tcgen05 GEMMs, GroupNorm is the repo's kernel, the
+            # memory slice of the encode level is already token-major (no permute); the 3x3 convolution is the library's
+            from .backbone import _conv_weights
+
+            B, C, H2, W2 = p2.shape
+            dt = memory.dtype
+            tok = p2.permute(0, 2, 3, 1).reshape(B * H2 * W2, C)
+            y = ops.linear_tc(tok, _conv_weights(self.lateral_conv, dt))
+            gw, gb = ops.packed(self.lateral_conv.norm, dt)
+            x = ops.groupnorm_nhwc(y.view(B, H2 * W2, -1), gw, gb, self.lateral_conv.norm.num_groups, self.lateral_conv.norm.eps)
+            hid = x.shape[-1]
+            if (h, w) == (H2, W2):  # same stride: the bilinear resize (:737-742) is the identity
+                x = x + memory[:, start:start + h * w]
+            else:
+                enc = memory[:, start:start + h * w].permute(0, 2, 1).reshape(B, hid, h, w)
+                x = x + F.interpolate(enc, size=(H2, W2), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).reshape(B, H2 * W2, hid)
+            z = F.conv2d(x.view(B, H2, W2, hid).permute(0, 3, 1, 2), _conv_weights(self.output_conv, dt), padding=1)  # cuDNN NHWC
+            z = z.permute(0, 2, 3, 1)
+            if not z.is_contiguous():
+                z = z.contiguous()
+            gw, gb = ops.packed(self.output_conv.norm, dt)
+            z = ops.groupnorm_nhwc(z.view(B, H2 * W2, hid), gw, gb, self.output_conv.norm.num_groups, self.output_conv.norm.eps)
+            z = F.relu(z)
+            mf = ops.linear_tc(z.view(B * H2 * W2, hid), _conv_weights(self.mask_conv, dt))
+            return mf.view(B, H2, W2, -1).permute(0, 3, 1, 2)  # NCHW view over token-major (channels_last) memory
         enc = memory[:, start:start + h * w].permute(0, 2, 1).reshape(memory.shape[0], -1, h, w)
         x = self.lateral_conv(features[self.mask_in_features[0]])
         x = x + F.interpolate(enc.to(x.dtype), size=x.shape[-2:], mode="bilinear", align_corners=False)
@@ -637,8 +674,24 @@ class DeformableDETRSegmVL(nn.Module):
             keep = [torch.arange(sem_cls.shape[1], device=sem_cls.device)] * sem_cls.shape[0]
         for b, (qi, size, inp) in enumerate(zip(keep, image_sizes, batched_inputs)):
             cls = F.softmax(sem_cls[b, qi].float().sigmoid() / 0.06, dim=-1)
-            m = F.interpolate(mask_pred[b, qi][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0].sigmoid()
-            result = torch.einsum("qc,qhw->chw", cls, m)  # stays on the GPU (the reference moves >1000 classes to the CPU, :896-898)
+            if self.engine_dtype in (torch.float16, torch.bfloat16) and mask_pred.is_cuda and len(qi) > 0:
+                # engine: einsum("qc,qhw->chw") (757 GFLOP at K = 300 kept queries x 1203 names x 1024^2) as ONE tcgen05 GEMM:
+                # the resize runs channels_last so that the sigmoid masks come out pixel-major [H*W, K] = the K-major operand
+                dt = self.engine_dtype
+                K = len(qi)
+                Kp = (K + 7) // 8 * 8
+                mp = mask_pred[b, qi][None].float()
+                if Kp != K:
+                    mp = torch.cat([mp, mp.new_zeros(1, Kp - K, *mp.shape[-2:])], 1)
+                mp = mp.contiguous(memory_format=torch.channels_last)
+                m = F.interpolate(mp, size=padded_hw, mode="bilinear", align_corners=False).sigmoid()
+                m = m.permute(0, 2, 3, 1).reshape(-1, Kp).to(dt)                               # [H*W, Kp]
+                ct = torch.zeros((cls.shape[1], Kp), dtype=dt, device=cls.device)
+                ct[:, :K] = cls.t().to(dt)                                                      # [N, Kp] (zero weight on the padding)
+                result = ops.linear_tc(ct, m, out_dtype=torch.float32).view(cls.shape[1], *padded_hw)
+            else:
+                m = F.interpolate(mask_pred[b, qi][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0].sigmoid()
+                result = torch.einsum("qc,qhw->chw", cls, m)  # stays on the GPU (the reference moves >1000 classes to the CPU, :896-898)
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
             sem = sem_seg_postprocess(result, size, h, w)
             if entity == "stuff" and stuff and stuff[0] == "things" and self.stuff_prob_thing > 0:

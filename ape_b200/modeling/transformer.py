@@ -29,26 +29,48 @@ class _SelfAttention(nn.Module):
         self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=0.0, batch_first=True)
 
     def _packed(self, dtype):
+        """In / out projections re-laid out for ape_attn_fwd: every head padded from E/nh to 64 channels with zero rows
+        (zero columns in the output projection), q | k | v thirds as the kernel's fused-qkv column layout."""
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
-        key = (dtype, w._version, b._version, w.data_ptr())
+        wo, bo = self.attn.out_proj.weight, self.attn.out_proj.bias
+        key = (dtype, w._version, b._version, wo._version, bo._version, w.data_ptr())
         if getattr(self, "_pk", (None,))[0] != key:
-            E = self.embed_dim
+            E, nh = self.embed_dim, self.num_heads
+            hd = E // nh
             with torch.no_grad():
-                self._pk = (key, w[: 2 * E].detach().to(dtype).contiguous(), b[: 2 * E].detach().float().contiguous(),
-                            w[2 * E:].detach().to(dtype).contiguous(), b[2 * E:].detach().float().contiguous())
+                def pad_rows(wpart, bpart):  # [E, E] / [E] -> [nh*64, E] / [nh*64]
+                    wp = wpart.new_zeros(nh, 64, E)
+                    wp[:, :hd] = wpart.view(nh, hd, E)
+                    bp = bpart.new_zeros(nh, 64)
+                    bp[:, :hd] = bpart.view(nh, hd)
+                    return wp.view(nh * 64, E), bp.view(nh * 64)
+                wq, bq = pad_rows(w[:E], b[:E])
+                wk, bk = pad_rows(w[E:2 * E], b[E:2 * E])
+                wv, bv = pad_rows(w[2 * E:], b[2 * E:])
+                wop = wo.new_zeros(E, nh, 64)
+                wop[:, :, :hd] = wo.view(E, nh, hd)
+                self._pk = (key, torch.cat([wq, wk], 0).detach().to(dtype).contiguous(), torch.cat([bq, bk]).detach().float().contiguous(),
+                            wv.detach().to(dtype).contiguous(), bv.detach().float().contiguous(),
+                            wop.view(E, nh * 64).detach().to(dtype).contiguous(), bo.detach().float().contiguous())
         return self._pk[1:]
 
     def forward(self, x, pos):
         E, nh = self.embed_dim, self.num_heads
-        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16):
-            # engine path: tcgen05 GEMMs for the in / out projections (residual in the epilogue)
-            wqk, bqk, wv, bv = self._packed(x.dtype)
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and E // nh <= 64:
+            # engine path: tcgen05 GEMMs for the in / out projections (residual in the epilogue) and the repo's tcgen05
+            # flash-attention kernel over the queries (rows padded to a multiple of 128, padded keys masked)
+            wqk, bqk, wv, bv, wo, bo = self._packed(x.dtype)
             B, N, _ = x.shape
-            qk = ops.linear_tc(x + pos.to(x.dtype), wqk, bqk).view(B, N, 2, nh, E // nh)
-            v = ops.linear_tc(x, wv, bv).view(B, N, nh, E // nh)
-            o = F.scaled_dot_product_attention(qk[:, :, 0].transpose(1, 2), qk[:, :, 1].transpose(1, 2), v.transpose(1, 2))
-            o = o.transpose(1, 2).reshape(B, N, E)
-            return ops.linear_module_tc(self.attn.out_proj, o, residual=x.contiguous(), out_dtype=torch.float32)
+            NP = (N + 127) // 128 * 128
+            C = nh * 64
+            buf = torch.zeros((B, NP, 3 * C), dtype=x.dtype, device=x.device)  # padded rows must be finite (zeros)
+            xp = x + pos.to(x.dtype)
+            for b in range(B):
+                ops.linear_tc(xp[b], wqk, bqk, out=buf[b, :N, : 2 * C])
+                ops.linear_tc(x[b], wv, bv, out=buf[b, :N, 2 * C:])
+            o = ops.attention_qkv(buf.view(B * NP, 3 * C), B, NP, nh, 64, (E // nh) ** -0.5, n_valid=N).view(B, NP, C)
+            return torch.stack([ops.linear_tc(o[b, :N], wo, bo, residual=x[b].contiguous(), out_dtype=torch.float32)
+                                for b in range(B)])
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
         qk = F.linear(x + pos, w[: 2 * E], b[: 2 * E])
         v = F.linear(x, w[2 * E:], b[2 * E:])

@@ -359,16 +359,17 @@ def attention_supported(n, head_dim, dtype):
     return head_dim == 64 and n % 128 == 0 and dtype in (torch.float16, torch.bfloat16)
 
 
-def attention_qkv(qkv, num_seq, n, heads, head_dim, scale):
+def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None):
     """softmax(q k^T * scale) v for every (sequence, head) straight from the fused qkv buffer [num_seq*n, 3*heads*64]
-    (ape_attn_fwd: flash attention on the tcgen05 tensor cores).  Returns [num_seq*n, heads*64]."""
+    (ape_attn_fwd: flash attention on the tcgen05 tensor cores).  Returns [num_seq*n, heads*64].
+    n_valid: sequences are padded to n rows and only the first n_valid keys count (rows beyond must be finite)."""
     _require(qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1, "attention: qkv must be a 2-D CUDA tensor")
     _require(qkv.shape[0] == num_seq * n and qkv.shape[1] == 3 * heads * head_dim, "attention: qkv shape")
     out = torch.empty((qkv.shape[0], heads * head_dim), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(qkv.device), _timed(("attention", num_seq, n, heads)):
-        rc = _lib.lib.ape_attn_fwd(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), int(num_seq), int(n),
-                                   int(heads), int(head_dim), float(scale), _lib.dtype_code(qkv.dtype),
-                                   _lib.current_stream_ptr())
+        rc = _lib.lib.ape_attn_fwd_ex(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), int(num_seq), int(n),
+                                      int(n if n_valid is None else n_valid), int(heads), int(head_dim), float(scale),
+                                      _lib.dtype_code(qkv.dtype), _lib.current_stream_ptr())
     _lib.check(rc, "ape_attn_fwd")
     return out
 

@@ -205,6 +205,11 @@ int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const float *sin_
  */
 int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads, int head_dim,
                  float scale, int dtype, void *stream);
+/* Same with sequences padded to n rows: only the first n_valid keys of every sequence take part in the softmax (the rows
+ * beyond must hold finite values, e.g. zeros).  Used for the self-attention over the 900 decoder queries
+ * (deformable_transformer_vl.py:142-147: nn.MultiheadAttention, 8 heads x 32 — heads zero-padded to 64 channels). */
+int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
+                    int head_dim, float scale, int dtype, void *stream);
 
 /*
  * Language-side attention pooling of VisionLanguageFusion for a single language token ("name" prompts):

@@ -32,17 +32,11 @@ def main():
 
     dev = torch.device("cuda", 0)
     tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
-    model = build_model(configs.APE_L_D, num_text=1203)
-    synthetic.fill_state_dict(model)
-    model.test_score_thresh = 0.1
-    model = model.to(dev)
+    from bench import bench_spec, bench_weights  # same spec / weights / threshold as the benchmarked step
+
+    model = bench_weights(build_model(bench_spec(), num_text=1203)).to(dev)
     model.engine_dtype = tdt
     model.use_cuda_graphs = tdt != torch.float32 and not args.no_graphs
-    model([{"image": synthetic.image(1024, 1024, seed=99), "height": 1024, "width": 1024}])
-    lg = model.last_outputs["pred_logits"].float().flatten()
-    kth = torch.topk(lg, 500).values[-1]
-    with torch.no_grad():
-        model.class_embed[len(model.class_embed) - 2].bias0.add_((math.log(0.1 / 0.9) - kth).to(model.class_embed[0].bias0.dtype))
     g = torch.Generator().manual_seed(0)
     imgs = [torch.randint(0, 256, (3, 1024, 1024), generator=g).to(torch.float32).to(dev) for _ in range(2)]
 

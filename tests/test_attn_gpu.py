@@ -47,3 +47,18 @@ def test_attention_large_logits_and_pitch(ops):
 def test_attention_rejects_unsupported(ops):
     with pytest.raises(RuntimeError):
         ops.attention_qkv(torch.zeros(100, 192, dtype=torch.float16, device=DEV), 1, 100, 1, 64, 1.0)  # n % 128 != 0
+
+
+@pytest.mark.parametrize("num_seq,n,n_valid,heads", [(1, 1024, 900, 8), (2, 128, 20, 4), (1, 256, 129, 2), (3, 384, 64, 1)])
+def test_attention_padded_sequences_mask_keys(ops, num_seq, n, n_valid, heads):
+    """Sequences padded to a multiple of 128 rows: only the first n_valid keys count (decoder self-attention over 900
+    queries, deformable_transformer_vl.py:142-147); the padded rows hold zeros."""
+    hd = 64
+    g = torch.Generator().manual_seed(n_valid)
+    qkv = torch.zeros(num_seq, n, 3 * heads * hd, dtype=torch.float16)
+    qkv[:, :n_valid] = torch.randn(num_seq, n_valid, 3 * heads * hd, generator=g).to(torch.float16)
+    qkv = qkv.to(DEV)
+    got = ops.attention_qkv(qkv.view(num_seq * n, -1), num_seq, n, heads, hd, 0.2, n_valid=n_valid).view(num_seq, n, -1)
+    want = ref_attention(qkv[:, :n_valid].reshape(num_seq * n_valid, -1), num_seq, n_valid, heads, hd, 0.2).view(num_seq, n_valid, -1)
+    torch.testing.assert_close(got[:, :n_valid].float(), want, rtol=2e-3, atol=2e-3)
+    assert torch.isfinite(got).all()
