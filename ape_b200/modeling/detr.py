@@ -327,9 +327,41 @@ class DeformableDETRSegmVL(nn.Module):
         for d in self.dataset_names:
             if sum([dd in dataset_name for dd in d.split("+")]):
                 self.eval_dataset_id = self.dataset_name_to_idx[d]
+                self.eval_dataset_entity = self._dataset_entity(d)
                 break
         else:
             self.eval_dataset_id = -1
+            self.eval_dataset_entity = ""
+
+    def _dataset_entity(self, name):
+        """deformable_detr.py:246-262: "thing+stuff" / "thing" / "stuff" from the class lists of the dataset
+        (`model.dataset_stuff[name] = (thing_classes, stuff_classes[, entity[, thing_ids]])`; the reference reads MetadataCatalog)."""
+        info = self.dataset_stuff.get(name)
+        if info is None:
+            return "thing"
+        if len(info) > 2 and info[2]:
+            return info[2]
+        things, stuff = info[0], info[1]
+        return "thing+stuff" if things and stuff else "stuff" if stuff else "thing"
+
+    def _detector_box_cls(self, box_cls):
+        """Class columns the instance branch may use (:575-593): thing classes only.  Disjoint thing / stuff vocabularies keep
+        the first len(thing_classes) columns; overlapping ones (one list a subset of the other) keep the thing ids and set the
+        rest to -inf."""
+        d = self.eval_dataset_id
+        if not (0 <= d < len(self.dataset_names)):
+            return box_cls
+        info = self.dataset_stuff.get(self.dataset_names[d])
+        if info is None or not info[0]:
+            return box_cls
+        things, stuff = list(info[0]), list(info[1] or [])
+        if things and stuff and (set(things) <= set(stuff) or set(stuff) <= set(things)):
+            ids = list(info[3]) if len(info) > 3 and info[3] is not None else list(range(len(things)))
+            out = torch.full_like(box_cls, float("-inf"))
+            idx = torch.as_tensor(ids, dtype=torch.long, device=box_cls.device)
+            out[..., idx] = box_cls[..., idx]
+            return out
+        return box_cls[..., : len(things)]
 
     def preprocess_image(self, batched_inputs):
         """:846-855 + ImageList.from_tensors with padding_constraints square_size (pads AFTER normalising)."""
@@ -338,6 +370,13 @@ class DeformableDETRSegmVL(nn.Module):
         sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in imgs]
         H = max(s[0] for s in sizes) if sq <= 0 else sq
         W = max(s[1] for s in sizes) if sq <= 0 else sq
+        div = int(self.backbone.padding_constraints.get("size_divisiblity", 0) or 0)  # (sic) detectron2's key
+        if sq <= 0 and div > 1:  # ImageList.from_tensors rounds the batch shape up to the size divisibility
+            H, W = -(-H // div) * div, -(-W // div) * div
+        for (h, w) in sizes:
+            if h > H or w > W:
+                raise ValueError(f"ape_b200: image of {h}x{w} does not fit the {H}x{W} padded batch (square_size={sq}); "
+                                 "resize it first (ResizeShortestEdge in the reference's predictor)")
         batch = torch.zeros((len(imgs), 3, H, W), dtype=self.pixel_mean.dtype, device=self.device)
         masks = torch.ones((len(imgs), H, W), dtype=self.pixel_mean.dtype, device=self.device)
         for i, im in enumerate(imgs):
@@ -425,8 +464,6 @@ class DeformableDETRSegmVL(nn.Module):
     def forward(self, batched_inputs: List[Dict], do_postprocess=True):
         if self.training:
             raise NotImplementedError("ape_b200 is an inference engine (SURVEY.md §8f row 4)")
-        if "mask_prompt" in batched_inputs[0]:
-            raise NotImplementedError("ape_b200: mask prompts")
         marks = [] if self.profile_stages else None
 
         def mark(name):
@@ -441,7 +478,8 @@ class DeformableDETRSegmVL(nn.Module):
         mark("preprocess")
         low = self.engine_dtype != torch.float32
         geo = self._geometry(images.shape, image_sizes, img_masks)
-        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1
+        mask_prompt_flatten = self._mask_prompt(batched_inputs, images.shape, geo) if "mask_prompt" in batched_inputs[0] else None
+        graphs = low and self.use_cuda_graphs and fusion is not None and fusion.shape[1] == 1 and mask_prompt_flatten is None
         need_masks = self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)
         with torch.autocast("cuda", dtype=self.engine_dtype, enabled=low):
             if graphs and not self.profile_stages:
@@ -461,7 +499,7 @@ class DeformableDETRSegmVL(nn.Module):
                         ("encode", tuple(images.shape), tuple(image_sizes), need_masks), self._stage_encode, (images, fusion), (geo,))
                 else:
                     memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features = \
-                        self._stage_encode(images, fusion, geo)
+                        self._stage_encode(images, fusion, geo, mask_prompt_flatten)
                 mark("encode")
                 topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
                 self.transformer.last_topk_proposals = topk
@@ -481,13 +519,19 @@ class DeformableDETRSegmVL(nn.Module):
         mask_pred = mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
+        # the three branches are gated by the entity of the evaluated dataset (:575-577, :628-630, :671-673)
+        ent = self.eval_dataset_entity
+        instance_on = self.instance_on and not (ent and "thing" not in ent)
+        semantic_on = self.semantic_on and not (ent and "stuff" not in ent)
+        panoptic_on = self.panoptic_on and not (ent and "thing+stuff" not in ent)
+        det_cls = self._detector_box_cls(box_cls) if instance_on else box_cls
         results = None
         if do_postprocess and box_cls.is_cuda and self.static_inference_cap > 0 and not need_masks:
-            results = self._inference_static(box_cls, box_pred, image_sizes)  # CPU Instances, one host sync
+            results = self._inference_static(det_cls, box_pred, image_sizes)  # CPU Instances, one host sync
         if results is None:
-            results = self.inference(box_cls, box_pred, image_sizes)
+            results = self.inference(det_cls, box_pred, image_sizes)
         padded_hw = tuple(images.shape[-2:])
-        if self.instance_on and self.test_mask_on:
+        if instance_on and self.test_mask_on:
             for b, r in enumerate(results):  # (:588-603) masks of the kept queries only (bilinear resize is per channel)
                 m = F.interpolate(mask_pred[b, r.query_index][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0]
                 m = bitmasks_crop_and_resize(m.sigmoid() > 0.5, r.pred_boxes.tensor.to(m.device), 128)
@@ -497,11 +541,11 @@ class DeformableDETRSegmVL(nn.Module):
         out = []
         for r, inp, size in zip(results, batched_inputs, image_sizes):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
-            out.append({"instances": detector_postprocess(r, h, w).to("cpu")} if self.instance_on else {})
-        if self.semantic_on:
+            out.append({"instances": detector_postprocess(r, h, w).to("cpu")} if instance_on else {})
+        if semantic_on:
             for o, sem in zip(out, self._semantic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
                 o["sem_seg"] = sem
-        if self.panoptic_on:
+        if panoptic_on:
             for o, pan in zip(out, self._panoptic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
                 o["panoptic_seg"] = pan
         mark("inference")
@@ -528,11 +572,25 @@ class DeformableDETRSegmVL(nn.Module):
             self._geo_cache[key] = geo
         return geo
 
-    def _stage_encode(self, images, fusion, geo):
+    def _mask_prompt(self, batched_inputs, batch_shape, geo):
+        """:394-412: region prompts.  Per-image masks padded like the image (ImageList.from_tensors), an all-zero batch means
+        "everywhere" (set to 255), resized bilinearly to every level and thresholded by `.to(bool)`; flattened like the features
+        (deformable_transformer_vl.py:465-470).  Proposals outside the prompt are disabled in the two-stage selection."""
+        H, W = batch_shape[-2], batch_shape[-1]
+        mp = torch.zeros((len(batched_inputs), H, W), dtype=self.pixel_mean.dtype, device=self.device)
+        for i, x in enumerate(batched_inputs):
+            m = x["mask_prompt"].to(self.device).to(self.pixel_mean.dtype)
+            mp[i, : m.shape[-2], : m.shape[-1]] = m
+        if mp.sum() == 0:
+            mp[...] = 255
+        levels = [F.interpolate(mp[None], size=sh, mode="bilinear").to(torch.bool).squeeze(0) for sh in geo["shapes"]]
+        return torch.cat([m.flatten(1) for m in levels], 1)
+
+    def _stage_encode(self, images, fusion, geo, mask_prompt_flatten=None):
         features = self.backbone(images.to(self.engine_dtype))
         feats = self.neck({f: features[f] for f in self.neck.in_features})
         memory, fusion_out, output_memory, enc_cls, enc_coord = self.transformer.stage_encode(
-            feats, geo, fusion, feat_flatten=getattr(self.neck, "last_flat", None))
+            feats, geo, fusion, mask_prompt_flatten=mask_prompt_flatten, feat_flatten=getattr(self.neck, "last_flat", None))
         mask_features = None
         if self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on):
             mask_features = self.maskdino_mask_features(memory, features, geo)

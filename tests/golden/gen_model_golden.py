@@ -24,6 +24,8 @@ CASES = {
     "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
     # referring expressions (prompt "expression": texts from `expressions`, one box per image; :184-193, :289-290)
     "expression": ([(64, 56, 128, 112)], ["the red apple on the left", "a dog"]),
+    # region prompt (`mask_prompt`, deformable_detr_segm_vl.py:394-412): proposals only inside the rectangle (y0, y1, x0, x1)
+    "maskprompt": ([(64, 64, 64, 64)], None, (8, 40, 16, 56)),
 }
 
 
@@ -45,12 +47,18 @@ def main(only=None):
     for i, layer in enumerate(model.transformer.encoder.vl_layers):
         layer.register_forward_hook(hook(f"vlf{i}"))
 
-    for cname, (sizes, text) in CASES.items():
+    for cname, case in CASES.items():
+        sizes, text = case[0], case[1]
+        rect = case[2] if len(case) > 2 else None
         if only and cname != only:
             continue
         inputs = []
         for i, (h, w, oh, ow) in enumerate(sizes):
             d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
+            if rect is not None:
+                mp = torch.zeros(h, w)
+                mp[rect[0]:rect[1], rect[2]:rect[3]] = 1.0
+                d["mask_prompt"] = mp
             if isinstance(text, list):
                 d["prompt"] = "expression"
                 d["expressions"] = list(text)

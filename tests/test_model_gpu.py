@@ -18,6 +18,7 @@ CASES = {
     "batch2": ([(64, 64, 64, 64), (40, 56, 80, 112)], None),
     "phrase": ([(64, 48, 64, 48)], "red apple,a dog on grass,tall tree"),
     "expression": ([(64, 56, 128, 112)], ["the red apple on the left", "a dog"]),
+    "maskprompt": ([(64, 64, 64, 64)], None, (8, 40, 16, 56)),
 }
 
 
@@ -41,11 +42,16 @@ def mini():
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_mini_matches_reference_golden(case, mini):
     model, _ = mini
-    sizes, text = CASES[case]
+    sizes, text = CASES[case][:2]
+    rect = CASES[case][2] if len(CASES[case]) > 2 else None
     g = load_golden(f"model_mini_{case}.npz")
     inputs = []
     for i, (h, w, oh, ow) in enumerate(sizes):
         d = {"image": synth.image(h, w, seed=i), "height": oh, "width": ow}
+        if rect is not None:
+            mp = torch.zeros(h, w)
+            mp[rect[0]:rect[1], rect[2]:rect[3]] = 1.0
+            d["mask_prompt"] = mp
         if isinstance(text, list):
             d.update(prompt="expression", expressions=list(text))
         elif text:
