@@ -52,6 +52,8 @@ def _declare(lib):
     lib.ape_msda_fused_fwd.restype = _i
     lib.ape_msda_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 9 + [_vp]
 
+    lib.ape_msda_bwd.restype = _i
+    lib.ape_msda_bwd.argtypes = [_vp] * 9 + [_i] * 8 + [_vp]
     lib.ape_msda_pair_values.restype = _i
     lib.ape_msda_pair_values.argtypes = [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]
     lib.ape_msda_pair_supported.restype = _i
@@ -110,6 +112,7 @@ EXPORTS = (
     "ape_msda_fwd",
     "ape_msda_fwd_variant",
     "ape_msda_fused_fwd",
+    "ape_msda_bwd",
     "ape_msda_pair_values",
     "ape_msda_pair_supported",
     "ape_msda_pair_fused_fwd",

@@ -465,10 +465,28 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     return nms(boxes + offsets[:, None], scores, iou_threshold)
 
 
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step=64):
+    """[grad_value, grad_sampling_loc, grad_attn_weight] (ape_msda_bwd; ms_deform_attn_cuda.cu:84-160).  grad_value is
+    accumulated in fp32 by vector atomics and cast to value's dtype at the end."""
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")  # ms_deform_attn.h:60
+    B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _require(grad_output.is_cuda and grad_output.is_contiguous(), "grad_output tensor has to be contiguous")
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == B * Q * H * D, "grad_output must be [B,Q,H*D] of value's dtype")
+    gv = torch.zeros((B, S, H, D), dtype=torch.float32, device=value.device)
+    gl = torch.empty_like(sampling_loc)
+    ga = torch.empty_like(attn_weight)
+    with torch.cuda.device(value.device), _timed(("msda_bwd", B, S, Q, L, P, value.element_size())):
+        rc = _lib.lib.ape_msda_bwd(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                                   attn_weight.data_ptr(), grad_output.data_ptr(), gv.data_ptr(), gl.data_ptr(), ga.data_ptr(),
+                                   B, S, H, D, L, Q, P, _lib.dtype_code(value.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_msda_bwd")
+    return [gv if value.dtype == torch.float32 else gv.to(value.dtype), gl, ga]
+
+
 def _ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                              grad_output, im2col_step):
-    raise RuntimeError(
-        "ape_b200: ms_deform_attn_backward is not implemented (inference engine; SURVEY.md §8f row 4)")
+    return ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step)
 
 
 def _register():
@@ -494,7 +512,8 @@ def _register():
         lib.impl("ms_deform_attn_forward", _fwd, "CUDA")
         lib.impl("ms_deform_attn_forward", _fwd_cpu, "CPU")
     if "ms_deform_attn_backward" in defined:
-        lib.impl("ms_deform_attn_backward", _ms_deform_attn_backward, "CompositeExplicitAutograd")
+        lib.impl("ms_deform_attn_backward", _ms_deform_attn_backward, "CUDA")
+        lib.impl("ms_deform_attn_backward", lambda *a: _fwd_cpu(*a[:6]), "CPU")
     return lib
 
 

@@ -120,6 +120,18 @@ int ape_msda_pair_fused_fwd(const void *value2, const int64_t *spatial_shapes, c
                             int L, int Q, int P, int dtype, int offs_dtype, int heads_per_cta, void *stream);
 
 /*
+ * Multi-scale deformable attention, backward  <- torch.ops.ape.ms_deform_attn_backward
+ *   (ape/layers/csrc/vision.cpp:78, ms_deform_attn.h:42-61, ms_deform_attn_cuda.cu:84-160,
+ *    ms_deform_im2col_cuda.cuh:86-146 per-sample arithmetic, :301-920 kernels).
+ * Inputs as ape_msda_fwd plus grad_out [B,Q,H*D] (dtype).  Outputs: grad_value_f32 [B,S,H,D] ALWAYS fp32 and pre-zeroed by
+ * the caller (vector atomics accumulate into it; the caller casts to dtype), grad_loc [B,Q,H,L,P,2] and grad_attn
+ * [B,Q,H,L,P] in dtype, fully overwritten.  fp32 arithmetic for every dtype.
+ */
+int ape_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t *level_start, const void *loc,
+                 const void *attn, const void *grad_out, float *grad_value_f32, void *grad_loc, void *grad_attn, int B,
+                 int S, int H, int D, int L, int Q, int P, int dtype, void *stream);
+
+/*
  * Tensor-core linear layer: C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual), tcgen05 / TMA / TMEM.
  * Replaces the nn.Linear (cuBLAS) calls of the detection path (vit_eva_clip.py:225-232,266-267,125-132;
  * deformable_transformer_vl.py:36-54; multi_scale_deform_attn.py:278-295,353; vision_language_align.py:36-48).
