@@ -59,7 +59,7 @@ def _declare(lib):
     lib.ape_msda_pair_supported.restype = _i
     lib.ape_msda_pair_supported.argtypes = [_vp, _i, _i, _i, _i, _i]
     lib.ape_msda_pair_fused_fwd.restype = _i
-    lib.ape_msda_pair_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 10 + [_vp]
+    lib.ape_msda_pair_fused_fwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _vp] + [_i] * 12 + [_vp]
     lib.ape_gemm_tn.restype = _i
     lib.ape_gemm_tn.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 7 + [_vp]
 

@@ -16,6 +16,8 @@
 //                               bias/act/residual in registers -> 16-bit pack -> 128B-swizzled smem slab
 //                               (32 rows x 64 cols) -> TMA store (coalesced, clips the M/N edges)
 //   TMEM holds two BN-column accumulators so tile i's epilogue overlaps tile i+1's main loop.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -58,11 +60,20 @@ struct alignas(1024) GemmSmem {
 
 constexpr int kThreads = 320;
 
-__device__ __forceinline__ float act_fn(float x, int act) {
-  if (act == ACT_RELU) return fmaxf(x, 0.f);
-  if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-  if (act == ACT_CLAMP) return fminf(fmaxf(x, -50000.f), 50000.f);  // vision_language_align.py:49-51
-  return x;
+// Activation over N accumulator values; the switch is OUTSIDE the unrolled loops (one uniform branch per chunk, not per
+// element: with the branch inside, the three-way select around the inlined erff made the ReLU epilogue 4x slower).
+template <int N>
+__device__ __forceinline__ void apply_act(float *v, int act) {
+  if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+  } else if (act == ACT_CLAMP) {  // vision_language_align.py:49-51
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], -50000.f), 50000.f);
+  }
 }
 
 // 32 accumulator columns of one row += residual[m, n0 .. n0+31] read in its own dtype (fp32 or 16-bit).
@@ -158,8 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
     }
     return;
   }
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = act_fn(v[i], p.act);
+  apply_act<32>(v, p.act);
   if (p.residual != nullptr) add_residual32(p, v, m, n0);
   store_row<TO>(C + (size_t)m * p.ldc + n0, v, nvalid);
 }
@@ -195,10 +205,7 @@ __device__ __forceinline__ void finish64(const GemmParams &p, float *v, int m, i
       v[4 * i + 3] = t3 * c.w + t2 * sn.w;
     }
   }
-  if (p.act == ACT_RELU || p.act == ACT_GELU || p.act == ACT_CLAMP) {
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = act_fn(v[i], p.act);
-  }
+  apply_act<64>(v, p.act);
   if (p.residual != nullptr && m < p.M) {
     add_residual32(p, v, m, n0);
     if (n0 + 32 < p.N) add_residual32(p, v + 32, m, n0 + 32);
@@ -328,10 +335,7 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
           if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
       }
     }
-    if (p.act == ACT_RELU || p.act == ACT_GELU || p.act == ACT_CLAMP) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = act_fn(v[i], p.act);
-    }
+    apply_act<32>(v, p.act);
     if (p.residual != nullptr && m < p.M) add_residual32(p, v, m, n0);
     if (lane == 0) tc::tma_store_wait_read0();
     __syncwarp();
@@ -804,7 +808,13 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   // cluster of 2 along M whenever there are at least two row blocks (tile_n bit 0x1000 forces single-CTA)
   // default variant per shape from the measured sweep (profiles/r01_gemm_sweep.txt): the multicast cluster only wins when
   // the K loop is long (K >= 2048: w3, FFN2); bit 0x4000 forces it, bit 0x1000 forces the single-CTA kernel
-  const bool single = (tile_n & 0x1000) != 0 || M <= BM || (K < 2048 && (tile_n & 0xE000) == 0);
+  // APE_GEMM_POLICY=mc|single overrides the per-shape default for A/B runs of the whole step (read once)
+  static const int policy = [] {
+    const char *e = getenv("APE_GEMM_POLICY");
+    return e == nullptr ? 0 : (e[0] == 'm' ? 1 : e[0] == 's' ? 2 : 0);
+  }();
+  const bool auto_single = policy == 2 || (policy == 0 && K < 2048);
+  const bool single = (tile_n & 0x1000) != 0 || M <= BM || (auto_single && (tile_n & 0xE000) == 0);
   // kernel variant: default = cluster of 2 along M sharing the weight tile by TMA multicast (1-CTA MMA); 0x2000 = CTA-pair
   // MMA (cta_group::2, 256 x bn tiles; measured equal or slower on B200 for these shapes, kept selectable);
   // 0x8000 = cluster of 4 along M (weight tile split four ways)

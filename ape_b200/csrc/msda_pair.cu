@@ -37,6 +37,11 @@ struct PairParams {
   int64_t offs_row_stride, logit_row_stride;
   int B, S, H, L, Q;
   int ht_log2, ref_dim;
+  // self-attention over the pyramid (Q == S): a CTA's queries form a tile_w x (QT / tile_w) pixel tile of one level, so
+  // the sampled texels overlap vertically as well as horizontally (tile_w = 0: QT consecutive queries)
+  int tile_w, n_tiles, head_major;
+  int tiles_cum[kPairMaxLevels + 1];  // first tile of every level
+  int tiles_x[kPairMaxLevels];        // tiles per row of every level
 };
 
 struct __align__(16) PairRec {
@@ -135,9 +140,25 @@ __global__ void __launch_bounds__(256) msda_pair_fused_kernel(const PairParams p
   const int r = tid >> 3, j = tid & 7;  // row inside the CTA, lane inside the row group
   const int HT = 1 << p.ht_log2, head_tiles = p.H >> p.ht_log2, QT = 32 >> p.ht_log2;
   const int b = blockIdx.y;
-  const int q = (blockIdx.x / head_tiles) * QT + (r >> p.ht_log2);
-  const int h = (blockIdx.x % head_tiles) * HT + (r & (HT - 1));
-  const bool active = q < p.Q;
+  const int tile = p.head_major ? (int)(blockIdx.x % (unsigned)p.n_tiles) : (int)(blockIdx.x / (unsigned)head_tiles);
+  const int htile = p.head_major ? (int)(blockIdx.x / (unsigned)p.n_tiles) : (int)(blockIdx.x % (unsigned)head_tiles);
+  const int h = htile * HT + (r & (HT - 1));
+  const int qi = r >> p.ht_log2;  // query inside the tile, 0 .. QT-1
+  int q;
+  bool active;
+  if (p.tile_w > 0) {
+    int l = 0;
+    while (l + 1 < p.L && tile >= p.tiles_cum[l + 1]) ++l;
+    const int t = tile - p.tiles_cum[l];
+    const int ty = t / p.tiles_x[l], tx = t - ty * p.tiles_x[l];
+    const int th = QT / p.tile_w;
+    const int x = tx * p.tile_w + qi % p.tile_w, y = ty * th + qi / p.tile_w;
+    active = x < s_lvl[l * 3 + 1] && y < s_lvl[l * 3];
+    q = s_lvl[l * 3 + 2] + y * s_lvl[l * 3 + 1] + x;
+  } else {
+    q = tile * QT + qi;
+    active = q < p.Q;
+  }
   PairRec *rec = reinterpret_cast<PairRec *>(smem_raw) + r * LP;
 
   // ---- records: lane j < L owns level j of this row ----------------------------------------------------------------
@@ -283,7 +304,7 @@ extern "C" int ape_msda_pair_supported(const int *host_shapes, int L, int H, int
 extern "C" int ape_msda_pair_fused_fwd(const void *value2, const int64_t *shapes, const int64_t *starts, const int *host_shapes,
                                        const void *offsets, int64_t offs_row_stride, const void *logits, int64_t logit_row_stride,
                                        const float *ref, int ref_dim, void *out, int B, int S, int H, int D, int L, int Q, int P,
-                                       int dtype, int offs_dtype, int heads_per_cta, void *stream) {
+                                       int dtype, int offs_dtype, int heads_per_cta, int tile_w, int head_major, void *stream) {
   if (!host_shapes) return fail(APE_ERR_NULL_PTR, "msda_pair: null host_shapes");
   if (!ape_msda_pair_supported(host_shapes, L, H, D, P, dtype))
     return fail(APE_ERR_UNSUPPORTED, "msda_pair: needs a 16-bit value with D=32, P=4, L<=8, power-of-two H, levels >= 2 wide");
@@ -311,7 +332,25 @@ extern "C" int ape_msda_pair_fused_fwd(const void *value2, const int64_t *shapes
   while ((1 << lg) < ht) ++lg;
   p.ht_log2 = lg;
   const int QT = 32 >> lg;
-  dim3 grid((unsigned)(((Q + QT - 1) / QT) * (H >> lg)), (unsigned)B);
+  if (tile_w < 0) tile_w = (Q == S && QT >= 8) ? 8 : 0;  // default for self-attention: 8 x (QT/8) pixel tiles
+  if (tile_w > 0 && (Q != S || QT % tile_w != 0 || (tile_w & (tile_w - 1))))
+    return fail(APE_ERR_INVALID_ARG, "msda_pair: tile_w=%d needs Q == S and a power of two dividing %d", tile_w, QT);
+  p.tile_w = tile_w;
+  p.head_major = head_major ? 1 : 0;
+  if (tile_w > 0) {
+    const int th = QT / tile_w;
+    int cum = 0;
+    for (int l = 0; l < L; ++l) {
+      p.tiles_cum[l] = cum;
+      p.tiles_x[l] = (host_shapes[2 * l + 1] + tile_w - 1) / tile_w;
+      cum += p.tiles_x[l] * ((host_shapes[2 * l] + th - 1) / th);
+    }
+    p.tiles_cum[L] = cum;
+    p.n_tiles = cum;
+  } else {
+    p.n_tiles = (Q + QT - 1) / QT;
+  }
+  dim3 grid((unsigned)(p.n_tiles * (H >> lg)), (unsigned)B);
   const size_t smem = (size_t)32 * L * 4 * sizeof(PairRec);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == APE_DTYPE_F16) {

@@ -31,18 +31,19 @@ class VisionLanguageAlign(nn.Module):
         """Text projection with 1 / (2 * exp(log_scale)) folded in (16-bit operand) and `bias_lang` as an 8-row weight."""
         lin = self.dot_product_projection_text
         ps = (lin.weight, lin.bias, self.log_scale, self.bias_lang, self.bias0)
-        key = (dtype, tuple(p._version for p in ps), lin.weight.data_ptr())
-        if getattr(self, "_pk", (None,))[0] != key:
-            with torch.no_grad():
-                inv = torch.exp(-self.log_scale.detach().float())
-                wt = (lin.weight.detach().float() * (0.5 * inv)).to(dtype).contiguous()
-                bt = (lin.bias.detach().float() * inv).contiguous()
-                wl = torch.zeros(8, lin.weight.shape[1], dtype=dtype, device=lin.weight.device)
-                wl[0] = self.bias_lang.detach().to(dtype)
-                bl = torch.zeros(8, dtype=torch.float32, device=lin.weight.device)
-                bl[0] = self.bias0.detach().float()[0]
-            self._pk = (key, wt, bt, wl, bl)
-        return self._pk[1:]
+        from .. import ops
+
+        def build():
+            inv = torch.exp(-self.log_scale.detach().float())
+            wt = (lin.weight.detach().float() * (0.5 * inv)).to(dtype).contiguous()
+            bt = (lin.bias.detach().float() * inv).contiguous()
+            wl = torch.zeros(8, lin.weight.shape[1], dtype=dtype, device=lin.weight.device)
+            wl[0] = self.bias_lang.detach().to(dtype)
+            bl = torch.zeros(8, dtype=torch.float32, device=lin.weight.device)
+            bl[0] = self.bias0.detach().float()[0]
+            return wt, bt, wl, bl
+
+        return ops.cached(self, "_pk", dtype, (tuple(p._version for p in ps), lin.weight.data_ptr()), build)
 
     def forward_engine(self, x, embedding):
         """Engine path (x [B,Q,C] fp16 / bf16 CUDA): the text projection, the language bias and the query x text contraction

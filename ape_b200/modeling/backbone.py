@@ -258,9 +258,10 @@ class ViT(nn.Module):
 
     def _pack(self, dtype, device):
         """Weights re-laid out once for the kernels (fused qkv, interleaved SwiGLU pairs, K padded to 8)."""
-        key = (dtype, str(device), tuple(p._version for p in self.parameters()))
-        if getattr(self, "_packed_key", None) == key:
-            return self._packed
+        key = (str(device), tuple(p._version for p in self.parameters()))
+        packs = self.__dict__.setdefault("_packs", {})  # one entry per engine dtype, never evicted (ops.cached)
+        if dtype in packs and packs[dtype][0] == key:
+            return packs[dtype][1]
         f32 = dict(dtype=torch.float32, device=device)
         packed = {"blocks": []}
         with torch.no_grad():
@@ -285,22 +286,22 @@ class ViT(nn.Module):
                     w12=w12.to(device, dtype).contiguous(), b12=b12.to(**f32).contiguous(),
                     fw=m.ffn_ln.weight.to(**f32).contiguous(), fb=m.ffn_ln.bias.to(**f32).contiguous(),
                     w3=w3, b3=m.w3.bias.to(**f32).contiguous(), hid=hid, hid_p=hid_p))
-        self._packed, self._packed_key = packed, key
-        self._geom = {}
+        packs[dtype] = (key, packed)
         return packed
 
     def _geometry(self, B, g, ws, dtype, device):
         """Per input geometry: window-major token permutation, abs-pos table, RoPE position maps."""
-        k = (B, g, ws, dtype, str(device))
-        if k in self._geom:
-            return self._geom[k]
+        k = (B, g, ws, dtype, str(device), self.pos_embed._version)
+        geom = self.__dict__.setdefault("_geom", {})
+        if k in geom:
+            return geom[k]
         nw = g // ws if ws else 1
         w = ws if ws else g
         ids = torch.arange(g * g, device=device).view(nw, w, nw, w).permute(0, 2, 1, 3).reshape(-1)  # window-major -> raster
         pos = get_abs_pos(self.pos_embed.detach().float(), self.pretrain_use_cls_token, (g, g)).reshape(g * g, -1)
         geo = dict(ids=ids, pos=pos[ids].float().repeat(B, 1).contiguous(),  # fp32: first value of the residual stream
                    glb_map=ids.to(torch.int32).repeat(B).contiguous(), inv=torch.argsort(ids))
-        self._geom[k] = geo
+        geom[k] = geo
         return geo
 
     def _engine_forward(self, img):
@@ -368,27 +369,17 @@ class ViT(nn.Module):
 
 def _convT_as_gemm(ct, dtype):
     """ConvTranspose2d(k=2, s=2) as a GEMM over tokens: weight [(dy,dx,co), ci], bias tiled 4x (cached)."""
-    key = ("ct", dtype, ct.weight._version, ct.weight.data_ptr())
-    c = ct.__dict__.get("_ape_packed")
-    if c is None or c[0] != key:
-        with torch.no_grad():
-            w = ct.weight.detach().permute(2, 3, 1, 0).reshape(-1, ct.weight.shape[0]).to(dtype).contiguous()
-            b = ct.bias.detach().float().repeat(4).contiguous()
-        c = (key, w, b)
-        ct.__dict__["_ape_packed"] = c
-    return c[1], c[2]
+    return ops.cached(ct, "_ape_packed_ct", dtype, (ct.weight._version, ct.weight.data_ptr()), lambda: (
+        ct.weight.detach().permute(2, 3, 1, 0).reshape(-1, ct.weight.shape[0]).to(dtype).contiguous(),
+        ct.bias.detach().float().repeat(4).contiguous()))
 
 
 def _conv_weights(conv, dtype):
-    key = ("cv", dtype, conv.weight._version, conv.weight.data_ptr())
-    c = conv.__dict__.get("_ape_packed")
-    if c is None or c[0] != key:
-        with torch.no_grad():
-            w = conv.weight.detach().to(dtype)
-            w = w.reshape(w.shape[0], -1).contiguous() if w.shape[-1] == 1 else w.contiguous(memory_format=torch.channels_last)
-        c = (key, w)
-        conv.__dict__["_ape_packed"] = c
-    return c[1]
+    def build():
+        w = conv.weight.detach().to(dtype)
+        return w.reshape(w.shape[0], -1).contiguous() if w.shape[-1] == 1 else w.contiguous(memory_format=torch.channels_last)
+
+    return ops.cached(conv, "_ape_packed_cv", dtype, (conv.weight._version, conv.weight.data_ptr()), build)
 
 
 class LastLevelMaxPool(nn.Module):

@@ -33,26 +33,26 @@ class _SelfAttention(nn.Module):
         (zero columns in the output projection), q | k | v thirds as the kernel's fused-qkv column layout."""
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
         wo, bo = self.attn.out_proj.weight, self.attn.out_proj.bias
-        key = (dtype, w._version, b._version, wo._version, bo._version, w.data_ptr())
-        if getattr(self, "_pk", (None,))[0] != key:
-            E, nh = self.embed_dim, self.num_heads
-            hd = E // nh
-            with torch.no_grad():
-                def pad_rows(wpart, bpart):  # [E, E] / [E] -> [nh*64, E] / [nh*64]
-                    wp = wpart.new_zeros(nh, 64, E)
-                    wp[:, :hd] = wpart.view(nh, hd, E)
-                    bp = bpart.new_zeros(nh, 64)
-                    bp[:, :hd] = bpart.view(nh, hd)
-                    return wp.view(nh * 64, E), bp.view(nh * 64)
-                wq, bq = pad_rows(w[:E], b[:E])
-                wk, bk = pad_rows(w[E:2 * E], b[E:2 * E])
-                wv, bv = pad_rows(w[2 * E:], b[2 * E:])
-                wop = wo.new_zeros(E, nh, 64)
-                wop[:, :, :hd] = wo.view(E, nh, hd)
-                self._pk = (key, torch.cat([wq, wk], 0).detach().to(dtype).contiguous(), torch.cat([bq, bk]).detach().float().contiguous(),
-                            wv.detach().to(dtype).contiguous(), bv.detach().float().contiguous(),
-                            wop.view(E, nh * 64).detach().to(dtype).contiguous(), bo.detach().float().contiguous())
-        return self._pk[1:]
+        E, nh = self.embed_dim, self.num_heads
+        hd = E // nh
+
+        def build():
+            def pad_rows(wpart, bpart):  # [E, E] / [E] -> [nh*64, E] / [nh*64]
+                wp = wpart.new_zeros(nh, 64, E)
+                wp[:, :hd] = wpart.view(nh, hd, E)
+                bp = bpart.new_zeros(nh, 64)
+                bp[:, :hd] = bpart.view(nh, hd)
+                return wp.view(nh * 64, E), bp.view(nh * 64)
+            wq, bq = pad_rows(w[:E], b[:E])
+            wk, bk = pad_rows(w[E:2 * E], b[E:2 * E])
+            wv, bv = pad_rows(w[2 * E:], b[2 * E:])
+            wop = wo.new_zeros(E, nh, 64)
+            wop[:, :, :hd] = wo.view(E, nh, hd)
+            return (torch.cat([wq, wk], 0).detach().to(dtype).contiguous(), torch.cat([bq, bk]).detach().float().contiguous(),
+                    wv.detach().to(dtype).contiguous(), bv.detach().float().contiguous(),
+                    wop.view(E, nh * 64).detach().to(dtype).contiguous(), bo.detach().float().contiguous())
+
+        return ops.cached(self, "_pk", dtype, (w._version, b._version, wo._version, bo._version, w.data_ptr()), build)
 
     def forward(self, x, pos):
         E, nh = self.embed_dim, self.num_heads
@@ -450,13 +450,14 @@ class DeformableDetrTransformerVL(nn.Module):
         if feat_flatten is None:
             feat_flatten = torch.cat([f.flatten(2).transpose(1, 2) for f in multi_level_feats], 1)
         engine_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else torch.float32
-        ck = ("pos_lvl", engine_dtype, self.level_embeds._version, self.level_embeds.data_ptr())
-        if geo.get("_pos_lvl_key") != ck:  # position embedding + level embedding: constant per geometry and weights
-            lvl_embed = torch.cat([self.level_embeds[i].view(1, 1, -1).expand(1, h * w, -1)
-                                   for i, (h, w) in enumerate(geo["shapes"])], 1)
-            geo["_pos_lvl"] = (geo["pos_flatten"] + lvl_embed.float()).to(engine_dtype).contiguous()
-            geo["_pos_lvl_key"] = ck
-        pos_flatten = geo["_pos_lvl"]
+        ck = (self.level_embeds._version, self.level_embeds.data_ptr())
+        cache = geo.setdefault("_pos_lvl", {})  # position + level embedding: constant per geometry and weights, one entry per dtype
+        if engine_dtype not in cache or cache[engine_dtype][0] != ck:
+            with torch.no_grad():
+                lvl_embed = torch.cat([self.level_embeds[i].view(1, 1, -1).expand(1, h * w, -1)
+                                       for i, (h, w) in enumerate(geo["shapes"])], 1)
+                cache[engine_dtype] = (ck, (geo["pos_flatten"] + lvl_embed.float()).to(engine_dtype).contiguous())
+        pos_flatten = cache[engine_dtype][1]
         memory, query_l = self.encoder(
             query=feat_flatten, key=None, value=None, query_l=query_l, attention_mask_l=attention_mask_l,
             query_pos=pos_flatten, query_key_padding_mask=geo["mask_flatten"] if geo["has_padding"] else None,
@@ -495,28 +496,26 @@ class DeformableDetrTransformerVL(nn.Module):
         cls_mods = [self.decoder.class_embed[nd]] + (list(self.decoder.class_embed_ambiguous) if self.proposal_ambiguous else [])
         box_mods = [self.decoder.bbox_embed[nd]] + (list(self.decoder.bbox_embed_ambiguous) if self.proposal_ambiguous else [])
         params = [p for m in cls_mods + box_mods for p in m.parameters()]
-        key = (dt, tuple(p._version for p in params), params[0].data_ptr())
-        if getattr(self, "_heads_pk", (None,))[0] != key:
-            with torch.no_grad():
-                E = self.embed_dim
-                n = len(cls_mods)
-                wc = torch.zeros(8, E, device=memory.device, dtype=dt)
-                bc = torch.zeros(8, device=memory.device, dtype=torch.float32)
-                for j, m in enumerate(cls_mods):
-                    wc[j] = m.weight[0].to(dt)
-                    bc[j] = m.bias[0].float()
-                w0 = torch.cat([m.layers[0].weight for m in box_mods], 0).to(dt).contiguous()
-                b0 = torch.cat([m.layers[0].bias for m in box_mods], 0).float().contiguous()
-                rest = []
-                for m in box_mods:
-                    mids = [(l.weight.detach().to(dt).contiguous(), l.bias.detach().float().contiguous()) for l in m.layers[1:-1]]
-                    wl = torch.zeros(8, m.layers[-1].weight.shape[1], device=memory.device, dtype=dt)
-                    bl = torch.zeros(8, device=memory.device, dtype=torch.float32)
-                    wl[:4] = m.layers[-1].weight.to(dt)
-                    bl[:4] = m.layers[-1].bias.float()
-                    rest.append((mids, wl, bl))
-                self._heads_pk = (key, wc, bc, w0, b0, rest, n)
-        _, wc, bc, w0, b0, rest, n = self._heads_pk
+        def build():
+            E = self.embed_dim
+            wc = torch.zeros(8, E, device=memory.device, dtype=dt)
+            bc = torch.zeros(8, device=memory.device, dtype=torch.float32)
+            for j, m in enumerate(cls_mods):
+                wc[j] = m.weight[0].to(dt)
+                bc[j] = m.bias[0].float()
+            w0 = torch.cat([m.layers[0].weight for m in box_mods], 0).to(dt).contiguous()
+            b0 = torch.cat([m.layers[0].bias for m in box_mods], 0).float().contiguous()
+            rest = []
+            for m in box_mods:
+                mids = [(l.weight.detach().to(dt).contiguous(), l.bias.detach().float().contiguous()) for l in m.layers[1:-1]]
+                wl = torch.zeros(8, m.layers[-1].weight.shape[1], device=memory.device, dtype=dt)
+                bl = torch.zeros(8, device=memory.device, dtype=torch.float32)
+                wl[:4] = m.layers[-1].weight.to(dt)
+                bl[:4] = m.layers[-1].bias.float()
+                rest.append((mids, wl, bl))
+            return wc, bc, w0, b0, rest, len(cls_mods)
+
+        wc, bc, w0, b0, rest, n = ops.cached(self, "_heads_pk", dt, (tuple(p._version for p in params), params[0].data_ptr()), build)
         om = ops.linear_module_tc(self.enc_output, memory.masked_fill(invalid, float(0)))
         output_memory = ops.layernorm_module(self.enc_output_norm, om)
         B, S, E = output_memory.shape

@@ -158,8 +158,12 @@ def msda_pair_values(value, num_heads, token_mask=None):
     return out
 
 
+PAIR_TILE_W, PAIR_HEAD_MAJOR = -1, 0  # CTA tiling of the pair kernel for Q == S (tests / sweeps override)
+
+
 def ms_deform_attn_pair_fused_forward(value2, spatial_shapes, level_start_index, host_shapes, sampling_offsets,
-                                      attention_logits, reference_points, num_points, heads_per_cta=0):
+                                      attention_logits, reference_points, num_points, heads_per_cta=0, tile_w=None,
+                                      head_major=None):
     """ms_deform_attn_fused_forward over the pair layout (ape_msda_pair_fused_fwd).  value2 [B,S,H,2,32]."""
     B, S, H, two, D = value2.shape
     L = spatial_shapes.shape[0]
@@ -174,7 +178,9 @@ def ms_deform_attn_pair_fused_forward(value2, spatial_shapes, level_start_index,
             value2.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs,
             sampling_offsets.data_ptr(), sampling_offsets.stride(1), attention_logits.data_ptr(),
             attention_logits.stride(1), ref.data_ptr(), ref.shape[-1], out.data_ptr(), B, S, H, D, L, Q, int(num_points),
-            _lib.dtype_code(value2.dtype), _lib.dtype_code(sampling_offsets.dtype), int(heads_per_cta), _lib.current_stream_ptr())
+            _lib.dtype_code(value2.dtype), _lib.dtype_code(sampling_offsets.dtype), int(heads_per_cta),
+            int(PAIR_TILE_W if tile_w is None else tile_w) if Q == S else 0,
+            int(PAIR_HEAD_MAJOR if head_major is None else head_major), _lib.current_stream_ptr())
     _lib.check(rc, "ape_msda_pair_fused_fwd")
     return out
 
@@ -245,19 +251,28 @@ def linear_rope_tc(x, weight, bias, cos, sin, num_channels, head_dim, pos_map=No
     return out
 
 
+def cached(obj, slot, dtype, key, build):
+    """Per-object cache of re-laid-out weights with ONE ENTRY PER ENGINE DTYPE: `build()` runs when the entry of `dtype` is
+    missing or its `key` (parameter versions / pointers) changed.  Entries of other dtypes are never evicted: a CUDA graph
+    captured in fp16 keeps reading its fp16 copies after the model has also run in bf16 (capturing a new graph calls
+    torch.cuda.empty_cache(), which would unmap an evicted copy under the old graph)."""
+    d = obj.__dict__.setdefault(slot, {})
+    e = d.get(dtype)
+    if e is None or e[0] != key:
+        with torch.no_grad():
+            e = (key, build())
+        d[dtype] = e
+    return e[1]
+
+
 def packed(module, dtype, extra=None):
     """(weight in `dtype`, fp32 bias) of an nn.Linear / nn.LayerNorm-like module, cached on the module and
     refreshed when its parameters change (load_state_dict, .to()).  LayerNorm weights stay fp32."""
     w, b = module.weight, getattr(module, "bias", None)
-    key = (dtype, w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
-    cache = module.__dict__.get("_ape_packed")
-    if cache is None or cache[0] != key:
-        with torch.no_grad():
-            wd = w.detach().to(dtype if w.dim() >= 2 else torch.float32).contiguous()
-            bd = None if b is None else b.detach().to(torch.float32).contiguous()
-        cache = (key, wd, bd)
-        module.__dict__["_ape_packed"] = cache
-    return cache[1], cache[2]
+    key = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+    return cached(module, "_ape_packed", dtype, key, lambda: (
+        w.detach().to(dtype if w.dim() >= 2 else torch.float32).contiguous(),
+        None if b is None else b.detach().to(torch.float32).contiguous()))
 
 
 def linear_module_tc(module, x, act=None, residual=None, out_dtype=None):

@@ -109,7 +109,10 @@ int ape_msda_fused_fwd(const void *value, const int64_t *spatial_shapes, const i
  *   ape_msda_pair_values     value [B,S,H*D] (row pitch ld elements) -> value2; token_mask [B*S] bytes or NULL zeroes masked
  *                            tokens (key_padding_mask, multi_scale_deform_attn.py:286-287)
  *   ape_msda_pair_supported  1 if the geometry is covered (host_shapes int32 [L,2] on the HOST: every level >= 2 wide)
- *   ape_msda_pair_fused_fwd  heads_per_cta: 0 = auto (1 for Q >= 128: a CTA's 32 rows are consecutive queries of one head)
+ *   ape_msda_pair_fused_fwd  heads_per_cta: 0 = auto (1 for Q >= 128: a CTA's 32 rows are queries of one head);
+ *                            tile_w: for Q == S the CTA's queries form a tile_w x (32 / heads_per_cta / tile_w) PIXEL tile of one
+ *                            level (texel re-use in both directions); 0 = consecutive queries, -1 = auto (8);
+ *                            head_major: CTA order (0: heads of one tile adjacent, 1: tiles of one head adjacent)
  */
 int ape_msda_pair_values(const void *value, int64_t ld, void *value2, const uint8_t *token_mask, int B, int S, int H, int D,
                          int dtype, void *stream);
@@ -117,7 +120,8 @@ int ape_msda_pair_supported(const int *host_shapes, int L, int H, int D, int P, 
 int ape_msda_pair_fused_fwd(const void *value2, const int64_t *spatial_shapes, const int64_t *level_start,
                             const int *host_shapes, const void *offsets, int64_t offs_row_stride, const void *logits,
                             int64_t logit_row_stride, const float *ref, int ref_dim, void *out, int B, int S, int H, int D,
-                            int L, int Q, int P, int dtype, int offs_dtype, int heads_per_cta, void *stream);
+                            int L, int Q, int P, int dtype, int offs_dtype, int heads_per_cta, int tile_w, int head_major,
+                            void *stream);
 
 /*
  * Multi-scale deformable attention, backward  <- torch.ops.ape.ms_deform_attn_backward

@@ -248,11 +248,11 @@ def _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale):
     return value, ss, st, qo, ref
 
 
-def _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, mask=None, hpc=0):
+def _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, mask=None, hpc=0, tile_w=None, head_major=None):
     B, S = value.shape[:2]
     v2 = ape.ops.msda_pair_values(value.view(B, S, -1), H, token_mask=mask)
     return ape.ops.ms_deform_attn_pair_fused_forward(v2, ss.to(DEV), st.to(DEV), shapes, qo[..., :n_off], qo[..., n_off:], ref, P,
-                                                     heads_per_cta=hpc)
+                                                     heads_per_cta=hpc, tile_w=tile_w, head_major=head_major)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -270,8 +270,9 @@ def test_pair_kernel_equals_generic_fused(ape, dtype, shapes):
     for seed, off_scale in ((17, 3.0), (18, 8.0), (19, 0.5), (20, 40.0)):  # (20: most samples out of range / on borders)
         value, ss, st, qo, ref = _encoder_like_case(shapes, B, H, D, P, dtype, seed, off_scale)
         a = ape.ops.ms_deform_attn_fused_forward(value, ss.to(DEV), st.to(DEV), qo[..., :n_off], qo[..., n_off:], ref, P)
-        for hpc in (0, 8):
-            b = _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, hpc=hpc)
+        # CTA mappings: auto (8-wide pixel tiles), all heads per CTA, consecutive queries, 16 / 32 / 4-wide tiles, head-major order
+        for hpc, tw, hm in ((0, None, None), (8, None, None), (0, 0, 0), (0, 16, 1), (0, 32, 0), (0, 4, 1), (2, 8, 1)):
+            b = _pair_run(ape, value, ss, st, shapes, qo, n_off, ref, P, H, hpc=hpc, tile_w=tw, head_major=hm)
             torch.testing.assert_close(b.float(), a.float(), rtol=tol, atol=tol)
     # arbitrary (non pixel-centre) reference points and boxes, fp32 offsets / logits, a token mask
     g = torch.Generator().manual_seed(23)
