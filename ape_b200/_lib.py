@@ -65,6 +65,8 @@ def _declare(lib):
 
     lib.ape_gemm_tn_ex.restype = _i
     lib.ape_gemm_tn_ex.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 8 + [_vp]
+    lib.ape_gemm_tn_fused.restype = _i
+    lib.ape_gemm_tn_fused.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64] + [_i] * 8 + [_vp, _i, _vp, ctypes.c_float, ctypes.c_float, _vp, _i, _vp]
     lib.ape_gemm_tn_rope.restype = _i
     lib.ape_gemm_tn_rope.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
 
@@ -83,7 +85,7 @@ def _declare(lib):
     lib.ape_attn_fwd.restype = _i
     lib.ape_attn_fwd.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
     lib.ape_attn_fwd_ex.restype = _i
-    lib.ape_attn_fwd_ex.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
+    lib.ape_attn_fwd_ex.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp, _vp]
     lib.ape_vlf_pool_workspace_bytes.restype = _i64
     lib.ape_vlf_pool_workspace_bytes.argtypes = [_i, _i, _i, _i]
     lib.ape_vlf_pool.restype = _i
@@ -118,6 +120,7 @@ EXPORTS = (
     "ape_msda_pair_fused_fwd",
     "ape_gemm_tn",
     "ape_gemm_tn_ex",
+    "ape_gemm_tn_fused",
     "ape_gemm_tn_rope",
     "ape_layernorm",
     "ape_layernorm_ex",

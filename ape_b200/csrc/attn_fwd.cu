@@ -43,6 +43,7 @@ struct AttnParams {
   int n;             // tokens per sequence (multiple of 128)
   int n_valid;       // keys >= n_valid of every sequence are masked out (rows padded up to n; n_valid <= n)
   int heads, C;      // C = heads * 64
+  float *stats_out;  // [rows, heads, 2] (sum, sum of squares) of each row's 64 stored output values per head, or nullptr
   float scale_log2;  // softmax scale * log2(e)
   uint32_t idesc_qk, idesc_pv;
 };
@@ -57,6 +58,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnThreads, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   AttnSmem &s = *reinterpret_cast<AttnSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -85,6 +87,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = s.tmem_base;
+  pdl_wait();  // barriers and tensor memory are set up; the previous kernel's output (qkv) may be read from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -233,6 +236,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     tc::fence_after_sync();
     const float inv = 1.f / l;
     T *dst = reinterpret_cast<T *>(p.out) + (size_t)(row0 + qblk * QM + row) * p.ldo + head * HD;
+    float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       uint32_t o[32];
@@ -243,9 +247,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * c + i]) * inv;
-        *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = Elem<T>::pack(f);
+        const uint4 pk = Elem<T>::pack(f);
+        *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = pk;
+        if (p.stats_out != nullptr) {  // statistics of the values as stored, for the LayerNorm folded into the next GEMM
+          float g[8];
+          Elem<T>::unpack(pk, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { st_sum += g[i]; st_sq += g[i] * g[i]; }
+        }
       }
     }
+    if (p.stats_out != nullptr)
+      *reinterpret_cast<float2 *>(p.stats_out + ((size_t)(row0 + qblk * QM + row) * p.heads + head) * 2) = make_float2(st_sum, st_sq);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -277,15 +290,15 @@ EncodeTiledFn attn_encoder() {
 using namespace ape;
 
 extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                               int head_dim, float scale, int dtype, void *stream);
+                               int head_dim, float scale, int dtype, float *stats_out, void *stream);
 
 extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads,
                             int head_dim, float scale, int dtype, void *stream) {
-  return ape_attn_fwd_ex(qkv, ld, out, ldo, num_seq, n, n, heads, head_dim, scale, dtype, stream);
+  return ape_attn_fwd_ex(qkv, ld, out, ldo, num_seq, n, n, heads, head_dim, scale, dtype, nullptr, stream);
 }
 
 extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                               int head_dim, float scale, int dtype, void *stream) {
+                               int head_dim, float scale, int dtype, float *stats_out, void *stream) {
   if (n_valid <= 0 || n_valid > n) return fail(APE_ERR_INVALID_ARG, "attn: n_valid=%d must be in [1, n=%d]", n_valid, n);
   if (dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16) return fail(APE_ERR_INVALID_ARG, "attn: fp16 / bf16 only (dtype %d)", dtype);
   if (head_dim != HD) return fail(APE_ERR_UNSUPPORTED, "attn: head_dim %d (only 64)", head_dim);
@@ -309,7 +322,7 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
   AttnParams p{};
-  p.out = out; p.ldo = ldo; p.n = n; p.n_valid = n_valid; p.heads = heads; p.C = C;
+  p.out = out; p.ldo = ldo; p.n = n; p.n_valid = n_valid; p.heads = heads; p.C = C; p.stats_out = stats_out;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int fmt = dtype == APE_DTYPE_BF16 ? 1 : 0;
   p.idesc_qk = tc::make_idesc_f16(QM, KN, fmt);
@@ -324,7 +337,7 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
       if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       set = true;
     }
-    attn_fwd_kernel<__half><<<grid, kAttnThreads, smem, st>>>(map, p);
+    APE_LAUNCH((attn_fwd_kernel<__half>), grid, kAttnThreads, smem, st, map, p);
   } else {
     static bool set = false;
     if (!set) {
@@ -332,7 +345,7 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
       if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       set = true;
     }
-    attn_fwd_kernel<__nv_bfloat16><<<grid, kAttnThreads, smem, st>>>(map, p);
+    APE_LAUNCH((attn_fwd_kernel<__nv_bfloat16>), grid, kAttnThreads, smem, st, map, p);
   }
   return check_launch("attn_fwd_kernel");
 }

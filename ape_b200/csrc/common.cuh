@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <utility>
 
 #include "ape_b200.h"
 
@@ -35,6 +36,40 @@ inline int check_launch(const char *what) {
 }
 
 inline int dtype_size(int dtype) { return dtype == APE_DTYPE_F32 ? 4 : 2; }
+
+// ---- programmatic dependent launch -------------------------------------------------------------
+// Every kernel of the library starts with pdl_prologue(): it tells the scheduler that the NEXT kernel of the stream may be
+// launched (its CTAs start as SM resources free up and run their own set-up), then waits until the PREVIOUS kernel has
+// completed and flushed its writes — before this kernel reads or writes any global memory.  Launches go through APE_LAUNCH,
+// which sets cudaLaunchAttributeProgrammaticStreamSerialization; between two kernels of the library the launch latency and
+// the prologue (barrier / tensor-memory set-up of the tcgen05 kernels) then overlap the tail of the previous kernel, in
+// eager mode and inside captured CUDA graphs alike.  A predecessor that is not one of ours never triggers early, so the
+// dependency degrades to ordinary stream order.  APE_PDL=0 in the environment disables the attribute (A/B runs).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+bool pdl_enabled();  // abi.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define APE_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)ape::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
 // ---- device helpers --------------------------------------------------------------------------
 // 128-bit read-only gather load (goes through L1; texels are re-used by neighbouring queries).

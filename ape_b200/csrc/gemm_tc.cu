@@ -46,6 +46,18 @@ struct GemmParams {
   int rope_cols, rope_npos;
   int tma_store;  // 16-bit output with 16-byte aligned rows: epilogue goes through smem + TMA store
   uint32_t idesc;
+  // LayerNorm folded around the GEMM (sub-LN of the EVA-02 block, vit_eva_clip.py:266,130: inner_attn_ln before proj, ffn_ln
+  // before w3).  The producer of A (attention / SwiGLU epilogue) leaves per-row partial (sum, sum of squares) of the 16-bit
+  // values it wrote; this GEMM runs on the RAW A with weights pre-scaled by gamma and finishes
+  //   LN(a) W^T = rstd * (a (gamma .* W)^T  -  mean * colsum)  +  (beta W^T + b)
+  // in the epilogue: no LayerNorm launch and no extra trip of the activations through HBM.
+  const float *ln_part;    // [M, ln_nparts, 2] partial (sum, sumsq) per row, fixed order (deterministic), or nullptr
+  const float *ln_colsum;  // [N] sum_k of the 16-bit pre-scaled weight row
+  int ln_nparts;
+  float ln_inv_c, ln_eps;
+  // SwiGLU epilogue: per-row (sum, sumsq) of every 64-column slab of the 16-bit output, [M, stats_nslab, 2]
+  float *stats_out;
+  int stats_nslab;
 };
 
 template <int BN, int STAGES>
@@ -228,6 +240,7 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
     for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 128) {
       if (lane == 0) tc::tma_store_wait_read0();
       __syncwarp();
+      float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[64];
@@ -263,8 +276,22 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int chunk = hh * 4 + j;
-          *reinterpret_cast<uint4 *>(my_row + ((chunk ^ (lane & 7)) << 4)) = Elem<TO>::pack(o + 8 * j);
+          const uint4 pk = Elem<TO>::pack(o + 8 * j);
+          *reinterpret_cast<uint4 *>(my_row + ((chunk ^ (lane & 7)) << 4)) = pk;
+          if (p.stats_out != nullptr) {  // statistics of the values as stored (16-bit), columns beyond N/2 excluded
+            float f[8];
+            Elem<TO>::unpack(pk, f);
+            const int col0 = n0 / 2 + 8 * j;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (col0 + i < p.N / 2) { st_sum += f[i]; st_sq += f[i] * f[i]; }
+          }
         }
+      }
+      if (p.stats_out != nullptr && m < p.M) {
+        const int slab_idx = (n_blk * BN + c0) / 128;
+        if (slab_idx < p.stats_nslab)
+          *reinterpret_cast<float2 *>(p.stats_out + ((size_t)m * p.stats_nslab + slab_idx) * 2) = make_float2(st_sum, st_sq);
       }
       tc::fence_proxy_async();
       __syncwarp();
@@ -312,6 +339,18 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
   const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16);
   uint8_t *my_row = slab + lane * 128;
   constexpr int HALF = BN / 2;
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  if (p.ln_part != nullptr && m < p.M) {  // row statistics from the producer's partials, summed in a fixed order
+    const float2 *pp = reinterpret_cast<const float2 *>(p.ln_part) + (size_t)m * p.ln_nparts;
+    float sum = 0.f, sq = 0.f;
+    for (int i = 0; i < p.ln_nparts; ++i) {
+      const float2 t = __ldg(pp + i);
+      sum += t.x;
+      sq += t.y;
+    }
+    ln_mean = sum * p.ln_inv_c;
+    ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+  }
 #pragma unroll 1
   for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 32) {
     const int n0 = n_blk * BN + c0;
@@ -322,6 +361,22 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (p.ln_part != nullptr) {  // rstd * (acc - mean * colsum); the bias below is beta W^T + b
+      if (n0 + 32 <= p.N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 c = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + n0) + i);
+          v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * c.x);
+          v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * c.y);
+          v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * c.z);
+          v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * c.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) v[i] = ln_rstd * (v[i] - ln_mean * __ldg(p.ln_colsum + n0 + i));
+      }
+    }
     if (p.bias != nullptr) {
       if (n0 + 32 <= p.N) {
 #pragma unroll
@@ -364,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   using Smem = GemmSmem<BN, STAGES>;
   Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
@@ -401,6 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CL > 1) tc::cluster_sync_all();  // peer barriers are initialised before any multicast can reach them
   tc::fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  pdl_wait();  // set-up done: operands / residual of the previous kernel may be read, C may be written from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -529,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   using Smem = PairSmem<BN, STAGES>;
   Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t CTA_STAGE_BYTES = (BM + BN / 2) * BK * 2;
@@ -567,6 +625,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -727,13 +786,15 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, ma, mb, mc, p);
   if (e != cudaSuccess) return fail((int)e, "gemm_tc_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_tc_kernel");
@@ -760,13 +821,15 @@ int launch_gemm_pair(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, ma, mb, mc, p);
   if (e != cudaSuccess) return fail((int)e, "gemm_pair_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_pair_kernel");
@@ -783,9 +846,17 @@ struct RopeArgs {
   int cols, npos;
 };
 
+struct FuseArgs {  // LayerNorm fold (consume) / SwiGLU row statistics (produce); see GemmParams
+  const float *ln_part, *ln_colsum;
+  int ln_nparts;
+  float ln_inv_c, ln_eps;
+  float *stats_out;
+  int stats_nslab;
+};
+
 static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
                      const float *bias, const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype,
-                     int out_dtype, int act, int tile_n, const RopeArgs *rope, void *stream) {
+                     int out_dtype, int act, int tile_n, const RopeArgs *rope, void *stream, const FuseArgs *fuse = nullptr) {
   if (residual && res_dtype != APE_DTYPE_F32 && res_dtype != APE_DTYPE_F16 && res_dtype != APE_DTYPE_BF16)
     return fail(APE_ERR_INVALID_ARG, "gemm: bad res_dtype %d", res_dtype);
   if (in_dtype != APE_DTYPE_F16 && in_dtype != APE_DTYPE_BF16)
@@ -836,6 +907,19 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
                 (act != ACT_SWIGLU || (bn == 256 && oe == 2)) && (oe == 2 || n_out >= 32);
   if (p.tma_store)  // one slab = 32 rows x 128 bytes
     if (int rc = make_map(&mc, C, out_dtype, M, n_out, ldc, 32, 128 / oe)) return rc;
+  if (fuse) {
+    if (fuse->ln_part) {
+      if (!p.tma_store || out_dtype != APE_DTYPE_F32 || !fuse->ln_colsum || fuse->ln_nparts <= 0 || act == ACT_SWIGLU)
+        return fail(APE_ERR_INVALID_ARG, "gemm+ln: needs an fp32 output with 16-byte aligned rows (N >= 32), column sums and partial statistics");
+      p.ln_part = fuse->ln_part; p.ln_colsum = fuse->ln_colsum; p.ln_nparts = fuse->ln_nparts;
+      p.ln_inv_c = fuse->ln_inv_c; p.ln_eps = fuse->ln_eps;
+    }
+    if (fuse->stats_out) {
+      if (!p.tma_store || act != ACT_SWIGLU || fuse->stats_nslab != (n_out + 63) / 64)
+        return fail(APE_ERR_INVALID_ARG, "gemm+stats: needs the SwiGLU epilogue with a 16-bit aligned output and stats_nslab = ceil(N/2/64)");
+      p.stats_out = fuse->stats_out; p.stats_nslab = fuse->stats_nslab;
+    }
+  }
   if (rope) {
     if (!p.tma_store || oe != 2 || act != ACT_NONE || rope->cols % 64 != 0 || rope->cols > N || rope->npos <= 0 || !rope->cos || !rope->sin)
       return fail(APE_ERR_INVALID_ARG, "gemm+rope: needs a 16-bit aligned output, no activation, rope_cols a multiple of 64 <= N");
@@ -870,6 +954,15 @@ extern "C" int ape_gemm_tn_ex(const void *A, int64_t lda, const void *W, int64_t
                               int in_dtype, int out_dtype, int act, int tile_n, void *stream) {
   return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, res_dtype, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr,
                    stream);
+}
+
+extern "C" int ape_gemm_tn_fused(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
+                                 const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype, int out_dtype,
+                                 int act, int tile_n, const float *ln_part, int ln_nparts, const float *ln_colsum, float ln_inv_c,
+                                 float ln_eps, float *stats_out, int stats_nslab, void *stream) {
+  FuseArgs f{ln_part, ln_colsum, ln_nparts, ln_inv_c, ln_eps, stats_out, stats_nslab};
+  return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, res_dtype, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr,
+                   stream, &f);
 }
 
 extern "C" int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,

@@ -239,6 +239,7 @@ msda_fwd_kernel(const MsdaParams p) {
 template <typename T, typename TO, int LPR, int U>
 __global__ void __launch_bounds__(threads_for(LPR))
 msda_fused_fwd_kernel(const MsdaParams p) {
+  pdl_prologue();
   using EO = Elem<TO>;
   constexpr int NT = threads_for(LPR);
   constexpr int R = NT / LPR;
@@ -440,7 +441,7 @@ int launch_fused(const MsdaParams &p, cudaStream_t st) {
   if (int rc = set_smem(k, smem)) return rc;
   const int QT = R >> p.ht_log2;
   dim3 grid((unsigned)(((p.Q + QT - 1) / QT) * (p.H >> p.ht_log2)), (unsigned)p.B);
-  k<<<grid, NT, smem, st>>>(p);
+  APE_LAUNCH(k, grid, NT, smem, st, p);
   return check_launch("msda_fused_fwd_kernel");
 }
 

@@ -126,6 +126,7 @@ __device__ __forceinline__ PairRec make_pair_rec(float x, float y, float a, int 
 // grid = (q_tiles * head_tiles, B), 256 threads = 32 rows (b, q, h) x 8 lanes; dynamic smem = 32 * 4L * 16 bytes.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) msda_pair_fused_kernel(const PairParams p) {
+  pdl_prologue();
   using V = typename H2<T>::V;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_lvl[kPairMaxLevels * 3];
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(256) msda_pair_fused_kernel(const PairParams p
 // multi_scale_deform_attn.py:286-287).  One thread per 16 bytes of output.
 __global__ void __launch_bounds__(256) msda_pair_values_kernel(const uint4 *__restrict__ value, long long ld16, uint4 *__restrict__ out,
                                                                const unsigned char *__restrict__ mask, int S, int H, long long total) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   // idx = (((b*S + s)*H + h)*2 + slot)*4 + c
@@ -285,7 +287,7 @@ extern "C" int ape_msda_pair_values(const void *value, int64_t ld, void *value2,
     return fail(APE_ERR_INVALID_ARG, "msda_pair_values: value rows must be 16-byte aligned, value2 128-byte aligned");
   const long long total = (long long)B * S * H * 8;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  msda_pair_values_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(value), ld * 2 / 16,
+  APE_LAUNCH((msda_pair_values_kernel), (unsigned)((total + 255) / 256), 256, 0, st, reinterpret_cast<const uint4 *>(value), ld * 2 / 16,
                                                                         reinterpret_cast<uint4 *>(value2), token_mask, S, H, total);
   return check_launch("msda_pair_values_kernel");
 }
@@ -354,11 +356,11 @@ extern "C" int ape_msda_pair_fused_fwd(const void *value2, const int64_t *shapes
   const size_t smem = (size_t)32 * L * 4 * sizeof(PairRec);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == APE_DTYPE_F16) {
-    if (offs_dtype == APE_DTYPE_F16) msda_pair_fused_kernel<__half, __half><<<grid, 256, smem, st>>>(p);
-    else msda_pair_fused_kernel<__half, float><<<grid, 256, smem, st>>>(p);
+    if (offs_dtype == APE_DTYPE_F16) APE_LAUNCH((msda_pair_fused_kernel<__half, __half>), grid, 256, smem, st, p);
+    else APE_LAUNCH((msda_pair_fused_kernel<__half, float>), grid, 256, smem, st, p);
   } else {
-    if (offs_dtype == APE_DTYPE_BF16) msda_pair_fused_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>(p);
-    else msda_pair_fused_kernel<__nv_bfloat16, float><<<grid, 256, smem, st>>>(p);
+    if (offs_dtype == APE_DTYPE_BF16) APE_LAUNCH((msda_pair_fused_kernel<__nv_bfloat16, __nv_bfloat16>), grid, 256, smem, st, p);
+    else APE_LAUNCH((msda_pair_fused_kernel<__nv_bfloat16, float>), grid, 256, smem, st, p);
   }
   return check_launch("msda_pair_fused_kernel");
 }

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy,
                  const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ row_map,
                  int rows, int C, float eps) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const TI *xr = x + (size_t)warp * ldx;
@@ -117,6 +118,7 @@ layernorm_ex_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y,
                     const float *__restrict__ b, float eps, const float *__restrict__ w2, const float *__restrict__ b2,
                     float eps2, const float *__restrict__ col_add, long long col_add_stride, int rows_per_image,
                     const TO *__restrict__ row_add, long long ld_add, TO *__restrict__ y2, long long ldy2, int rows, int C) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const TI *xr = x + (size_t)warp * ldx;
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(256)
 layernorm_wide_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy,
                       const float *__restrict__ w, const float *__restrict__ b, const int *__restrict__ row_map,
                       int rows, int C, float eps) {
+  pdl_prologue();
   __shared__ float s_part[8];
   const int row = blockIdx.x;
   const bool wb_aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
@@ -297,6 +300,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rope_qk_kernel(T *__restrict__ qkv, long long ld, const float *__restrict__ cosr, const float *__restrict__ sinr,
                const int *__restrict__ pos_map, int M, int C, int hd, int npos) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vec_per_row = 2 * C / 8;  // q and k only
   if (idx >= (long long)M * vec_per_row) return;
@@ -322,11 +326,11 @@ int launch_ln(const void *x, long long ldx, void *y, long long ldy, const float 
   const int blocks = (rows + 7) / 8;
   const bool aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
   if (C <= 256 && aligned)
-    layernorm_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+    APE_LAUNCH((layernorm_kernel<TI, TO, 1>), blocks, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
   else if (C <= 1024 && aligned)
-    layernorm_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+    APE_LAUNCH((layernorm_kernel<TI, TO, 4>), blocks, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
   else  // one CTA per row, row held in registers (also valid in place)
-    layernorm_wide_kernel<TI, TO><<<rows, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
+    APE_LAUNCH((layernorm_wide_kernel<TI, TO>), rows, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, w, b, row_map, rows, C, eps);
   return check_launch("layernorm_kernel");
 }
 
@@ -383,10 +387,10 @@ extern "C" int ape_layernorm_ex(const void *x, int64_t ldx, void *y, int64_t ldy
 #define APE_LNX(TI, TO)                                                                                                   \
   do {                                                                                                                    \
     if (C <= 256)                                                                                                         \
-      ape::layernorm_ex_kernel<TI, TO, 1><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
+      APE_LAUNCH((ape::layernorm_ex_kernel<TI, TO, 1>), blocks, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
           col_add, col_add_stride, rows_per_image > 0 ? rows_per_image : 1, (const TO *)row_add, ld_add, (TO *)y2, ldy2, rows, C);  \
     else                                                                                                                  \
-      ape::layernorm_ex_kernel<TI, TO, 4><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
+      APE_LAUNCH((ape::layernorm_ex_kernel<TI, TO, 4>), blocks, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, weight, bias, eps, weight2, bias2, eps2, \
           col_add, col_add_stride, rows_per_image > 0 ? rows_per_image : 1, (const TO *)row_add, ld_add, (TO *)y2, ldy2, rows, C);  \
     return check_launch("layernorm_ex_kernel");                                                                          \
   } while (0)
@@ -411,11 +415,11 @@ extern "C" int ape_rope_qk(void *qkv, int64_t ld, const float *cos_table, const 
   const long long n = (long long)M * (2 * C / 8);
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (dtype == APE_DTYPE_F32)
-    rope_qk_kernel<float><<<blocks, 256, 0, st>>>((float *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+    APE_LAUNCH((rope_qk_kernel<float>), blocks, 256, 0, st, (float *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
   else if (dtype == APE_DTYPE_F16)
-    rope_qk_kernel<__half><<<blocks, 256, 0, st>>>((__half *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+    APE_LAUNCH((rope_qk_kernel<__half>), blocks, 256, 0, st, (__half *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
   else if (dtype == APE_DTYPE_BF16)
-    rope_qk_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16 *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
+    APE_LAUNCH((rope_qk_kernel<__nv_bfloat16>), blocks, 256, 0, st, (__nv_bfloat16 *)qkv, ld, cos_table, sin_table, pos_map, M, C, head_dim, npos);
   else
     return fail(APE_ERR_INVALID_ARG, "rope: unknown dtype %d", dtype);
   return check_launch("rope_qk_kernel");
@@ -436,6 +440,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gn_partial_kernel(const T *__restrict__ x, long long ldx, int rows_per_image, int C, int cpg,
                   float *__restrict__ partial /* [B, strips, C/8, 2] */) {
+  pdl_prologue();
   const int vec_per_row = C / 8;
   const int b = blockIdx.y, strip = blockIdx.x;
   const int r0 = strip * kGnRowsPerCta, r1 = min(rows_per_image, r0 + kGnRowsPerCta);
@@ -464,6 +469,7 @@ gn_partial_kernel(const T *__restrict__ x, long long ldx, int rows_per_image, in
 // one warp per (b, group): lanes stride over the strips (fixed assignment -> deterministic), fp64 fold
 __global__ void gn_finalize_kernel(const float *__restrict__ partial, int B, int strips, int vec_per_row, int vec_per_group,
                                    float count, float eps, float *__restrict__ stats /* [B, G, 2] mean, rstd */) {
+  pdl_prologue();
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int G = vec_per_row / vec_per_group;
   if (idx >= B * G) return;
@@ -493,6 +499,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const TI *__restrict__ x, long long ldx, TO *__restrict__ y, long long ldy, long long y_batch_stride,
                 const float *__restrict__ w, const float *__restrict__ bias, const float *__restrict__ stats, int rows_per_image,
                 long long total_rows, int C, int vec_per_group) {
+  pdl_prologue();
   const int vec_per_row = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_rows * vec_per_row) return;
@@ -533,15 +540,15 @@ extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t l
   const int vpr = C / 8, vpg = C / groups / 8;
   float *partial = reinterpret_cast<float *>(workspace);
   float *stats = partial + (size_t)B * strips * vpr * 2;
-  if (in_dtype == APE_DTYPE_F32) gn_partial_kernel<float><<<dim3(strips, B), 256, 0, st>>>((const float *)x, ldx, rows_per_image, C, C / groups, partial);
-  else if (in_dtype == APE_DTYPE_F16) gn_partial_kernel<__half><<<dim3(strips, B), 256, 0, st>>>((const __half *)x, ldx, rows_per_image, C, C / groups, partial);
-  else gn_partial_kernel<__nv_bfloat16><<<dim3(strips, B), 256, 0, st>>>((const __nv_bfloat16 *)x, ldx, rows_per_image, C, C / groups, partial);
+  if (in_dtype == APE_DTYPE_F32) APE_LAUNCH((gn_partial_kernel<float>), dim3(strips, B), 256, 0, st, (const float *)x, ldx, rows_per_image, C, C / groups, partial);
+  else if (in_dtype == APE_DTYPE_F16) APE_LAUNCH((gn_partial_kernel<__half>), dim3(strips, B), 256, 0, st, (const __half *)x, ldx, rows_per_image, C, C / groups, partial);
+  else APE_LAUNCH((gn_partial_kernel<__nv_bfloat16>), dim3(strips, B), 256, 0, st, (const __nv_bfloat16 *)x, ldx, rows_per_image, C, C / groups, partial);
   if (int rc = check_launch("gn_partial_kernel")) return rc;
-  gn_finalize_kernel<<<(B * groups + 3) / 4, 128, 0, st>>>(partial, B, strips, vpr, vpg, (float)rows_per_image * (C / groups), eps, stats);
+  APE_LAUNCH((gn_finalize_kernel), (B * groups + 3) / 4, 128, 0, st, partial, B, strips, vpr, vpg, (float)rows_per_image * (C / groups), eps, stats);
   if (int rc = check_launch("gn_finalize_kernel")) return rc;
   const long long total_rows = (long long)B * rows_per_image;
   const unsigned blocks = (unsigned)((total_rows * vpr + 255) / 256);
-#define APE_GN(TI, TO) gn_apply_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI *)x, ldx, (TO *)y, ldy, y_batch_stride, weight, bias, stats, rows_per_image, total_rows, C, vpg)
+#define APE_GN(TI, TO) APE_LAUNCH((gn_apply_kernel<TI, TO>), blocks, 256, 0, st, (const TI *)x, ldx, (TO *)y, ldy, y_batch_stride, weight, bias, stats, rows_per_image, total_rows, C, vpg)
   if (in_dtype == APE_DTYPE_F32 && out_dtype == APE_DTYPE_F32) APE_GN(float, float);
   else if (in_dtype == APE_DTYPE_F16 && out_dtype == APE_DTYPE_F16) APE_GN(__half, __half);
   else if (in_dtype == APE_DTYPE_BF16 && out_dtype == APE_DTYPE_BF16) APE_GN(__nv_bfloat16, __nv_bfloat16);

@@ -34,6 +34,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 vlf_scores_kernel(const T *__restrict__ v, const float *__restrict__ qa, const float *__restrict__ qc,
                   float *__restrict__ scores, float *__restrict__ blockmax, int S, int NH, int strip) {
+  pdl_prologue();
   constexpr int C = 256;
   __shared__ float s_max[8][kMaxHeads];
   const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,6 +98,7 @@ vlf_scores_kernel(const T *__restrict__ v, const float *__restrict__ qa, const f
 // one warp per (b, h) pair (round-robin), lanes stride over the per-CTA maxima of pass 1.
 __global__ void __launch_bounds__(1024)
 vlf_max_kernel(const float *__restrict__ blockmax, int B, int nblk, int NH, float *__restrict__ maxes) {
+  pdl_prologue();
   __shared__ float s_row[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = warp; t < B * NH; t += 32) {
@@ -125,6 +127,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 vlf_pool_kernel(const T *__restrict__ v, const float *__restrict__ scores, const float *__restrict__ maxes,
                 float *__restrict__ partial, int S, int NH, int strip, int stable_2d) {
+  pdl_prologue();
   constexpr int C = 256;
   __shared__ __align__(16) float s_e[kMaxStrip][kMaxHeads];
   __shared__ __align__(16) float s_red[8][C];
@@ -222,15 +225,15 @@ extern "C" int ape_vlf_pool(const void *v, const float *qa, const float *qc, voi
   float *maxes = blockmax + (size_t)B * nct * NH;
   float *partial = maxes + 1 + (size_t)B * NH;
   const dim3 grid(nct, B);
-  if (dtype == APE_DTYPE_F32) vlf_scores_kernel<float><<<grid, 256, 0, st>>>((const float *)v, qa, qc, scores, blockmax, S, NH, strip);
-  else if (dtype == APE_DTYPE_F16) vlf_scores_kernel<__half><<<grid, 256, 0, st>>>((const __half *)v, qa, qc, scores, blockmax, S, NH, strip);
-  else vlf_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, qa, qc, scores, blockmax, S, NH, strip);
+  if (dtype == APE_DTYPE_F32) APE_LAUNCH((vlf_scores_kernel<float>), grid, 256, 0, st, (const float *)v, qa, qc, scores, blockmax, S, NH, strip);
+  else if (dtype == APE_DTYPE_F16) APE_LAUNCH((vlf_scores_kernel<__half>), grid, 256, 0, st, (const __half *)v, qa, qc, scores, blockmax, S, NH, strip);
+  else APE_LAUNCH((vlf_scores_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16 *)v, qa, qc, scores, blockmax, S, NH, strip);
   if (int rc = check_launch("vlf_scores_kernel")) return rc;
-  vlf_max_kernel<<<1, 1024, 0, st>>>(blockmax, B, nct, NH, maxes);
+  APE_LAUNCH((vlf_max_kernel), 1, 1024, 0, st, blockmax, B, nct, NH, maxes);
   if (int rc = check_launch("vlf_max_kernel")) return rc;
-  if (dtype == APE_DTYPE_F32) vlf_pool_kernel<float><<<grid, 256, 0, st>>>((const float *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
-  else if (dtype == APE_DTYPE_F16) vlf_pool_kernel<__half><<<grid, 256, 0, st>>>((const __half *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
-  else vlf_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
+  if (dtype == APE_DTYPE_F32) APE_LAUNCH((vlf_pool_kernel<float>), grid, 256, 0, st, (const float *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
+  else if (dtype == APE_DTYPE_F16) APE_LAUNCH((vlf_pool_kernel<__half>), grid, 256, 0, st, (const __half *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
+  else APE_LAUNCH((vlf_pool_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16 *)v, scores, maxes, partial, S, NH, strip, stable_softmax_2d);
   if (partial_out) *partial_out = partial;
   if (strips_out) *strips_out = nct;
   return check_launch("vlf_pool_kernel");

@@ -212,6 +212,9 @@ class ViT(nn.Module):
             for i in range(depth)])
         self.fused_rope = False
         self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
+        # inner_attn_ln / ffn_ln folded around proj / w3 (ape_gemm_tn_fused): two LayerNorm launches and two trips of the
+        # activations through HBM fewer per block
+        self.fold_sub_layernorms = True
         self._out_feature_channels = {out_feature: embed_dim}
         self._out_feature_strides = {out_feature: patch_size}
         self._out_features = [out_feature]
@@ -286,6 +289,16 @@ class ViT(nn.Module):
                     w12=w12.to(device, dtype).contiguous(), b12=b12.to(**f32).contiguous(),
                     fw=m.ffn_ln.weight.to(**f32).contiguous(), fb=m.ffn_ln.bias.to(**f32).contiguous(),
                     w3=w3, b3=m.w3.bias.to(**f32).contiguous(), hid=hid, hid_p=hid_p))
+                # sub-LayerNorms folded around the GEMM that follows them (ape_gemm_tn_fused): gamma .* W as the 16-bit
+                # operand, its row sums, and beta W^T + b as the bias
+                d = packed["blocks"][-1]
+                wp = (a.proj.weight.float() * a.inner_attn_ln.weight.float()[None, :]).to(device, dtype).contiguous()
+                d.update(wproj_ln=wp, sproj=wp.float().sum(1).contiguous(),
+                         bproj_ln=(a.proj.weight.float() @ a.inner_attn_ln.bias.float() + a.proj.bias.float()).to(**f32).contiguous())
+                w3l = torch.zeros(m.w3.weight.shape[0], hid_p, dtype=dtype, device=device)
+                w3l[:, :hid] = (m.w3.weight.float() * m.ffn_ln.weight.float()[None, :]).to(dtype)
+                d.update(w3_ln=w3l, s3=w3l.float().sum(1).contiguous(),
+                         b3_ln=(m.w3.weight.float() @ m.ffn_ln.bias.float() + m.w3.bias.float()).to(**f32).contiguous())
         packs[dtype] = (key, packed)
         return packed
 
@@ -350,19 +363,31 @@ class ViT(nn.Module):
                     qkv = ops.linear_tc(h, p["wqkv"], p["bqkv"])
                     ops.rope_qk_(qkv, rope_glb[0], rope_glb[1], C, hd, pos_map=geo["glb_map"])
                 nb, n = B, g * g
+            fold = self.fold_sub_layernorms
             if self.engine_attention and ops.attention_supported(n, hd, qkv.dtype):
-                o = ops.attention_qkv(qkv, nb, n, heads, hd, blk.attn.scale)  # tcgen05 flash attention, no head-split copies
+                # tcgen05 flash attention, no head-split copies; with `fold` it also leaves per-(row, head) statistics
+                o = ops.attention_qkv(qkv, nb, n, heads, hd, blk.attn.scale, stats_out=fold)
+                o, st = o if fold else (o, None)
             else:
                 q5 = qkv.view(nb, n, 3, heads, hd)
                 o = F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2),
                                                    q5[:, :, 2].transpose(1, 2), scale=blk.attn.scale)
-                o = o.transpose(1, 2).reshape(M, C)
-            a = ops.layernorm(o, p["lnw"], p["lnb"], eps=1e-6)
-            x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x, out_dtype=torch.float32)
+                o, st = o.transpose(1, 2).reshape(M, C), None
+            if st is not None:  # inner_attn_ln folded into proj: the raw attention output is the GEMM operand
+                x = ops.linear_tc(o, p["wproj_ln"], p["bproj_ln"], residual=x, out_dtype=torch.float32,
+                                  ln_fold=(st, p["sproj"], C, 1e-6))
+            else:
+                a = ops.layernorm(o, p["lnw"], p["lnb"], eps=1e-6)
+                x = ops.linear_tc(a, p["wproj"], p["bproj"], residual=x, out_dtype=torch.float32)
             h = ops.layernorm(x, p["n2w"], p["n2b"], eps=1e-6, out_dtype=dtype)
-            ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]])
-            ops.layernorm(hbuf[:, :p["hid"]], p["fw"], p["fb"], eps=1e-6, out=hbuf2[:, :p["hid"]])
-            x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x, out_dtype=torch.float32)
+            if fold:  # ffn_ln folded into w3: the SwiGLU epilogue leaves the row statistics of the hidden it writes
+                _, st2 = ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]], stats_out=True)
+                x = ops.linear_tc(hbuf[:, :p["hid"]], p["w3_ln"][:, :p["hid"]], p["b3_ln"], residual=x, out_dtype=torch.float32,
+                                  ln_fold=(st2, p["s3"], p["hid"], 1e-6))
+            else:
+                ops.linear_tc(h, p["w12"], p["b12"], act="swiglu", out=hbuf[:, :p["hid"]])
+                ops.layernorm(hbuf[:, :p["hid"]], p["fw"], p["fb"], eps=1e-6, out=hbuf2[:, :p["hid"]])
+                x = ops.linear_tc(hbuf2[:, :p["hid"]], p["w3"][:, :p["hid"]], p["b3"], residual=x, out_dtype=torch.float32)
         # back to raster order: [B, g, g, C] tokens (NHWC memory), 16-bit operand of the pyramid GEMMs
         return x.to(dtype).view(B, g * g, C)[:, geo["inv"]].view(B, g, g, C)
 

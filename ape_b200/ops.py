@@ -188,11 +188,14 @@ def ms_deform_attn_pair_fused_forward(value2, spatial_shapes, level_start_index,
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "swiglu": 3, "clamp": 4}
 
 
-def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0, out=None):
+def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, tile_n=0, out=None, ln_fold=None, stats_out=False):
     """act(x @ weight.T + bias) (+ residual) on the tcgen05 tensor cores (ape_gemm_tn).
 
     x [..., K] and weight [N, K] fp16/bf16 with unit inner stride; bias fp32 [N] (or None); residual
-    [..., N] fp32 / fp16 / bf16 (any of them with any output dtype: fp32 sums over 16-bit operands).  act="swiglu": weight rows are interleaved (gate_j, up_j) pairs and the
+    [..., N] fp32 / fp16 / bf16 (any of them with any output dtype: fp32 sums over 16-bit operands).
+    ln_fold = (part [M, nparts, 2] fp32, colsum [N] fp32, C, eps): a LayerNorm over x's C columns folded around the GEMM
+    (ape_gemm_tn_fused): x is the RAW tensor, weight = gamma .* W, bias = beta W^T + b, fp32 output.
+    stats_out=True (act "swiglu"): also returns fp32 [M, ceil(N/2/64), 2] row statistics of the output slabs.  act="swiglu": weight rows are interleaved (gate_j, up_j) pairs and the
     result has N/2 columns."""
     _require(x.is_cuda and weight.is_cuda, "linear_tc: CUDA tensors only")
     _require(x.dtype == weight.dtype and x.dtype in (torch.float16, torch.bfloat16), "linear_tc: fp16/bf16 operands")
@@ -220,13 +223,36 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
         res_ptr, ldr, res_dt = r2.data_ptr(), r2.stride(0), _lib.dtype_code(r2.dtype)
     if bias is not None:
         _require(bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == N, "linear_tc: bias must be fp32 [N]")
-    with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
-        rc = _lib.lib.ape_gemm_tn_ex(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
-                                     out.stride(0), bias.data_ptr() if bias is not None else None, res_ptr, ldr, res_dt,
-                                     M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
-                                     _lib.current_stream_ptr())
-    _lib.check(rc, "ape_gemm_tn")
-    return out.view(*x.shape[:-1], n_out) if ret_view else out
+    stats = None
+    if ln_fold is not None or stats_out:
+        part, colsum, nparts, inv_c, eps = None, None, 0, 0.0, 0.0
+        if ln_fold is not None:
+            part, colsum, C, eps = ln_fold
+            _require(part.dtype == torch.float32 and part.is_contiguous() and part.dim() == 3 and part.shape[0] == M and
+                     part.shape[2] == 2, "linear_tc: ln_fold partials must be fp32 [M, nparts, 2]")
+            _require(colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == N, "linear_tc: colsum fp32 [N]")
+            nparts, inv_c = part.shape[1], 1.0 / float(C)
+        nslab = 0
+        if stats_out:
+            nslab = (n_out + 63) // 64
+            stats = torch.empty((M, nslab, 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
+            rc = _lib.lib.ape_gemm_tn_fused(
+                x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(), out.stride(0),
+                bias.data_ptr() if bias is not None else None, res_ptr, ldr, res_dt, M, N, K, _lib.dtype_code(x.dtype),
+                _lib.dtype_code(out_dtype), ACT[act], int(tile_n), part.data_ptr() if part is not None else None, int(nparts),
+                colsum.data_ptr() if colsum is not None else None, float(inv_c), float(eps),
+                stats.data_ptr() if stats is not None else None, int(nslab), _lib.current_stream_ptr())
+        _lib.check(rc, "ape_gemm_tn_fused")
+    else:
+        with torch.cuda.device(x.device), _timed(("gemm_tn", M, N, K)):
+            rc = _lib.lib.ape_gemm_tn_ex(x2.data_ptr(), x2.stride(0), weight.data_ptr(), weight.stride(0), out.data_ptr(),
+                                         out.stride(0), bias.data_ptr() if bias is not None else None, res_ptr, ldr, res_dt,
+                                         M, N, K, _lib.dtype_code(x.dtype), _lib.dtype_code(out_dtype), ACT[act], int(tile_n),
+                                         _lib.current_stream_ptr())
+        _lib.check(rc, "ape_gemm_tn")
+    res = out.view(*x.shape[:-1], n_out) if ret_view else out
+    return (res, stats) if stats_out else res
 
 
 def linear_rope_tc(x, weight, bias, cos, sin, num_channels, head_dim, pos_map=None):
@@ -374,19 +400,22 @@ def attention_supported(n, head_dim, dtype):
     return head_dim == 64 and n % 128 == 0 and dtype in (torch.float16, torch.bfloat16)
 
 
-def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None):
+def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None, stats_out=False):
     """softmax(q k^T * scale) v for every (sequence, head) straight from the fused qkv buffer [num_seq*n, 3*heads*64]
     (ape_attn_fwd: flash attention on the tcgen05 tensor cores).  Returns [num_seq*n, heads*64].
-    n_valid: sequences are padded to n rows and only the first n_valid keys count (rows beyond must be finite)."""
+    n_valid: sequences are padded to n rows and only the first n_valid keys count (rows beyond must be finite).
+    stats_out=True: also returns fp32 [rows, heads, 2] (sum, sum of squares of each row's stored values per head)."""
     _require(qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1, "attention: qkv must be a 2-D CUDA tensor")
     _require(qkv.shape[0] == num_seq * n and qkv.shape[1] == 3 * heads * head_dim, "attention: qkv shape")
     out = torch.empty((qkv.shape[0], heads * head_dim), dtype=qkv.dtype, device=qkv.device)
+    stats = torch.empty((qkv.shape[0], heads, 2), dtype=torch.float32, device=qkv.device) if stats_out else None
     with torch.cuda.device(qkv.device), _timed(("attention", num_seq, n, heads)):
         rc = _lib.lib.ape_attn_fwd_ex(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), int(num_seq), int(n),
                                       int(n if n_valid is None else n_valid), int(heads), int(head_dim), float(scale),
-                                      _lib.dtype_code(qkv.dtype), _lib.current_stream_ptr())
+                                      _lib.dtype_code(qkv.dtype), stats.data_ptr() if stats is not None else None,
+                                      _lib.current_stream_ptr())
     _lib.check(rc, "ape_attn_fwd")
-    return out
+    return (out, stats) if stats_out else out
 
 
 def vlf_pool(v, qa, qc, stable_softmax_2d=True):

@@ -160,6 +160,19 @@ int ape_gemm_tn_ex(const void *A, int64_t lda, const void *W, int64_t ldw, void 
                    int act, int tile_n, void *stream);
 
 /*
+ * ape_gemm_tn_ex with a LayerNorm folded around it (the sub-LayerNorms of the EVA-02 block, vit_eva_clip.py:266,130):
+ *   consume: ln_part [M, ln_nparts, 2] per-row partial (sum, sum of squares) of the RAW 16-bit A written by its producer;
+ *            W must hold gamma .* W, ln_colsum [N] its row sums (of the 16-bit values), bias = beta W^T + b; the epilogue forms
+ *            rstd * (A W'^T - mean * colsum) + bias (+ residual); fp32 output only.  ln_inv_c = 1 / C, ln_eps as the LayerNorm.
+ *   produce: stats_out [M, ceil(N/2/64), 2] with act = SwiGLU: (sum, sum of squares) of every 64-column slab of the output.
+ * Either half may be disabled with NULL.
+ */
+int ape_gemm_tn_fused(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
+                      const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype, int out_dtype,
+                      int act, int tile_n, const float *ln_part, int ln_nparts, const float *ln_colsum, float ln_inv_c,
+                      float ln_eps, float *stats_out, int stats_nslab, void *stream);
+
+/*
  * ape_gemm_tn with the 2-D rotary embedding of the ViT (VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346) fused into
  * the epilogue: C = A W^T + bias, then t' = t*cos + rotate_half(t)*sin on output columns [0, rope_cols) — the q and k
  * thirds of the fused qkv projection (vit_eva_clip.py:225-262) — in fp32 before the single rounding to the 16-bit
@@ -224,8 +237,10 @@ int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_se
 /* Same with sequences padded to n rows: only the first n_valid keys of every sequence take part in the softmax (the rows
  * beyond must hold finite values, e.g. zeros).  Used for the self-attention over the 900 decoder queries
  * (deformable_transformer_vl.py:142-147: nn.MultiheadAttention, 8 heads x 32 — heads zero-padded to 64 channels). */
+/* stats_out (or NULL): fp32 [rows, heads, 2] — per row and head the (sum, sum of squares) of the 64 output values as stored,
+ * consumed by ape_gemm_tn_fused to fold the LayerNorm that follows (inner_attn_ln, vit_eva_clip.py:266) into the projection. */
 int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                    int head_dim, float scale, int dtype, void *stream);
+                    int head_dim, float scale, int dtype, float *stats_out, void *stream);
 
 /*
  * Language-side attention pooling of VisionLanguageFusion for a single language token ("name" prompts):

@@ -62,3 +62,14 @@ def test_attention_padded_sequences_mask_keys(ops, num_seq, n, n_valid, heads):
     want = ref_attention(qkv[:, :n_valid].reshape(num_seq * n_valid, -1), num_seq, n_valid, heads, hd, 0.2).view(num_seq, n_valid, -1)
     torch.testing.assert_close(got[:, :n_valid].float(), want, rtol=2e-3, atol=2e-3)
     assert torch.isfinite(got).all()
+
+
+def test_attention_row_statistics_output(ops):
+    """stats_out: per (row, head) sum and sum of squares of the stored 16-bit outputs (for the LayerNorm folded into proj)."""
+    num_seq, n, heads, hd = 2, 256, 4, 64
+    qkv = torch.randn(num_seq * n, 3 * heads * hd, generator=torch.Generator().manual_seed(5)).to(DEV, torch.float16)
+    out, st = ops.attention_qkv(qkv, num_seq, n, heads, hd, 0.125, stats_out=True)
+    assert st.shape == (num_seq * n, heads, 2)
+    o = out.float().view(num_seq * n, heads, hd)
+    torch.testing.assert_close(st[..., 0], o.sum(-1), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(st[..., 1], (o ** 2).sum(-1), rtol=1e-5, atol=1e-4)

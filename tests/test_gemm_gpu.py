@@ -172,3 +172,57 @@ def test_qkv_projection_with_fused_rope(ops, dtype, tol, use_map):
 
     want = torch.cat([rope(y[:, :C]), rope(y[:, C:2 * C]), y[:, 2 * C:]], 1)
     torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,nparts", [(256, 256, 256, 4), (4096, 1024, 1024, 16), (4096, 1024, 2730, 43), (300, 96, 200, 4)])
+def test_fp32_output_residual_dtypes_and_layernorm_fold(ops, dtype, M, N, K, nparts):
+    """fp32 output through the TMA epilogue with a 16-bit / fp32 residual, and a LayerNorm folded around the GEMM
+    (ape_gemm_tn_fused): rstd * (a (gamma .* W)^T - mean * colsum) + (beta W^T + b) == Linear(LayerNorm(a))."""
+    Kp = (K + 7) // 8 * 8
+    a = torch.zeros(M, Kp, dtype=dtype, device=DEV)
+    a[:, :K] = rnd(M, K, dtype=dtype, seed=1, scale=2.0) + 0.7      # non-zero mean rows
+    w = rnd(N, K, dtype=torch.float32, seed=2, scale=K ** -0.5)
+    b = rnd(N, dtype=torch.float32, seed=3)
+    gamma = 1.0 + 0.1 * rnd(K, dtype=torch.float32, seed=4)
+    beta = 0.1 * rnd(K, dtype=torch.float32, seed=5)
+    res16 = rnd(M, N, dtype=dtype, seed=6)
+    res32 = rnd(M, N, dtype=torch.float32, seed=7)
+    # plain fp32-out paths
+    w16 = torch.zeros(N, Kp, dtype=dtype, device=DEV)
+    w16[:, :K] = w.to(dtype)
+    for res in (None, res16, res32):
+        got = ops.linear_tc(a[:, :K], w16[:, :K], b, residual=res, out_dtype=torch.float32)
+        want = ref_linear(a[:, :K], w16[:, :K], b, residual=res)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-3)
+    # LayerNorm fold: partial statistics in `nparts` chunks, as a producer kernel would leave them
+    af = a[:, :K].float()
+    edges = torch.linspace(0, K, nparts + 1).round().long().tolist()
+    part = torch.stack([torch.stack([af[:, s:e].sum(1), (af[:, s:e] ** 2).sum(1)], -1) for s, e in zip(edges[:-1], edges[1:])], 1).contiguous()
+    wl = torch.zeros(N, Kp, dtype=dtype, device=DEV)
+    wl[:, :K] = (w * gamma[None, :]).to(dtype)
+    colsum = wl.float().sum(1).contiguous()
+    bias = (w @ beta + b).contiguous()
+    got = ops.linear_tc(a[:, :K], wl[:, :K], bias, residual=res32, out_dtype=torch.float32, ln_fold=(part, colsum, K, 1e-6))
+    want = F.linear(F.layer_norm(af, (K,), gamma, beta, 1e-6), wl[:, :K].float() / gamma[None, :], b) + res32
+    # the reference applies gamma after normalising, the fold before rounding W: identical up to the 16-bit rounding of W'
+    torch.testing.assert_close(got, want, rtol=2e-3, atol=2e-2 if dtype == torch.bfloat16 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_swiglu_epilogue_row_statistics(ops, dtype):
+    M, K, hid = 300, 256, 2730
+    x = rnd(M, K, dtype=dtype, seed=11)
+    w = rnd(2 * hid, K, dtype=dtype, seed=12, scale=K ** -0.5)
+    b = rnd(2 * hid, dtype=torch.float32, seed=13)
+    hp = (hid + 7) // 8 * 8
+    buf = torch.zeros(M, hp, dtype=dtype, device=DEV)
+    out, st = ops.linear_tc(x, w, b, act="swiglu", out=buf[:, :hid], stats_out=True)
+    nslab = (hid + 63) // 64
+    assert st.shape == (M, nslab, 2)
+    of = out.float()
+    for sidx in (0, 1, nslab // 2, nslab - 1):
+        sl = of[:, sidx * 64: min(hid, sidx * 64 + 64)]
+        torch.testing.assert_close(st[:, sidx, 0], sl.sum(1), rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(st[:, sidx, 1], (sl ** 2).sum(1), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(st[..., 0].sum(1), of.sum(1), rtol=1e-4, atol=1e-2)
