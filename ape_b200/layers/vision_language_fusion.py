@@ -36,6 +36,36 @@ class BiMultiHeadAttention(nn.Module):
             nn.init.xavier_uniform_(m.weight)
             m.bias.data.fill_(0)
 
+    def forward_engine(self, v, l):
+        """Engine path for several language tokens (phrase / text prompts): the six projections are tcgen05 GEMMs and
+        each softmax direction is ONE flash-attention pass of ape_attn_cross_fwd over 256-channel heads — the S x N_t
+        score matrix of fuse_helper.py:86 (31 GB per head set at 1536^2 / 5 000 phrases) is never materialised, there is
+        no host synchronisation and no data-dependent choice of algorithm.  v [B,S,v_dim] 16-bit and l [B,N,l_dim] are the
+        layer-normed inputs.  Returns (delta_v [B,S,v_dim] 16-bit, delta_l [B,N,l_dim] fp32)."""
+        from .. import ops
+
+        dt = v.dtype
+        B, S, _ = v.shape
+        N = l.shape[1]
+        nh, hd, E = self.num_heads, self.head_dim, self.embed_dim
+        Sp, Np = (S + 127) // 128 * 128, (N + 127) // 128 * 128  # padded rows (zeros): queries in tiles of 128, keys of 64
+        l16 = l.to(dt)
+        qv = torch.zeros((B, Sp, E), dtype=dt, device=v.device)   # v_proj(v): queries of direction 1, keys of direction 2
+        vv = torch.zeros((B, Sp, E), dtype=dt, device=v.device)   # values_v_proj(v)
+        kl = torch.zeros((B, Np, E), dtype=dt, device=v.device)   # l_proj(l)
+        vl = torch.zeros((B, Np, E), dtype=dt, device=v.device)   # values_l_proj(l)
+        for b in range(B):
+            ops.linear_module_tc(self.v_proj, v[b], out=qv[b, :S])
+            ops.linear_module_tc(self.values_v_proj, v[b], out=vv[b, :S])
+            ops.linear_module_tc(self.l_proj, l16[b], out=kl[b, :N])
+            ops.linear_module_tc(self.values_l_proj, l16[b], out=vl[b, :N])
+        # vision <- language: softmax over the N phrases (fuse_helper.py:127-141);  language <- vision: over the S tokens (:94-125)
+        out_v = ops.attention_cross(qv.view(B * Sp, E), kl.view(B * Np, E), vl.view(B * Np, E), B, Sp, Np, N, nh, hd, self.scale)
+        out_l = ops.attention_cross(kl.view(B * Np, E), qv.view(B * Sp, E), vv.view(B * Sp, E), B, Np, Sp, S, nh, hd, self.scale)
+        dv = torch.stack([ops.linear_module_tc(self.out_v_proj, out_v.view(B, Sp, E)[b, :S]) for b in range(B)])
+        dl = torch.stack([ops.linear_module_tc(self.out_l_proj, out_l.view(B, Np, E)[b, :N], out_dtype=torch.float32) for b in range(B)])
+        return dv, dl
+
     def _clamp(self, w):
         if self.clamp_min_for_underflow:
             w = torch.clamp(w, min=-50000)
@@ -102,6 +132,17 @@ class BiAttentionBlock(nn.Module):
 
     def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
         # fuse_helper.py:221-232 — note the residual is added to the *normalised* v / l
+        a = self.attn
+        if v.is_cuda and v.dtype in (torch.float16, torch.bfloat16) and l.shape[1] > 1 and attention_mask_l is None and \
+                not (a.use_attention_mask_v and attention_mask_v is not None) and a.head_dim in (64, 256) and \
+                v.shape[-1] % 8 == 0 and l.shape[-1] % 8 == 0:
+            from .. import ops  # engine: LayerNorm kernel, tcgen05 GEMMs, two flash-attention passes (forward_engine)
+
+            vn = ops.layernorm_module(self.layer_norm_v, v.contiguous())
+            with torch.autocast("cuda", enabled=False):
+                ln = self.layer_norm_l(l.float())
+            dv, dl = a.forward_engine(vn, ln)
+            return vn + self.gamma_v.to(vn.dtype) * dv, ln + self.gamma_l.float() * dl
         v = self.layer_norm_v(v)
         l = self.layer_norm_l(l)
         if l.shape[1] == 1 and attention_mask_l is None and not (self.attn.use_attention_mask_v and attention_mask_v is not None):

@@ -301,10 +301,10 @@ def packed(module, dtype, extra=None):
         None if b is None else b.detach().to(torch.float32).contiguous()))
 
 
-def linear_module_tc(module, x, act=None, residual=None, out_dtype=None):
+def linear_module_tc(module, x, act=None, residual=None, out_dtype=None, out=None):
     """nn.Linear forward on the tensor cores (weights packed once per dtype)."""
     w, b = packed(module, x.dtype)
-    return linear_tc(x, w, b, act=act, residual=residual, out_dtype=out_dtype)
+    return linear_tc(x, w, b, act=act, residual=residual, out_dtype=out_dtype, out=out)
 
 
 def layernorm_module(module, x, out_dtype=None):
@@ -416,6 +416,23 @@ def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None, stats_o
                                       _lib.current_stream_ptr())
     _lib.check(rc, "ape_attn_fwd")
     return (out, stats) if stats_out else out
+
+
+def attention_cross(q, k, v, num_seq, nq, nkv, n_valid, heads, head_dim, scale):
+    """softmax(q k^T * scale) v with separate tensors and 64- / 256-channel heads (ape_attn_cross_fwd).
+    q [num_seq*nq, heads*head_dim], k / v [num_seq*nkv, heads*head_dim] (rows may be column slices of wider buffers);
+    nq % 128 == 0, nkv % 64 == 0, keys >= n_valid masked.  Returns [num_seq*nq, heads*head_dim]."""
+    for t in (q, k, v):
+        _require(t.is_cuda and t.dim() == 2 and t.stride(1) == 1 and t.dtype == q.dtype, "attention_cross: 2-D CUDA tensors of one dtype")
+    C = heads * head_dim
+    _require(q.shape == (num_seq * nq, C) and k.shape == (num_seq * nkv, C) and v.shape == (num_seq * nkv, C), "attention_cross: shapes")
+    out = torch.empty((num_seq * nq, C), dtype=q.dtype, device=q.device)
+    with torch.cuda.device(q.device), _timed(("attention_cross", num_seq, nq, n_valid, heads, head_dim)):
+        rc = _lib.lib.ape_attn_cross_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                         out.data_ptr(), out.stride(0), int(num_seq), int(nq), int(nkv), int(n_valid), int(heads),
+                                         int(head_dim), float(scale), _lib.dtype_code(q.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_attn_cross_fwd")
+    return out
 
 
 def vlf_pool(v, qa, qc, stable_softmax_2d=True):

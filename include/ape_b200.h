@@ -243,6 +243,19 @@ int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num
                     int head_dim, float scale, int dtype, float *stats_out, void *stream);
 
 /*
+ * Cross attention with separate Q / K / V tensors and 64- or 256-channel heads: the two softmax attentions of
+ * VisionLanguageFusion for phrase / text prompts (BiMultiHeadAttention.forward, ape/layers/fuse_helper.py:67-166: 8 heads x 256;
+ * vision <- language: queries = S vision tokens, keys = N_t phrases; language <- vision: the transposed roles), one
+ * flash-attention pass per direction — the S x N_t score matrix (31 GB in fp32 at 1536^2 / 5 000 phrases) is never formed.
+ * q [num_seq * nq, >= heads*head_dim], k / v [num_seq * nkv, ...], out like q; nq a multiple of 128, nkv a multiple of 64 (rows
+ * padded by the caller with finite values), only the first n_valid keys of every sequence count.  fp16 / bf16, fp32 softmax
+ * statistics and accumulation.  The reference's global-max shift and +-5e4 clamps are softmax-invariant for LayerNormed
+ * inputs (see csrc/attn_xfwd.cu).
+ */
+int ape_attn_cross_fwd(const void *q, int64_t ldq, const void *k, int64_t ldk, const void *v, int64_t ldv, void *out, int64_t ldo,
+                       int num_seq, int nq, int nkv, int n_valid, int heads, int head_dim, float scale, int dtype, void *stream);
+
+/*
  * Language-side attention pooling of VisionLanguageFusion for a single language token ("name" prompts):
  * softmax over the S vision tokens of scores t[s,h] = v_s . qa[h] + qc[h] (with the reference's global-max shift
  * and +-5e4 clamps, fuse_helper.py:88-110) and the p-weighted sum of v.  v [B,S,C] dtype; qa [B,NH,C], qc [B,NH] fp32.

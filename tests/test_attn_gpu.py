@@ -73,3 +73,25 @@ def test_attention_row_statistics_output(ops):
     o = out.float().view(num_seq * n, heads, hd)
     torch.testing.assert_close(st[..., 0], o.sum(-1), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(st[..., 1], (o ** 2).sum(-1), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 3e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("num_seq,nq,nk,heads,hd", [(1, 128, 64, 1, 256), (2, 256, 200, 8, 256), (1, 384, 1203, 2, 256),
+                                                    (1, 128, 5000, 1, 256), (2, 256, 130, 3, 64)])
+def test_cross_attention_wide_heads(ops, dtype, tol, num_seq, nq, nk, heads, hd):
+    """ape_attn_cross_fwd (separate Q / K / V, 256-channel heads, padded + masked keys) against fp32 softmax attention."""
+    g = torch.Generator().manual_seed(nk + heads)
+    C = heads * hd
+    nkp = (nk + 63) // 64 * 64
+    q = torch.randn(num_seq, nq, C, generator=g).to(DEV, dtype)
+    k = torch.zeros(num_seq, nkp, C, dtype=dtype, device=DEV)
+    v = torch.zeros(num_seq, nkp, C, dtype=dtype, device=DEV)
+    k[:, :nk] = torch.randn(num_seq, nk, C, generator=g).to(DEV, dtype)
+    v[:, :nk] = torch.randn(num_seq, nk, C, generator=g).to(DEV, dtype)
+    scale = hd ** -0.5
+    got = ops.attention_cross(q.view(-1, C), k.view(-1, C), v.view(-1, C), num_seq, nq, nkp, nk, heads, hd, scale).view(num_seq, nq, C)
+    qh = q.float().view(num_seq, nq, heads, hd).transpose(1, 2)
+    kh = k[:, :nk].float().view(num_seq, nk, heads, hd).transpose(1, 2)
+    vh = v[:, :nk].float().view(num_seq, nk, heads, hd).transpose(1, 2)
+    want = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(num_seq, nq, C)
+    torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
