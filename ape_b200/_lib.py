@@ -85,7 +85,7 @@ def _declare(lib):
     lib.ape_attn_fwd.restype = _i
     lib.ape_attn_fwd.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
     lib.ape_attn_fwd_ex.restype = _i
-    lib.ape_attn_fwd_ex.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp, _vp]
+    lib.ape_attn_fwd_ex.argtypes = [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp, _i, _i, _i64, _vp]
     lib.ape_attn_cross_fwd.restype = _i
     lib.ape_attn_cross_fwd.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, ctypes.c_float, _i, _vp]
     lib.ape_vlf_pool_workspace_bytes.restype = _i64

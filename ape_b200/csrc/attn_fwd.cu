@@ -42,6 +42,8 @@ struct AttnParams {
   long long ldo;     // elements
   int n;             // tokens per sequence (multiple of 128)
   int n_valid;       // keys >= n_valid of every sequence are masked out (rows padded up to n; n_valid <= n)
+  int seq_stride;    // rows between the starts of consecutive sequences (n unless sequences are packed tighter than the tile)
+  int causal;        // key t attends only to keys <= t (text tower, eva02_clip/transformer.py:714-720)
   int heads, C;      // C = heads * 64
   float *stats_out;  // [rows, heads, 2] (sum, sum of squares) of each row's 64 stored output values per head, or nullptr
   float scale_log2;  // softmax scale * log2(e)
@@ -62,8 +64,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   AttnSmem &s = *reinterpret_cast<AttnSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
-  const int row0 = seq * p.n;            // first token row of this sequence in the qkv buffer
-  const int nkv = (p.n_valid + KN - 1) / KN;  // key blocks that hold at least one real key
+  const int row0 = seq * p.seq_stride;   // first token row of this sequence in the qkv buffer
+  // key blocks that hold at least one key some row of this tile attends to
+  const int nkv = ((p.causal ? min(p.n_valid, (qblk + 1) * QM) : p.n_valid) + KN - 1) / KN;
   constexpr uint32_t TMEM_COLS = 128;    // S (64 fp32 columns) | O (64)
 
   if (warp == 0 && lane == 0) {
@@ -152,7 +155,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       // pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling); S is read from tensor
       // memory twice instead of being held in 64 registers — 4 CTAs per SM need the threads under 85 registers
       float m8[8];
-      const int kvalid = p.n_valid - j * KN;  // real keys in this block (>= 1; < 64 only in the last block of a padded sequence)
+      // real keys of this block the row may attend to: padding beyond n_valid, and (causal) keys after the query's own position
+      const int kvalid = p.causal ? min(p.n_valid, qblk * QM + row + 1) - j * KN : p.n_valid - j * KN;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t r[32];
@@ -237,6 +241,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     const float inv = 1.f / l;
     T *dst = reinterpret_cast<T *>(p.out) + (size_t)(row0 + qblk * QM + row) * p.ldo + head * HD;
     float st_sum = 0.f, st_sq = 0.f;
+    // packed sequences (seq_stride < n): rows past the sequence belong to the next one and must not be written
+    const bool store_row = p.seq_stride >= p.n || qblk * QM + row < p.n_valid;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       uint32_t o[32];
@@ -248,7 +254,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * c + i]) * inv;
         const uint4 pk = Elem<T>::pack(f);
-        *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = pk;
+        if (store_row) *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = pk;
         if (p.stats_out != nullptr) {  // statistics of the values as stored, for the LayerNorm folded into the next GEMM
           float g[8];
           Elem<T>::unpack(pk, g);
@@ -257,7 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         }
       }
     }
-    if (p.stats_out != nullptr)
+    if (p.stats_out != nullptr && store_row)
       *reinterpret_cast<float2 *>(p.stats_out + ((size_t)(row0 + qblk * QM + row) * p.heads + head) * 2) = make_float2(st_sum, st_sq);
   }
   tc::fence_before_sync();
@@ -290,16 +296,22 @@ EncodeTiledFn attn_encoder() {
 using namespace ape;
 
 extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                               int head_dim, float scale, int dtype, float *stats_out, void *stream);
+                               int head_dim, float scale, int dtype, float *stats_out, int seq_stride, int causal, int64_t total_rows,
+                               void *stream);
 
 extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads,
                             int head_dim, float scale, int dtype, void *stream) {
-  return ape_attn_fwd_ex(qkv, ld, out, ldo, num_seq, n, n, heads, head_dim, scale, dtype, nullptr, stream);
+  return ape_attn_fwd_ex(qkv, ld, out, ldo, num_seq, n, n, heads, head_dim, scale, dtype, nullptr, 0, 0, 0, stream);
 }
 
 extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                               int head_dim, float scale, int dtype, float *stats_out, void *stream) {
+                               int head_dim, float scale, int dtype, float *stats_out, int seq_stride, int causal, int64_t total_rows,
+                               void *stream) {
   if (n_valid <= 0 || n_valid > n) return fail(APE_ERR_INVALID_ARG, "attn: n_valid=%d must be in [1, n=%d]", n_valid, n);
+  if (seq_stride <= 0) seq_stride = n;
+  if (seq_stride < n_valid) return fail(APE_ERR_INVALID_ARG, "attn: seq_stride=%d smaller than n_valid=%d", seq_stride, n_valid);
+  if (total_rows <= 0) total_rows = (int64_t)(num_seq - 1) * seq_stride + n;
+  if (total_rows < (int64_t)(num_seq - 1) * seq_stride + n_valid) return fail(APE_ERR_INVALID_ARG, "attn: total_rows too small");
   if (dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16) return fail(APE_ERR_INVALID_ARG, "attn: fp16 / bf16 only (dtype %d)", dtype);
   if (head_dim != HD) return fail(APE_ERR_UNSUPPORTED, "attn: head_dim %d (only 64)", head_dim);
   if (num_seq < 0 || n <= 0 || n % QM != 0 || heads <= 0 || heads > 65535 || num_seq > 65535)
@@ -313,7 +325,7 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
   EncodeTiledFn enc = attn_encoder();
   if (!enc) return fail(APE_ERR_UNSUPPORTED, "attn: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap map;
-  cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)((long long)num_seq * n)};
+  cuuint64_t dims[2] = {(cuuint64_t)(3 * C), (cuuint64_t)total_rows};  // rows past the buffer read as zeros (TMA)
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)HD, (cuuint32_t)KN};  // 64 channels x 64 rows; Q takes two boxes
   cuuint32_t estr[2] = {1, 1};
@@ -323,6 +335,7 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
   if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "attn: cuTensorMapEncodeTiled failed (%d)", (int)r);
   AttnParams p{};
   p.out = out; p.ldo = ldo; p.n = n; p.n_valid = n_valid; p.heads = heads; p.C = C; p.stats_out = stats_out;
+  p.seq_stride = seq_stride; p.causal = causal ? 1 : 0;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int fmt = dtype == APE_DTYPE_BF16 ? 1 : 0;
   p.idesc_qk = tc::make_idesc_f16(QM, KN, fmt);

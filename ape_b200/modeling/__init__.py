@@ -7,6 +7,7 @@ import torch.nn as nn
 from ..layers import VisionLanguageFusion
 from .backbone import LastLevelMaxPool, ShapeSpec, SimpleFeaturePyramid, ViT
 from .detr import ChannelMapper, DeformableDETRSegmVL, PositionEmbeddingSine, SomeThing, _Criterion
+from .text import EVA02CLIP, TextTransformer  # noqa: F401
 from .transformer import (DeformableDetrTransformerDecoderVL, DeformableDetrTransformerEncoderVL,
                           DeformableDetrTransformerVL)
 

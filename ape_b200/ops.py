@@ -400,20 +400,23 @@ def attention_supported(n, head_dim, dtype):
     return head_dim == 64 and n % 128 == 0 and dtype in (torch.float16, torch.bfloat16)
 
 
-def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None, stats_out=False):
+def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None, stats_out=False, seq_stride=None, causal=False):
     """softmax(q k^T * scale) v for every (sequence, head) straight from the fused qkv buffer [num_seq*n, 3*heads*64]
     (ape_attn_fwd: flash attention on the tcgen05 tensor cores).  Returns [num_seq*n, heads*64].
     n_valid: sequences are padded to n rows and only the first n_valid keys count (rows beyond must be finite).
-    stats_out=True: also returns fp32 [rows, heads, 2] (sum, sum of squares of each row's stored values per head)."""
+    stats_out=True: also returns fp32 [rows, heads, 2] (sum, sum of squares of each row's stored values per head).
+    seq_stride: rows between sequences when they are packed tighter than n (then n_valid <= seq_stride < n; rows of a tile
+    past n_valid are not written); causal: key t attends to keys <= t."""
     _require(qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1, "attention: qkv must be a 2-D CUDA tensor")
-    _require(qkv.shape[0] == num_seq * n and qkv.shape[1] == 3 * heads * head_dim, "attention: qkv shape")
+    stride = n if seq_stride is None else int(seq_stride)
+    _require(qkv.shape[0] >= (num_seq - 1) * stride + (n_valid or n) and qkv.shape[1] == 3 * heads * head_dim, "attention: qkv shape")
     out = torch.empty((qkv.shape[0], heads * head_dim), dtype=qkv.dtype, device=qkv.device)
     stats = torch.empty((qkv.shape[0], heads, 2), dtype=torch.float32, device=qkv.device) if stats_out else None
     with torch.cuda.device(qkv.device), _timed(("attention", num_seq, n, heads)):
         rc = _lib.lib.ape_attn_fwd_ex(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), int(num_seq), int(n),
                                       int(n if n_valid is None else n_valid), int(heads), int(head_dim), float(scale),
                                       _lib.dtype_code(qkv.dtype), stats.data_ptr() if stats is not None else None,
-                                      _lib.current_stream_ptr())
+                                      stride, 1 if causal else 0, int(qkv.shape[0]), _lib.current_stream_ptr())
     _lib.check(rc, "ape_attn_fwd")
     return (out, stats) if stats_out else out
 

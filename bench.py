@@ -286,6 +286,84 @@ def msda_microbench(dev, quick=False):
             "rows": rows}
 
 
+def phrase_bench(args, rank, local_rank, world):
+    """BASELINE.json configs[3]: APE-L_D at 1536 x 1536, 5 000 free-text phrases ("text" prompt -> "phrase" routing:
+    VisionLanguageFusion and the classifier both see N_t = 5 000), batch 4 on one GPU.  Stresses the bi-directional
+    fusion attention (S = 196 416 vision tokens x 5 000 phrases x 8 heads of 256: 12 TFLOP per layer and image) and the
+    text-feature path.  Reports images/s, the fusion attention's TFLOP/s and the peak device memory."""
+    import copy
+
+    assert args.impl != "reference", "the CPU port does not cover the 1536^2 / 5 000-phrase configuration in bounded time"
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in ape_b200)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import ape_b200
+    from ape_b200 import configs, ops
+    from ape_b200.modeling import build_model
+
+    n_phr, B, side = args.phrases, args.batch, 1536
+    spec = copy.deepcopy(configs.APE_L_D_1536)
+    spec["test_score_thresh"] = BENCH_SCORE_THRESH
+    tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    model = bench_weights(build_model(spec, num_text=1203)).to(dev)
+    model.engine_dtype = tdt
+    phrases = ",".join(f"object number {i}" for i in range(n_phr))  # contain spaces -> "phrase" (deformable_detr_segm_vl.py:229-232)
+    g = torch.Generator().manual_seed(rank)
+    host = [torch.randint(0, 256, (3, side, side), generator=g).to(torch.float32).pin_memory() for _ in range(B)]
+
+    def step(use_host=True):
+        imgs = host if use_host else [t.to(dev) for t in host]
+        return model([{"image": im, "height": side, "width": side, "prompt": "text", "text_prompt": phrases} for im in imgs])
+
+    torch.cuda.reset_peak_memory_stats()
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        out = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    ops.PROFILE_EVENTS = []
+    n0 = ape_b200._lib.launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches = ape_b200._lib.launch_count() - n0
+    events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
+    own = {}
+    for (t, x, y) in events:
+        own[t[0]] = own.get(t[0], 0.0) + x.elapsed_time(y)
+    xs = [(t, x.elapsed_time(y)) for (t, x, y) in events if t[0] == "attention_cross"]
+    # flops of one cross-attention launch: 4 * seqs * heads * nq * n_valid * head_dim (QK^T and PV)
+    xflops = sum(4.0 * t[1] * t[4] * t[2] * t[3] * t[5] for t, _ in xs)
+    xms = sum(d for _, d in xs)
+    clocks = sampler.stop()
+    tpeak = 1590.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        tpeak = float(json.load(open(pk)).get("bf16_tflops", 0) or 0) or tpeak
+    line = {"metric": "images_per_sec", "value": B * 1e3 / ms, "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
+            "config": {"workload": f"APE-L_D detection forward, {side}x{side} images, {n_phr} free-text phrases (phrase prompt), batch {B} on one GPU",
+                       "weights": "random init of the real architecture", "text": "seeded synthetic phrase features (text tower out of path)"},
+            "e2e": {"value": B * 1e3 / ms, "unit": "images/s", "h2d_bytes_per_step": B * 3 * side * side * 4,
+                    "d2h_bytes_per_step": int(sum(len(o["instances"]) for o in out) * 36), "ms_per_step": ms,
+                    "note": "the timed steps already take pinned host images and return host detections"},
+            "roofline": {"bound": "tensor", "achieved": xflops / (xms * 1e-3) / 1e12 if xms > 0 else None, "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": (xflops / (xms * 1e-3) / 1e12 / tpeak) if xms > 0 else None, "traffic": None,
+                         "kernel": "attn_xfwd_kernel (VisionLanguageFusion, 12 launches per step)", "flops_per_step": xflops, "ms_per_step": xms},
+            "gpu_launches": int(launches) * args.steps, "clocks": clocks,
+            "peak_memory_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "own_kernel_ms_per_step": {k: round(v, 2) for k, v in sorted(own.items(), key=lambda kv: -kv[1])},
+            "detections": [len(o["instances"]) for o in out]}
+    print(json.dumps(line))
+
+
 def model_bench(args, rank, local_rank, world):
     n_text = 1203
     # identical in both arms (the driver compares it): nothing below depends on which implementation runs
@@ -496,7 +574,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="ape_l_d", choices=["ape_l_d", "msda"])
+    ap.add_argument("--workload", default="ape_l_d", choices=["ape_l_d", "msda", "ape_l_d_1536_phrase"])
+    ap.add_argument("--phrases", type=int, default=5000, help="ape_l_d_1536_phrase: number of free-text phrases")
+    ap.add_argument("--batch", type=int, default=4, help="ape_l_d_1536_phrase: images per step")
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -518,6 +598,8 @@ def main():
 
     if args.workload == "ape_l_d":
         return model_bench(args, rank, local_rank, world)
+    if args.workload == "ape_l_d_1536_phrase":
+        return phrase_bench(args, rank, local_rank, world)
 
     if args.impl == "reference":
         if rank != 0:

@@ -238,9 +238,13 @@ int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_se
  * beyond must hold finite values, e.g. zeros).  Used for the self-attention over the 900 decoder queries
  * (deformable_transformer_vl.py:142-147: nn.MultiheadAttention, 8 heads x 32 — heads zero-padded to 64 channels). */
 /* stats_out (or NULL): fp32 [rows, heads, 2] — per row and head the (sum, sum of squares) of the 64 output values as stored,
- * consumed by ape_gemm_tn_fused to fold the LayerNorm that follows (inner_attn_ln, vit_eva_clip.py:266) into the projection. */
+ * consumed by ape_gemm_tn_fused to fold the LayerNorm that follows (inner_attn_ln, vit_eva_clip.py:266) into the projection.
+ * seq_stride (0 = n): rows between consecutive sequences; sequences may be packed tighter than the 128-row tile (the text
+ * tower packs 77-token prompts at a stride of 80 rows): rows of a tile past n_valid are then neither attended nor written.
+ * causal: key t only sees keys <= t (eva02_clip/transformer.py:714-720).  total_rows (0 = derived): rows of the qkv buffer. */
 int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
-                    int head_dim, float scale, int dtype, float *stats_out, void *stream);
+                    int head_dim, float scale, int dtype, float *stats_out, int seq_stride, int causal, int64_t total_rows,
+                    void *stream);
 
 /*
  * Cross attention with separate Q / K / V tensors and 64- or 256-channel heads: the two softmax attentions of

@@ -95,3 +95,22 @@ def test_cross_attention_wide_heads(ops, dtype, tol, num_seq, nq, nk, heads, hd)
     vh = v[:, :nk].float().view(num_seq, nk, heads, hd).transpose(1, 2)
     want = (torch.softmax(qh @ kh.transpose(-1, -2) * scale, -1) @ vh).transpose(1, 2).reshape(num_seq, nq, C)
     torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("num_seq,n_valid,stride,heads", [(5, 77, 80, 20), (3, 128, 128, 2), (4, 200, 200, 3), (2, 77, 128, 1)])
+def test_attention_causal_and_packed_sequences(ops, num_seq, n_valid, stride, heads):
+    """Causal attention over sequences packed at a row stride smaller than the 128-row tile (EVA02-CLIP text tower: 77-token
+    prompts, 20 heads x 64, eva02_clip/transformer.py:714-720): rows past a sequence are neither attended nor overwritten."""
+    hd = 64
+    n = (n_valid + 127) // 128 * 128
+    g = torch.Generator().manual_seed(stride + heads)
+    rows = (num_seq - 1) * stride + max(stride, n_valid)
+    qkv = torch.randn(rows, 3 * heads * hd, generator=g).to(DEV, torch.float16)
+    out = ops.attention_qkv(qkv, num_seq, n, heads, hd, 0.125, n_valid=n_valid, seq_stride=stride, causal=True)
+    assert out.shape[0] == rows
+    for s_ in range(num_seq):
+        x = qkv[s_ * stride: s_ * stride + n_valid].float().view(n_valid, 3, heads, hd).permute(1, 2, 0, 3)
+        sc = x[0] @ x[1].transpose(-1, -2) * 0.125
+        sc = sc.masked_fill(torch.triu(torch.ones(n_valid, n_valid, dtype=torch.bool, device=DEV), 1), float("-inf"))
+        want = (torch.softmax(sc, -1) @ x[2]).permute(1, 0, 2).reshape(n_valid, heads * hd)
+        torch.testing.assert_close(out[s_ * stride: s_ * stride + n_valid].float(), want, rtol=2e-3, atol=2e-3)
