@@ -519,6 +519,8 @@ class DeformableDETRSegmVL(nn.Module):
         mask_pred = mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
+        if do_postprocess == "raw":  # forward_packed: logits / boxes stay on the device, no selection here
+            return box_cls, box_pred, image_sizes
         # the three branches are gated by the entity of the evaluated dataset (:575-577, :628-630, :671-673)
         ent = self.eval_dataset_entity
         instance_on = self.instance_on and not (ent and "thing" not in ent)
@@ -795,47 +797,7 @@ class DeformableDETRSegmVL(nn.Module):
             return None
         classwise = bool(getattr(self, "_static_overflowed", False))
         for attempt in range(2):
-            packs = []
-            for b, (h, w) in enumerate(image_sizes):
-                scores = box_cls[b].float().sigmoid().contiguous()                              # [Q, N] (bg column dropped again, :772)
-                xyxy = box_cxcywh_to_xyxy(box_pred[b].float())
-                boxes = torch.stack((xyxy[:, 0] * float(w), xyxy[:, 1] * float(h), xyxy[:, 2] * float(w), xyxy[:, 3] * float(h)), dim=-1)
-                valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)     # fast_rcnn.py:120-123
-                qmap = valid.cumsum(0) - 1                                                       # row index after the filter
-                boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
-                                     boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1).contiguous()
-                mask = (scores > self.test_score_thresh) & valid[:, None]
-                n = mask.sum().to(torch.int32).reshape(1)
-                Q, N = scores.shape
-                if classwise:
-                    k = min(topk, Q * N)
-                    surv = ops.nms_classwise(boxes, scores, self.test_score_thresh, self.test_nms_thresh,
-                                             row_valid=valid.to(torch.uint8))                   # [N, Q], -inf = gone
-                    topv, topi = torch.topk(surv.flatten(), k)                                  # descending score
-                    c, q = topi // Q, topi % Q
-                    nk = torch.isfinite(topv).sum().to(torch.float32)
-                    pack = torch.cat([boxes[q], topv[:, None], c[:, None].float(), qmap[q, None].float(),
-                                      torch.stack([n[0].float(), nk]).expand(k, 2)], dim=1)
-                    if k < topk:
-                        pack = torch.cat([pack, pack.new_zeros(topk - k, 9)], 0)
-                    packs.append(pack)
-                    continue
-                flat = torch.nonzero_static(mask.flatten(), size=cap, fill_value=0)[:, 0]
-                slot_ok = torch.arange(cap, device=flat.device) < n
-                q, c = flat // N, flat % N
-                cb = boxes[q]
-                cs = torch.where(slot_ok, scores.flatten()[flat], scores.new_full((), float("-inf")))
-                # batched_nms: boxes + class * (max coordinate over the candidates + 1), scores sorted descending
-                mx = torch.where(slot_ok[:, None], cb, cb.new_full((), float("-inf"))).max()
-                nb = cb + (c.to(cb) * (mx + 1))[:, None]
-                order = cs.sort(0, descending=True)[1]
-                keep, _ = ops.nms_sorted_mask(nb.index_select(0, order).contiguous(), self.test_nms_thresh, n_valid=n)
-                pos = torch.nonzero_static(keep, size=topk, fill_value=0)[:, 0]
-                nk = keep.sum().clamp(max=topk).to(torch.float32)
-                sel = order[pos]
-                packs.append(torch.cat([cb[sel], cs[sel, None], c[sel, None].float(), qmap[q[sel], None].float(),
-                                        torch.stack([n[0].float(), nk]).expand(topk, 2)], dim=1))  # [topk, 9]
-            host = torch.stack(packs).to("cpu")  # the one synchronising copy
+            host = self._select_device(box_cls, box_pred, image_sizes, classwise).to("cpu")  # the one synchronising copy
             over = any(int(host[b, 0, 7].item()) > cap for b in range(len(image_sizes)))
             if over == classwise:
                 break
@@ -849,6 +811,67 @@ class DeformableDETRSegmVL(nn.Module):
             results.append(Instances((h, w), pred_boxes=Boxes(p[:, :4].contiguous()), scores=p[:, 4].contiguous(),
                                      pred_classes=p[:, 5].to(torch.int64), query_index=p[:, 6].to(torch.int64)))
         return results
+
+    def _select_device(self, box_cls, box_pred, image_sizes, classwise):
+        """Device half of `_inference_static`: [B, topk, 9] fp32 = (x1, y1, x2, y2, score, class, query index, number of
+        candidates, number kept) per detection slot; static shapes, no host synchronisation (CUDA-graph / NCCL friendly)."""
+        cap, topk = int(self.static_inference_cap), int(self.test_topk_per_image)
+        packs = []
+        for b, (h, w) in enumerate(image_sizes):
+            scores = box_cls[b].float().sigmoid().contiguous()                              # [Q, N] (bg column dropped again, :772)
+            xyxy = box_cxcywh_to_xyxy(box_pred[b].float())
+            boxes = torch.stack((xyxy[:, 0] * float(w), xyxy[:, 1] * float(h), xyxy[:, 2] * float(w), xyxy[:, 3] * float(h)), dim=-1)
+            valid = torch.isfinite(boxes).all(dim=1) & torch.isfinite(scores).all(dim=1)     # fast_rcnn.py:120-123
+            qmap = valid.cumsum(0) - 1                                                       # row index after the filter
+            boxes = torch.stack((boxes[:, 0].clamp(min=0, max=w), boxes[:, 1].clamp(min=0, max=h),
+                                 boxes[:, 2].clamp(min=0, max=w), boxes[:, 3].clamp(min=0, max=h)), dim=-1).contiguous()
+            mask = (scores > self.test_score_thresh) & valid[:, None]
+            n = mask.sum().to(torch.int32).reshape(1)
+            Q, N = scores.shape
+            if classwise:
+                k = min(topk, Q * N)
+                surv = ops.nms_classwise(boxes, scores, self.test_score_thresh, self.test_nms_thresh,
+                                         row_valid=valid.to(torch.uint8))                   # [N, Q], -inf = gone
+                topv, topi = torch.topk(surv.flatten(), k)                                  # descending score
+                c, q = topi // Q, topi % Q
+                nk = torch.isfinite(topv).sum().to(torch.float32)
+                pack = torch.cat([boxes[q], topv[:, None], c[:, None].float(), qmap[q, None].float(),
+                                  torch.stack([n[0].float(), nk]).expand(k, 2)], dim=1)
+                if k < topk:
+                    pack = torch.cat([pack, pack.new_zeros(topk - k, 9)], 0)
+                packs.append(pack)
+                continue
+            flat = torch.nonzero_static(mask.flatten(), size=cap, fill_value=0)[:, 0]
+            slot_ok = torch.arange(cap, device=flat.device) < n
+            q, c = flat // N, flat % N
+            cb = boxes[q]
+            cs = torch.where(slot_ok, scores.flatten()[flat], scores.new_full((), float("-inf")))
+            # batched_nms: boxes + class * (max coordinate over the candidates + 1), scores sorted descending
+            mx = torch.where(slot_ok[:, None], cb, cb.new_full((), float("-inf"))).max()
+            nb = cb + (c.to(cb) * (mx + 1))[:, None]
+            order = cs.sort(0, descending=True)[1]
+            keep, _ = ops.nms_sorted_mask(nb.index_select(0, order).contiguous(), self.test_nms_thresh, n_valid=n)
+            pos = torch.nonzero_static(keep, size=topk, fill_value=0)[:, 0]
+            nk = keep.sum().clamp(max=topk).to(torch.float32)
+            sel = order[pos]
+            packs.append(torch.cat([cb[sel], cs[sel, None], c[sel, None].float(), qmap[q[sel], None].float(),
+                                    torch.stack([n[0].float(), nk]).expand(topk, 2)], dim=1))  # [topk, 9]
+        return torch.stack(packs)
+
+    def forward_packed(self, batched_inputs):
+        """Detections as ONE device tensor [B, topk, 13] (the 9 columns of `_select_device` + padded image height / width and
+        requested output height / width), without touching the host: the multi-GPU path hands it straight to one NCCL
+        gather on the compute stream (ape_b200.parallel.gather_packed) and only the destination rank copies to the host.
+        Boxes only (instance masks travel separately).  The selection path (candidate list vs class-wise NMS) is the one
+        the last host-synchronised forward found appropriate; the packed rows carry the candidate count so the receiver can
+        tell if that choice was wrong for an image (count > static_inference_cap on the candidate-list path)."""
+        assert not (self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)), "forward_packed: boxes only"
+        box_cls, box_pred, image_sizes = self.forward(batched_inputs, do_postprocess="raw")
+        pack = self._select_device(self._detector_box_cls(box_cls), box_pred, image_sizes, bool(getattr(self, "_static_overflowed", False)))
+        extra = torch.tensor([[float(h), float(w), float(inp.get("height", h)), float(inp.get("width", w))]
+                              for (h, w), inp in zip(image_sizes, batched_inputs)], dtype=torch.float32)
+        extra = extra.to(pack.device, non_blocking=True)[:, None, :].expand(-1, pack.shape[1], -1)
+        return torch.cat([pack, extra], dim=2)
 
     def inference(self, box_cls, box_pred, image_sizes):
         """:759-810 + fast_rcnn.py:40-95.  CUDA: the static-shape selection above (device results; bounded memory for any

@@ -59,3 +59,41 @@ def gather_detections(instances: List[Instances], max_det: int, device, dst: int
         return unpack_detections(torch.cat(bufs, 0))
     dist.gather(packed, None, dst=dst, group=group)
     return None
+
+
+# ---- device-side path: no host round trip before the collective ---------------------------------------------------
+def unpack_packed(packed: torch.Tensor) -> List[dict]:
+    """Rows of `DeformableDETRSegmVL.forward_packed` ([images, topk, 13], any device) -> the reference's output list
+    [{"instances": Instances}] on the host: the kept detections rescaled to the requested output size, clipped, empty boxes
+    dropped (detectron2 detector_postprocess).  One device->host copy for everything."""
+    host = packed.to("cpu")
+    out = []
+    for p in host:
+        nk = int(p[0, 8])
+        h, w, oh, ow = (float(v) for v in p[0, 9:13])
+        r = p[:nk]
+        b = r[:, :4].clone()
+        if h > 0 and w > 0:
+            b[:, 0::2] *= ow / w
+            b[:, 1::2] *= oh / h
+        b = torch.stack((b[:, 0].clamp(min=0, max=ow), b[:, 1].clamp(min=0, max=oh), b[:, 2].clamp(min=0, max=ow),
+                         b[:, 3].clamp(min=0, max=oh)), dim=-1)
+        keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
+        out.append({"instances": Instances((int(oh), int(ow)), pred_boxes=Boxes(b[keep]), scores=r[keep, 4].clone(),
+                                           pred_classes=r[keep, 5].to(torch.int64), query_index=r[keep, 6].to(torch.int64)),
+                    "num_candidates": int(p[0, 7])})
+    return out
+
+
+def gather_packed(packed: torch.Tensor, dst: int = 0, group: Optional[dist.ProcessGroup] = None) -> Optional[List[dict]]:
+    """ONE collective on the packed DEVICE tensor (NCCL gather on the compute stream; gloo in the CPU tests): non-destination
+    ranks neither copy to the host nor synchronise.  Returns the per-image results of all ranks on `dst`, None elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return unpack_packed(packed)
+    world = dist.get_world_size(group)
+    if dist.get_rank(group) == dst:
+        buf = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+        dist.gather(packed, list(buf.unbind(0)), dst=dst, group=group)
+        return unpack_packed(buf.flatten(0, 1))
+    dist.gather(packed, None, dst=dst, group=group)
+    return None

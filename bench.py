@@ -415,10 +415,15 @@ def model_bench(args, rank, local_rank, world):
 
     def step(i, host):
         img = host_imgs[i % NIMG] if host else dev_imgs[i % NIMG]
-        out = model([{"image": img, "height": 1024, "width": 1024}])
-        if world > 1:  # the one collective of the path: packed detections -> rank 0 (NCCL over NVLink)
-            parallel.gather_detections([o["instances"] for o in out], 300, dev, dst=0)
-        return out
+        inputs = [{"image": img, "height": 1024, "width": 1024}]
+        if world > 1:
+            # the one collective of the path: the packed detections stay on the device and go straight into ONE NCCL gather
+            # on the compute stream; only rank 0 copies to the host (no per-rank D2H / Python packing / H2D round trip)
+            out = parallel.gather_packed(model.forward_packed(inputs), dst=0)
+            if out is None:
+                torch.cuda.current_stream().synchronize()  # a step ends when this rank's contribution has left
+            return out
+        return model(inputs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -444,15 +449,18 @@ def model_bench(args, rank, local_rank, world):
     # Per-kernel durations for the roofline object: CUDA events cannot be recorded inside a graph replay, so
     # the same steps are run a few more times eagerly (same kernels, same inputs, same stream) with an event
     # pair around every launch of our library; launches per step are counted here too.
+    def local(i):  # the rank's own forward without the collective (per-kernel / per-stage profiling passes)
+        return model([{"image": dev_imgs[i % NIMG], "height": 1024, "width": 1024}])
+
     model.profile_stages = True
     stage_acc = {}
     for i in range(5):
-        step(i, False)
+        local(i)
         for k, v in model.stage_ms.items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / 5
     model.profile_stages = False
     graphs_on, model.use_cuda_graphs = model.use_cuda_graphs, False
-    step(0, False)
+    local(0)
     barrier()
     ops.PROFILE_EVENTS = []
     n0 = ape_b200._lib.launch_count()
@@ -464,7 +472,7 @@ def model_bench(args, rank, local_rank, world):
             torch.cuda._sleep(int(1.2e8))
         except Exception:  # noqa: BLE001  (private helper; the numbers are then upper bounds for short kernels)
             pass
-        step(i, False)
+        local(i)
     barrier()
     launches = (ape_b200._lib.launch_count() - n0) // prof_steps * args.steps
     events, ops.PROFILE_EVENTS = ops.PROFILE_EVENTS, None
@@ -521,7 +529,7 @@ def model_bench(args, rank, local_rank, world):
             traffic = json.load(open(tp)).get(f"msda_fused_enc_{args.dtype}")
         inst = out[0]["instances"]
         d2h = sum(v.tensor.numel() * 4 if hasattr(v, "tensor") else v.numel() * v.element_size()
-                  for v in inst.get_fields().values())
+                  for v in inst.get_fields().values()) if world == 1 else world * 300 * 13 * 4
         line = {
             "metric": "images_per_sec", "value": world * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

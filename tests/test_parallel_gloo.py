@@ -76,3 +76,44 @@ def test_bench_reference_arm_under_torchrun():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def _packed_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from ape_b200 import parallel
+
+    topk = 6
+    pack = torch.zeros(1, topk, 13)
+    nk = 2 + rank                                           # rank r keeps 2 + r detections
+    pack[0, :, 7], pack[0, :, 8] = 40 + rank, nk            # candidates, kept
+    pack[0, :, 9:13] = torch.tensor([100.0, 200.0, 50.0, 100.0])  # padded image 100x200 -> output 50x100
+    for i in range(nk):
+        pack[0, i, :7] = torch.tensor([10.0 * i, 10.0 * i, 10.0 * i + 40, 10.0 * i + 20, 0.9 - 0.1 * i, float(rank * 10 + i), float(i)])
+    out = parallel.gather_packed(pack, dst=0)
+    if rank == 0:
+        q.put([(len(o["instances"]), o["instances"].image_size, o["instances"].pred_classes.tolist(),
+                o["instances"].pred_boxes.tensor[0].tolist(), o["num_candidates"]) for o in out])
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_packed_device_tensor_over_gloo():
+    """parallel.gather_packed: one collective on the packed tensor of DeformableDETRSegmVL.forward_packed, unpacked (rescaled
+    to the requested output size) on the destination rank only."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 2000
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [2, 3] and res[0][1] == (50, 100)
+    assert res[1][2] == [10, 11, 12] and res[1][4] == 41
+    assert res[0][3] == [0.0, 0.0, 20.0, 10.0]  # 40 x 20 box halved by the 100x200 -> 50x100 rescale
