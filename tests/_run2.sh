@@ -1,10 +1,12 @@
 bash tests/gpu_all.sh
-echo "== msda pair sweep"; timeout 600 python tests/perf_msda_pair.py > gpurun_out/msda_pair_sweep.txt 2>&1; grep -E "generic|pairing" gpurun_out/msda_pair_sweep.txt; grep "1024 float16" gpurun_out/msda_pair_sweep.txt | sort -k 12 -n | head -8
-echo "== bench with APE_GEMM_POLICY=mc"; APE_GEMM_POLICY=mc timeout 600 python bench.py --no-cpu-baseline --no-microbench 2>/dev/null | tail -1 | tee gpurun_out/bench_mc.json | cut -c1-200
+echo "== msda pair sweep"; timeout 600 python tests/perf_msda_pair.py > gpurun_out/msda_pair_sweep.txt 2>&1; grep -E "generic|pairing" gpurun_out/msda_pair_sweep.txt; grep "1024 float16" gpurun_out/msda_pair_sweep.txt | grep pair | sort -t' ' -k 12 -n | awk '{print}' | sort -k12 -n | head -8
+echo "== A/B: APE_GEMM_POLICY=mc | APE_PDL=0 | no LN fold"
+APE_GEMM_POLICY=mc timeout 600 python bench.py --no-cpu-baseline --no-microbench 2>/dev/null | tail -1 > gpurun_out/bench_mc.json
+APE_PDL=0 timeout 600 python bench.py --no-cpu-baseline --no-microbench 2>/dev/null | tail -1 > gpurun_out/bench_nopdl.json
 python - <<'PY'
 import json
-for f in ("gpurun_out/bench.json","gpurun_out/bench_mc.json"):
+for f in ("gpurun_out/bench.json","gpurun_out/bench_mc.json","gpurun_out/bench_nopdl.json"):
     try:
-        b=json.loads(open(f).read()); print(f, b["value"], b["ms_per_step"], b.get("roofline_gemm",{}).get("ms_per_step"))
+        b=json.loads(open(f).read()); print(f, round(b["value"],2), "img/s", round(b["ms_per_step"],3), "ms; gemm ms", round(b.get("roofline_gemm",{}).get("ms_per_step",0),3), "msda ms", round(b["roofline"]["launch_ms"],4))
     except Exception as e: print(f, "ERR", e)
 PY
