@@ -149,45 +149,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     float m_ref = -INFINITY, l = 0.f;
     uint8_t *prow = s.p + row * 128;
+    // Per key block the scores are read from tensor memory ONCE: exponentials are formed against the reference maximum
+    // carried over from the previous blocks while the block's own maximum is tracked on the side; only when some row of
+    // the warp outgrows the reference by more than 2^8 (P would leave the 16-bit range) is the block redone against the new
+    // reference (and O rescaled) — rare after the first block, which takes its reference from its own scores up front.
+    auto load_half = [&](int hh, int kvalid, uint32_t *r) {
+      tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
+      tc::tmem_ld_wait();
+      if (kvalid < KN) {  // padded / future keys score -inf: ex2(-inf) = 0
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * hh + i >= kvalid) r[i] = 0xff800000u;
+      }
+    };
+    auto exp_half = [&](int hh, const uint32_t *r, float *s8) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          e[i] = ex2(fmaf(__uint_as_float(r[8 * c + i]), p.scale_log2, -m_ref));
+          s8[i] += e[i];
+        }
+        *reinterpret_cast<uint4 *>(prow + (((4 * hh + c) ^ (row & 7)) << 4)) = Elem<T>::pack(e);
+      }
+    };
+    auto release_s = [&]() {  // S_j is in registers: the tensor core may compute S_{j+1}
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.s_empty);
+    };
     for (int j = 0; j < nkv; ++j) {
       tc::mbar_wait(&s.s_full, j & 1);
       tc::fence_after_sync();
-      // pass 1: row maximum of the raw scores (scale > 0, so max commutes with the scaling); S is read from tensor
-      // memory twice instead of being held in 64 registers — 4 CTAs per SM need the threads under 85 registers
-      float m8[8];
       // real keys of this block the row may attend to: padding beyond n_valid, and (causal) keys after the query's own position
       const int kvalid = p.causal ? min(p.n_valid, qblk * QM + row + 1) - j * KN : p.n_valid - j * KN;
+      uint32_t r[32];
+      if (j == 0) {  // first block: the reference is this block's own row maximum (every row sees key 0)
+        float m = -INFINITY;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
-        tc::tmem_ld_wait();
-        if (kvalid < KN) {  // warp-uniform: padded keys score -inf
+        for (int hh = 0; hh < 2; ++hh) {
+          load_half(hh, kvalid, r);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * hh + i >= kvalid) r[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = __uint_as_float(r[i]);
-          m8[i & 7] = (hh == 0 && i < 8) ? x : fmaxf(m8[i & 7], x);
-        }
-      }
-      const float mx = p.scale_log2 *
-          fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-      // move the reference only when some row of this warp outgrew it by 2^8 (always on the first block)
-      const bool moved = __any_sync(0xffffffffu, mx > m_ref + kRescaleThreshold);
-      float alpha = 1.f;
-      if (moved) {
-        const float m_new = fmaxf(m_ref, mx);
-        alpha = ex2(m_ref - m_new);  // 0 on the first block (m_ref = -inf)
-        m_ref = m_new;
-        l *= alpha;
-      }
-      if (j > 0) {  // P_{j-1} has been consumed and O holds blocks 0..j-1
+        m_ref = p.scale_log2 * m;
+      } else {  // P_{j-1} has been consumed and O holds blocks 0..j-1
         tc::mbar_wait(&s.pv_done, (j - 1) & 1);
         tc::fence_after_sync();
-        if (moved) {  // warp-uniform: rescale this warp's 32 rows of O in place
+      }
+      float s8[8], m4[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m4[i] = -INFINITY;
+      load_half(0, kvalid, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+      exp_half(0, r, s8);
+      load_half(1, kvalid, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+      const float mx = p.scale_log2 * fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const bool moved = __any_sync(0xffffffffu, mx > m_ref + kRescaleThreshold);
+      if (!moved) {
+        release_s();
+        exp_half(1, r, s8);
+      } else {  // warp-uniform, rare: new reference, rescale this warp's rows of O in place, redo the block's exponentials
+        const float m_new = fmaxf(m_ref, mx);
+        const float alpha = ex2(m_ref - m_new);
+        m_ref = m_new;
+        l *= alpha;
+        if (j > 0) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t o[32];
@@ -199,36 +232,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
           }
           tc::tmem_st_wait();
         }
-      }
-      // pass 2: exponentials -> 16 bit -> swizzled shared memory
-      float s8[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s8[i] = 0.f;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tc::tmem_ld_32x32b_x32(trow + 32 * hh, r);
-        tc::tmem_ld_wait();
-        if (hh == 1) {  // S is in registers now: the tensor core may compute S_{j+1}
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&s.s_empty);
-        }
-        if (kvalid < KN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * hh + i >= kvalid) r[i] = 0xff800000u;  // ex2(-inf) = 0: no weight on padded keys
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            e[i] = ex2(fmaf(__uint_as_float(r[8 * c + i]), p.scale_log2, -m_ref));
-            s8[i] += e[i];
-          }
-          *reinterpret_cast<uint4 *>(prow + (((4 * hh + c) ^ (row & 7)) << 4)) = Elem<T>::pack(e);
-        }
+        for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+        load_half(0, kvalid, r);
+        exp_half(0, r, s8);
+        load_half(1, kvalid, r);
+        release_s();
+        exp_half(1, r, s8);
       }
       l += ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
       tc::fence_proxy_async();  // P visible to the tensor core's (async proxy) reads

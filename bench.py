@@ -406,6 +406,10 @@ def model_bench(args, rank, local_rank, world):
     model = bench_weights(build_model(bench_spec(), num_text=n_text)).to(dev)
     model.engine_dtype = tdt  # parameters stay fp32; 16-bit = tensor-core engine path
     model.use_cuda_graphs = tdt != torch.float32 and not args.no_graphs
+    masks_on = args.workload == "ape_l_d_masks"  # BASELINE.json configs[2]: boxes + instance masks + semantic map
+    if masks_on:
+        model.test_mask_on, model.semantic_on = True, True
+        config["workload"] = config["workload"].replace("boxes only", "boxes + instance masks (128^2 per box, pasted) + semantic map (1203 x 1024^2)")
     g = torch.Generator().manual_seed(rank)
     NIMG = 4
     host_imgs = [torch.randint(0, 256, (3, 1024, 1024), generator=g).to(torch.float32).pin_memory() for _ in range(NIMG)]
@@ -416,6 +420,10 @@ def model_bench(args, rank, local_rank, world):
     def step(i, host):
         img = host_imgs[i % NIMG] if host else dev_imgs[i % NIMG]
         inputs = [{"image": img, "height": 1024, "width": 1024}]
+        if world > 1 and masks_on:  # masks stay on their rank (evaluators consume them there); boxes go to rank 0
+            out = model(inputs)
+            parallel.gather_detections([o["instances"] for o in out], 300, dev, dst=0)
+            return out
         if world > 1:
             # the one collective of the path: the packed detections stay on the device and go straight into ONE NCCL gather
             # on the compute stream; only rank 0 copies to the host (no per-rank D2H / Python packing / H2D round trip)
@@ -582,7 +590,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="ape_l_d", choices=["ape_l_d", "msda", "ape_l_d_1536_phrase"])
+    ap.add_argument("--workload", default="ape_l_d", choices=["ape_l_d", "ape_l_d_masks", "msda", "ape_l_d_1536_phrase"])
     ap.add_argument("--phrases", type=int, default=5000, help="ape_l_d_1536_phrase: number of free-text phrases")
     ap.add_argument("--batch", type=int, default=4, help="ape_l_d_1536_phrase: images per step")
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
@@ -604,7 +612,7 @@ def main():
               "loc": "uniform(0,1) seed 3 (SURVEY 8d)", "l2": "4 rotating input sets (1.4 GB fp32) > 126 MB L2",
               "parallelism": f"dp{args.gpus} (one image per GPU, no data-path collective)"}
 
-    if args.workload == "ape_l_d":
+    if args.workload in ("ape_l_d", "ape_l_d_masks"):
         return model_bench(args, rank, local_rank, world)
     if args.workload == "ape_l_d_1536_phrase":
         return phrase_bench(args, rank, local_rank, world)
