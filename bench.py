@@ -531,6 +531,9 @@ def model_bench(args, rank, local_rank, world):
         enc_ms = sum(x for _, x in enc) / len(enc) + pairing_ms  # one logical op = pairing pass + gather kernel
         nbytes = fused_msda_bytes(B, S, Q, L, e, eo)
         achieved = nbytes / (enc_ms * 1e-3) / 1e9
+        lsu_bytes = B * Q * H * L * P * 4 * D * e
+        props = torch.cuda.get_device_properties(dev)
+        lsu_peak = props.multi_processor_count * 128 * float((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -550,7 +553,11 @@ def model_bench(args, rank, local_rank, world):
                          "launches_per_step": len(enc) / prof_steps,
                          "share_of_step": enc_ms * len(enc) / prof_steps / ms_per_step,
                          "timing": "event pairs around each launch in 3 eager (non-graph) repeats of the step",
-                         "decoder_launch_ms": (sum(x for _, x in dec) / len(dec)) if dec else None},
+                         "decoder_launch_ms": (sum(x for _, x in dec) / len(dec)) if dec else None,
+                         # the bound this gather actually works against: every sample moves 4 corner rows (2 paired 128-byte
+                         # lines) through the L1 / LSU data pipe, 128 B/clk/SM
+                         "lsu_bytes_per_launch": lsu_bytes, "lsu_peak_GBps": lsu_peak,
+                         "lsu_frac": lsu_bytes / (enc_ms * 1e-3) / 1e9 / lsu_peak},
             "e2e": {"value": world * 1e3 / e2e_ms, "unit": "images/s", "h2d_bytes_per_step": host_imgs[0].numel() * 4,
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "clocks": clocks,
