@@ -486,10 +486,19 @@ class DeformableDETRSegmVL(nn.Module):
                 # encode -> select -> decode in ONE graph: the selection is written with static shapes and no host
                 # synchronisation (transformer.select_proposals), so nothing between the image upload and the final
                 # thresholding touches the host
+                # the final selection (threshold, class-aware NMS, top-k: static shapes) rides in the same graph when boxes are
+                # all that is asked for; its configuration is part of the graph key
+                sel = None
+                if do_postprocess is True and not need_masks and self.static_inference_cap > 0 and self.test_topk_per_image >= 0 \
+                        and self.num_queries <= 1024:
+                    ent = self.eval_dataset_entity
+                    sel = (tuple(image_sizes), bool(getattr(self, "_static_overflowed", False)), float(self.test_score_thresh),
+                           float(self.test_nms_thresh), int(self.test_topk_per_image), int(self.static_inference_cap),
+                           self.eval_dataset_id, bool(self.instance_on and not (ent and "thing" not in ent)))
                 (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
-                 init_reference, inter_references, mask_logits) = self._graphed(
-                    ("forward", prompt, tuple(images.shape), tuple(image_sizes), tuple(features_l.shape), need_masks),
-                    self._stage_all, (images, fusion, features_l), (geo, prompt))
+                 init_reference, inter_references, mask_logits, graph_pack) = self._graphed(
+                    ("forward", prompt, tuple(images.shape), tuple(image_sizes), tuple(features_l.shape), need_masks, sel),
+                    self._stage_all, (images, fusion, features_l), (geo, prompt, sel))
                 self.transformer.last_topk_proposals = topk
                 mark("encode")
                 mark("select")
@@ -513,6 +522,8 @@ class DeformableDETRSegmVL(nn.Module):
                 else:
                     box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits = self._stage_decode(
                         topk, features_l, memory, output_memory, enc_coord, geo, mask_features)
+        if not (graphs and not self.profile_stages):
+            graph_pack = None
         self.last_outputs = dict(pred_logits=box_cls, pred_boxes=box_pred, memory=memory, inter_states=inter_states,
                                  init_reference=init_reference, inter_references=inter_references,
                                  features=features, neck=feats)
@@ -529,7 +540,8 @@ class DeformableDETRSegmVL(nn.Module):
         det_cls = self._detector_box_cls(box_cls) if instance_on else box_cls
         results = None
         if do_postprocess and box_cls.is_cuda and self.static_inference_cap > 0 and not need_masks:
-            results = self._inference_static(det_cls, box_pred, image_sizes)  # CPU Instances, one host sync
+            # CPU Instances, one host sync; `graph_pack` = the selection already computed inside the CUDA graph
+            results = self._inference_static(det_cls, box_pred, image_sizes, first_pack=graph_pack)
         if results is None:
             results = self.inference(det_cls, box_pred, image_sizes)
         padded_hw = tuple(images.shape[-2:])
@@ -606,14 +618,18 @@ class DeformableDETRSegmVL(nn.Module):
             return features_l
         return 0.0 * features_l + 1.0 * fusion_out.float()  # (:448)
 
-    def _stage_all(self, images, fusion, features_l, geo, prompt):
+    def _stage_all(self, images, fusion, features_l, geo, prompt, sel=None):
         memory, fusion_out, output_memory, enc_cls, enc_coord, features, feats, mask_features = self._stage_encode(images, fusion, geo)
         topk = self.transformer.stage_select(enc_cls, enc_coord, geo)
         features_l = self._mix_text(prompt, features_l, fusion_out)
         box_cls, box_pred, inter_states, init_reference, inter_references, mask_logits = self._stage_decode(
             topk, features_l, memory, output_memory, enc_coord, geo, mask_features)
+        pack = None
+        if sel is not None:  # (image sizes, class-wise path?, thresholds ..., instance branch on?) — see forward()
+            det_cls = self._detector_box_cls(box_cls) if sel[7] else box_cls
+            pack = self._select_device(det_cls, box_pred, sel[0], sel[1])
         return (memory, output_memory, enc_cls, enc_coord, features, feats, topk, box_cls, box_pred, inter_states,
-                init_reference, inter_references, mask_logits)
+                init_reference, inter_references, mask_logits, pack)
 
     def _stage_decode(self, topk, features_l, memory, output_memory, enc_coord, geo, mask_features=None):
         inter_states, init_reference, inter_references = self.transformer.stage_decode(
@@ -783,7 +799,7 @@ class DeformableDETRSegmVL(nn.Module):
                                              bool(stuff) and stuff[0] == "things", self.panoptic_configs))
         return outs
 
-    def _inference_static(self, box_cls, box_pred, image_sizes):
+    def _inference_static(self, box_cls, box_pred, image_sizes, first_pack=None):
         """`inference` (:759-810 + fast_rcnn.py:97-201) with static shapes and ONE device->host copy + synchronisation per
         batch instead of four per image.  Two device paths, chosen by the number n of (query, class) pairs above the score
         threshold (as torchvision's batched_nms switches strategy by size):
@@ -797,7 +813,9 @@ class DeformableDETRSegmVL(nn.Module):
             return None
         classwise = bool(getattr(self, "_static_overflowed", False))
         for attempt in range(2):
-            host = self._select_device(box_cls, box_pred, image_sizes, classwise).to("cpu")  # the one synchronising copy
+            dev_pack = first_pack if (attempt == 0 and first_pack is not None) else \
+                self._select_device(box_cls, box_pred, image_sizes, classwise)
+            host = dev_pack.to("cpu")  # the one synchronising copy
             over = any(int(host[b, 0, 7].item()) > cap for b in range(len(image_sizes)))
             if over == classwise:
                 break
