@@ -58,6 +58,10 @@ struct GemmParams {
   // SwiGLU epilogue: per-row (sum, sumsq) of every 64-column slab of the 16-bit output, [M, stats_nslab, 2]
   float *stats_out;
   int stats_nslab;
+  // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over an NHWC image: an m block is a conv_tw x conv_th pixel
+  // tile of one image, k block kb = (filter tap kb / conv_cblks, 64-channel block kb % conv_cblks); map_a / map_c are 4-D
+  int conv;  // 0 = plain GEMM
+  int conv_tw, conv_th, conv_tiles_x, conv_tiles_img, conv_cblks;
 };
 
 template <int BN, int STAGES>
@@ -322,7 +326,14 @@ __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensor
     tc::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      tc::tma_store_2d(map_c, slab, n0, row0);
+      if (p.conv) {  // the slab's 32 tile rows are min(tw, 32) x 32 / min(tw, 32) pixels of the output image
+        const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
+        const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
+        const int r0 = quad * 32;
+        tc::tma_store_4d(map_c, slab, n0, tx * p.conv_tw + r0 % p.conv_tw, ty * p.conv_th + r0 / p.conv_tw, img);
+      } else {
+        tc::tma_store_2d(map_c, slab, n0, row0);
+      }
       tc::tma_store_commit();
     }
   }
@@ -470,7 +481,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
           tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
-          tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
+          if (p.conv) {
+            const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
+            const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
+            const int tap = kb / p.conv_cblks, cb = kb - tap * p.conv_cblks;
+            tc::tma_load_4d(s.a[stage], &map_a, &s.full[stage], cb * BK, tx * p.conv_tw + tap % 3 - 1, ty * p.conv_th + tap / 3 - 1, img);
+          } else {
+            tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
+          }
           if (CL == 1) {
             tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
           } else {
@@ -963,6 +981,57 @@ extern "C" int ape_gemm_tn_fused(const void *A, int64_t lda, const void *W, int6
   FuseArgs f{ln_part, ln_colsum, ln_nparts, ln_inv_c, ln_eps, stats_out, stats_nslab};
   return gemm_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, res_dtype, M, N, K, in_dtype, out_dtype, act, tile_n, nullptr,
                    stream, &f);
+}
+
+// 4-D tensor map over an NHWC image [B, H, W, C] (16-bit): box = 64 channels x bw x bh pixels of one image, 128 B swizzle.
+static int make_map_nhwc(CUtensorMap *map, const void *base, int dtype, int B, int H, int W, int C, int bw, int bh) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return fail(APE_ERR_UNSUPPORTED, "conv: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dtype == APE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(APE_ERR_INVALID_ARG, "conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return APE_OK;
+}
+
+// 3x3 convolution, stride 1, zero padding 1, no dilation / groups, over NHWC activations as an implicit GEMM on the tcgen05
+// kernel: M = B*H*W output pixels, N = Cout, K = 9*Cin walked as (filter tap, 64-channel block).  The A tile of tap
+// (dy, dx) is the 128-pixel tile shifted by (dy-1, dx-1): one 4-D TMA box, out-of-image parts arrive as zeros.
+extern "C" int ape_conv3x3_nhwc(const void *x, const void *w, void *y, const float *bias, int B, int H, int W, int Cin, int Cout,
+                                int dtype, int act, void *stream) {
+  if (dtype != APE_DTYPE_F16 && dtype != APE_DTYPE_BF16) return fail(APE_ERR_INVALID_ARG, "conv3x3: fp16 / bf16 only");
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return fail(APE_ERR_INVALID_ARG, "conv3x3: bad sizes");
+  if (Cin % 64 || Cout % 8) return fail(APE_ERR_UNSUPPORTED, "conv3x3: Cin must be a multiple of 64 and Cout of 8 (got %d, %d)", Cin, Cout);
+  if (act != ACT_NONE && act != ACT_RELU && act != ACT_GELU) return fail(APE_ERR_INVALID_ARG, "conv3x3: activation %d", act);
+  int tw = 128;
+  while (tw > 8 && W % tw) tw >>= 1;
+  const int th = 128 / tw;
+  if (W % tw || H % th) return fail(APE_ERR_UNSUPPORTED, "conv3x3: %dx%d image is not a whole number of %dx%d pixel tiles", H, W, th, tw);
+  if (!x || !w || !y) return fail(APE_ERR_NULL_PTR, "conv3x3: null pointer argument");
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(APE_ERR_INVALID_ARG, "conv3x3: tensors must be 16-byte aligned");
+  const int K = 9 * Cin, M = B * H * W, N = Cout;
+  const int bn = N > 128 ? 256 : 128;
+  CUtensorMap ma, mb, mc;
+  if (int rc = make_map_nhwc(&ma, x, dtype, B, H, W, Cin, tw, th)) return rc;
+  if (int rc = make_map(&mb, w, dtype, N, K, K, bn)) return rc;
+  const int sw = tw < 32 ? tw : 32;
+  if (int rc = make_map_nhwc(&mc, y, dtype, B, H, W, Cout, sw, 32 / sw)) return rc;
+  GemmParams p{};
+  p.C = y; p.bias = bias; p.ldc = N; p.M = M; p.N = N; p.K = K;
+  p.m_blocks = M / BM;
+  p.k_blocks = K / BK;
+  p.out_dtype = dtype; p.res_dtype = dtype; p.act = act;
+  p.idesc = tc::make_idesc_f16(BM, bn, dtype == APE_DTYPE_BF16 ? 1 : 0);
+  p.tma_store = 1;
+  p.conv = 1; p.conv_tw = tw; p.conv_th = th; p.conv_tiles_x = W / tw; p.conv_tiles_img = (W / tw) * (H / th); p.conv_cblks = Cin / 64;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256, 4, 1>(ma, mb, mc, p, st);
+  return launch_gemm<128, 6, 1>(ma, mb, mc, p, st);
 }
 
 extern "C" int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,

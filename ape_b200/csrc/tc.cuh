@@ -57,6 +57,20 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
+// 4-D tile load (c0 innermost): the A operand of an implicit-GEMM convolution — a box of 64 channels x tw x th pixels of an
+// NHWC image at a shifted position; coordinates outside the image are filled with zeros (= the convolution's zero padding).
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // Same, multicast to every CTA of the cluster whose bit is set in cta_mask: the tile lands at the same
 // CTA-relative shared-memory offset in each destination and completes tx bytes on the mbarrier at the same
 // CTA-relative offset there.

@@ -7,6 +7,7 @@ same constructor arguments, same parameter / buffer names, so `DetectionCheckpoi
 them.  Only the configuration APE uses is implemented (sub-LN, naive SwiGLU, 2-D RoPE, q/v bias,
 window + global blocks, no rel-pos bias, pre-norm, no layer scale); other switches raise."""
 import math
+import os
 from functools import partial
 
 import torch
@@ -399,6 +400,22 @@ def _convT_as_gemm(ct, dtype):
         ct.bias.detach().float().repeat(4).contiguous()))
 
 
+def _conv_weights_ohwi(conv, dtype):
+    """3x3 Conv2d weight as [Cout, 3, 3, Cin] (the K-major operand of ape_conv3x3_nhwc)."""
+    return ops.cached(conv, "_ape_packed_ohwi", dtype, (conv.weight._version, conv.weight.data_ptr()),
+                      lambda: conv.weight.detach().permute(0, 2, 3, 1).to(dtype).contiguous())
+
+
+def conv3x3_tokens(conv, y, B, H, W, engine):
+    """3x3 convolution (no bias) over token-major activations y [B*H*W, C] -> [B, H, W, Cout] contiguous: the repo's implicit-GEMM
+    kernel when `engine` and the geometry is covered, else cuDNN on the channels_last view (no copies)."""
+    ch = y.shape[-1]
+    if engine and conv.bias is None and ops.conv3x3_supported(H, W, ch, conv.weight.shape[0], y.dtype):
+        return ops.conv3x3_nhwc(y.view(B, H, W, ch), _conv_weights_ohwi(conv, y.dtype))
+    z = F.conv2d(y.view(B, H, W, ch).permute(0, 3, 1, 2), _conv_weights(conv, y.dtype), padding=1).permute(0, 2, 3, 1)
+    return z if z.is_contiguous() else z.contiguous()
+
+
 def _conv_weights(conv, dtype):
     def build():
         w = conv.weight.detach().to(dtype)
@@ -458,6 +475,8 @@ class SimpleFeaturePyramid(nn.Module):
         self._out_feature_channels = {k: out_channels for k in self._out_features}
         self._size_divisibility = strides[-1]
         self._square_pad = square_pad
+        # 3x3 convolutions on the repo's implicit-GEMM kernel (ape_conv3x3_nhwc) instead of cuDNN
+        self.conv3x3_engine = os.environ.get("APE_CONV3X3", "0") == "1"
 
     @property
     def size_divisibility(self):
@@ -526,10 +545,7 @@ class SimpleFeaturePyramid(nn.Module):
                 nw, nb = ops.packed(c1.norm, dt)
                 y = ops.layernorm(y, nw, nb, eps=c1.norm.eps)
             ch = y.shape[-1]
-            z = F.conv2d(y.view(B, hw, hw, ch).permute(0, 3, 1, 2), _conv_weights(c3, dt), padding=1)  # cuDNN NHWC
-            z = z.permute(0, 2, 3, 1)
-            if not z.is_contiguous():
-                z = z.contiguous()
+            z = conv3x3_tokens(c3, y, B, hw, hw, self.conv3x3_engine)
             nw, nb = ops.packed(c3.norm, dt)
             z = ops.layernorm(z.view(-1, ch), nw, nb, eps=c3.norm.eps)
             results[name] = z.view(B, hw, hw, ch).permute(0, 3, 1, 2)

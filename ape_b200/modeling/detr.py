@@ -723,10 +723,9 @@ class DeformableDETRSegmVL(nn.Module):
             else:
                 enc = memory[:, start:start + h * w].permute(0, 2, 1).reshape(B, hid, h, w)
                 x = x + F.interpolate(enc, size=(H2, W2), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).reshape(B, H2 * W2, hid)
-            z = F.conv2d(x.view(B, H2, W2, hid).permute(0, 3, 1, 2), _conv_weights(self.output_conv, dt), padding=1)  # cuDNN NHWC
-            z = z.permute(0, 2, 3, 1)
-            if not z.is_contiguous():
-                z = z.contiguous()
+            from .backbone import conv3x3_tokens
+
+            z = conv3x3_tokens(self.output_conv, x.reshape(B * H2 * W2, hid), B, H2, W2, getattr(self.backbone, "conv3x3_engine", False))
             gw, gb = ops.packed(self.output_conv.norm, dt)
             z = ops.groupnorm_nhwc(z.view(B, H2 * W2, hid), gw, gb, self.output_conv.norm.num_groups, self.output_conv.norm.eps)
             z = F.relu(z)

@@ -255,6 +255,32 @@ def linear_tc(x, weight, bias=None, act=None, out_dtype=None, residual=None, til
     return (res, stats) if stats_out else res
 
 
+def conv3x3_supported(H, W, Cin, Cout, dtype):
+    if dtype not in (torch.float16, torch.bfloat16) or Cin % 64 or Cout % 8:
+        return False
+    tw = 128
+    while tw > 8 and W % tw:
+        tw >>= 1
+    return W % tw == 0 and H % (128 // tw) == 0
+
+
+def conv3x3_nhwc(x, weight_ohwi, bias=None, act=None):
+    """3x3 / stride 1 / zero padding 1 convolution over token-major activations x [B,H,W,Cin] (ape_conv3x3_nhwc: implicit GEMM on
+    the tcgen05 kernel, 4-D TMA boxes at shifted positions).  weight_ohwi [Cout,3,3,Cin] contiguous, same 16-bit dtype."""
+    _require(x.is_cuda and x.dim() == 4 and x.is_contiguous() and weight_ohwi.is_contiguous() and x.dtype == weight_ohwi.dtype,
+             "conv3x3: contiguous CUDA NHWC input and OHWI weight of one dtype")
+    B, H, W, Cin = x.shape
+    Cout = weight_ohwi.shape[0]
+    _require(tuple(weight_ohwi.shape) == (Cout, 3, 3, Cin), "conv3x3: weight must be [Cout,3,3,Cin]")
+    y = torch.empty((B, H, W, Cout), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device), _timed(("conv3x3", B * H * W, Cout, 9 * Cin)):
+        rc = _lib.lib.ape_conv3x3_nhwc(x.data_ptr(), weight_ohwi.data_ptr(), y.data_ptr(),
+                                       bias.data_ptr() if bias is not None else None, B, H, W, Cin, Cout,
+                                       _lib.dtype_code(x.dtype), ACT[act], _lib.current_stream_ptr())
+    _lib.check(rc, "ape_conv3x3_nhwc")
+    return y
+
+
 def linear_rope_tc(x, weight, bias, cos, sin, num_channels, head_dim, pos_map=None):
     """Fused qkv projection + 2-D RoPE on the q and k thirds (ape_gemm_tn_rope): x [M, K] @ weight[3C, K]^T + bias with the
     rotary embedding applied in the GEMM epilogue (fp32, before the single rounding).  Returns [M, 3C]."""

@@ -173,6 +173,16 @@ int ape_gemm_tn_fused(const void *A, int64_t lda, const void *W, int64_t ldw, vo
                       float ln_eps, float *stats_out, int stats_nslab, void *stream);
 
 /*
+ * 3x3 convolution (stride 1, zero padding 1) over NHWC activations as an implicit GEMM on the tcgen05 kernel: the 3x3
+ * convolutions of SimpleFeaturePyramid (vit_eva_clip.py:804-847) and of the mask head (deformable_detr_segm_vl.py:741-747).
+ * x [B,H,W,Cin], w [Cout,3,3,Cin] (= the Conv2d weight permuted (0,2,3,1)), y [B,H,W,Cout], bias fp32 [Cout] or NULL;
+ * fp16 / bf16, fp32 accumulation; act 0 / 1 (ReLU) / 2 (GELU).  Cin % 64 == 0; the image must be a whole number of
+ * tw x (128/tw) pixel tiles, tw the largest power of two <= 128 dividing W.
+ */
+int ape_conv3x3_nhwc(const void *x, const void *w, void *y, const float *bias, int B, int H, int W, int Cin, int Cout,
+                     int dtype, int act, void *stream);
+
+/*
  * ape_gemm_tn with the 2-D rotary embedding of the ViT (VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346) fused into
  * the epilogue: C = A W^T + bias, then t' = t*cos + rotate_half(t)*sin on output columns [0, rope_cols) — the q and k
  * thirds of the fused qkv projection (vit_eva_clip.py:225-262) — in fp32 before the single rounding to the 16-bit

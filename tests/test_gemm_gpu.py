@@ -226,3 +226,18 @@ def test_swiglu_epilogue_row_statistics(ops, dtype):
         torch.testing.assert_close(st[:, sidx, 0], sl.sum(1), rtol=1e-4, atol=1e-3)
         torch.testing.assert_close(st[:, sidx, 1], (sl ** 2).sum(1), rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(st[..., 0].sum(1), of.sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 256, 256), (2, 64, 64, 256, 256), (1, 16, 16, 64, 128), (1, 256, 256, 256, 256),
+                                            (1, 8, 8, 128, 64), (1, 48, 96, 64, 256)])
+def test_conv3x3_implicit_gemm_matches_conv2d(ops, dtype, B, H, W, Cin, Cout):
+    """ape_conv3x3_nhwc (implicit GEMM: 4-D TMA boxes at shifted positions, zero fill = zero padding) vs F.conv2d in fp32."""
+    assert ops.conv3x3_supported(H, W, Cin, Cout, dtype)
+    g = torch.Generator().manual_seed(H + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g).to(DEV, dtype)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(DEV, dtype)
+    got = ops.conv3x3_nhwc(x, w.permute(0, 2, 3, 1).contiguous())
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
