@@ -194,9 +194,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
           for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
         }
         m_ref = p.scale_log2 * m;
-      } else {  // P_{j-1} has been consumed and O holds blocks 0..j-1
-        tc::mbar_wait(&s.pv_done, (j - 1) & 1);
-        tc::fence_after_sync();
       }
       float s8[8], m4[4];
 #pragma unroll
@@ -206,6 +203,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
       load_half(0, kvalid, r);
 #pragma unroll
       for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+      if (j > 0) {  // before the first write of P_j: P_{j-1} has been consumed (and O holds blocks 0..j-1)
+        tc::mbar_wait(&s.pv_done, (j - 1) & 1);
+        tc::fence_after_sync();
+      }
       exp_half(0, r, s8);
       load_half(1, kvalid, r);
 #pragma unroll
