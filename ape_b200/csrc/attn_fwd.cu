@@ -17,6 +17,9 @@
 // unit, the others' MMAs and loads proceed.  S_{j+1} is issued as soon as S_j has been read into registers.
 // Bound: for head dim 64 the 16 ex2/clk/SM of the SFU cap attention near half of the tensor peak (4 x 64 flops per
 // exponential); see DESIGN.md.
+#include <stdlib.h>
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -26,6 +29,7 @@ namespace {
 constexpr int QM = 128, KN = 64, HD = 64;
 constexpr int kAttnThreads = 192;
 constexpr float kRescaleThreshold = 8.f;  // log2 units
+constexpr int kDefaultAttnVariant = 0;
 
 struct alignas(1024) AttnSmem {
   uint8_t q[QM * HD * 2];   // 16 KB
@@ -285,6 +289,231 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// attn_fwd5_kernel — second structure for the same op.  ncu on the kernel above shows neither the tensor pipe nor the
+// exponential unit saturated; the accounting of its SHARED-MEMORY traffic explains why: per key block a CTA moves 16 KB of
+// Q + 8 KB of K + 16 KB of P + 8 KB of V through the MMA operand path, writes 16 KB of P and receives 16 KB of K / V from TMA
+// = 80 KB; four resident CTAs per SM need 2 560 clocks of the 128 B/clk port per round of blocks, more than the 2 048 clocks
+// the exponentials take.  This variant takes P out of shared memory altogether:
+//   * P_j is written with tcgen05.st into TENSOR memory (16-bit pairs, lane = query row) and consumed by P.V as the A operand
+//     of tcgen05.mma (the `[a_tmem]` form); per block 48 KB cross the shared-memory port instead of 80;
+//   * 256 tensor-memory columns per CTA: S0 | S1 (double-buffered scores) | P0 | P1 | O — two CTAs per SM; S_{j+1} is computed
+//     while the softmax of block j runs, P.V of block j while the softmax of block j+1 runs: the softmax warps never wait for
+//     the tensor core in the steady state (only the rare O rescale needs the previous P.V to have landed);
+//   * with two CTAs per SM a softmax thread may hold its whole score row (64 fp32) in registers: exact row maximum first, then
+//     the exponentials — one tensor-memory read per block, no redo path;
+//   * K and V are double-buffered in shared memory (48 KB per CTA).
+struct alignas(1024) AttnSmem5 {
+  uint8_t q[QM * HD * 2];
+  uint8_t k[2][KN * HD * 2];
+  uint8_t v[2][KN * HD * 2];
+  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+  uint32_t tmem_base;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  AttnSmem5 &s = *reinterpret_cast<AttnSmem5 *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int row0 = seq * p.seq_stride;
+  const int nkv = ((p.causal ? min(p.n_valid, (qblk + 1) * QM) : p.n_valid) + KN - 1) / KN;
+  constexpr uint32_t TMEM_COLS = 256;  // S0 [0,64) | S1 [64,128) | P0 [128,160) | P1 [160,192) | O [192,256)
+  constexpr uint32_t COL_P = 128, COL_O = 192;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tensormap(&map_qkv);
+    tc::mbar_init(&s.q_full, 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&s.k_full[b], 1);
+      tc::mbar_init(&s.k_empty[b], 1);
+      tc::mbar_init(&s.v_full[b], 1);
+      tc::mbar_init(&s.v_empty[b], 1);
+      tc::mbar_init(&s.s_full[b], 1);
+      tc::mbar_init(&s.s_empty[b], 4);  // one arrival per softmax warp
+      tc::mbar_init(&s.p_full[b], 4);
+      tc::mbar_init(&s.p_empty[b], 1);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(&s.tmem_base, TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s.tmem_base;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc::mbar_expect_tx(&s.q_full, QM * HD * 2);
+      tc::tma_load_2d(s.q, &map_qkv, &s.q_full, head * HD, row0 + qblk * QM);
+      tc::tma_load_2d(s.q + KN * HD * 2, &map_qkv, &s.q_full, head * HD, row0 + qblk * QM + KN);
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1, n = j >> 1;
+        tc::mbar_wait(&s.k_empty[b], (n & 1) ^ 1);
+        tc::mbar_expect_tx(&s.k_full[b], KN * HD * 2);
+        tc::tma_load_2d(s.k[b], &map_qkv, &s.k_full[b], p.C + head * HD, row0 + j * KN);
+        tc::mbar_wait(&s.v_empty[b], (n & 1) ^ 1);
+        tc::mbar_expect_tx(&s.v_full[b], KN * HD * 2);
+        tc::tma_load_2d(s.v[b], &map_qkv, &s.v_full[b], 2 * p.C + head * HD, row0 + j * KN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      tc::mbar_wait(&s.q_full, 0);
+      tc::fence_after_sync();
+      const uint64_t dq = tc::make_smem_desc_sw128(tc::smem_u32(s.q));
+      auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
+        const int b = j & 1, n = j >> 1;
+        tc::mbar_wait(&s.k_full[b], n & 1);
+        tc::mbar_wait(&s.s_empty[b], (n & 1) ^ 1);  // the softmax warps hold S_{j-2} in registers
+        tc::fence_after_sync();
+        const uint64_t dk = tc::make_smem_desc_sw128(tc::smem_u32(s.k[b]));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) tc::mma_f16(tmem + 64 * b, dq + 2 * k, dk + 2 * k, p.idesc_qk, k != 0);
+        tc::mma_commit(&s.s_full[b]);
+        tc::mma_commit(&s.k_empty[b]);
+      };
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int b = j & 1, n = j >> 1;
+        if (j + 1 < nkv) issue_qk(j + 1);
+        tc::mbar_wait(&s.v_full[b], n & 1);
+        tc::mbar_wait(&s.p_full[b], n & 1);  // P_j is in tensor memory (and O was rescaled if it had to be)
+        tc::fence_after_sync();
+        const uint64_t dv = tc::make_smem_desc_sw128(tc::smem_u32(s.v[b]));
+#pragma unroll
+        for (int k = 0; k < KN / 16; ++k)  // A: 16 keys = 8 packed columns of P; B (MN-major): +16 key rows = 2 KB
+          tc::mma_f16_ts(tmem + COL_O, tmem + COL_P + 32 * b + 8 * k, dv + 128 * k, p.idesc_pv, (j | k) != 0);
+        tc::mma_commit(&s.p_empty[b]);  // P buffer b free again = O holds blocks 0..j
+        tc::mma_commit(&s.v_empty[b]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax (warps 2..5; thread = query row = tensor-memory lane) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1, n = j >> 1;
+      tc::mbar_wait(&s.s_full[b], n & 1);
+      tc::fence_after_sync();
+      uint32_t r[64];
+      tc::tmem_ld_32x32b_x32(trow + 64 * b, r);
+      tc::tmem_ld_32x32b_x32(trow + 64 * b + 32, r + 32);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.s_empty[b]);  // S_j is in registers: S_{j+2} may overwrite the buffer
+      const int kvalid = p.causal ? min(p.n_valid, qblk * QM + row + 1) - j * KN : p.n_valid - j * KN;
+      if (kvalid < KN) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= kvalid) r[i] = 0xff800000u;
+      }
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+      const float mx = p.scale_log2 * fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const bool moved = __any_sync(0xffffffffu, mx > m_ref + kRescaleThreshold);
+      if (moved) {  // warp-uniform; always on the first block (m_ref = -inf), rare afterwards
+        const float m_new = fmaxf(m_ref, mx);
+        const float alpha = ex2(m_ref - m_new);
+        m_ref = m_new;
+        l *= alpha;
+        if (j > 0) {  // O must hold blocks 0..j-1 before it is rescaled in place
+          tc::mbar_wait(&s.p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc::fence_after_sync();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32];
+            tc::tmem_ld_32x32b_x32(trow + COL_O + 32 * hh, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st_32x32b_x32(trow + COL_O + 32 * hh, o);
+          }
+          tc::tmem_st_wait();
+        }
+      }
+      if (j >= 2) {  // P buffer b is free once P_{j-2}.V_{j-2} has completed (long ago in the steady state)
+        tc::mbar_wait(&s.p_empty[b], (n - 1) & 1);
+        tc::fence_after_sync();
+      }
+      uint32_t pk[32];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_ref));
+        const float e1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_ref));
+        s4[i & 1] += e0;
+        s4[2 + (i & 1)] += e1;
+        if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+          const __half2 h = __floats2half2_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t *>(&h);
+        } else {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+          pk[i] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+      }
+      l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      tc::tmem_st_32x32b_x32(trow + COL_P + 32 * b, pk);  // P_j: keys 2i / 2i+1 in the halves of column i
+      tc::tmem_st_wait();
+      tc::fence_before_sync();  // P (and a rescaled O) ordered before the MMA that reads them
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s.p_full[b]);
+    }
+    tc::mbar_wait(&s.p_empty[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+    tc::fence_after_sync();
+    const float inv = 1.f / l;
+    T *dst = reinterpret_cast<T *>(p.out) + (size_t)(row0 + qblk * QM + row) * p.ldo + head * HD;
+    float st_sum = 0.f, st_sq = 0.f;
+    const bool store_row = p.seq_stride >= p.n || qblk * QM + row < p.n_valid;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t o[32];
+      tc::tmem_ld_32x32b_x32(trow + COL_O + 32 * hh, o);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * c + i]) * inv;
+        const uint4 pk4 = Elem<T>::pack(f);
+        if (store_row) *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * c) = pk4;
+        if (p.stats_out != nullptr) {
+          float g[8];
+          Elem<T>::unpack(pk4, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { st_sum += g[i]; st_sq += g[i] * g[i]; }
+        }
+      }
+    }
+    if (p.stats_out != nullptr && store_row)
+      *reinterpret_cast<float2 *>(p.stats_out + ((size_t)(row0 + qblk * QM + row) * p.heads + head) * 2) = make_float2(st_sum, st_sq);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -309,6 +538,18 @@ using namespace ape;
 extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int n_valid, int heads,
                                int head_dim, float scale, int dtype, float *stats_out, int seq_stride, int causal, int64_t total_rows,
                                void *stream);
+
+// Kernel structure used by ape_attn_fwd*: 0 = attn_fwd_kernel (P through shared memory, 4 CTAs / SM), 1 = attn_fwd5_kernel (P in
+// tensor memory, 2 CTAs / SM).  set >= 0 selects it for the process (tests / tuning); returns the value in force.  The initial
+// value comes from APE_ATTN_VARIANT or the built-in default.
+extern "C" int ape_attn_variant(int set) {
+  static int current = [] {
+    const char *e = getenv("APE_ATTN_VARIANT");
+    return e != nullptr ? atoi(e) : kDefaultAttnVariant;
+  }();
+  if (set >= 0) current = set ? 1 : 0;
+  return current;
+}
 
 extern "C" int ape_attn_fwd(const void *qkv, int64_t ld, void *out, int64_t ldo, int num_seq, int n, int heads,
                             int head_dim, float scale, int dtype, void *stream) {
@@ -352,24 +593,28 @@ extern "C" int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t l
   p.idesc_qk = tc::make_idesc_f16(QM, KN, fmt);
   p.idesc_pv = tc::make_idesc_f16(QM, HD, fmt) | (1u << 16);  // B (= V, [key][channel]) is MN-major
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const size_t smem = sizeof(AttnSmem) + 1024;
   dim3 grid((unsigned)(n / QM), (unsigned)heads, (unsigned)num_seq);
-  if (dtype == APE_DTYPE_F16) {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      set = true;
-    }
-    APE_LAUNCH((attn_fwd_kernel<__half>), grid, kAttnThreads, smem, st, map, p);
+  // kernel structure: 0 = P through shared memory, 4 CTAs / SM (attn_fwd_kernel); 1 = P in tensor memory, double-buffered
+  // S / P / K / V, 2 CTAs / SM (attn_fwd5_kernel).  APE_ATTN_VARIANT overrides the default (read once).
+  const int variant = ape_attn_variant(-1);
+#define APE_ATTN_LAUNCH(KERNEL, SMEM_T)                                                                            \
+  do {                                                                                                             \
+    const size_t smem = sizeof(SMEM_T) + 1024;                                                                     \
+    static bool set = false;                                                                                       \
+    if (!set) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));         \
+      set = true;                                                                                                  \
+    }                                                                                                              \
+    APE_LAUNCH((KERNEL), grid, kAttnThreads, smem, st, map, p);                                                    \
+  } while (0)
+  if (variant == 1) {
+    if (dtype == APE_DTYPE_F16) APE_ATTN_LAUNCH(attn_fwd5_kernel<__half>, AttnSmem5);
+    else APE_ATTN_LAUNCH(attn_fwd5_kernel<__nv_bfloat16>, AttnSmem5);
   } else {
-    static bool set = false;
-    if (!set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return fail((int)e, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      set = true;
-    }
-    APE_LAUNCH((attn_fwd_kernel<__nv_bfloat16>), grid, kAttnThreads, smem, st, map, p);
+    if (dtype == APE_DTYPE_F16) APE_ATTN_LAUNCH(attn_fwd_kernel<__half>, AttnSmem);
+    else APE_ATTN_LAUNCH(attn_fwd_kernel<__nv_bfloat16>, AttnSmem);
   }
+#undef APE_ATTN_LAUNCH
   return check_launch("attn_fwd_kernel");
 }

@@ -132,6 +132,17 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand in TENSOR memory (lane = row of A, 16-bit elements packed two per 32-bit column, K-major): the
+// flash-attention kernel keeps P there (written by tcgen05.st) instead of round-tripping it through shared memory.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued MMAs of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {

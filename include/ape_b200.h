@@ -256,6 +256,11 @@ int ape_attn_fwd_ex(const void *qkv, int64_t ld, void *out, int64_t ldo, int num
                     int head_dim, float scale, int dtype, float *stats_out, int seq_stride, int causal, int64_t total_rows,
                     void *stream);
 
+/* Kernel structure behind ape_attn_fwd*: 0 = P through shared memory (4 CTAs / SM), 1 = P in tensor memory as the A operand of
+ * tcgen05.mma, double-buffered scores (2 CTAs / SM).  set >= 0 selects it for the process; returns the value in force
+ * (initially APE_ATTN_VARIANT or the built-in default). */
+int ape_attn_variant(int set);
+
 /*
  * Cross attention with separate Q / K / V tensors and 64- or 256-channel heads: the two softmax attentions of
  * VisionLanguageFusion for phrase / text prompts (BiMultiHeadAttention.forward, ape/layers/fuse_helper.py:67-166: 8 heads x 256;

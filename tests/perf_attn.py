@@ -11,7 +11,13 @@ for (nb, n) in ((4, 1024), (1, 4096)):
     heads, hd = 16, 64
     qkv = torch.randn(nb * n, 3 * heads * hd, device=DEV, dtype=torch.float16)
     q5 = qkv.view(nb, n, 3, heads, hd)
-    fns = {"own": lambda: ops.attention_qkv(qkv, nb, n, heads, hd, 0.125),
+    def own(variant):
+        def f():
+            ape_b200._lib.lib.ape_attn_variant(variant)
+            return ops.attention_qkv(qkv, nb, n, heads, hd, 0.125)
+        return f
+
+    fns = {"own_smemP": own(0), "own_tmemP": own(1),
            "sdpa": lambda: F.scaled_dot_product_attention(q5[:, :, 0].transpose(1, 2), q5[:, :, 1].transpose(1, 2), q5[:, :, 2].transpose(1, 2), scale=0.125)}
     for name, fn in fns.items():
         for _ in range(3): fn()

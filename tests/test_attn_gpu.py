@@ -7,11 +7,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=[0, 1], ids=["smemP", "tmemP"])
+def ops(request):
+    """Every test of this file runs against both structures of the ViT attention kernel (ape_attn_variant)."""
     import ape_b200
 
-    return ape_b200.ops
+    prev = ape_b200._lib.lib.ape_attn_variant(-1)
+    ape_b200._lib.lib.ape_attn_variant(request.param)
+    yield ape_b200.ops
+    ape_b200._lib.lib.ape_attn_variant(prev)
 
 
 def ref_attention(qkv, num_seq, n, heads, hd, scale):
