@@ -34,7 +34,7 @@ struct BwdParams {
 // flags: 1 = x1 distinct texel, 2 = y1 distinct texel, 4 = left column valid, 8 = right column valid,
 //        16 = top row valid, 32 = bottom row valid (all validity bits are 0 for an out-of-range sample)
 struct __align__(16) BRec {
-  int off_flags;  // byte offset of corner (y0, x0) in `value` (multiple of the >= 16-byte row) | flags
+  unsigned off_flags;  // (byte offset of corner (y0, x0) in `value`, in 16-byte units) << 6 | flags
   float a, lh, lw;
 };
 
@@ -47,9 +47,9 @@ __device__ __forceinline__ BRec make_brec(float x, float y, float a, int Hl, int
   const int y0 = max(hc, 0), x0 = max(wc, 0);
   const int y1 = min(hc + 1, Hl - 1), x1 = min(wc + 1, Wl - 1);
   BRec r;
-  int f = (x1 != x0 ? 1 : 0) | (y1 != y0 ? 2 : 0);
+  unsigned f = (x1 != x0 ? 1 : 0) | (y1 != y0 ? 2 : 0);
   if (in_range) f |= (w_low >= 0 ? 4 : 0) | (w_low < Wl - 1 ? 8 : 0) | (h_low >= 0 ? 16 : 0) | (h_low < Hl - 1 ? 32 : 0);
-  r.off_flags = (((start + y0 * Wl + x0) * H + h) * row_bytes) | f;
+  r.off_flags = ((unsigned)(((start + y0 * Wl + x0) * H + h) * (row_bytes >> 4)) << 6) | f;
   r.a = in_range ? a : 0.f;
   r.lh = in_range ? h_im - floorf(h_im) : 0.f;
   r.lw = in_range ? w_im - floorf(w_im) : 0.f;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(LPR >= 4 ? 256 : 64 * LPR) msda_bwd_kernel(con
   for (int i = tid; i < R * LP; i += NT) {
     const int r = i / LP, s = i - r * LP;
     const int q = q0 + (r >> p.ht_log2), h = h0 + (r & (HT - 1));
-    BRec rec = {0, 0.f, 0.f, 0.f};
+    BRec rec = {0u, 0.f, 0.f, 0.f};
     if (q < p.Q) {
       const int l = s / p.P;
       const size_t e = (((size_t)b * p.Q + q) * p.H + h) * LP + s;
@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(LPR >= 4 ? 256 : 64 * LPR) msda_bwd_kernel(con
 #pragma unroll 1
     for (int pp = 0; pp < p.P; ++pp) {
       const BRec rc = recs[l * p.P + pp];
-      const int f = rc.off_flags;
-      const unsigned o0 = (unsigned)f & ~15u;
+      const unsigned f = rc.off_flags;
+      const unsigned o0 = (f >> 6) << 4;
       const unsigned ox = (f & 1) ? dxb : 0u, oy = (f & 2) ? dyb : 0u;
       const bool L_ok = f & 4, R_ok = f & 8, T_ok = f & 16, B_ok = f & 32;
       const unsigned off[4] = {o0, o0 + ox, o0 + oy, o0 + oy + ox};
@@ -207,7 +207,7 @@ extern "C" int ape_msda_bwd(const void *value, const int64_t *shapes, const int6
     return fail(APE_ERR_INVALID_ARG, "msda_bwd: unknown dtype %d", dtype);
   if (B < 0 || S < 0 || Q < 0 || H <= 0 || D <= 0 || L <= 0 || P <= 0 || L > kBwdMaxLevels || B > 65535)
     return fail(APE_ERR_INVALID_ARG, "msda_bwd: bad sizes B=%d S=%d H=%d D=%d L=%d Q=%d P=%d", B, S, H, D, L, Q, P);
-  if ((long long)S * H * D >= (1LL << 31) / 4) return fail(APE_ERR_UNSUPPORTED, "msda_bwd: S*H*D too large for 32-bit byte offsets");
+  if ((long long)S * H * D * dtype_size(dtype) >= (1LL << 30)) return fail(APE_ERR_UNSUPPORTED, "msda_bwd: one image's value tensor must stay below 1 GiB (26-bit offsets in 16-byte units)");
   if (B == 0 || Q == 0) return APE_OK;
   if (!value || !shapes || !starts || !loc || !attn || !grad_out || !grad_value_f32 || !grad_loc || !grad_attn)
     return fail(APE_ERR_NULL_PTR, "msda_bwd: null pointer argument");

@@ -335,6 +335,7 @@ extern "C" int ape_msda_pair_fused_fwd(const void *value2, const int64_t *shapes
   p.ht_log2 = lg;
   const int QT = 32 >> lg;
   if (tile_w < 0) tile_w = (Q == S && QT >= 8) ? 8 : 0;  // default for self-attention: 8 x (QT/8) pixel tiles
+  while (tile_w > QT && !(tile_w & (tile_w - 1))) tile_w >>= 1;  // small calls run with fewer queries per CTA than the tile asked for
   if (tile_w > 0 && (Q != S || QT % tile_w != 0 || (tile_w & (tile_w - 1))))
     return fail(APE_ERR_INVALID_ARG, "msda_pair: tile_w=%d needs Q == S and a power of two dividing %d", tile_w, QT);
   p.tile_w = tile_w;

@@ -5,6 +5,7 @@ checkpoints load, same forward signature and semantics — but the tail (softmax
 arithmetic, bilinear gather) is ONE launch of libape_b200's fused kernel, and the two
 query-side linears run as one GEMM.  CUDA only; no CPU / PyTorch fallback."""
 import math
+import os
 import warnings
 from typing import Optional
 
@@ -52,8 +53,12 @@ class MultiScaleDeformableAttention(nn.Module):
         self.output_proj = nn.Linear(embed_dim, embed_dim)
         # accepted for config compatibility; this engine has exactly one (CUDA) path
         self.pytorch_attn = pytorch_attn
-        # engine: calls with at least this many queries (the encoder) gather from the pair layout (csrc/msda_pair.cu)
-        self.pair_layout_min_queries = 2048
+        # engine: calls with at least this many queries gather from the pair layout (csrc/msda_pair.cu).  Off by default
+        # (None): measured on B200 the pair kernel is 265-275 us against 293 us for the generic fused kernel on the
+        # encoder call, but the pairing pass costs 33 us, a net loss in the model;
+        # APE_MSDA_PAIR=<min queries> (e.g. 2048) switches it on for A/B runs.
+        env = os.environ.get("APE_MSDA_PAIR", "")
+        self.pair_layout_min_queries = int(env) if env.isdigit() and int(env) > 0 else None
         self._qcat = None
         self.init_weights()
 
@@ -132,7 +137,8 @@ class MultiScaleDeformableAttention(nn.Module):
         ref32 = reference_points.to(torch.float32).contiguous()
         host_shapes = kwargs.get("host_shapes")
         head_dim = self.embed_dim // self.num_heads
-        if engine and host_shapes is not None and num_query >= self.pair_layout_min_queries and \
+        if engine and host_shapes is not None and self.pair_layout_min_queries is not None and \
+                num_query >= self.pair_layout_min_queries and \
                 ops.msda_pair_supported(host_shapes, self.num_heads, head_dim, self.num_points, value.dtype):
             # many queries: pair layout (token s | token s+1 in one 128-byte line) + 16-bit corner blend
             value2 = ops.msda_pair_values(value, self.num_heads, token_mask=key_padding_mask)

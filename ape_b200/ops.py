@@ -436,7 +436,10 @@ def attention_qkv(qkv, num_seq, n, heads, head_dim, scale, n_valid=None, stats_o
     _require(qkv.is_cuda and qkv.dim() == 2 and qkv.stride(1) == 1, "attention: qkv must be a 2-D CUDA tensor")
     stride = n if seq_stride is None else int(seq_stride)
     _require(qkv.shape[0] >= (num_seq - 1) * stride + (n_valid or n) and qkv.shape[1] == 3 * heads * head_dim, "attention: qkv shape")
-    out = torch.empty((qkv.shape[0], heads * head_dim), dtype=qkv.dtype, device=qkv.device)
+    # packed sequences leave the rows between n_valid and the stride unwritten; they come back as masked KEYS of the next
+    # layer, and 0 * NaN in P V would poison it: those rows must stay finite
+    alloc = torch.zeros if (stride < n or (n_valid is not None and n_valid < n)) else torch.empty
+    out = alloc((qkv.shape[0], heads * head_dim), dtype=qkv.dtype, device=qkv.device)
     stats = torch.empty((qkv.shape[0], heads, 2), dtype=torch.float32, device=qkv.device) if stats_out else None
     with torch.cuda.device(qkv.device), _timed(("attention", num_seq, n, heads)):
         rc = _lib.lib.ape_attn_fwd_ex(qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), int(num_seq), int(n),

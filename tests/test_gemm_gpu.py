@@ -230,10 +230,11 @@ def test_swiglu_epilogue_row_statistics(ops, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 256, 256), (2, 64, 64, 256, 256), (1, 16, 16, 64, 128), (1, 256, 256, 256, 256),
-                                            (1, 8, 8, 128, 64), (1, 48, 96, 64, 256)])
+                                            (1, 16, 8, 128, 64), (1, 48, 96, 64, 256)])
 def test_conv3x3_implicit_gemm_matches_conv2d(ops, dtype, B, H, W, Cin, Cout):
     """ape_conv3x3_nhwc (implicit GEMM: 4-D TMA boxes at shifted positions, zero fill = zero padding) vs F.conv2d in fp32."""
     assert ops.conv3x3_supported(H, W, Cin, Cout, dtype)
+    assert not ops.conv3x3_supported(8, 8, Cin, Cout, dtype)  # a 128-pixel tile does not fit an 8 x 8 map: callers fall back
     g = torch.Generator().manual_seed(H + Cin)
     x = torch.randn(B, H, W, Cin, generator=g).to(DEV, dtype)
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(DEV, dtype)
