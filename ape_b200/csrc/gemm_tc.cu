@@ -62,7 +62,14 @@ struct GemmParams {
   // tile of one image, k block kb = (filter tap kb / conv_cblks, 64-channel block kb % conv_cblks); map_a / map_c are 4-D
   int conv;  // 0 = plain GEMM
   int conv_tw, conv_th, conv_tiles_x, conv_tiles_img, conv_cblks;
+  // development aid (ape_gemm_set_trace): 8 clock64 stamps per CTA — 0 entry, 1 set-up done, 2 first operands landed,
+  // 3 last MMA issued, 4 first accumulator complete, 5 last accumulator complete, 6 epilogue drained, 7 exit
+  long long *trace;
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmParams &p, int slot) {
+  if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
 
 template <int BN, int STAGES>
 struct alignas(1024) GemmSmem {
@@ -431,6 +438,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   using Smem = GemmSmem<BN, STAGES>;
   Smem &s = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
@@ -469,6 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc::fence_after_sync();
   const uint32_t tmem_base = s.tmem_base;
   pdl_wait();  // set-up done: operands / residual of the previous kernel may be read, C may be written from here on
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -512,6 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.full[stage], phase);
           tc::fence_after_sync();
+          if (kb == 0 && tile == first) trace_stamp(p, 2);
           const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(s.a[stage]));
           const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(s.b[stage]));
 #pragma unroll
@@ -527,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc::mma_commit(&s.tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      trace_stamp(p, 3);
     }
     __syncwarp();
   } else {
@@ -541,6 +552,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int m_blk = mg * CL + rank;
       tc::mbar_wait(&s.tmem_full[acc], acc_phase);
       tc::fence_after_sync();
+      if (warp == 2 && lane == 0) {
+        if (tile == first) trace_stamp(p, 4);
+        trace_stamp(p, 5);
+      }
       if (p.tma_store) {
         if (p.out_dtype == APE_DTYPE_F32)
           epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
@@ -570,6 +585,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (p.tma_store && lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA exits
     __syncwarp();
+    if (warp == 2 && lane == 0) trace_stamp(p, 6);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -578,6 +594,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) trace_stamp(p, 7);
 }
 
 // CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs owns a 256 x BN output tile.  CTA r loads its own
@@ -872,6 +889,12 @@ struct FuseArgs {  // LayerNorm fold (consume) / SwiGLU row statistics (produce)
   int stats_nslab;
 };
 
+static long long *g_gemm_trace = nullptr;
+
+// Development aid: device buffer of 8 * grid long long receiving clock64 stamps of the next single-CTA / multicast GEMM
+// launches (see GemmParams::trace); nullptr switches it off.  Not for concurrent use.
+extern "C" void ape_gemm_set_trace(long long *device_buffer) { g_gemm_trace = device_buffer; }
+
 static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc,
                      const float *bias, const void *residual, int64_t ldr, int res_dtype, int M, int N, int K, int in_dtype,
                      int out_dtype, int act, int tile_n, const RopeArgs *rope, void *stream, const FuseArgs *fuse = nullptr) {
@@ -916,6 +939,7 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   p.m_blocks = (M + BM - 1) / BM;
   p.k_blocks = (K + BK - 1) / BK;
   p.out_dtype = out_dtype; p.act = act; p.res_dtype = res_dtype;
+  p.trace = g_gemm_trace;
   p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
   // 16-bit outputs with 16-byte aligned rows leave through shared memory + TMA stores
   const int n_out = act == ACT_SWIGLU ? N / 2 : N;

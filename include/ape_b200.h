@@ -193,6 +193,14 @@ int ape_gemm_tn_rope(const void *A, int64_t lda, const void *W, int64_t ldw, voi
                      const int *pos_map, int npos, int head_dim, int rope_cols, int tile_n, void *stream);
 
 /*
+ * Development aid (no reference counterpart): when device_buffer is not NULL, every CTA of the following ape_gemm_tn*
+ * launches (single-CTA / multicast variants) writes 8 clock64() stamps to device_buffer[8 * blockIdx.x ..]:
+ * entry, set-up done, first operands landed, last MMA issued, first / last accumulator complete, epilogue drained, exit.
+ * NULL switches it off.  Process-wide, not for concurrent use.
+ */
+void ape_gemm_set_trace(long long *device_buffer);
+
+/*
  * LayerNorm over the last dimension (nn.LayerNorm / inner_attn_ln / ffn_ln of vit_eva_clip.py:505-523,266,130;
  * norms of the detrex transformer layers).  fp32 statistics; x [rows, C] pitch ldx (in_dtype), y pitch ldy
  * (out_dtype); weight/bias fp32 [C].  Pitches must cover C rounded up to 8 elements; padding elements

@@ -73,8 +73,31 @@ def main():
     for n, t, c in tab[:70]:
         print(f"{t:10.1f} us {c:7.1f}x  {'OWN' if any(m in n for m in OWN_MARKERS) else 'lib'}  {n[:150]}")
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    json.dump({"step_ms": step_ms, "kernel_us_per_step": total, "own_us_per_step": own,
-               "kernels": [{"name": n, "us_per_step": t, "launches_per_step": c} for n, t, c in tab]},
+    by_grid = []
+    try:  # the chrome trace carries grid / block of every kernel record: split the table by launch geometry
+        tmp = args.out + ".trace.json"
+        prof.export_chrome_trace(tmp)
+        g = {}
+        events = json.load(open(tmp))["traceEvents"]
+        os.remove(tmp)
+        t0 = None
+        for ev in events:
+            if ev.get("cat") == "kernel":
+                a = ev.get("args", {})
+                key = (ev["name"], str(a.get("grid")), str(a.get("block")))
+                r = g.setdefault(key, [0.0, 0])
+                r[0] += ev["dur"]
+                r[1] += 1
+                t0 = ev["ts"] if t0 is None else min(t0, ev["ts"])
+        by_grid = sorted(([n, gr, bl, t / args.steps, c / args.steps] for (n, gr, bl), (t, c) in g.items()), key=lambda r: -r[3])
+        print("-- by launch geometry (us per step, launches per step, us per launch)")
+        for n, gr, bl, t, c in by_grid[:60]:
+            print(f"{t:10.1f} us {c:6.1f}x {t / c:8.2f}  {gr:>16s} {bl:>14s}  {n[:110]}")
+    except Exception as ex:  # noqa: BLE001
+        print("no per-geometry table:", ex)
+    json.dump({"step_ms": step_ms, "kernel_us_per_step": total, "own_us_per_step": own, "pdl": os.environ.get("APE_PDL", "1"),
+               "kernels": [{"name": n, "us_per_step": t, "launches_per_step": c} for n, t, c in tab],
+               "by_geometry": [{"name": n, "grid": gr, "block": bl, "us_per_step": t, "launches_per_step": c} for n, gr, bl, t, c in by_grid]},
               open(args.out, "w"), indent=0)
 
 
