@@ -72,6 +72,42 @@ def run(sets, act, tile, i):
     return ops.linear_tc(x, w, b, act=act, tile_n=256 | tile if w.shape[0] > 128 else tile, out=out, **kw)
 
 
+class Clocks:
+    """SM clock / power sampled by NVML in a thread while a measurement runs."""
+
+    def __init__(self):
+        import threading
+
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(0)
+        self.samples, self.stop = [], threading.Event()
+        self.t = threading.Thread(target=self._loop, daemon=True)
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                self.samples.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM), self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3))
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.02)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.t.join()
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return None
+        c = sorted(x[0] for x in self.samples)
+        return {"sm_mhz_median": c[len(c) // 2], "sm_mhz_min": c[0], "power_w_max": round(max(x[1] for x in self.samples)), "n": len(c)}
+
+
 def graph_time(sets, act, tile, launches=20, reps=10):
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -93,6 +129,30 @@ def graph_time(sets, act, tile, launches=20, reps=10):
     e.record()
     torch.cuda.synchronize()
     return a.elapsed_time(e) / (reps * launches) * 1e3
+
+
+def sustained(sets, act, tile, seconds=1.5):
+    """The same graph replayed back to back for `seconds`: (us per launch, clocks under that load)."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(20):
+            run(sets, act, tile, i)
+    g.replay()
+    torch.cuda.synchronize()
+    import time
+    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    with Clocks() as ck:
+        t0 = time.time()
+        a.record()
+        while time.time() - t0 < seconds:
+            for _ in range(20):
+                g.replay()
+            n += 20
+            torch.cuda.synchronize()
+        e.record()
+        torch.cuda.synchronize()
+    return a.elapsed_time(e) / (n * 20) * 1e3, ck.summary()
 
 
 def phases(sets, act, tile):
@@ -131,6 +191,9 @@ def main():
                            ms_per_step_cold=round(us * cnt / 1e3, 3))
                 if name != "pair":
                     rec["cycles"] = phases(warm, act, tile)
+                if name == "single" and M >= 4096:
+                    us, ck = sustained(warm, act, tile)
+                    rec.update(us_sustained=round(us, 2), tflops_sustained=round(flops / us / 1e6, 1), clocks_sustained=ck)
             except Exception as ex:  # noqa: BLE001
                 rec["error"] = str(ex)[:300]
             print(json.dumps(rec), flush=True)
