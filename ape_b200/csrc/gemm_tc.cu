@@ -198,165 +198,169 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams &p, const uint32
 }
 
 
-// 64 accumulator columns of one row -> +bias, activation, +residual (all fp32) in place.
-template <typename TO>
-__device__ __forceinline__ void finish64(const GemmParams &p, float *v, int m, int n0) {
-  if (p.bias != nullptr) {
-    if (n0 + 64 <= p.N) {
+// bias[n0 .. n0+31] added to 32 accumulator columns (columns >= N untouched).
+__device__ __forceinline__ void add_bias32(const GemmParams &p, float *v, int n0) {
+  if (p.bias == nullptr) return;
+  if (n0 + 32 <= p.N) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
-        v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 64; ++i)
-        if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
     }
-  }
-  if (p.rope_cos != nullptr && n0 < p.rope_cols && m < p.M) {  // this 64-column chunk is one head of q or k
-    const int pos = p.rope_pos ? __ldg(p.rope_pos + m) : m % p.rope_npos;
-    const float4 *c4 = reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64);
-    const float4 *s4 = reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64);
+  } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 c = __ldg(c4 + i), sn = __ldg(s4 + i);
-      const float t0 = v[4 * i], t1 = v[4 * i + 1], t2 = v[4 * i + 2], t3 = v[4 * i + 3];
-      v[4 * i] = t0 * c.x - t1 * sn.x;       // rotate_half pairs (2i, 2i+1) -> (-t[2i+1], t[2i])
-      v[4 * i + 1] = t1 * c.y + t0 * sn.y;
-      v[4 * i + 2] = t2 * c.z - t3 * sn.z;
-      v[4 * i + 3] = t3 * c.w + t2 * sn.w;
-    }
-  }
-  apply_act<64>(v, p.act);
-  if (p.residual != nullptr && m < p.M) {
-    add_residual32(p, v, m, n0);
-    if (n0 + 32 < p.N) add_residual32(p, v + 32, m, n0 + 32);
+    for (int i = 0; i < 32; ++i)
+      if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
   }
 }
 
-// Epilogue of one warp for its (32 rows) x (BN/2 accumulator columns) part of a tile, 16-bit output,
-// staged through a swizzled shared-memory slab and written with TMA stores.
+// 2-D rotary embedding on 32 accumulator columns n0..n0+31 of row m (half of one 64-channel head of q or k).
+__device__ __forceinline__ void rope32(const GemmParams &p, float *v, int m, int n0) {
+  const int pos = p.rope_pos ? __ldg(p.rope_pos + m) : m % p.rope_npos;
+  const float4 *c4 = reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64 + (n0 & 63));
+  const float4 *s4 = reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64 + (n0 & 63));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 c = __ldg(c4 + i), sn = __ldg(s4 + i);
+    const float t0 = v[4 * i], t1 = v[4 * i + 1], t2 = v[4 * i + 2], t3 = v[4 * i + 3];
+    v[4 * i] = t0 * c.x - t1 * sn.x;       // rotate_half pairs (2i, 2i+1) -> (-t[2i+1], t[2i])
+    v[4 * i + 1] = t1 * c.y + t0 * sn.y;
+    v[4 * i + 2] = t2 * c.z - t3 * sn.z;
+    v[4 * i + 3] = t3 * c.w + t2 * sn.w;
+  }
+}
+
+// Epilogue of one warp for its (32 rows) x (BN/2 accumulator columns) part of a tile, 16-bit output, staged through a
+// swizzled shared-memory slab (32 rows x 64 output columns) and written with TMA stores.
+//
+// The accumulator is walked in pieces of 32 columns, ONE PIECE AHEAD: the tcgen05.ld of piece i+1 is in flight while piece i
+// is finished and written, so the tensor-memory read port (64 B/clk per SM: 2048 clocks for a 128x256 fp32 tile) streams
+// instead of alternating with the arithmetic.  Measured before this change (clock64 stamps, profiles/r02_gemm_phases.txt):
+// ~4400-4950 clocks per tile, which bounded every K = 256 GEMM of the encoder (mainloop floor 2048 clocks per tile).
 template <typename TO, int BN>
 __device__ __forceinline__ void epilogue_tma(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab,
-                                             uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk) {
+                                             uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk,
+                                             uint64_t *full_bar, uint32_t full_phase) {
   const int row0 = m_blk * BM + quad * 32;
   const int m = row0 + lane;
   const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16);
   uint8_t *my_row = slab + lane * 128;
   constexpr int HALF = BN / 2;
-  if (p.act == ACT_SWIGLU) {
-    // 128 accumulator columns (64 gate/up pairs) -> 64 output columns = one slab
+  const bool swiglu = p.act == ACT_SWIGLU;
+  const int per_slab = swiglu ? 4 : 2;  // pieces (32 accumulator columns) per 64-column output slab
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+  tc::mbar_wait(full_bar, full_phase);
+  tc::fence_after_sync();
+  if (n_blk * BN + c_begin >= p.N) return;
+  uint32_t rn[32];
+  tc::tmem_ld_32x32b_x32(trow + c_begin, rn);
+  float st_sum = 0.f, st_sq = 0.f;
+  bool dirty = false;
+  int slab_c0 = c_begin;  // accumulator column (inside the tile) of the slab being filled
 #pragma unroll 1
-    for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 128) {
-      if (lane == 0) tc::tma_store_wait_read0();
+  for (int c = c_begin; c < c_end; c += 32) {
+    const int n0 = n_blk * BN + c;
+    if (n0 >= p.N) break;
+    const int q = ((c - c_begin) >> 5) % per_slab;
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
+    if (c + 32 < c_end && n0 + 32 < p.N) tc::tmem_ld_32x32b_x32(trow + c + 32, rn);
+    add_bias32(p, v, n0);
+    if (q == 0) {
+      slab_c0 = c;
+      if (lane == 0) tc::tma_store_wait_read0();  // the previous store of this warp has drained the slab
       __syncwarp();
-      float st_sum = 0.f, st_sq = 0.f;
+    }
+    if (swiglu) {
+      // interleaved (gate, up) column pairs -> silu(gate) * up: 16 outputs (vit_eva_clip.py:126-128)
+      float o[16];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[64];
-        tc::tmem_ld_32x32b_x32(trow + c0 + hh * 64, r);
-        tc::tmem_ld_32x32b_x32(trow + c0 + hh * 64 + 32, r + 32);
-        tc::tmem_ld_wait();
-        float v[64];
+      for (int i = 0; i < 16; ++i) {
+        const float g = v[2 * i];
+        o[i] = g / (1.f + __expf(-g)) * v[2 * i + 1];
+      }
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-        GemmParams q = p;
-        q.residual = nullptr;
-        const int n0 = n_blk * BN + c0 + hh * 64;
-        // bias only (activation is the gate below)
-        if (p.bias != nullptr) {
-          if (n0 + 64 <= p.N) {
+      for (int j = 0; j < 2; ++j) {
+        const uint4 pk = Elem<TO>::pack(o + 8 * j);
+        *reinterpret_cast<uint4 *>(my_row + (((2 * q + j) ^ (lane & 7)) << 4)) = pk;
+        if (p.stats_out != nullptr) {  // statistics of the values as stored (16-bit), columns beyond N/2 excluded
+          float f[8];
+          Elem<TO>::unpack(pk, f);
+          const int col0 = n0 / 2 + 8 * j;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
-              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
-          }
-        }
-        float o[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float g = v[2 * i];
-          o[i] = g / (1.f + __expf(-g)) * v[2 * i + 1];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = hh * 4 + j;
-          const uint4 pk = Elem<TO>::pack(o + 8 * j);
-          *reinterpret_cast<uint4 *>(my_row + ((chunk ^ (lane & 7)) << 4)) = pk;
-          if (p.stats_out != nullptr) {  // statistics of the values as stored (16-bit), columns beyond N/2 excluded
-            float f[8];
-            Elem<TO>::unpack(pk, f);
-            const int col0 = n0 / 2 + 8 * j;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (col0 + i < p.N / 2) { st_sum += f[i]; st_sq += f[i] * f[i]; }
-          }
+          for (int i = 0; i < 8; ++i)
+            if (col0 + i < p.N / 2) { st_sum += f[i]; st_sq += f[i] * f[i]; }
         }
       }
-      if (p.stats_out != nullptr && m < p.M) {
-        const int slab_idx = (n_blk * BN + c0) / 128;
+    } else {
+      if (p.rope_cos != nullptr && n0 < p.rope_cols && m < p.M) rope32(p, v, m, n0);
+      apply_act<32>(v, p.act);
+      if (p.residual != nullptr && m < p.M) add_residual32(p, v, m, n0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4 *>(my_row + (((4 * q + j) ^ (lane & 7)) << 4)) = Elem<TO>::pack(v + 8 * j);
+    }
+    dirty = true;
+    if (q == per_slab - 1 || c + 32 >= c_end || n0 + 32 >= p.N) {  // slab complete (or last piece of this warp): store it
+      const int out_n0 = swiglu ? (n_blk * BN + slab_c0) / 2 : n_blk * BN + slab_c0;
+      if (swiglu && p.stats_out != nullptr && m < p.M) {
+        const int slab_idx = (n_blk * BN + slab_c0) / 128;
         if (slab_idx < p.stats_nslab)
           *reinterpret_cast<float2 *>(p.stats_out + ((size_t)m * p.stats_nslab + slab_idx) * 2) = make_float2(st_sum, st_sq);
+        st_sum = 0.f; st_sq = 0.f;
       }
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tc::tma_store_2d(map_c, slab, (n_blk * BN + c0) / 2, row0);
+        if (p.conv) {  // the slab's 32 tile rows are min(tw, 32) x 32 / min(tw, 32) pixels of the output image
+          const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
+          const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
+          const int r0 = quad * 32;
+          tc::tma_store_4d(map_c, slab, out_n0, tx * p.conv_tw + r0 % p.conv_tw, ty * p.conv_th + r0 / p.conv_tw, img);
+        } else {
+          tc::tma_store_2d(map_c, slab, out_n0, row0);
+        }
         tc::tma_store_commit();
       }
-    }
-    return;
-  }
-#pragma unroll 1
-  for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 64) {
-    const int n0 = n_blk * BN + c0;
-    if (n0 >= p.N) break;
-    uint32_t r[64];
-    tc::tmem_ld_32x32b_x32(trow + c0, r);
-    tc::tmem_ld_32x32b_x32(trow + c0 + 32, r + 32);
-    tc::tmem_ld_wait();
-    float v[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
-    finish64<TO>(p, v, m, n0);
-    if (lane == 0) tc::tma_store_wait_read0();  // previous store of this warp has drained the slab
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<uint4 *>(my_row + ((j ^ (lane & 7)) << 4)) = Elem<TO>::pack(v + 8 * j);
-    tc::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      if (p.conv) {  // the slab's 32 tile rows are min(tw, 32) x 32 / min(tw, 32) pixels of the output image
-        const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
-        const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
-        const int r0 = quad * 32;
-        tc::tma_store_4d(map_c, slab, n0, tx * p.conv_tw + r0 % p.conv_tw, ty * p.conv_th + r0 / p.conv_tw, img);
-      } else {
-        tc::tma_store_2d(map_c, slab, n0, row0);
-      }
-      tc::tma_store_commit();
+      dirty = false;
     }
   }
+  (void)dirty;
 }
 
-// fp32 output: the warp's (32 rows) x (BN/2 columns) part of a tile in steps of 32 columns = one 128-byte-swizzled slab
+// fp32 output: the warp's (32 rows) x (BN/2 columns) part of a tile in pieces of 32 columns = one 128-byte-swizzled slab
 // (32 rows x 128 B) per TMA store.  Used for the residual stream (sum kept in fp32 between the 16-bit GEMMs) and for
 // logits that feed top-k / NMS.
+//
+// Everything this epilogue reads from global memory is requested BEFORE it is needed: the row statistics and the first
+// piece's residual before the accumulator is even complete, the residual of piece i+1 (and its tcgen05.ld) while piece i
+// is finished and stored.  Measured before (clock64 stamps): 25-28 k clocks for the one tile of a proj / w3 CTA against a
+// 10 k-clock mainloop — three dependent round trips (colsum, bias, residual) per piece behind the tensor-memory wait.
 template <int BN>
 __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab,
-                                                 uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk) {
+                                                 uint32_t tmem_tile, int quad, int half, int lane, int m_blk, int n_blk,
+                                                 uint64_t *full_bar, uint32_t full_phase) {
   const int row0 = m_blk * BM + quad * 32;
   const int m = row0 + lane;
   const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16);
   uint8_t *my_row = slab + lane * 128;
   constexpr int HALF = BN / 2;
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+  // residual rows that may be fetched as aligned float4 ahead of time
+  const bool fast_res = p.residual != nullptr && p.res_dtype == APE_DTYPE_F32 && (p.ldr & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && m < p.M;
+  const float *res_row = reinterpret_cast<const float *>(p.residual) + (size_t)m * p.ldr;
+  float4 rs_next[8];
+  auto fetch_res = [&](int n0) {
+    if (fast_res && n0 + 32 <= p.N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs_next[i] = __ldg(reinterpret_cast<const float4 *>(res_row + n0) + i);
+    }
+  };
+  const int n_first = n_blk * BN + c_begin;
+  if (n_first < p.N) fetch_res(n_first);
   float ln_mean = 0.f, ln_rstd = 1.f;
   if (p.ln_part != nullptr && m < p.M) {  // row statistics from the producer's partials, summed in a fixed order
     const float2 *pp = reinterpret_cast<const float2 *>(p.ln_part) + (size_t)m * p.ln_nparts;
@@ -369,25 +373,35 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
     ln_mean = sum * p.ln_inv_c;
     ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
   }
+  tc::mbar_wait(full_bar, full_phase);
+  tc::fence_after_sync();
+  if (n_first >= p.N) return;
+  uint32_t rn[32];
+  tc::tmem_ld_32x32b_x32(trow + c_begin, rn);
 #pragma unroll 1
-  for (int c0 = half * HALF; c0 < (half + 1) * HALF; c0 += 32) {
-    const int n0 = n_blk * BN + c0;
+  for (int c = c_begin; c < c_end; c += 32) {
+    const int n0 = n_blk * BN + c;
     if (n0 >= p.N) break;
-    uint32_t r[32];
-    tc::tmem_ld_32x32b_x32(trow + c0, r);
     tc::tmem_ld_wait();
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
+    float4 rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rs[i] = rs_next[i];
+    if (c + 32 < c_end && n0 + 32 < p.N) {
+      tc::tmem_ld_32x32b_x32(trow + c + 32, rn);
+      fetch_res(n0 + 32);
+    }
     if (p.ln_part != nullptr) {  // rstd * (acc - mean * colsum); the bias below is beta W^T + b
       if (n0 + 32 <= p.N) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 c = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + n0) + i);
-          v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * c.x);
-          v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * c.y);
-          v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * c.z);
-          v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * c.w);
+          const float4 cs = __ldg(reinterpret_cast<const float4 *>(p.ln_colsum + n0) + i);
+          v[4 * i] = ln_rstd * (v[4 * i] - ln_mean * cs.x);
+          v[4 * i + 1] = ln_rstd * (v[4 * i + 1] - ln_mean * cs.y);
+          v[4 * i + 2] = ln_rstd * (v[4 * i + 2] - ln_mean * cs.z);
+          v[4 * i + 3] = ln_rstd * (v[4 * i + 3] - ln_mean * cs.w);
         }
       } else {
 #pragma unroll
@@ -395,21 +409,16 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
           if (n0 + i < p.N) v[i] = ln_rstd * (v[i] - ln_mean * __ldg(p.ln_colsum + n0 + i));
       }
     }
-    if (p.bias != nullptr) {
-      if (n0 + 32 <= p.N) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + i);
-          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
-      }
-    }
+    add_bias32(p, v, n0);
     apply_act<32>(v, p.act);
-    if (p.residual != nullptr && m < p.M) add_residual32(p, v, m, n0);
+    if (fast_res && n0 + 32 <= p.N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[4 * i] += rs[i].x; v[4 * i + 1] += rs[i].y; v[4 * i + 2] += rs[i].z; v[4 * i + 3] += rs[i].w;
+      }
+    } else if (p.residual != nullptr && m < p.M) {
+      add_residual32(p, v, m, n0);
+    }
     if (lane == 0) tc::tma_store_wait_read0();
     __syncwarp();
 #pragma unroll
@@ -550,20 +559,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
       const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
       const int m_blk = mg * CL + rank;
-      tc::mbar_wait(&s.tmem_full[acc], acc_phase);
-      tc::fence_after_sync();
-      if (warp == 2 && lane == 0) {
-        if (tile == first) trace_stamp(p, 4);
-        trace_stamp(p, 5);
+      if (p.trace != nullptr && warp == 2) {  // (tracing only: the stamp needs the wait here; it is repeated below at no cost)
+        tc::mbar_wait(&s.tmem_full[acc], acc_phase);
+        if (lane == 0) {
+          if (tile == first) trace_stamp(p, 4);
+          trace_stamp(p, 5);
+        }
       }
-      if (p.tma_store) {
+      if (p.tma_store) {  // these wait for the accumulator themselves, after requesting what they read from global memory
         if (p.out_dtype == APE_DTYPE_F32)
-          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
         else if (p.out_dtype == APE_DTYPE_F16)
-          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
         else
-          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
       } else {
+        tc::mbar_wait(&s.tmem_full[acc], acc_phase);
+        tc::fence_after_sync();
         const int m = m_blk * BM + quad * 32 + lane;
 #pragma unroll 1
         for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
@@ -714,16 +726,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_pairs;
       const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
       const int m_blk = mg * 2 + (int)rank;
-      tc::mbar_wait(&s.tmem_full[acc], acc_phase);
-      tc::fence_after_sync();
-      if (p.tma_store) {
+      if (p.tma_store) {  // these wait for the accumulator themselves, after requesting what they read from global memory
         if (p.out_dtype == APE_DTYPE_F32)
-          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
         else if (p.out_dtype == APE_DTYPE_F16)
-          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
         else
-          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk);
+          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
       } else {
+        tc::mbar_wait(&s.tmem_full[acc], acc_phase);
+        tc::fence_after_sync();
         const int m = m_blk * BM + quad * 32 + lane;
 #pragma unroll 1
         for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
