@@ -108,6 +108,18 @@ def _declare(lib):
     lib.ape_nms_classwise_workspace_bytes.argtypes = [_i]
     lib.ape_nms_classwise.restype = _i
     lib.ape_nms_classwise.argtypes = [_vp, _vp, _i64, _vp, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]
+    lib.ape_mask_crop_workspace_bytes.restype = _i64
+    lib.ape_mask_crop_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.ape_mask_crop.restype = _i
+    lib.ape_mask_crop.argtypes = [_vp] * 5 + [_i] * 7 + [_vp]
+    lib.ape_mask_paste.restype = _i
+    lib.ape_mask_paste.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]
+    lib.ape_resample_ksize.restype = _i
+    lib.ape_resample_ksize.argtypes = [_i, _i]
+    lib.ape_resample_coeffs_u8.restype = _i
+    lib.ape_resample_coeffs_u8.argtypes = [_i, _i, _vp, _vp]
+    lib.ape_resample_u8.restype = _i
+    lib.ape_resample_u8.argtypes = [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i, _vp, _vp, _i] + [_i] * 6 + [_vp]
 
 
 
@@ -148,6 +160,12 @@ EXPORTS = (
     "ape_nms_sorted_dev",
     "ape_nms_classwise_workspace_bytes",
     "ape_nms_classwise",
+    "ape_mask_crop_workspace_bytes",
+    "ape_mask_crop",
+    "ape_mask_paste",
+    "ape_resample_ksize",
+    "ape_resample_coeffs_u8",
+    "ape_resample_u8",
 )
 
 

@@ -157,6 +157,8 @@ def paste_masks_in_image(masks, boxes, image_shape, threshold=0.5):
     img_h, img_w = int(image_shape[0]), int(image_shape[1])
     if N == 0:
         return masks.new_empty((0, img_h, img_w), dtype=torch.bool)
+    if masks.is_cuda:  # ape_mask_paste: the sampling grid lives in registers (the library path below is the host route)
+        return ops.paste_masks_in_image(masks, boxes, (img_h, img_w), threshold)
     out = torch.zeros((N, img_h, img_w), device=masks.device, dtype=torch.bool)
     chunk = max(1, int((1 << 30) // (img_h * img_w * 4)))  # GPU_MEM_LIMIT of 1 GiB, as detectron2
     for i0 in range(0, N, chunk):
@@ -547,8 +549,11 @@ class DeformableDETRSegmVL(nn.Module):
         padded_hw = tuple(images.shape[-2:])
         if instance_on and self.test_mask_on:
             for b, r in enumerate(results):  # (:588-603) masks of the kept queries only (bilinear resize is per channel)
-                m = F.interpolate(mask_pred[b, r.query_index][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0]
-                m = bitmasks_crop_and_resize(m.sigmoid() > 0.5, r.pred_boxes.tensor.to(m.device), 128)
+                if mask_pred.is_cuda:  # upsample > 0 as bits + ROIAlign over the bits (csrc/mask_post.cu): no fp32 full-size maps
+                    m = ops.mask_crop_and_resize(mask_pred[b].contiguous(), r.query_index, r.pred_boxes.tensor, padded_hw, 128)
+                else:
+                    m = F.interpolate(mask_pred[b, r.query_index][None].float(), size=padded_hw, mode="bilinear", align_corners=False)[0]
+                    m = bitmasks_crop_and_resize(m.sigmoid() > 0.5, r.pred_boxes.tensor.to(m.device), 128)
                 r.pred_masks = m.unsqueeze(1).to(torch.float32)
         if not do_postprocess:
             return results, None, None

@@ -558,6 +558,95 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     return nms(boxes + offsets[:, None], scores, iou_threshold)
 
 
+def mask_crop_and_resize(mask_logits, index, boxes, padded_hw, mask_size=128):
+    """`BitMasks(F.interpolate(mask_logits[index], padded_hw, "bilinear").sigmoid() > 0.5).crop_and_resize(boxes, mask_size)`
+    (deformable_detr_segm_vl.py:569-598) for the kept queries of one image: mask_logits [Q,h,w] (fp32 / fp16 / bf16, CUDA),
+    index int64 [K], boxes fp32 [K,4] in padded-image pixels -> bool [K,mask_size,mask_size].  One bit per upsampled pixel of
+    workspace; the fp32 full-resolution maps are never formed."""
+    _require(mask_logits.is_cuda and mask_logits.dim() == 3 and mask_logits.is_contiguous(), "mask_crop: contiguous CUDA logits [Q,h,w]")
+    K = int(index.numel())
+    out = torch.empty((K, mask_size, mask_size), dtype=torch.uint8, device=mask_logits.device)
+    if K == 0:
+        return out.bool()
+    index = index.to(device=mask_logits.device, dtype=torch.int64).contiguous()
+    boxes = boxes.to(device=mask_logits.device, dtype=torch.float32).contiguous()
+    _require(tuple(boxes.shape) == (K, 4), "mask_crop: boxes must be [K,4]")
+    Hp, Wp = int(padded_hw[0]), int(padded_hw[1])
+    ws = torch.empty((int(_lib.lib.ape_mask_crop_workspace_bytes(K, Hp, Wp)),), dtype=torch.uint8, device=mask_logits.device)
+    with torch.cuda.device(mask_logits.device), _timed(("mask_crop", K, Hp, Wp)):
+        rc = _lib.lib.ape_mask_crop(mask_logits.data_ptr(), index.data_ptr(), boxes.data_ptr(), ws.data_ptr(), out.data_ptr(), K,
+                                    mask_logits.shape[1], mask_logits.shape[2], Hp, Wp, int(mask_size),
+                                    _lib.dtype_code(mask_logits.dtype), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_mask_crop")
+    return out.view(torch.bool)
+
+
+def paste_masks_in_image(masks, boxes, image_shape, threshold=0.5):
+    """detectron2.layers.mask_ops.paste_masks_in_image for 0 / 1 masks [N,S,S] (bool or float) and boxes [N,4] (output-image
+    pixels) -> bool [N,H,W] (ape_mask_paste: no sampling grid, no float maps in memory)."""
+    N, S = masks.shape[0], masks.shape[-1]
+    img_h, img_w = int(image_shape[0]), int(image_shape[1])
+    out = torch.empty((N, img_h, img_w), dtype=torch.uint8, device=masks.device)
+    if N == 0:
+        return out.view(torch.bool)
+    _require(masks.is_cuda and masks.dim() == 3 and masks.shape[1] == S, "mask_paste: CUDA masks [N,S,S]")
+    m8 = masks.view(torch.uint8) if masks.dtype == torch.bool else (masks >= 0.5).to(torch.uint8)
+    m8 = m8.contiguous()
+    boxes = boxes.to(device=masks.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(masks.device), _timed(("mask_paste", N, img_h, img_w)):
+        rc = _lib.lib.ape_mask_paste(m8.data_ptr(), boxes.data_ptr(), out.data_ptr(), N, S, img_h, img_w, float(threshold),
+                                     _lib.current_stream_ptr())
+    _lib.check(rc, "ape_mask_paste")
+    return out.view(torch.bool)
+
+
+_RESAMPLE_TABLES = {}
+
+
+def resample_tables(in_size, out_size, device):
+    """Pillow's bilinear taps for one axis (ape_resample_coeffs_u8, the arithmetic of libImaging/Resample.c:precompute_coeffs +
+    normalize_coeffs_8bpc) as device tensors: (bounds int32 [out,2], taps int32 [out,ksize], ksize).  Cached per geometry."""
+    key = (int(in_size), int(out_size), str(device))
+    hit = _RESAMPLE_TABLES.get(key)
+    if hit is None:
+        ksize = int(_lib.lib.ape_resample_ksize(int(in_size), int(out_size)))
+        _lib.check(0 if ksize > 0 else ksize, "ape_resample_ksize")
+        bounds = torch.empty((out_size, 2), dtype=torch.int32)
+        kk = torch.empty((out_size, ksize), dtype=torch.int32)
+        _lib.check(_lib.lib.ape_resample_coeffs_u8(int(in_size), int(out_size), bounds.data_ptr(), kk.data_ptr()), "ape_resample_coeffs_u8")
+        if len(_RESAMPLE_TABLES) > 64:
+            _RESAMPLE_TABLES.clear()
+        hit = _RESAMPLE_TABLES[key] = (bounds.to(device), kk.to(device), ksize)
+    return hit
+
+
+def resize_u8_bilinear(img, new_h, new_w, flip_channels=False, out=None):
+    """PIL `Image.fromarray(img).resize((new_w, new_h), BILINEAR)` of a uint8 HWC (or HW) image on the device, bit for bit,
+    returned as the float32 [C, new_h, new_w] tensor the predictor puts into the model's input dict
+    (ape/engine/defaults.py:221-222: `torch.as_tensor(image.astype("float32").transpose(2, 0, 1))`).
+    img: CUDA uint8 [H,W,C] / [H,W] with contiguous pixels (rows may be pitched); flip_channels folds the `[:, :, ::-1]` of
+    defaults.py:218-220 into the write; out: optional float32 [C,>=new_h,>=new_w] view to write into (e.g. a padded batch)."""
+    _require(img.is_cuda and img.dtype == torch.uint8 and img.dim() in (2, 3), "resize_u8_bilinear: CUDA uint8 [H,W,C] or [H,W] image")
+    if img.dim() == 2:
+        img = img.unsqueeze(-1)
+    H, W, C = img.shape
+    _require(1 <= C <= 4 and img.stride(2) == 1 and img.stride(1) == C, "resize_u8_bilinear: pixels must be contiguous (1-4 channels)")
+    new_h, new_w = int(new_h), int(new_w)
+    if out is None:
+        out = torch.empty((C, new_h, new_w), dtype=torch.float32, device=img.device)
+    _require(out.is_cuda and out.dtype == torch.float32 and out.dim() == 3 and out.shape[0] == C and out.shape[1] >= new_h and
+             out.shape[2] >= new_w and out.stride(2) == 1, "resize_u8_bilinear: out must be float32 [C,>=new_h,>=new_w] with unit column stride")
+    bh, kh, ksh = resample_tables(W, new_w, img.device)
+    bv, kv, ksv = resample_tables(H, new_h, img.device)
+    tmp = torch.empty((H, new_w, C), dtype=torch.uint8, device=img.device)
+    with torch.cuda.device(img.device), _timed(("resample", H, W, new_h, new_w)):
+        rc = _lib.lib.ape_resample_u8(img.data_ptr(), img.stride(0), tmp.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1),
+                                      bh.data_ptr(), kh.data_ptr(), ksh, bv.data_ptr(), kv.data_ptr(), ksv, H, W, C, new_h, new_w,
+                                      1 if flip_channels else 0, _lib.current_stream_ptr())
+    _lib.check(rc, "ape_resample_u8")
+    return out[:, :new_h, :new_w]
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, im2col_step=64):
     """[grad_value, grad_sampling_loc, grad_attn_weight] (ape_msda_bwd; ms_deform_attn_cuda.cu:84-160).  grad_value is
     accumulated in fp32 by vector atomics and cast to value's dtype at the end."""

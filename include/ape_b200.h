@@ -320,6 +320,40 @@ int64_t ape_nms_classwise_workspace_bytes(int Q);
 int ape_nms_classwise(const float *boxes, const float *scores, int64_t ld_scores, const uint8_t *row_valid, int Q, int N,
                       float score_thresh, float iou_threshold, void *workspace, float *out, void *stream);
 
+/*
+ * Input pipeline of the predictor: the ResizeShortestEdge of DefaultPredictor.__call__
+ * (ape/engine/defaults.py:203-230 -> detectron2 ResizeTransform.apply_image -> PIL Image.resize(BILINEAR) for uint8 images)
+ * on the device, BIT-EXACT with Pillow's libImaging/Resample.c (triangle filter widened by the down-scaling factor, 22-bit
+ * fixed-point taps, uint8 intermediate between the horizontal and the vertical pass).
+ *   ape_resample_ksize      taps per output sample for one axis (host)
+ *   ape_resample_coeffs_u8  HOST tables of one axis: bounds [out,2] int32 (first source sample, tap count), kk [out,ksize] int32
+ *   ape_resample_u8         src [H,W,C] uint8 (row pitch src_pitch bytes) -> out float32 planes [C][new_h][new_w] with element
+ *                           strides (plane_stride, row_stride); tmp [H,new_w,C] uint8 workspace; tables as DEVICE copies;
+ *                           flip_channels: source channel c lands in plane C-1-c (BGR -> RGB, defaults.py:218-220)
+ */
+int ape_resample_ksize(int in_size, int out_size);
+int ape_resample_coeffs_u8(int in_size, int out_size, int *bounds_host, int *kk_host);
+int ape_resample_u8(const uint8_t *src, int64_t src_pitch, uint8_t *tmp, float *out, int64_t plane_stride, int64_t row_stride,
+                    const int *bounds_h, const int *kk_h, int ksize_h, const int *bounds_v, const int *kk_v, int ksize_v, int H,
+                    int W, int C, int new_h, int new_w, int flip_channels, void *stream);
+
+/*
+ * Instance-mask post-processing for the detections that survive the final selection (deformable_detr_segm_vl.py:569-603 and
+ * detectron2 detector_postprocess / paste_masks_in_image), without the full-resolution fp32 maps:
+ *   ape_mask_crop   logits [Q,h,w] dtype (one image), index [K] int64 kept queries, boxes [K,4] fp32 xyxy in padded-image
+ *                   pixels -> out [K,S,S] bytes = (ROIAlign(S, scale 1, sampling_ratio 0, aligned) of (bilinear upsample to
+ *                   Hp x Wp, align_corners=False, > 0) >= 0.5), i.e. BitMasks(sigmoid(mask) > 0.5).crop_and_resize(boxes, S).
+ *                   workspace: ape_mask_crop_workspace_bytes(K, Hp, Wp) (one bit per upsampled pixel).
+ *   ape_mask_paste  masks [N,S,S] bytes (0 / 1), boxes [N,4] fp32 in OUTPUT-image pixels -> out [N,img_h,img_w] bytes (bool):
+ *                   bilinear grid_sample (zeros padding, align_corners=False) of the mask inside its box >= threshold.
+ * boxes 16-byte aligned.
+ */
+int64_t ape_mask_crop_workspace_bytes(int K, int Hp, int Wp);
+int ape_mask_crop(const void *logits, const int64_t *index, const float *boxes, void *workspace, uint8_t *out, int K, int h, int w,
+                  int Hp, int Wp, int S, int dtype, void *stream);
+int ape_mask_paste(const uint8_t *masks, const float *boxes, uint8_t *out, int N, int S, int img_h, int img_w, float threshold,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif
