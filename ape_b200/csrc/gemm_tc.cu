@@ -60,6 +60,14 @@ struct GemmParams {
   int stats_nslab;
   // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over an NHWC image: an m block is a conv_tw x conv_th pixel
   // tile of one image, k block kb = (filter tap kb / conv_cblks, 64-channel block kb % conv_cblks); map_a / map_c are 4-D
+  // operand kept in shared memory for GEMMs with a short K loop (K <= STAGES * 64; single-CTA kernel only).  The L2 -> SM
+  // fabric delivers ~6300 B/clk to the whole chip (~42 B/clk per SM): a 128 x 256 tile with K = 256 fetches 192 KB for 2048
+  // clocks of MMA, i.e. it is operand-fetch bound at ~4500 clocks per tile (measured 4400-4950).
+  //   1: W resident — one column block (N <= BN): the whole weight matrix is loaded once per CTA, only A tiles stream (64 KB per tile)
+  //   2: A resident — a CTA owns whole row blocks: the A rows are loaded once per row block and only W tiles stream (128 KB)
+  int resident;
+  int lean;      // lean whole-tile epilogue selected on the host (epilogue_dispatch), 0 = general code only
+  int prefetch;  // bit 0: bias / column sums into L1, bit 1: residual rows into L2, one tile ahead (epilogue_prefetch)
   int conv;  // 0 = plain GEMM
   int conv_tw, conv_th, conv_tiles_x, conv_tiles_img, conv_cblks;
   // development aid (ape_gemm_set_trace): 8 clock64 stamps per CTA — 0 entry, 1 set-up done, 2 first operands landed,
@@ -78,10 +86,47 @@ struct alignas(1024) GemmSmem {
   uint8_t c[8][32 * 128];  // per epilogue warp: 32 rows x 64 16-bit columns, 128-byte swizzle (1024 B aligned)
   uint64_t full[STAGES], empty[STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t res_full, res_empty;  // resident operand landed / no longer read by any MMA
   uint32_t tmem_base;
 };
 
 constexpr int kThreads = 320;
+
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *ptr) {  // read once: keep it out of L1 (bias / column sums stay)
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+  return r;
+}
+
+// What the epilogue of tile (m_blk, n_blk) will read from global memory, requested ahead of time by the warp that will need it
+// (rows quad*32 + lane, columns half * BN/2 ...): bias and LayerNorm column sums into L1, the residual rows into L2.  Called one
+// tile ahead (and for a CTA's first tile at kernel start, while the main loop runs), so that the accumulator wait is followed by
+// cache hits instead of dependent round trips to HBM: the epilogue tail of a one-tile CTA (proj / w3: 128 tiles on 148 SMs) was
+// 23-28 k clocks against a 10 k-clock main loop.
+template <int BN>
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams &p, int quad, int half, int lane, int m_blk, int n_blk) {
+  constexpr int HALF = BN / 2;
+  const int n0 = n_blk * BN + half * HALF;
+  if (n0 >= p.N) return;
+  const int ncols = min(HALF, p.N - n0);
+  if (p.prefetch & 1) {
+    if (lane < 4) {
+      if (p.bias != nullptr && 32 * lane < ncols) prefetch_l1(p.bias + n0 + 32 * lane);
+    } else if (lane < 8) {
+      if (p.ln_colsum != nullptr && 32 * (lane - 4) < ncols) prefetch_l1(p.ln_colsum + n0 + 32 * (lane - 4));
+    }
+  }
+  if (!(p.prefetch & 2)) return;
+  const int m = m_blk * BM + quad * 32 + lane;
+  if (p.residual != nullptr && m < p.M) {
+    const int es = p.res_dtype == APE_DTYPE_F32 ? 4 : 2;
+    const char *row = reinterpret_cast<const char *>(p.residual) + ((size_t)m * p.ldr + n0) * es;
+    for (int off = 0; off < ncols * es; off += 128) prefetch_l2(row + off);
+  }
+  if (p.ln_part != nullptr && m < p.M && half == 0) prefetch_l2(p.ln_part + (size_t)m * p.ln_nparts * 2);
+}
 
 // Activation over N accumulator values; the switch is OUTSIDE the unrolled loops (one uniform branch per chunk, not per
 // element: with the branch inside, the three-way select around the inlined erff made the ReLU epilogue 4x slower).
@@ -435,6 +480,282 @@ __device__ __forceinline__ void epilogue_tma_f32(const GemmParams &p, const CUte
   }
 }
 
+// ---- lean epilogues -------------------------------------------------------------------------------------------------
+// ncu on the K = 256 encoder GEMMs (profiles/r02_gemm_ffn1_ncu_source.txt): the general epilogues above execute ~270 SASS
+// instructions per piece of 32 columns where the arithmetic needs ~90 (address / predicate / branch code for ragged edges,
+// rotary embedding, residual dtypes and activation selection inside the piece loop, IEEE division in the SwiGLU gate), and with
+// two epilogue warps per scheduler the tile time follows the instruction count: ~8 k clocks per 128 x 256 tile against a
+// 2 k-clock main loop.  Every GEMM of the step was bounded by that (single CTA = multicast = CTA pair to within noise).
+// The functions below cover the whole-tile cases the model actually runs — everything decided at compile time, piece loop
+// fully unrolled, shared-memory stores through 32-bit shared addresses, the next piece's tensor-memory read and bias in
+// flight while the current one is finished — and fall back to the general code for ragged column blocks / other options.
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 16-bit output, bias (optional), ACT in {none, relu}: the warp's 32 rows x BN/2 columns = BN/128 slabs of 64 columns.
+template <typename TO, int ACT, bool HAS_BIAS, int BN>
+__device__ __forceinline__ void epi16_fast(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab, uint32_t tmem_tile,
+                                           int quad, int half, int lane, int m_blk, int n_blk, uint64_t *full_bar,
+                                           uint32_t full_phase) {
+  constexpr int HALF = BN / 2, PIECES = HALF / 32;
+  const int row0 = m_blk * BM + quad * 32;
+  const int n0 = n_blk * BN + half * HALF;
+  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF;
+  const uint32_t my_row = tc::smem_u32(slab) + lane * 128;
+  const uint32_t sw = lane & 7;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + n0);
+  float4 bn[8];
+  if (HAS_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bn[i] = __ldg(bias4 + i);
+  }
+  tc::mbar_wait(full_bar, full_phase);
+  tc::fence_after_sync();
+  uint32_t rn[32];
+  tc::tmem_ld_32x32b_x32(trow, rn);
+#pragma unroll
+  for (int q = 0; q < PIECES; ++q) {
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
+    if (HAS_BIAS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[4 * i] += bn[i].x; v[4 * i + 1] += bn[i].y; v[4 * i + 2] += bn[i].z; v[4 * i + 3] += bn[i].w;
+      }
+    }
+    if (q + 1 < PIECES) {
+      tc::tmem_ld_32x32b_x32(trow + 32 * (q + 1), rn);
+      if (HAS_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bn[i] = __ldg(bias4 + 8 * (q + 1) + i);
+      }
+    }
+    if (ACT == ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if ((q & 1) == 0) {
+      if (lane == 0) tc::tma_store_wait_read0();  // the previous store of this warp has drained the slab
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sts_v4(my_row + (((4 * (q & 1) + j) ^ sw) << 4), Elem<TO>::pack(v + 8 * j));
+    if (q & 1) {
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tc::tma_store_2d(map_c, slab, n0 + 64 * (q >> 1), row0);
+        tc::tma_store_commit();
+      }
+    }
+  }
+}
+
+// SwiGLU: interleaved (gate, up) accumulator columns -> silu(gate) * up, BN/4 output columns per warp (vit_eva_clip.py:126-128);
+// STATS: per-row (sum, sum of squares) of every 64-column output slab as stored (LayerNorm fold of the next GEMM).
+template <typename TO, bool STATS, int BN>
+__device__ __forceinline__ void epi16_swiglu_fast(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab, uint32_t tmem_tile,
+                                                  int quad, int half, int lane, int m_blk, int n_blk, uint64_t *full_bar,
+                                                  uint32_t full_phase) {
+  constexpr int HALF = BN / 2, PIECES = HALF / 32;  // 4 pieces of 32 accumulator columns = 16 outputs each -> one slab
+  static_assert(PIECES == 4, "SwiGLU epilogue: 256-wide tiles");
+  const int row0 = m_blk * BM + quad * 32;
+  const int m = row0 + lane;
+  const int n0 = n_blk * BN + half * HALF;
+  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF;
+  const uint32_t my_row = tc::smem_u32(slab) + lane * 128;
+  const uint32_t sw = lane & 7;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + n0);
+  float4 bn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bn[i] = __ldg(bias4 + i);
+  tc::mbar_wait(full_bar, full_phase);
+  tc::fence_after_sync();
+  uint32_t rn[32];
+  tc::tmem_ld_32x32b_x32(trow, rn);
+  float st_sum = 0.f, st_sq = 0.f;
+  if (lane == 0) tc::tma_store_wait_read0();
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < PIECES; ++q) {
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i] += bn[i].x; v[4 * i + 1] += bn[i].y; v[4 * i + 2] += bn[i].z; v[4 * i + 3] += bn[i].w;
+    }
+    if (q + 1 < PIECES) {
+      tc::tmem_ld_32x32b_x32(trow + 32 * (q + 1), rn);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bn[i] = __ldg(bias4 + 8 * (q + 1) + i);
+    }
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float g = v[2 * i];
+      o[i] = __fdividef(g, 1.f + __expf(-g)) * v[2 * i + 1];
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 pk = Elem<TO>::pack(o + 8 * j);
+      sts_v4(my_row + (((2 * q + j) ^ sw) << 4), pk);
+      if (STATS) {
+        float f[8];
+        Elem<TO>::unpack(pk, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { st_sum += f[i]; st_sq = fmaf(f[i], f[i], st_sq); }
+      }
+    }
+  }
+  if (STATS && m < p.M) {
+    const int slab_idx = n0 / 128;
+    if (slab_idx < p.stats_nslab)
+      *reinterpret_cast<float2 *>(p.stats_out + ((size_t)m * p.stats_nslab + slab_idx) * 2) = make_float2(st_sum, st_sq);
+  }
+  tc::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tc::tma_store_2d(map_c, slab, n0 / 2, row0);
+    tc::tma_store_commit();
+  }
+}
+
+// fp32 output (+ fp32 residual, + LayerNorm fold), no activation: pieces of 32 columns = one 128-byte-wide slab each.
+//   LN:  out = rstd * acc + (bias - rstd * mean * colsum) + residual        (two FMAs and one add per element)
+template <bool HAS_RES, bool LN, int BN>
+__device__ __forceinline__ void epi32_fast(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab, uint32_t tmem_tile,
+                                           int quad, int half, int lane, int m_blk, int n_blk, uint64_t *full_bar,
+                                           uint32_t full_phase) {
+  constexpr int HALF = BN / 2, PIECES = HALF / 32;
+  const int row0 = m_blk * BM + quad * 32;
+  const int m = min(row0 + lane, p.M - 1);  // rows past M: read a valid row, the TMA store clips them
+  const int n0 = n_blk * BN + half * HALF;
+  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF;
+  const uint32_t my_row = tc::smem_u32(slab) + lane * 128;
+  const uint32_t sw = lane & 7;
+  const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + n0);
+  const float4 *cs4 = reinterpret_cast<const float4 *>(p.ln_colsum + n0);
+  const float4 *res4 = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.residual) + (size_t)m * p.ldr + n0);
+  float4 rs_next[8];
+  if (HAS_RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rs_next[i] = __ldg(res4 + i);
+  }
+  float ln_rstd = 1.f, ln_shift = 0.f;  // ln_shift = rstd * mean
+  if (LN) {
+    const float2 *pp = reinterpret_cast<const float2 *>(p.ln_part) + (size_t)m * p.ln_nparts;
+    float sum = 0.f, sq = 0.f;
+    for (int i = 0; i < p.ln_nparts; ++i) {
+      const float2 t = __ldg(pp + i);
+      sum += t.x;
+      sq += t.y;
+    }
+    const float mean = sum * p.ln_inv_c;
+    ln_rstd = rsqrtf(fmaxf(sq * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
+    ln_shift = ln_rstd * mean;
+  }
+  tc::mbar_wait(full_bar, full_phase);
+  tc::fence_after_sync();
+  uint32_t rn[32];
+  tc::tmem_ld_32x32b_x32(trow, rn);
+#pragma unroll
+  for (int q = 0; q < PIECES; ++q) {
+    float4 t[8];  // per column: bias - rstd * mean * colsum (LN) or bias
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      t[i] = __ldg(bias4 + 8 * q + i);
+      if (LN) {
+        const float4 cs = __ldg(cs4 + 8 * q + i);
+        t[i].x = fmaf(-ln_shift, cs.x, t[i].x); t[i].y = fmaf(-ln_shift, cs.y, t[i].y);
+        t[i].z = fmaf(-ln_shift, cs.z, t[i].z); t[i].w = fmaf(-ln_shift, cs.w, t[i].w);
+      }
+    }
+    tc::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
+    float4 rs[8];
+    if (HAS_RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs[i] = rs_next[i];
+    }
+    if (q + 1 < PIECES) {
+      tc::tmem_ld_32x32b_x32(trow + 32 * (q + 1), rn);
+      if (HAS_RES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs_next[i] = __ldg(res4 + 8 * (q + 1) + i);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (LN) {
+        v[4 * i] = fmaf(ln_rstd, v[4 * i], t[i].x); v[4 * i + 1] = fmaf(ln_rstd, v[4 * i + 1], t[i].y);
+        v[4 * i + 2] = fmaf(ln_rstd, v[4 * i + 2], t[i].z); v[4 * i + 3] = fmaf(ln_rstd, v[4 * i + 3], t[i].w);
+      } else {
+        v[4 * i] += t[i].x; v[4 * i + 1] += t[i].y; v[4 * i + 2] += t[i].z; v[4 * i + 3] += t[i].w;
+      }
+      if (HAS_RES) {
+        v[4 * i] += rs[i].x; v[4 * i + 1] += rs[i].y; v[4 * i + 2] += rs[i].z; v[4 * i + 3] += rs[i].w;
+      }
+    }
+    if (lane == 0) tc::tma_store_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(my_row + ((j ^ sw) << 4), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                  __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+    tc::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tc::tma_store_2d(map_c, slab, n0 + 32 * q, row0);
+      tc::tma_store_commit();
+    }
+  }
+}
+
+// Epilogue of one warp for its part of tile (m_blk, n_blk) through shared memory + TMA stores: the lean whole-tile variants
+// where they apply (GemmParams::lean, decided on the host), the general code otherwise.
+template <int BN>
+__device__ __forceinline__ void epilogue_dispatch(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab, uint32_t tmem_tile,
+                                                  int quad, int half, int lane, int m_blk, int n_blk, uint64_t *full_bar,
+                                                  uint32_t full_phase) {
+  constexpr int HALF = BN / 2;
+#define APE_EPI_ARGS p, map_c, slab, tmem_tile, quad, half, lane, m_blk, n_blk, full_bar, full_phase
+  if (p.lean != 0 && n_blk * BN + (half + 1) * HALF <= p.N) {  // whole column range of this warp inside N
+    const bool f16 = p.out_dtype == APE_DTYPE_F16;
+    switch (p.lean) {
+      case 1:  // 16-bit, no activation
+        if (p.bias != nullptr) { if (f16) epi16_fast<__half, ACT_NONE, true, BN>(APE_EPI_ARGS); else epi16_fast<__nv_bfloat16, ACT_NONE, true, BN>(APE_EPI_ARGS); }
+        else { if (f16) epi16_fast<__half, ACT_NONE, false, BN>(APE_EPI_ARGS); else epi16_fast<__nv_bfloat16, ACT_NONE, false, BN>(APE_EPI_ARGS); }
+        return;
+      case 2:  // 16-bit, ReLU (bias present)
+        if (f16) epi16_fast<__half, ACT_RELU, true, BN>(APE_EPI_ARGS); else epi16_fast<__nv_bfloat16, ACT_RELU, true, BN>(APE_EPI_ARGS);
+        return;
+      case 3:  // SwiGLU
+        if constexpr (BN == 256) {
+          if (p.stats_out != nullptr) { if (f16) epi16_swiglu_fast<__half, true, BN>(APE_EPI_ARGS); else epi16_swiglu_fast<__nv_bfloat16, true, BN>(APE_EPI_ARGS); }
+          else { if (f16) epi16_swiglu_fast<__half, false, BN>(APE_EPI_ARGS); else epi16_swiglu_fast<__nv_bfloat16, false, BN>(APE_EPI_ARGS); }
+          return;
+        }
+        break;
+      case 4: epi32_fast<false, false, BN>(APE_EPI_ARGS); return;  // fp32 = acc + bias
+      case 5: epi32_fast<true, false, BN>(APE_EPI_ARGS); return;   // + fp32 residual
+      case 6: epi32_fast<true, true, BN>(APE_EPI_ARGS); return;    // + LayerNorm fold
+      case 7: epi32_fast<false, true, BN>(APE_EPI_ARGS); return;
+      default: break;
+    }
+  }
+  if (p.out_dtype == APE_DTYPE_F32) epilogue_tma_f32<BN>(APE_EPI_ARGS);
+  else if (p.out_dtype == APE_DTYPE_F16) epilogue_tma<__half, BN>(APE_EPI_ARGS);
+  else epilogue_tma<__nv_bfloat16, BN>(APE_EPI_ARGS);
+#undef APE_EPI_ARGS
+}
+
 // CL = cluster size along M (1 or 2).  With CL == 2 the two CTAs of a cluster work on vertically adjacent
 // 128-row tiles of the same BN-column block: each loads half of the B (weight) tile and TMA-multicasts it into
 // both CTAs' shared memory, so the L2 -> SM traffic per CTA drops from 48 KB to 32 KB per k-block (these GEMMs
@@ -459,6 +780,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int m_groups = (p.m_blocks + CL - 1) / CL;
   const int num_tiles = m_groups * p.n_blocks;
   const int first = blockIdx.x / CL, stride = gridDim.x / CL;
+  const bool w_res = CL == 1 && p.resident == 1, a_res = CL == 1 && p.resident == 2;
+  // t-th tile of this CTA.  Default: tiles first, first + stride, ... of the (row group, column block) grid; A resident: the
+  // CTA owns row blocks first, first + stride, ... and walks all column blocks of one row block before the next.
+  auto tile_at = [&](int t, int &m_blk, int &n_blk) -> bool {
+    if (a_res) {
+      const int r = t / p.n_blocks;
+      const int mb = first + r * stride;
+      if (mb >= p.m_blocks) return false;
+      m_blk = mb;
+      n_blk = t - r * p.n_blocks;
+      return true;
+    }
+    const int tile = first + t * stride;
+    if (tile >= num_tiles) return false;
+    const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
+    n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
+    m_blk = mg * CL + rank;
+    return true;
+  };
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tensormap(&map_a);
@@ -474,6 +814,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc::mbar_init(&s.tmem_full[i], 1);
       tc::mbar_init(&s.tmem_empty[i], 8);  // one arrival per epilogue warp
     }
+    tc::mbar_init(&s.res_full, 1);
+    tc::mbar_init(&s.res_empty, 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) {
@@ -492,29 +834,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = first; tile < num_tiles; tile += stride) {
-        const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
-        const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
-        const int m_blk = mg * CL + rank;
+      constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+      if (w_res) {  // the whole weight matrix (one column block, K <= STAGES * 64): loaded once, b[kb] = k block kb
+        tc::mbar_expect_tx(&s.res_full, (uint32_t)p.k_blocks * B_BYTES);
+        for (int kb = 0; kb < p.k_blocks; ++kb) tc::tma_load_2d(s.b[kb], &map_b, &s.res_full, kb * BK, 0);
+      }
+      int m_blk, n_blk, rows_done = 0;
+      for (int t = 0; tile_at(t, m_blk, n_blk); ++t) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
+          tc::mbar_expect_tx(&s.full[stage], w_res ? A_BYTES : a_res ? B_BYTES : STAGE_BYTES);
           if (p.conv) {
-            const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
-            const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
+            const int img = m_blk / p.conv_tiles_img, tt = m_blk - img * p.conv_tiles_img;
+            const int ty = tt / p.conv_tiles_x, tx = tt - ty * p.conv_tiles_x;
             const int tap = kb / p.conv_cblks, cb = kb - tap * p.conv_cblks;
             tc::tma_load_4d(s.a[stage], &map_a, &s.full[stage], cb * BK, tx * p.conv_tw + tap % 3 - 1, ty * p.conv_th + tap / 3 - 1, img);
-          } else {
+          } else if (!a_res) {
             tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
           }
           if (CL == 1) {
-            tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
+            if (!w_res) tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
           } else {
             constexpr int HALF_ROWS = BN / CL;
             tc::tma_load_2d_multicast(s.b[stage] + rank * HALF_ROWS * BK * 2, &map_b, &s.full[stage], kb * BK,
                                       n_blk * BN + rank * HALF_ROWS, (uint16_t)((1u << CL) - 1));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (a_res && n_blk == 0) {
+          // A rows of this row block, a[kb] = k block kb — requested AFTER the first tile's weight blocks so that those
+          // are already on their way while the last MMAs of the previous row block still read the old rows
+          tc::mbar_wait(&s.res_empty, (rows_done & 1) ^ 1);
+          tc::mbar_expect_tx(&s.res_full, (uint32_t)p.k_blocks * A_BYTES);
+          for (int kb = 0; kb < p.k_blocks; ++kb) tc::tma_load_2d(s.a[kb], &map_a, &s.res_full, kb * BK, m_blk * BM);
+          ++rows_done;
         }
       }
     }
@@ -523,16 +876,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = first; tile < num_tiles; tile += stride) {
+      if (w_res) {
+        tc::mbar_wait(&s.res_full, 0);
+        tc::fence_after_sync();
+      }
+      int m_blk, n_blk, rows_done = 0;
+      for (int t = 0; tile_at(t, m_blk, n_blk); ++t) {
+        if (a_res && n_blk == 0) {
+          tc::mbar_wait(&s.res_full, rows_done & 1);
+          tc::fence_after_sync();
+          ++rows_done;
+        }
         tc::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.full[stage], phase);
           tc::fence_after_sync();
-          if (kb == 0 && tile == first) trace_stamp(p, 2);
-          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(s.a[stage]));
-          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(s.b[stage]));
+          if (kb == 0 && t == 0) trace_stamp(p, 2);
+          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(a_res ? s.a[kb] : s.a[stage]));
+          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(w_res ? s.b[kb] : s.b[stage]));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
@@ -544,6 +907,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit(&s.tmem_full[acc]);  // accumulator complete -> epilogue
+        if (a_res && n_blk == p.n_blocks - 1) tc::mma_commit(&s.res_empty);  // every MMA that reads these A rows has completed
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       trace_stamp(p, 3);
@@ -555,24 +919,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 2) / 4;  // which half of the tile's columns
     uint8_t *slab = s.c[warp - 2];
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = first; tile < num_tiles; tile += stride) {
-      const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
-      const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_groups;
-      const int m_blk = mg * CL + rank;
+    int m_blk = 0, n_blk = 0;
+    bool have = tile_at(0, m_blk, n_blk);
+    if (have && p.tma_store) epilogue_prefetch<BN>(p, quad, half, lane, m_blk, n_blk);  // overlaps the first main loop
+    for (int t = 0; have; ++t) {
+      int m_next = 0, n_next = 0;
+      const bool have_next = tile_at(t + 1, m_next, n_next);
+      if (have_next && p.tma_store) epilogue_prefetch<BN>(p, quad, half, lane, m_next, n_next);  // one tile ahead
       if (p.trace != nullptr && warp == 2) {  // (tracing only: the stamp needs the wait here; it is repeated below at no cost)
         tc::mbar_wait(&s.tmem_full[acc], acc_phase);
         if (lane == 0) {
-          if (tile == first) trace_stamp(p, 4);
+          if (t == 0) trace_stamp(p, 4);
           trace_stamp(p, 5);
         }
       }
       if (p.tma_store) {  // these wait for the accumulator themselves, after requesting what they read from global memory
-        if (p.out_dtype == APE_DTYPE_F32)
-          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
-        else if (p.out_dtype == APE_DTYPE_F16)
-          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
-        else
-          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
+        epilogue_dispatch<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
       } else {
         tc::mbar_wait(&s.tmem_full[acc], acc_phase);
         tc::fence_after_sync();
@@ -594,6 +956,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s.tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      m_blk = m_next; n_blk = n_next; have = have_next;
     }
     if (p.tma_store && lane == 0) tc::tma_store_wait_all();  // global writes complete before the CTA exits
     __syncwarp();
@@ -722,17 +1085,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int half = (warp - 2) / 4;
     uint8_t *slab = s.c[warp - 2];
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = first; tile < num_tiles; tile += stride) {
+    auto pair_tile = [&](int tile, int &m_blk, int &n_blk) {
       const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_pairs;
-      const int n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
-      const int m_blk = mg * 2 + (int)rank;
+      n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
+      m_blk = mg * 2 + (int)rank;
+    };
+    if (first < num_tiles && p.tma_store) {  // what the first tile's epilogue reads: requested while its main loop runs
+      int m0, n0;
+      pair_tile(first, m0, n0);
+      epilogue_prefetch<BN>(p, quad, half, lane, m0, n0);
+    }
+    for (int tile = first; tile < num_tiles; tile += stride) {
+      int m_blk, n_blk;
+      pair_tile(tile, m_blk, n_blk);
+      if (tile + stride < num_tiles && p.tma_store) {  // one tile ahead
+        int m1, n1;
+        pair_tile(tile + stride, m1, n1);
+        epilogue_prefetch<BN>(p, quad, half, lane, m1, n1);
+      }
       if (p.tma_store) {  // these wait for the accumulator themselves, after requesting what they read from global memory
-        if (p.out_dtype == APE_DTYPE_F32)
-          epilogue_tma_f32<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
-        else if (p.out_dtype == APE_DTYPE_F16)
-          epilogue_tma<__half, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
-        else
-          epilogue_tma<__nv_bfloat16, BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
+        epilogue_dispatch<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
       } else {
         tc::mbar_wait(&s.tmem_full[acc], acc_phase);
         tc::fence_after_sync();
@@ -825,7 +1197,18 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
   }
   p.n_blocks = (p.N + BN - 1) / BN;
   p.n_fastest = p.n_blocks <= 8;  // few column blocks: keep the A rows of a group hot instead of re-reading A per column block
-  const int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
+  // short K loop: keep one operand in shared memory (see GemmParams::resident); APE_GEMM_RESIDENT=0 switches it off (A/B runs)
+  static const int resident_mask = [] {  // bit 0: W resident, bit 1: A resident
+    const char *e = getenv("APE_GEMM_RESIDENT");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  p.resident = 0;
+  if (CL == 1 && resident_mask && !p.conv && p.k_blocks <= STAGES) {
+    if (p.n_blocks == 1 && p.m_blocks > num_sms() && (resident_mask & 1)) p.resident = 1;        // several row tiles per CTA share the weights
+    else if (p.n_blocks > 1 && p.m_blocks >= num_sms() && (resident_mask & 2)) p.resident = 2;   // a CTA keeps a row block for all its column blocks
+  }
+  int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
+  if (p.resident == 2) groups = p.m_blocks;  // work items are whole row blocks
   const int max_clusters = num_sms() / CL;
   const int clusters = groups < max_clusters ? groups : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -937,12 +1320,21 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
     const char *e = getenv("APE_GEMM_POLICY");
     return e == nullptr ? 0 : (e[0] == 'm' ? 1 : e[0] == 's' ? 2 : 0);
   }();
-  const bool auto_single = policy == 2 || (policy == 0 && K < 2048);
+  const int bn_pre = (tile_n & 0xfff) > 0 ? (tile_n & 0xfff) : (N > 128 ? 256 : 128);
+  const bool pair_shape = K >= 2048 || ((N + bn_pre - 1) / bn_pre <= 4 && M >= 4096) || N >= 4096;
+  const bool auto_single = policy == 2 || (policy == 0 && !pair_shape);
   const bool single = (tile_n & 0x1000) != 0 || M <= BM || (auto_single && (tile_n & 0xE000) == 0);
   // kernel variant: default = cluster of 2 along M sharing the weight tile by TMA multicast (1-CTA MMA); 0x2000 = CTA-pair
   // MMA (cta_group::2, 256 x bn tiles; measured equal or slower on B200 for these shapes, kept selectable);
   // 0x8000 = cluster of 4 along M (weight tile split four ways)
-  const bool pair = !single && (tile_n & 0x2000) != 0;
+  // measured (profiles/r02_gemm_phases.jsonl): the CTA pair is the fastest variant for the long K loops (w3 4096x1024x2730:
+  // 33.6 us against 37.7 single / 38.6 multicast; FFN2 87296x256x2048: 105.9 against 113.3 / 116.3)
+  // with the lean epilogues (profiles/r02_gemm_phases_lean.jsonl) it also wins where a CTA has few column blocks to walk
+  // (proj 20.6 us against 23.6 single, the 87296 x 256 x 256 projections 27.9 / 30.2, qo 48.7 / 53.8) and on the widest GEMM
+  // (w12 44.1 / 46.9); the single-CTA kernel keeps qkv (27.6 / 28.8), FFN1 (115 / 164) and the 900-row decoder GEMMs
+  const int n_blocks_bn = (N + bn - 1) / bn;
+  const bool auto_pair = K >= 2048 || (n_blocks_bn <= 4 && M >= 4096) || N >= 4096;
+  const bool pair = !single && ((tile_n & 0x2000) != 0 || (policy == 0 && auto_pair && (tile_n & 0xC000) == 0));
   const bool quad = !single && !pair && (tile_n & 0x8000) != 0 && M > 2 * BM;
   if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : quad ? bn / 4 : bn / 2)) return rc;
   GemmParams p{};
@@ -952,6 +1344,11 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   p.k_blocks = (K + BK - 1) / BK;
   p.out_dtype = out_dtype; p.act = act; p.res_dtype = res_dtype;
   p.trace = g_gemm_trace;
+  static const int prefetch_mask = [] {
+    const char *e = getenv("APE_GEMM_PREFETCH");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  p.prefetch = prefetch_mask;
   p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
   // 16-bit outputs with 16-byte aligned rows leave through shared memory + TMA stores
   const int n_out = act == ACT_SWIGLU ? N / 2 : N;
@@ -978,6 +1375,23 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
     if (!p.tma_store || oe != 2 || act != ACT_NONE || rope->cols % 64 != 0 || rope->cols > N || rope->npos <= 0 || !rope->cos || !rope->sin)
       return fail(APE_ERR_INVALID_ARG, "gemm+rope: needs a 16-bit aligned output, no activation, rope_cols a multiple of 64 <= N");
     p.rope_cos = rope->cos; p.rope_sin = rope->sin; p.rope_pos = rope->pos; p.rope_cols = rope->cols; p.rope_npos = rope->npos;
+  }
+  // lean epilogue (see epilogue_dispatch): whole-tile cases with 16-byte aligned vectors; APE_GEMM_LEAN=0 disables (A/B runs)
+  static const bool lean_on = [] {
+    const char *e = getenv("APE_GEMM_LEAN");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  p.lean = 0;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(fuse ? fuse->ln_colsum : nullptr)) & 15) == 0;
+  if (lean_on && p.tma_store && !rope && al16) {
+    if (oe == 2 && act == ACT_SWIGLU && bias != nullptr && bn == 256) p.lean = 3;
+    else if (oe == 2 && residual == nullptr && act == ACT_NONE) p.lean = 1;
+    else if (oe == 2 && residual == nullptr && act == ACT_RELU && bias != nullptr) p.lean = 2;
+    else if (oe == 4 && act == ACT_NONE && bias != nullptr && !(fuse && fuse->stats_out)) {
+      const bool res_ok = residual == nullptr || (res_dtype == APE_DTYPE_F32 && (ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0);
+      const bool ln = fuse != nullptr && fuse->ln_part != nullptr;
+      if (res_ok) p.lean = residual != nullptr ? (ln ? 6 : 5) : (ln ? 7 : 4);
+    }
   }
   if (pair) {
     p.idesc = tc::make_idesc_f16(2 * BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);

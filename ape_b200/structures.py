@@ -45,6 +45,22 @@ class Instances:
         return self._fields
 
     def to(self, device):
+        """Device -> host moves of large fields (pasted instance masks: 314 MB for 300 detections at 1024^2) go through pinned
+        memory from PyTorch's caching host allocator (asynchronous copies at PCIe speed, one synchronisation for all fields)
+        instead of a pageable copy per field."""
+        if torch.device(device).type == "cpu":
+            out, big = {}, False
+            for k, v in self._fields.items():
+                t = v.tensor if isinstance(v, Boxes) else v
+                if torch.is_tensor(t) and t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
+                    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    host.copy_(t, non_blocking=True)
+                    out[k], big = (Boxes(host) if isinstance(v, Boxes) else host), True
+                else:
+                    out[k] = v.to(device) if hasattr(v, "to") else v
+            if big:
+                torch.cuda.current_stream().synchronize()
+            return Instances(self._image_size, **out)
         return Instances(self._image_size, **{k: (v.to(device) if hasattr(v, "to") else v) for k, v in self._fields.items()})
 
     def __len__(self):

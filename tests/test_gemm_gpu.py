@@ -242,3 +242,32 @@ def test_conv3x3_implicit_gemm_matches_conv2d(ops, dtype, B, H, W, Cin, Cout):
     want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
     tol = 4e-3 if dtype == torch.float16 else 3e-2
     torch.testing.assert_close(got.float(), want, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("M,N,K,act,out32", [
+    (19100, 256, 256, None, False),     # W resident: one column block, 150 row tiles on 148 CTAs (second round for two of them)
+    (40000, 256, 192, "relu", False),   # W resident, 3 k blocks, several tiles per CTA, ragged last tile
+    (25000, 200, 256, None, True),      # W resident, N < tile, fp32 output + residual
+    (19000, 2048, 256, "relu", False),  # A resident: 149 row blocks x 8 column blocks (encoder FFN1 geometry)
+    (30000, 480, 256, None, False),     # A resident, ragged second column block (stacked offsets / logits projection)
+    (20000, 1024, 200, None, True),     # A resident, K not a multiple of 64, fp32 output + residual
+])
+def test_resident_operand_schedules(ops, M, N, K, act, out32):
+    """K <= 256: one operand stays in shared memory (GemmParams::resident) — the weights when there is a single column block,
+    the A rows of a row block otherwise.  Same results as the streaming schedule, row block by row block."""
+    dtype = torch.float16
+    x = rnd(M, K + (-K) % 8, dtype=dtype, seed=11)[:, :K]
+    w = rnd(N, K + (-K) % 8, dtype=dtype, seed=12, scale=K ** -0.5)[:, :K]
+    b = rnd(N, dtype=torch.float32, seed=13)
+    res = rnd(M, N, dtype=torch.float32, seed=14) if out32 else None
+    y = ops.linear_tc(x, w, b, act=act, residual=res, out_dtype=torch.float32 if out32 else None)
+    want = ref_linear(x, w, b, act=act, residual=res)
+    if out32:
+        torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-4)
+    else:
+        torch.testing.assert_close(y.float(), want, rtol=1e-2, atol=2e-3)
+    # every row block was written exactly once with its own rows: compare a shuffled-row run
+    perm = torch.randperm(M, device=DEV)
+    y2 = ops.linear_tc(x[perm].contiguous(), w, b, act=act, residual=res[perm].contiguous() if out32 else None,
+                       out_dtype=torch.float32 if out32 else None)
+    assert torch.equal(y2, y[perm])
