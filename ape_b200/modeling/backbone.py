@@ -211,7 +211,8 @@ class ViT(nn.Module):
             Block(embed_dim, num_heads, mlp_ratio, norm_layer, window_size if i in window_block_indexes else 0,
                   self.rope_win if i in window_block_indexes else self.rope_glb, subln=variant_l, packed_swiglu=variant_ti)
             for i in range(depth)])
-        self.fused_rope = False
+        # RoPE in the qkv GEMM's (lean) epilogue instead of the in-place ape_rope_qk pass; APE_FUSED_ROPE=0/1 for A/B runs
+        self.fused_rope = os.environ.get("APE_FUSED_ROPE", "0") == "1"
         self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
         # inner_attn_ln / ffn_ln folded around proj / w3 (ape_gemm_tn_fused): two LayerNorm launches and two trips of the
         # activations through HBM fewer per block
