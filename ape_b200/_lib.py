@@ -108,6 +108,10 @@ def _declare(lib):
     lib.ape_nms_classwise_workspace_bytes.argtypes = [_i]
     lib.ape_nms_classwise.restype = _i
     lib.ape_nms_classwise.argtypes = [_vp, _vp, _i64, _vp, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]
+    lib.ape_ref_update.restype = _i
+    lib.ape_ref_update.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.c_float, _vp]
+    lib.ape_gemv_f32.restype = _i
+    lib.ape_gemv_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]
     lib.ape_mask_crop_workspace_bytes.restype = _i64
     lib.ape_mask_crop_workspace_bytes.argtypes = [_i, _i, _i]
     lib.ape_mask_crop.restype = _i
@@ -160,6 +164,8 @@ EXPORTS = (
     "ape_nms_sorted_dev",
     "ape_nms_classwise_workspace_bytes",
     "ape_nms_classwise",
+    "ape_ref_update",
+    "ape_gemv_f32",
     "ape_mask_crop_workspace_bytes",
     "ape_mask_crop",
     "ape_mask_paste",

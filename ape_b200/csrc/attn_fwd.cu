@@ -60,6 +60,30 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// Packed fp32 pairs (sm_100: fma / add .f32x2 process two lanes of a 64-bit register pair per instruction).  ncu's source view of
+// the softmax loop (profiles/r02_attn_global_ncu_raw.csv): 411 instructions per warp and key block, 64 of them the scale FFMAs
+// and 64 the row-sum FADDs, with the exponential unit and the issue slots saturating together at ~53 % — halving those two
+// groups takes 15 % of the instructions out of the loop.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4 &v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kAttnThreads, 4)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p) {
@@ -152,7 +176,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
     const int row = quad * 32 + lane;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     float m_ref = -INFINITY, l = 0.f;
-    uint8_t *prow = s.p + row * 128;
+    const uint32_t prow = tc::smem_u32(s.p) + row * 128;
+    const uint64_t sc2 = pk2(p.scale_log2, p.scale_log2);
     // Per key block the scores are read from tensor memory ONCE: exponentials are formed against the reference maximum
     // carried over from the previous blocks while the block's own maximum is tracked on the side; only when some row of
     // the warp outgrows the reference by more than 2^8 (P would leave the 16-bit range) is the block redone against the new
@@ -166,16 +191,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
           if (32 * hh + i >= kvalid) r[i] = 0xff800000u;
       }
     };
-    auto exp_half = [&](int hh, const uint32_t *r, float *s8) {
+    auto exp_half = [&](int hh, const uint32_t *r, uint64_t *s4) {  // s4: four packed pairs of partial row sums
+      const uint64_t nm2 = pk2(-m_ref, -m_ref);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = ex2(fmaf(__uint_as_float(r[8 * c + i]), p.scale_log2, -m_ref));
-          s8[i] += e[i];
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t x2 = fma2(pk2(__uint_as_float(r[8 * c + 2 * i]), __uint_as_float(r[8 * c + 2 * i + 1])), sc2, nm2);
+          float x0, x1;
+          up2(x2, x0, x1);
+          e[2 * i] = ex2(x0);
+          e[2 * i + 1] = ex2(x1);
+          s4[i] = add2(s4[i], pk2(e[2 * i], e[2 * i + 1]));
         }
-        *reinterpret_cast<uint4 *>(prow + (((4 * hh + c) ^ (row & 7)) << 4)) = Elem<T>::pack(e);
+        sts_v4(prow + (((4 * hh + c) ^ (row & 7)) << 4), Elem<T>::pack(e));
       }
     };
     auto release_s = [&]() {  // S_j is in registers: the tensor core may compute S_{j+1}
@@ -199,9 +229,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
         }
         m_ref = p.scale_log2 * m;
       }
-      float s8[8], m4[4];
+      uint64_t s8[4];
+      float m4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+      for (int i = 0; i < 4; ++i) s8[i] = 0ull;
 #pragma unroll
       for (int i = 0; i < 4; ++i) m4[i] = -INFINITY;
       load_half(0, kvalid, r);
@@ -238,14 +269,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnParams p)
           tc::tmem_st_wait();
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+        for (int i = 0; i < 4; ++i) s8[i] = 0ull;
         load_half(0, kvalid, r);
         exp_half(0, r, s8);
         load_half(1, kvalid, r);
         release_s();
         exp_half(1, r, s8);
       }
-      l += ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+      {
+        float a0, a1, b0, b1;
+        up2(add2(s8[0], s8[1]), a0, a1);
+        up2(add2(s8[2], s8[3]), b0, b1);
+        l += (a0 + a1) + (b0 + b1);
+      }
       tc::fence_proxy_async();  // P visible to the tensor core's (async proxy) reads
       tc::fence_before_sync();  // ... and the O rescale ordered before the MMA that accumulates into it
       __syncwarp();

@@ -547,7 +547,14 @@ __device__ __forceinline__ void epi16_fast(const GemmParams &p, const CUtensorMa
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tc::tma_store_2d(map_c, slab, n0 + 64 * (q >> 1), row0);
+        if (p.conv) {  // the slab's 32 tile rows are min(tw, 32) x 32 / min(tw, 32) pixels of the output image
+          const int img = m_blk / p.conv_tiles_img, t = m_blk - img * p.conv_tiles_img;
+          const int ty = t / p.conv_tiles_x, tx = t - ty * p.conv_tiles_x;
+          const int r0 = quad * 32;
+          tc::tma_store_4d(map_c, slab, n0 + 64 * (q >> 1), tx * p.conv_tw + r0 % p.conv_tw, ty * p.conv_th + r0 / p.conv_tw, img);
+        } else {
+          tc::tma_store_2d(map_c, slab, n0 + 64 * (q >> 1), row0);
+        }
         tc::tma_store_commit();
       }
     }
@@ -1132,7 +1139,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
           if (leader) tc::mbar_expect_tx(&s.full[stage], 2 * CTA_STAGE_BYTES);
           const uint32_t full_leader = tc::mapa_u32(&s.full[stage], 0);
-          tc::tma_load_2d_pair(s.a[stage], &map_a, full_leader, kb * BK, m_blk * BM);
+          if (p.conv) {  // implicit-GEMM 3x3 convolution: the pixel tile shifted by the filter tap (see gemm_tc_kernel)
+            const int img = m_blk / p.conv_tiles_img, tt = m_blk - img * p.conv_tiles_img;
+            const int ty = tt / p.conv_tiles_x, tx = tt - ty * p.conv_tiles_x;
+            const int tap = kb / p.conv_cblks, cb = kb - tap * p.conv_cblks;
+            tc::tma_load_4d_pair(s.a[stage], &map_a, full_leader, cb * BK, tx * p.conv_tw + tap % 3 - 1, ty * p.conv_th + tap / 3 - 1, img);
+          } else {
+            tc::tma_load_2d_pair(s.a[stage], &map_a, full_leader, kb * BK, m_blk * BM);
+          }
           tc::tma_load_2d_pair(s.b[stage], &map_b, full_leader, kb * BK, n_blk * BN + (int)rank * (BN / 2));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -1562,8 +1576,23 @@ extern "C" int ape_conv3x3_nhwc(const void *x, const void *w, void *y, const flo
   p.out_dtype = dtype; p.res_dtype = dtype; p.act = act;
   p.idesc = tc::make_idesc_f16(BM, bn, dtype == APE_DTYPE_BF16 ? 1 : 0);
   p.tma_store = 1;
+  if (((reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {  // lean whole-tile epilogue (epi16_fast) for the cases the pyramid / mask head run
+    if (act == ACT_NONE) p.lean = 1;
+    else if (act == ACT_RELU && bias != nullptr) p.lean = 2;
+  }
   p.conv = 1; p.conv_tw = tw; p.conv_th = th; p.conv_tiles_x = W / tw; p.conv_tiles_img = (W / tw) * (H / th); p.conv_cblks = Cin / 64;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // K = 9 * Cin is a long loop: the CTA pair (half of the weight tile per SM) when the row blocks pair up; APE_CONV_PAIR=0 -> single
+  static const bool conv_pair = [] {
+    const char *e = getenv("APE_CONV_PAIR");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (conv_pair && p.m_blocks % 2 == 0 && p.m_blocks >= 2) {
+    if (int rc = make_map(&mb, w, dtype, N, K, K, bn / 2)) return rc;
+    p.idesc = tc::make_idesc_f16(2 * BM, bn, dtype == APE_DTYPE_BF16 ? 1 : 0);
+    if (bn == 256) return launch_gemm_pair<256, 5>(ma, mb, mc, p, st);
+    return launch_gemm_pair<128, 6>(ma, mb, mc, p, st);
+  }
   if (bn == 256) return launch_gemm<256, 4, 1>(ma, mb, mc, p, st);
   return launch_gemm<128, 6, 1>(ma, mb, mc, p, st);
 }

@@ -558,3 +558,85 @@ extern "C" int ape_groupnorm_nhwc(const void *x, int64_t ldx, void *y, int64_t l
 #undef APE_GN
   return check_launch("gn_apply_kernel");
 }
+
+
+// ---- small fp32 GEMV: y[b, n] = W[n, :] . x[b, :] + bias[n] ---------------------------------------------------------------
+// The language side of VisionLanguageFusion for "name" prompts is two affine maps of ONE 1024-wide token per encoder layer
+// (vision_language_fusion.py:_folded_language_maps: [2312, 1024] and [1024, 2048] fp32 matrices); PyTorch runs them as cuBLAS
+// GEMV kernels.  One warp per output row, 128-bit loads of the weight row, up to 4 input rows held against it.
+namespace ape {
+namespace {
+__global__ void __launch_bounds__(256) gemv_f32_kernel(const float *__restrict__ W, const float *__restrict__ x,
+                                                       const float *__restrict__ bias, float *__restrict__ y, int B, int N, int K) {
+  pdl_prologue();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)warp * K);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K / 4; k += 32) {
+    const float4 w = __ldg(w4 + k);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b < B) {
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)b * K) + k);
+        acc[b] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, acc[b]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+  }
+  if (lane == 0) {
+    const float bb = bias != nullptr ? __ldg(bias + warp) : 0.f;
+    for (int b = 0; b < B && b < 4; ++b) y[(size_t)b * N + warp] = acc[b] + bb;
+  }
+}
+}  // namespace
+}  // namespace ape
+
+extern "C" int ape_gemv_f32(const float *W, const float *x, const float *bias, float *y, int B, int N, int K, void *stream) {
+  using namespace ape;
+  if (!W || !x || !y) return fail(APE_ERR_NULL_PTR, "gemv: null pointer");
+  if (B <= 0 || B > 4 || N <= 0 || K <= 0 || K % 4) return fail(APE_ERR_UNSUPPORTED, "gemv: B=%d (1..4) N=%d K=%d (multiple of 4)", B, N, K);
+  if ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x)) & 15) return fail(APE_ERR_INVALID_ARG, "gemv: W / x must be 16-byte aligned");
+  APE_LAUNCH(gemv_f32_kernel, (N + 7) / 8, 256, 0, (cudaStream_t)stream, W, x, bias, y, B, N, K);
+  return check_launch("gemv_f32_kernel");
+}
+
+
+// ---- decoder reference-point update ---------------------------------------------------------------------------------------
+// DeformableDetrTransformerDecoderVL.forward (deformable_transformer_vl.py:268-300, boxes as reference points):
+//   new_ref = sigmoid(bbox_embed(output) + inverse_sigmoid(ref))                 detrex inverse_sigmoid, eps 1e-3
+//   ref_in  = new_ref[:, :, None] * cat([valid_ratios, valid_ratios], -1)[:, None]   (input of the next layer's cross attention)
+// Nine elementwise launches per decoder layer in PyTorch; one here, with the same fp32 operations in the same order
+// (clamp, clamp, clamp, divide, logf, add, 1 / (1 + expf(-x)), multiply) so that the results are the same bits.
+namespace ape {
+namespace {
+__global__ void __launch_bounds__(256) ref_update_kernel(const float *__restrict__ delta, const float *__restrict__ ref,
+                                                         const float *__restrict__ valid_ratios, float *__restrict__ new_ref,
+                                                         float *__restrict__ ref_in, int rows, int Q, int L, float eps) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (row, coordinate)
+  if (i >= rows * 4) return;
+  const int row = i >> 2, c = i & 3, b = row / Q;
+  float x = fminf(fmaxf(__ldg(ref + i), 0.f), 1.f);
+  const float x1 = fmaxf(x, eps), x2 = fmaxf(1.f - x, eps);
+  const float y = __ldg(delta + i) + logf(x1 / x2);
+  const float r = 1.f / (1.f + expf(-y));
+  new_ref[i] = r;
+  for (int l = 0; l < L; ++l) ref_in[((size_t)row * L + l) * 4 + c] = r * __ldg(valid_ratios + ((size_t)b * L + l) * 2 + (c & 1));
+}
+}  // namespace
+}  // namespace ape
+
+extern "C" int ape_ref_update(const float *delta, const float *ref, const float *valid_ratios, float *new_ref, float *ref_in, int B,
+                              int Q, int L, float eps, void *stream) {
+  using namespace ape;
+  if (!delta || !ref || !valid_ratios || !new_ref || !ref_in) return fail(APE_ERR_NULL_PTR, "ref_update: null pointer");
+  if (B <= 0 || Q <= 0 || L <= 0) return fail(APE_ERR_INVALID_ARG, "ref_update: B=%d Q=%d L=%d", B, Q, L);
+  const int n = B * Q * 4;
+  APE_LAUNCH(ref_update_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, delta, ref, valid_ratios, new_ref, ref_in, B * Q, Q, L, eps);
+  return check_launch("ref_update_kernel");
+}

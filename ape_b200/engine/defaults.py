@@ -145,16 +145,17 @@ class DefaultPredictor:
         current stream)."""
         if not (isinstance(image, np.ndarray) and image.dtype == np.uint8):
             return image
-        src = torch.from_numpy(np.ascontiguousarray(image))
-        buf = self._staging[slot]
-        if buf is None or buf.numel() < src.numel():
-            buf = self._staging[slot] = torch.empty((max(src.numel(), 1 << 22),), dtype=torch.uint8, pin_memory=True)
+        n = int(image.size)
+        ent = self._staging[slot]
+        if ent is None or ent[0].numel() < n:
+            buf = torch.empty((max(n, 1 << 22),), dtype=torch.uint8, pin_memory=True)
+            ent = self._staging[slot] = (buf, buf.numpy())  # the numpy view shares the pinned pages
         if self._staged[slot] is not None:
             self._staged[slot].synchronize()  # the previous upload out of this buffer has finished
-        host = buf[: src.numel()].view(src.shape)
-        host.copy_(src)
-        dev = host.to(self.device, non_blocking=True)
-        self._staged[slot] = torch.cuda.Event()
+        np.copyto(ent[1][:n].reshape(image.shape), image)  # one plain memcpy (a torch CPU copy_ spins up the intra-op pool)
+        dev = ent[0][:n].view(image.shape).to(self.device, non_blocking=True)
+        if self._staged[slot] is None:
+            self._staged[slot] = torch.cuda.Event()
         self._staged[slot].record(torch.cuda.current_stream(self.device))
         return dev
 
@@ -177,25 +178,34 @@ class DefaultPredictor:
             return self.model([self.preprocess(original_image, text_prompt, mask_prompt)])[0]
 
     def predict_batch(self, images, text_prompt=None):
-        """One image after the other through the same model (batch 1 per step, the reference's evaluation setting), the
-        upload + resize of image i+1 on a side stream while image i runs.  Returns the list of output dicts."""
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        main = torch.cuda.current_stream(self.device)
-        outs, nxt, ready = [], None, None
+        """One image after the other through the same model (batch 1 per step, the reference's evaluation setting), software
+        pipelined: while the device runs the forward of image i, the host stages, uploads and resizes image i+1 and unpacks the
+        detections of image i-1 — the device never waits for the host between images.  Boxes-only configurations go through
+        `model.forward_packed` (results stay on the device until one small pinned copy); configurations with masks / semantic /
+        panoptic outputs run one by one (their post-processing synchronises).  Returns the list of output dicts."""
+        from ..parallel import unpack_packed
+
+        m = getattr(self.model, "model_vision", self.model)
+        with_masks = getattr(m, "semantic_on", False) or getattr(m, "panoptic_on", False) or \
+            (getattr(m, "instance_on", True) and getattr(m, "test_mask_on", False))
+        if with_masks or not hasattr(m, "forward_packed"):
+            return [self(im, text_prompt) for im in images]
+        outs, pending = [], None  # pending = (device rows of the previous image, index)
+        stream = torch.cuda.current_stream(self.device)
         with torch.no_grad():
             for i in range(len(images) + 1):
-                cur, cur_ready = nxt, ready
-                if i < len(images):
-                    self._side.wait_stream(main)  # the staging slot / previous tensors of this slot are no longer in use
-                    with torch.cuda.stream(self._side):
-                        nxt = self.preprocess(images[i], text_prompt, slot=i & 1)
-                        ready = torch.cuda.Event()
-                        ready.record(self._side)
-                    for v in nxt.values():
-                        if torch.is_tensor(v):
-                            v.record_stream(main)
-                if cur is not None:
-                    main.wait_event(cur_ready)
-                    outs.append(self.model([cur])[0])
+                inp = self.preprocess(images[i], text_prompt, slot=i & 1) if i < len(images) else None
+                host, done = None, None
+                if pending is not None:  # D2H of the previous image's rows BEFORE the next forward is enqueued
+                    host = torch.empty(pending.shape, dtype=pending.dtype, pin_memory=True)
+                    host.copy_(pending, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(stream)
+                pending = m.forward_packed([inp]) if inp is not None else None
+                if host is not None:
+                    done.synchronize()
+                    r = unpack_packed(host)[0]
+                    if r.pop("num_candidates") > getattr(m, "static_inference_cap", 1 << 30) and not getattr(m, "_static_overflowed", False):
+                        r = self(images[i - 1], text_prompt)  # the candidate list overflowed: take the host-synchronised route
+                    outs.append(r)
         return outs

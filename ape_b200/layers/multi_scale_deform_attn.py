@@ -55,7 +55,7 @@ class MultiScaleDeformableAttention(nn.Module):
         self.pytorch_attn = pytorch_attn
         # engine: calls with at least this many queries gather from the pair layout (csrc/msda_pair.cu).  Off by default
         # (None): measured on B200 the pair kernel is 265-275 us against 293 us for the generic fused kernel on the
-        # encoder call, but the pairing pass costs 33 us, a net loss in the model (DESIGN.md section 10.3);
+        # encoder call, but the pairing pass costs 33 us, a net loss in the model (DESIGN.md section 9);
         # APE_MSDA_PAIR=<min queries> (e.g. 2048) switches it on for A/B runs.
         env = os.environ.get("APE_MSDA_PAIR", "")
         self.pair_layout_min_queries = int(env) if env.isdigit() and int(env) > 0 else None

@@ -206,7 +206,9 @@ class BiAttentionBlock(nn.Module):
             with torch.autocast("cuda", enabled=False):
                 G, g0, _, _ = self._folded_language_maps()
                 B = l.shape[0]
-                y = F.linear(l.float().reshape(B, -1), G, g0)
+                from .. import ops
+
+                y = ops.gemv_f32(l.float().reshape(B, -1), G, g0)  # own fp32 GEMV (PyTorch would run cuBLAS gemv kernels here)
                 C = a.v_proj.weight.shape[1]
                 return y[:, nh * C + nh:].reshape(B, 1, C), y[:, : nh * C].reshape(B, nh, C), y[:, nh * C: nh * C + nh]
         with torch.autocast("cuda", enabled=False):
@@ -248,7 +250,9 @@ class BiAttentionBlock(nn.Module):
                 pooled = pooled - shift.reshape(B, 1, -1).float()
             if v.is_cuda and self.fold_language_side:
                 _, _, E, e0 = self._folded_language_maps()
-                return F.linear(pooled.reshape(B, 1, -1), E, e0)
+                from .. import ops
+
+                return ops.gemv_f32(pooled.reshape(B, 1, -1).contiguous(), E, e0)
             wvv = a.values_v_proj.weight.float().view(nh, hd, -1)
             out_l = torch.einsum("bhc,hdc->bhd", pooled, wvv) + a.values_v_proj.bias.float().view(nh, hd)
             dl = F.linear(out_l.reshape(B, 1, nh * hd), a.out_l_proj.weight.float(), a.out_l_proj.bias.float())

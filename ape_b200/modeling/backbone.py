@@ -477,7 +477,7 @@ class SimpleFeaturePyramid(nn.Module):
         self._size_divisibility = strides[-1]
         self._square_pad = square_pad
         # 3x3 convolutions on the repo's implicit-GEMM kernel (ape_conv3x3_nhwc) instead of cuDNN
-        self.conv3x3_engine = os.environ.get("APE_CONV3X3", "0") == "1"
+        self.conv3x3_engine = os.environ.get("APE_CONV3X3", "1") == "1"
 
     @property
     def size_divisibility(self):

@@ -63,14 +63,19 @@ class _SelfAttention(nn.Module):
             B, N, _ = x.shape
             NP = (N + 127) // 128 * 128
             C = nh * 64
-            buf = torch.zeros((B, NP, 3 * C), dtype=x.dtype, device=x.device)  # padded rows must be finite (zeros)
+            # padded rows must be finite (zeros): they are never written, so one zero-filled buffer per geometry serves every call
+            # (a fresh torch.zeros here was a fill kernel per layer inside the captured graph)
+            bk = (B, NP, C, x.dtype, str(x.device))
+            if getattr(self, "_qkv_buf", (None,))[0] != bk:
+                self._qkv_buf = (bk, torch.zeros((B, NP, 3 * C), dtype=x.dtype, device=x.device))
+            buf = self._qkv_buf[1]
             xp = x + pos.to(x.dtype)
             for b in range(B):
                 ops.linear_tc(xp[b], wqk, bqk, out=buf[b, :N, : 2 * C])
                 ops.linear_tc(x[b], wv, bv, out=buf[b, :N, 2 * C:])
             o = ops.attention_qkv(buf.view(B * NP, 3 * C), B, NP, nh, 64, (E // nh) ** -0.5, n_valid=N).view(B, NP, C)
-            return torch.stack([ops.linear_tc(o[b, :N], wo, bo, residual=x[b].contiguous(), out_dtype=torch.float32)
-                                for b in range(B)])
+            outs = [ops.linear_tc(o[b, :N], wo, bo, residual=x[b].contiguous(), out_dtype=torch.float32) for b in range(B)]
+            return outs[0].unsqueeze(0) if B == 1 else torch.stack(outs)
         w, b = self.attn.in_proj_weight, self.attn.in_proj_bias
         qk = F.linear(x + pos, w[: 2 * E], b[: 2 * E])
         v = F.linear(x, w[2 * E:], b[2 * E:])
@@ -204,7 +209,8 @@ class DeformableDetrTransformerEncoderVL(nn.Module):
         for i, (vl_layer, layer) in enumerate(zip(self.vl_layers, self.layers)):
             b = vl_layer.b_attn
             with torch.autocast("cuda", enabled=False):
-                ln_l = b.layer_norm_l(query_l.float())
+                ln_l = ops.layernorm(query_l.float().contiguous(), b.layer_norm_l.weight.float(), b.layer_norm_l.bias.float(),
+                                     eps=b.layer_norm_l.eps, out_dtype=torch.float32)  # own row kernel (fp32 in / out)
                 dv, qa, qc = b.single_token_language_side(ln_l)
                 shift = (b.gamma_v.float() * dv.float()).reshape(x.shape[0], -1).contiguous()  # [B, C]
             vw, vb = ops.packed(b.layer_norm_v, dt)
@@ -248,8 +254,15 @@ class DeformableDetrTransformerDecoderVL(nn.Module):
         if engine_dtype is not None and value.dtype == engine_dtype:
             output, query_pos = output.to(engine_dtype), query_pos.to(engine_dtype)
         intermediate, intermediate_ref = [], []
+        # engine: the reference-point arithmetic between two layers (inverse_sigmoid, add, sigmoid, scaling by the valid ratios:
+        # nine elementwise launches) is one kernel with the same fp32 operations in the same order (ape_ref_update)
+        fused_ref = engine_dtype is not None and self.bbox_embed is not None and reference_points.is_cuda and \
+            reference_points.shape[-1] == 4 and reference_points.dtype == torch.float32
+        next_ref_in = None
         for i, layer in enumerate(self.layers):
-            if reference_points.shape[-1] == 4:
+            if next_ref_in is not None:
+                ref_in = next_ref_in
+            elif reference_points.shape[-1] == 4:
                 ref_in = reference_points[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
             else:
                 ref_in = reference_points[:, :, None] * valid_ratios[:, None]
@@ -257,7 +270,9 @@ class DeformableDetrTransformerDecoderVL(nn.Module):
                            kwargs["level_start_index"])
             if self.bbox_embed is not None:
                 tmp = self.bbox_embed[i](output, out_dtype=torch.float32).float()
-                if reference_points.shape[-1] == 4:
+                if fused_ref:
+                    new_ref, next_ref_in = ops.ref_update(tmp, reference_points, valid_ratios)
+                elif reference_points.shape[-1] == 4:
                     new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()
                 else:
                     new_ref = tmp

@@ -558,6 +558,45 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     return nms(boxes + offsets[:, None], scores, iou_threshold)
 
 
+def ref_update(delta, ref, valid_ratios, eps=1e-3):
+    """(sigmoid(delta + inverse_sigmoid(ref)), new_ref[:, :, None] * cat(valid_ratios, valid_ratios)[:, None]) for 4-d reference
+    points (ape_ref_update): delta / ref fp32 [B,Q,4], valid_ratios fp32 [B,L,2] -> fp32 [B,Q,4], [B,Q,L,4]."""
+    _require(delta.is_cuda and delta.dtype == torch.float32 and ref.dtype == torch.float32 and delta.shape == ref.shape and
+             delta.shape[-1] == 4 and delta.dim() == 3, "ref_update: CUDA fp32 [B,Q,4] tensors")
+    B, Q, _ = delta.shape
+    L = valid_ratios.shape[1]
+    delta, ref = delta.contiguous(), ref.contiguous()
+    vr = valid_ratios.float().contiguous()
+    new_ref = torch.empty_like(delta)
+    ref_in = torch.empty((B, Q, L, 4), dtype=torch.float32, device=delta.device)
+    with torch.cuda.device(delta.device), _timed(("ref_update", B, Q, L)):
+        rc = _lib.lib.ape_ref_update(delta.data_ptr(), ref.data_ptr(), vr.data_ptr(), new_ref.data_ptr(), ref_in.data_ptr(), B, Q, L,
+                                     float(eps), _lib.current_stream_ptr())
+    _lib.check(rc, "ape_ref_update")
+    return new_ref, ref_in
+
+
+def gemv_f32(x, weight, bias=None):
+    """F.linear(x, weight, bias) in fp32 for 1..4 rows of x (ape_gemv_f32: one warp per output row); larger batches are split."""
+    _require(x.is_cuda and weight.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32, "gemv_f32: CUDA fp32 tensors")
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K).contiguous()
+    weight = weight.contiguous()
+    _require(weight.shape[1] == K and K % 4 == 0, "gemv_f32: weight [N,K], K a multiple of 4")
+    y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+    bptr = None
+    if bias is not None:
+        bias = bias.float().contiguous()
+        bptr = bias.data_ptr()
+    with torch.cuda.device(x.device), _timed(("gemv", x2.shape[0], N, K)):
+        for b0 in range(0, x2.shape[0], 4):
+            nb = min(4, x2.shape[0] - b0)
+            rc = _lib.lib.ape_gemv_f32(weight.data_ptr(), x2[b0:].data_ptr(), bptr, y[b0:].data_ptr(), nb, N, K, _lib.current_stream_ptr())
+            _lib.check(rc, "ape_gemv_f32")
+    return y.view(*x.shape[:-1], N)
+
+
 def mask_crop_and_resize(mask_logits, index, boxes, padded_hw, mask_size=128):
     """`BitMasks(F.interpolate(mask_logits[index], padded_hw, "bilinear").sigmoid() > 0.5).crop_and_resize(boxes, mask_size)`
     (deformable_detr_segm_vl.py:569-598) for the kept queries of one image: mask_logits [Q,h,w] (fp32 / fp16 / bf16, CUDA),

@@ -337,6 +337,16 @@ int ape_resample_u8(const uint8_t *src, int64_t src_pitch, uint8_t *tmp, float *
                     const int *bounds_h, const int *kk_h, int ksize_h, const int *bounds_v, const int *kk_v, int ksize_v, int H,
                     int W, int C, int new_h, int new_w, int flip_channels, void *stream);
 
+/* Decoder reference-point update (deformable_transformer_vl.py:268-300, 4-d reference points): new_ref [B,Q,4] =
+ * sigmoid(delta + inverse_sigmoid(ref, eps)) and ref_in [B,Q,L,4] = new_ref[:,:,None] * cat(valid_ratios, valid_ratios)[:,None]
+ * (valid_ratios [B,L,2]); all fp32, same operation order as the PyTorch sequence. */
+int ape_ref_update(const float *delta, const float *ref, const float *valid_ratios, float *new_ref, float *ref_in, int B, int Q,
+                   int L, float eps, void *stream);
+
+/* y[b,n] = W[n,:] . x[b,:] + bias[n] in fp32 for 1..4 input rows (the folded language-side maps of VisionLanguageFusion for one
+ * language token, ape/layers/fuse_helper.py:67-166 restructured): W [N,K] row-major, K a multiple of 4, W / x 16-byte aligned. */
+int ape_gemv_f32(const float *W, const float *x, const float *bias, float *y, int B, int N, int K, void *stream);
+
 /*
  * Instance-mask post-processing for the detections that survive the final selection (deformable_detr_segm_vl.py:569-603 and
  * detectron2 detector_postprocess / paste_masks_in_image), without the full-resolution fp32 maps:

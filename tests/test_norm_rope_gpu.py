@@ -124,3 +124,39 @@ def test_layernorm_ex(ops, dtype, second, col, row, C):
         assert torch.equal(y2, (y.float() + ra.float()).to(dtype))  # exactly `y + row_add` on the stored tensors
     else:
         assert y2 is None
+
+
+@pytest.mark.parametrize("B,N,K", [(1, 2312, 1024), (2, 1024, 2048), (4, 37, 256), (7, 300, 64)])
+def test_gemv_f32_matches_linear(B, N, K):
+    """ape_gemv_f32 (the folded language-side maps of VisionLanguageFusion) against F.linear in fp64."""
+    import ape_b200
+
+    g = torch.Generator().manual_seed(B * 1000 + N)
+    x = torch.randn(B, 1, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    n0 = ape_b200._lib.launch_count()
+    y = ape_b200.ops.gemv_f32(x, w, b)
+    assert ape_b200._lib.launch_count() - n0 == (B + 3) // 4
+    want = torch.nn.functional.linear(x.double(), w.double(), b.double()).float()
+    assert y.shape == (B, 1, N)
+    torch.testing.assert_close(y, want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ape_b200.ops.gemv_f32(x, w), want - b, rtol=1e-5, atol=1e-5)
+
+
+def test_ref_update_equals_the_pytorch_sequence_bit_for_bit():
+    """ape_ref_update against the decoder's elementwise sequence (deformable_transformer_vl.py:268-300; detrex inverse_sigmoid)."""
+    import ape_b200
+    from ape_b200.layers.common import inverse_sigmoid
+
+    g = torch.Generator().manual_seed(5)
+    B, Q, L = 2, 900, 5
+    ref = torch.rand(B, Q, 4, generator=g).cuda()
+    ref[0, :5] = torch.tensor([0.0, 1.0, 1e-4, 0.9995])  # the clamps of inverse_sigmoid bite
+    delta = (torch.randn(B, Q, 4, generator=g) * 2).cuda()
+    vr = (0.5 + 0.5 * torch.rand(B, L, 2, generator=g)).cuda()
+    new_ref, ref_in = ape_b200.ops.ref_update(delta, ref, vr)
+    want = (delta + inverse_sigmoid(ref)).sigmoid()
+    want_in = want[:, :, None] * torch.cat([vr, vr], -1)[:, None]
+    assert torch.equal(new_ref, want), (new_ref - want).abs().max().item()
+    assert torch.equal(ref_in, want_in)
