@@ -561,86 +561,6 @@ __device__ __forceinline__ void epi16_fast(const GemmParams &p, const CUtensorMa
   }
 }
 
-// 16-bit output + bias + 2-D rotary embedding on the columns below rope_cols (q and k thirds of the fused qkv projection;
-// VisionRotaryEmbeddingFast, utils_eva02.py:248-252,346) in the epilogue instead of the in-place ape_rope_qk pass (8.7 us per
-// block).  MEASURED SLOWER in the step (14.52 against 14.07 ms, profiles/r02_ab_lean.txt): every thread reads its own cos / sin row
-// (32 different 128-byte lines per warp load), +27 us per qkv GEMM — the same loss as the general epilogue showed.  Kept selectable
-// (APE_FUSED_ROPE=1); off by default.
-template <typename TO, int BN>
-__device__ __forceinline__ void epi16_rope_fast(const GemmParams &p, const CUtensorMap *map_c, uint8_t *slab, uint32_t tmem_tile,
-                                                int quad, int half, int lane, int m_blk, int n_blk, uint64_t *full_bar,
-                                                uint32_t full_phase) {
-  constexpr int HALF = BN / 2, PIECES = HALF / 32;
-  const int row0 = m_blk * BM + quad * 32;
-  const int m = min(row0 + lane, p.M - 1);
-  const int n0 = n_blk * BN + half * HALF;
-  const uint32_t trow = tmem_tile + ((uint32_t)(quad * 32) << 16) + half * HALF;
-  const uint32_t my_row = tc::smem_u32(slab) + lane * 128;
-  const uint32_t sw = lane & 7;
-  const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias + n0);
-  const int pos = p.rope_pos ? __ldg(p.rope_pos + m) : m % p.rope_npos;
-  const float4 *cos_row = reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64);
-  const float4 *sin_row = reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64);
-  tc::mbar_wait(full_bar, full_phase);
-  tc::fence_after_sync();
-  uint32_t rn[32];
-  tc::tmem_ld_32x32b_x32(trow, rn);
-#pragma unroll
-  for (int q = 0; q < PIECES; ++q) {
-    const int nq = n0 + 32 * q;
-    const bool rot = nq < p.rope_cols;  // rope_cols is a multiple of 64: whole pieces
-    const int c0 = (nq & 63) >> 2;      // float4 index inside the 64-channel head
-    float4 b[8], cs[4], sn[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = __ldg(bias4 + 8 * q + i);
-    if (rot) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { cs[i] = __ldg(cos_row + c0 + i); sn[i] = __ldg(sin_row + c0 + i); }
-    }
-    tc::tmem_ld_wait();
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rn[i]);
-    if (q + 1 < PIECES) tc::tmem_ld_32x32b_x32(trow + 32 * (q + 1), rn);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      v[4 * i] += b[i].x; v[4 * i + 1] += b[i].y; v[4 * i + 2] += b[i].z; v[4 * i + 3] += b[i].w;
-    }
-    if (rot) {
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        if (hh == 1) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cs[i] = __ldg(cos_row + c0 + 4 + i); sn[i] = __ldg(sin_row + c0 + 4 + i); }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {  // rotate_half pairs (2j, 2j+1) -> (-t[2j+1], t[2j])
-          float *w = v + 16 * hh + 4 * i;
-          const float t0 = w[0], t1 = w[1], t2 = w[2], t3 = w[3];
-          w[0] = t0 * cs[i].x - t1 * sn[i].x;
-          w[1] = t1 * cs[i].y + t0 * sn[i].y;
-          w[2] = t2 * cs[i].z - t3 * sn[i].z;
-          w[3] = t3 * cs[i].w + t2 * sn[i].w;
-        }
-      }
-    }
-    if ((q & 1) == 0) {
-      if (lane == 0) tc::tma_store_wait_read0();
-      __syncwarp();
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sts_v4(my_row + (((4 * (q & 1) + j) ^ sw) << 4), Elem<TO>::pack(v + 8 * j));
-    if (q & 1) {
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        tc::tma_store_2d(map_c, slab, n0 + 64 * (q >> 1), row0);
-        tc::tma_store_commit();
-      }
-    }
-  }
-}
-
 // SwiGLU: interleaved (gate, up) accumulator columns -> silu(gate) * up, BN/4 output columns per warp (vit_eva_clip.py:126-128);
 // STATS: per-row (sum, sum of squares) of every 64-column output slab as stored (LayerNorm fold of the next GEMM).
 template <typename TO, bool STATS, int BN>
@@ -830,9 +750,6 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmParams &p, const CUt
           return;
         }
         break;
-      case 8:  // 16-bit + bias + rotary embedding
-        if (f16) epi16_rope_fast<__half, BN>(APE_EPI_ARGS); else epi16_rope_fast<__nv_bfloat16, BN>(APE_EPI_ARGS);
-        return;
       case 4: epi32_fast<false, false, BN>(APE_EPI_ARGS); return;  // fp32 = acc + bias
       case 5: epi32_fast<true, false, BN>(APE_EPI_ARGS); return;   // + fp32 residual
       case 6: epi32_fast<true, true, BN>(APE_EPI_ARGS); return;    // + LayerNorm fold
@@ -1480,7 +1397,6 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   }();
   p.lean = 0;
   const bool al16 = ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(fuse ? fuse->ln_colsum : nullptr)) & 15) == 0;
-  if (lean_on && p.tma_store && rope && al16 && oe == 2 && bias != nullptr && residual == nullptr) p.lean = 8;
   if (lean_on && p.tma_store && !rope && al16) {
     if (oe == 2 && act == ACT_SWIGLU && bias != nullptr && bn == 256) p.lean = 3;
     else if (oe == 2 && residual == nullptr && act == ACT_NONE) p.lean = 1;

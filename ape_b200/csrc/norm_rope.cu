@@ -573,6 +573,7 @@ __global__ void __launch_bounds__(256) gemv_f32_kernel(const float *__restrict__
   if (warp >= N) return;
   const float4 *w4 = reinterpret_cast<const float4 *>(W + (size_t)warp * K);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
   for (int k = lane; k < K / 4; k += 32) {
     const float4 w = __ldg(w4 + k);
 #pragma unroll

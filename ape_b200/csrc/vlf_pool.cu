@@ -52,9 +52,9 @@ vlf_scores_kernel(const T *__restrict__ v, const float *__restrict__ qa, const f
   const float myqc = myh < NH ? qc[b * NH + myh] : 0.f;
   const int s0 = blockIdx.x * strip, s1 = min(S, s0 + strip);
   float wmax = -INFINITY;
-  for (int s = s0 + warp; s < s1; s += 8) {
-    float f[8];
-    load_row8<T>(v + ((size_t)b * S + s) * C + lane * 8, f);
+  // one token: 8 per-head partial dot products per lane, reduced over the warp by the halving butterfly; lane L ends with head
+  // myh's total
+  auto score = [&](const float *f, int s) {
     float a[kMaxHeads];
 #pragma unroll
     for (int h = 0; h < kMaxHeads; ++h) {
@@ -84,6 +84,16 @@ vlf_scores_kernel(const T *__restrict__ v, const float *__restrict__ qa, const f
     const float t = c1 + myqc;
     if ((lane & 3) == 0 && myh < NH) scores[((size_t)b * NH + myh) * S + s] = t;
     wmax = fmaxf(wmax, t);
+  };
+  // two tokens per iteration: both rows are requested before either is reduced (the loop is bound by the latency of one
+  // 512-byte row load per warp at two CTAs per SM: 32 us for the 45 MB of the 1024^2 encoder, 4.5x the HBM time)
+  for (int s = s0 + warp; s < s1; s += 16) {
+    const bool two = s + 8 < s1;  // warp-uniform
+    float f0[8], f1[8];
+    load_row8<T>(v + ((size_t)b * S + s) * C + lane * 8, f0);
+    if (two) load_row8<T>(v + ((size_t)b * S + s + 8) * C + lane * 8, f1);
+    score(f0, s);
+    if (two) score(f1, s + 8);
   }
   if ((lane & 3) == 0) s_max[warp][myh] = wmax;
   __syncthreads();
@@ -154,9 +164,8 @@ vlf_pool_kernel(const T *__restrict__ v, const float *__restrict__ scores, const
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[h][k] = 0.f;
   }
-  for (int r = warp; r < n; r += 8) {
-    float f[8], e[8];
-    load_row8<T>(v + ((size_t)b * S + s0 + r) * C + lane * 8, f);
+  auto accumulate = [&](const float *f, int r) {
+    float e[8];
     load8f(&s_e[r][0], e);
 #pragma unroll
     for (int h = 0; h < kMaxHeads; ++h) {
@@ -164,6 +173,14 @@ vlf_pool_kernel(const T *__restrict__ v, const float *__restrict__ scores, const
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[h][k] = fmaf(e[h], f[k], acc[h][k]);
     }
+  };
+  for (int r = warp; r < n; r += 16) {  // two rows in flight per warp (same fixed accumulation order: r, then r + 8)
+    const bool two = r + 8 < n;
+    float f0[8], f1[8];
+    load_row8<T>(v + ((size_t)b * S + s0 + r) * C + lane * 8, f0);
+    if (two) load_row8<T>(v + ((size_t)b * S + s0 + r + 8) * C + lane * 8, f1);
+    accumulate(f0, r);
+    if (two) accumulate(f1, r + 8);
   }
   if (lane == 0) {
 #pragma unroll

@@ -211,7 +211,9 @@ class ViT(nn.Module):
             Block(embed_dim, num_heads, mlp_ratio, norm_layer, window_size if i in window_block_indexes else 0,
                   self.rope_win if i in window_block_indexes else self.rope_glb, subln=variant_l, packed_swiglu=variant_ti)
             for i in range(depth)])
-        # RoPE in the qkv GEMM's (lean) epilogue instead of the in-place ape_rope_qk pass; APE_FUSED_ROPE=0/1 for A/B runs
+        # RoPE in the qkv GEMM's epilogue (ape_gemm_tn_rope) instead of the in-place ape_rope_qk pass: measured slower twice
+        # (+26 us per GEMM with the general epilogue, +27 us with a lean one: per-thread cos / sin rows are 32 different lines per
+        # warp load) against 8.7 us for the pass; APE_FUSED_ROPE=1 switches it on for A/B runs
         self.fused_rope = os.environ.get("APE_FUSED_ROPE", "0") == "1"
         self.engine_attention = True  # ape_attn_fwd (own tcgen05 kernel) for head_dim 64 / n % 128 == 0, else library SDPA
         # inner_attn_ln / ffn_ln folded around proj / w3 (ape_gemm_tn_fused): two LayerNorm launches and two trips of the
