@@ -491,8 +491,8 @@ class DeformableDETRSegmVL(nn.Module):
                 # the final selection (threshold, class-aware NMS, top-k: static shapes) rides in the same graph when boxes are
                 # all that is asked for; its configuration is part of the graph key
                 sel = None
-                if do_postprocess is True and not need_masks and self.static_inference_cap > 0 and self.test_topk_per_image >= 0 \
-                        and self.num_queries <= 1024:
+                if do_postprocess in (True, "packed") and not need_masks and self.static_inference_cap > 0 and \
+                        self.test_topk_per_image >= 0 and self.num_queries <= 1024:
                     ent = self.eval_dataset_entity
                     sel = (tuple(image_sizes), bool(getattr(self, "_static_overflowed", False)), float(self.test_score_thresh),
                            float(self.test_nms_thresh), int(self.test_topk_per_image), int(self.static_inference_cap),
@@ -532,8 +532,10 @@ class DeformableDETRSegmVL(nn.Module):
         mask_pred = mask_logits if need_masks else None  # [B, Q, h, w] logits of the last decoder level
         self.last_outputs["pred_masks"] = mask_pred
         mark("decode")
-        if do_postprocess == "raw":  # forward_packed: logits / boxes stay on the device, no selection here
+        if do_postprocess == "raw":  # logits / boxes stay on the device, no selection here
             return box_cls, box_pred, image_sizes
+        if do_postprocess == "packed":  # forward_packed: the selection computed INSIDE the captured graph when there is one
+            return box_cls, box_pred, image_sizes, graph_pack
         # the three branches are gated by the entity of the evaluated dataset (:575-577, :628-630, :671-673)
         ent = self.eval_dataset_entity
         instance_on = self.instance_on and not (ent and "thing" not in ent)
@@ -888,12 +890,20 @@ class DeformableDETRSegmVL(nn.Module):
         the last host-synchronised forward found appropriate; the packed rows carry the candidate count so the receiver can
         tell if that choice was wrong for an image (count > static_inference_cap on the candidate-list path)."""
         assert not (self.semantic_on or self.panoptic_on or (self.instance_on and self.test_mask_on)), "forward_packed: boxes only"
-        box_cls, box_pred, image_sizes = self.forward(batched_inputs, do_postprocess="raw")
-        pack = self._select_device(self._detector_box_cls(box_cls), box_pred, image_sizes, bool(getattr(self, "_static_overflowed", False)))
-        extra = torch.tensor([[float(h), float(w), float(inp.get("height", h)), float(inp.get("width", w))]
-                              for (h, w), inp in zip(image_sizes, batched_inputs)], dtype=torch.float32)
-        extra = extra.to(pack.device, non_blocking=True)[:, None, :].expand(-1, pack.shape[1], -1)
-        return torch.cat([pack, extra], dim=2)
+        box_cls, box_pred, image_sizes, pack = self.forward(batched_inputs, do_postprocess="packed")
+        if pack is None:  # no graph for this call (fp32 mode, phrase prompts ...): the same selection, eagerly
+            ent = self.eval_dataset_entity
+            det_cls = self._detector_box_cls(box_cls) if (self.instance_on and not (ent and "thing" not in ent)) else box_cls
+            pack = self._select_device(det_cls, box_pred, image_sizes, bool(getattr(self, "_static_overflowed", False)))
+        rows = tuple((float(h), float(w), float(inp.get("height", h)), float(inp.get("width", w)))
+                     for (h, w), inp in zip(image_sizes, batched_inputs))
+        cache = self.__dict__.setdefault("_packed_extra", {})  # the four size columns per geometry: no pageable upload per call
+        extra = cache.get((rows, str(pack.device)))
+        if extra is None:
+            if len(cache) > 64:
+                cache.clear()
+            extra = cache[(rows, str(pack.device))] = torch.tensor(rows, dtype=torch.float32).to(pack.device)
+        return torch.cat([pack, extra[:, None, :].expand(-1, pack.shape[1], -1)], dim=2)
 
     def inference(self, box_cls, box_pred, image_sizes):
         """:759-810 + fast_rcnn.py:40-95.  CUDA: the static-shape selection above (device results; bounded memory for any

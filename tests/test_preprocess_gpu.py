@@ -81,6 +81,17 @@ def test_default_predictor_equals_the_reference_pipeline_on_the_host(built):
     for a, b in zip(one_by_one, piped):
         assert torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor) and torch.equal(a.scores, b.scores)
 
+    # the shipped mode: 16-bit engine + CUDA graph; predict_batch rides the same graph (selection inside) through forward_packed
+    model.engine_dtype, model.use_cuda_graphs = torch.float16, True
+    same = [g.integers(0, 256, (45, 60, 3), dtype=np.uint8) for _ in range(5)]
+    one_by_one = [pred(im)["instances"] for im in same]
+    piped = [o["instances"] for o in pred.predict_batch(same)]
+    for a, b in zip(one_by_one, piped):
+        assert len(a) == len(b) > 0
+        assert torch.equal(a.pred_boxes.tensor, b.pred_boxes.tensor) and torch.equal(a.scores, b.scores)
+        assert torch.equal(a.pred_classes, b.pred_classes)
+    model.engine_dtype, model.use_cuda_graphs = torch.float32, False
+
     # a mask prompt rides the same transform (defaults.py:227-229); uint8 masks follow PIL's single-channel path
     mask = (g.random((45, 60)) > 0.6).astype(np.uint8) * 255
     mp = pred.preprocess(bgr, mask_prompt=mask)["mask_prompt"]
