@@ -563,11 +563,15 @@ class DeformableDETRSegmVL(nn.Module):
         for r, inp, size in zip(results, batched_inputs, image_sizes):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
             out.append({"instances": detector_postprocess(r, h, w).to("cpu")} if instance_on else {})
+        # the semantic / panoptic branches select queries with the same threshold + NMS + top-k as the instance branch; when their
+        # class logits are the instance branch's (no thing-class slicing, no "things" stuff column) the kept queries are reused
+        # instead of running the selection two more times
+        shared_keep = [r.query_index for r in results] if (instance_on and det_cls is box_cls and results is not None) else None
         if semantic_on:
-            for o, sem in zip(out, self._semantic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
+            for o, sem in zip(out, self._semantic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs, shared_keep)):
                 o["sem_seg"] = sem
         if panoptic_on:
-            for o, pan in zip(out, self._panoptic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs)):
+            for o, pan in zip(out, self._panoptic(box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs, shared_keep)):
                 o["panoptic_seg"] = pan
         mark("inference")
         if marks is not None:
@@ -743,14 +747,16 @@ class DeformableDETRSegmVL(nn.Module):
         x = x + F.interpolate(enc.to(x.dtype), size=x.shape[-2:], mode="bilinear", align_corners=False)
         return self.mask_conv(self.output_conv(x))
 
-    def _semantic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs):
+    def _semantic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs, shared_keep=None):
         """Semantic branch (:628-666, `_postprocess_semantic` :875-918): class scores of the queries that survive the
         detection NMS, softmax(sigmoid / 0.06) over classes, times the sigmoid masks at padded-image resolution."""
         name = self.dataset_names[self.eval_dataset_id] if self.dataset_names else None
         things, stuff, entity = self.dataset_stuff.get(name, (None, None, "thing"))
         sem_cls = get_stuff_score(box_cls, things or [], stuff or [], entity)
         outs = []
-        if self.semantic_post_nms:
+        if self.semantic_post_nms and shared_keep is not None and sem_cls.shape == box_cls.shape:  # plain clone of the same logits
+            keep = shared_keep
+        elif self.semantic_post_nms:
             keep = [r.query_index for r in self.inference(sem_cls, box_pred, image_sizes)]
         else:
             keep = [torch.arange(sem_cls.shape[1], device=sem_cls.device)] * sem_cls.shape[0]
@@ -781,7 +787,7 @@ class DeformableDETRSegmVL(nn.Module):
             outs.append(sem)
         return outs
 
-    def _panoptic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs):
+    def _panoptic(self, box_cls, box_pred, mask_pred, image_sizes, padded_hw, batched_inputs, shared_keep=None):
         """Panoptic branch (:671-696): queries that survive the detection NMS, merged by
         `postprocess.postprocess_panoptic` (the reference's `_postprocess_panoptic`, :919-998, without its per-segment
         host round trips).  Needs the thing / stuff split of the evaluated dataset in `self.dataset_stuff`."""
@@ -793,7 +799,9 @@ class DeformableDETRSegmVL(nn.Module):
         things, stuff, _ = self.dataset_stuff[name]
         things, stuff = list(things or []), list(stuff or [])
         thing_ids = range(len(things))  # contiguous ids of the thing classes (metadata.thing_dataset_id_to_contiguous_id.values())
-        if self.panoptic_post_nms:
+        if self.panoptic_post_nms and shared_keep is not None:
+            keep = shared_keep
+        elif self.panoptic_post_nms:
             keep = [r.query_index for r in self.inference(box_cls, box_pred, image_sizes)]
         else:
             keep = [torch.arange(box_cls.shape[1], device=box_cls.device)] * box_cls.shape[0]
