@@ -60,14 +60,7 @@ struct GemmParams {
   int stats_nslab;
   // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over an NHWC image: an m block is a conv_tw x conv_th pixel
   // tile of one image, k block kb = (filter tap kb / conv_cblks, 64-channel block kb % conv_cblks); map_a / map_c are 4-D
-  // operand kept in shared memory for GEMMs with a short K loop (K <= STAGES * 64; single-CTA kernel only).  The L2 -> SM
-  // fabric delivers ~6300 B/clk to the whole chip (~42 B/clk per SM): a 128 x 256 tile with K = 256 fetches 192 KB for 2048
-  // clocks of MMA, i.e. it is operand-fetch bound at ~4500 clocks per tile (measured 4400-4950).
-  //   1: W resident — one column block (N <= BN): the whole weight matrix is loaded once per CTA, only A tiles stream (64 KB per tile)
-  //   2: A resident — a CTA owns whole row blocks: the A rows are loaded once per row block and only W tiles stream (128 KB)
-  int resident;
   int lean;      // lean whole-tile epilogue selected on the host (epilogue_dispatch), 0 = general code only
-  int prefetch;  // bit 0: bias / column sums into L1, bit 1: residual rows into L2, one tile ahead (epilogue_prefetch)
   int conv;  // 0 = plain GEMM
   int conv_tw, conv_th, conv_tiles_x, conv_tiles_img, conv_cblks;
   // development aid (ape_gemm_set_trace): 8 clock64 stamps per CTA — 0 entry, 1 set-up done, 2 first operands landed,
@@ -86,47 +79,10 @@ struct alignas(1024) GemmSmem {
   uint8_t c[8][32 * 128];  // per epilogue warp: 32 rows x 64 16-bit columns, 128-byte swizzle (1024 B aligned)
   uint64_t full[STAGES], empty[STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
-  uint64_t res_full, res_empty;  // resident operand landed / no longer read by any MMA
   uint32_t tmem_base;
 };
 
 constexpr int kThreads = 320;
-
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-__device__ __forceinline__ float4 ldg_stream_f4(const float4 *ptr) {  // read once: keep it out of L1 (bias / column sums stay)
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
-  return r;
-}
-
-// What the epilogue of tile (m_blk, n_blk) will read from global memory, requested ahead of time by the warp that will need it
-// (rows quad*32 + lane, columns half * BN/2 ...): bias and LayerNorm column sums into L1, the residual rows into L2.  Called one
-// tile ahead (and for a CTA's first tile at kernel start, while the main loop runs), so that the accumulator wait is followed by
-// cache hits instead of dependent round trips to HBM: the epilogue tail of a one-tile CTA (proj / w3: 128 tiles on 148 SMs) was
-// 23-28 k clocks against a 10 k-clock main loop.
-template <int BN>
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams &p, int quad, int half, int lane, int m_blk, int n_blk) {
-  constexpr int HALF = BN / 2;
-  const int n0 = n_blk * BN + half * HALF;
-  if (n0 >= p.N) return;
-  const int ncols = min(HALF, p.N - n0);
-  if (p.prefetch & 1) {
-    if (lane < 4) {
-      if (p.bias != nullptr && 32 * lane < ncols) prefetch_l1(p.bias + n0 + 32 * lane);
-    } else if (lane < 8) {
-      if (p.ln_colsum != nullptr && 32 * (lane - 4) < ncols) prefetch_l1(p.ln_colsum + n0 + 32 * (lane - 4));
-    }
-  }
-  if (!(p.prefetch & 2)) return;
-  const int m = m_blk * BM + quad * 32 + lane;
-  if (p.residual != nullptr && m < p.M) {
-    const int es = p.res_dtype == APE_DTYPE_F32 ? 4 : 2;
-    const char *row = reinterpret_cast<const char *>(p.residual) + ((size_t)m * p.ldr + n0) * es;
-    for (int off = 0; off < ncols * es; off += 128) prefetch_l2(row + off);
-  }
-  if (p.ln_part != nullptr && m < p.M && half == 0) prefetch_l2(p.ln_part + (size_t)m * p.ln_nparts * 2);
-}
 
 // Activation over N accumulator values; the switch is OUTSIDE the unrolled loops (one uniform branch per chunk, not per
 // element: with the branch inside, the three-way select around the inlined erff made the ReLU epilogue 4x slower).
@@ -787,18 +743,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int m_groups = (p.m_blocks + CL - 1) / CL;
   const int num_tiles = m_groups * p.n_blocks;
   const int first = blockIdx.x / CL, stride = gridDim.x / CL;
-  const bool w_res = CL == 1 && p.resident == 1, a_res = CL == 1 && p.resident == 2;
-  // t-th tile of this CTA.  Default: tiles first, first + stride, ... of the (row group, column block) grid; A resident: the
-  // CTA owns row blocks first, first + stride, ... and walks all column blocks of one row block before the next.
+  // t-th tile of this CTA: tiles first, first + stride, ... of the (row group, column block) grid
   auto tile_at = [&](int t, int &m_blk, int &n_blk) -> bool {
-    if (a_res) {
-      const int r = t / p.n_blocks;
-      const int mb = first + r * stride;
-      if (mb >= p.m_blocks) return false;
-      m_blk = mb;
-      n_blk = t - r * p.n_blocks;
-      return true;
-    }
     const int tile = first + t * stride;
     if (tile >= num_tiles) return false;
     const int mg = p.n_fastest ? tile / p.n_blocks : tile % m_groups;
@@ -821,8 +767,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc::mbar_init(&s.tmem_full[i], 1);
       tc::mbar_init(&s.tmem_empty[i], 8);  // one arrival per epilogue warp
     }
-    tc::mbar_init(&s.res_full, 1);
-    tc::mbar_init(&s.res_empty, 1);
     tc::fence_mbar_init();
   }
   if (warp == 1) {
@@ -841,40 +785,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-      if (w_res) {  // the whole weight matrix (one column block, K <= STAGES * 64): loaded once, b[kb] = k block kb
-        tc::mbar_expect_tx(&s.res_full, (uint32_t)p.k_blocks * B_BYTES);
-        for (int kb = 0; kb < p.k_blocks; ++kb) tc::tma_load_2d(s.b[kb], &map_b, &s.res_full, kb * BK, 0);
-      }
-      int m_blk, n_blk, rows_done = 0;
+      int m_blk, n_blk;
       for (int t = 0; tile_at(t, m_blk, n_blk); ++t) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           tc::mbar_wait(&s.empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&s.full[stage], w_res ? A_BYTES : a_res ? B_BYTES : STAGE_BYTES);
+          tc::mbar_expect_tx(&s.full[stage], STAGE_BYTES);
           if (p.conv) {
             const int img = m_blk / p.conv_tiles_img, tt = m_blk - img * p.conv_tiles_img;
             const int ty = tt / p.conv_tiles_x, tx = tt - ty * p.conv_tiles_x;
             const int tap = kb / p.conv_cblks, cb = kb - tap * p.conv_cblks;
             tc::tma_load_4d(s.a[stage], &map_a, &s.full[stage], cb * BK, tx * p.conv_tw + tap % 3 - 1, ty * p.conv_th + tap / 3 - 1, img);
-          } else if (!a_res) {
+          } else {
             tc::tma_load_2d(s.a[stage], &map_a, &s.full[stage], kb * BK, m_blk * BM);
           }
           if (CL == 1) {
-            if (!w_res) tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
+            tc::tma_load_2d(s.b[stage], &map_b, &s.full[stage], kb * BK, n_blk * BN);
           } else {
             constexpr int HALF_ROWS = BN / CL;
             tc::tma_load_2d_multicast(s.b[stage] + rank * HALF_ROWS * BK * 2, &map_b, &s.full[stage], kb * BK,
                                       n_blk * BN + rank * HALF_ROWS, (uint16_t)((1u << CL) - 1));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (a_res && n_blk == 0) {
-          // A rows of this row block, a[kb] = k block kb — requested AFTER the first tile's weight blocks so that those
-          // are already on their way while the last MMAs of the previous row block still read the old rows
-          tc::mbar_wait(&s.res_empty, (rows_done & 1) ^ 1);
-          tc::mbar_expect_tx(&s.res_full, (uint32_t)p.k_blocks * A_BYTES);
-          for (int kb = 0; kb < p.k_blocks; ++kb) tc::tma_load_2d(s.a[kb], &map_a, &s.res_full, kb * BK, m_blk * BM);
-          ++rows_done;
         }
       }
     }
@@ -883,17 +814,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      if (w_res) {
-        tc::mbar_wait(&s.res_full, 0);
-        tc::fence_after_sync();
-      }
-      int m_blk, n_blk, rows_done = 0;
+      int m_blk, n_blk;
       for (int t = 0; tile_at(t, m_blk, n_blk); ++t) {
-        if (a_res && n_blk == 0) {
-          tc::mbar_wait(&s.res_full, rows_done & 1);
-          tc::fence_after_sync();
-          ++rows_done;
-        }
         tc::mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc::fence_after_sync();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -901,8 +823,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc::mbar_wait(&s.full[stage], phase);
           tc::fence_after_sync();
           if (kb == 0 && t == 0) trace_stamp(p, 2);
-          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(a_res ? s.a[kb] : s.a[stage]));
-          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(w_res ? s.b[kb] : s.b[stage]));
+          const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(s.a[stage]));
+          const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(s.b[stage]));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in the >>4 address field
@@ -914,7 +836,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc::mma_commit(&s.tmem_full[acc]);  // accumulator complete -> epilogue
-        if (a_res && n_blk == p.n_blocks - 1) tc::mma_commit(&s.res_empty);  // every MMA that reads these A rows has completed
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       trace_stamp(p, 3);
@@ -928,11 +849,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t acc = 0, acc_phase = 0;
     int m_blk = 0, n_blk = 0;
     bool have = tile_at(0, m_blk, n_blk);
-    if (have && p.tma_store) epilogue_prefetch<BN>(p, quad, half, lane, m_blk, n_blk);  // overlaps the first main loop
     for (int t = 0; have; ++t) {
       int m_next = 0, n_next = 0;
       const bool have_next = tile_at(t + 1, m_next, n_next);
-      if (have_next && p.tma_store) epilogue_prefetch<BN>(p, quad, half, lane, m_next, n_next);  // one tile ahead
       if (p.trace != nullptr && warp == 2) {  // (tracing only: the stamp needs the wait here; it is repeated below at no cost)
         tc::mbar_wait(&s.tmem_full[acc], acc_phase);
         if (lane == 0) {
@@ -1104,19 +1023,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       n_blk = p.n_fastest ? tile % p.n_blocks : tile / m_pairs;
       m_blk = mg * 2 + (int)rank;
     };
-    if (first < num_tiles && p.tma_store) {  // what the first tile's epilogue reads: requested while its main loop runs
-      int m0, n0;
-      pair_tile(first, m0, n0);
-      epilogue_prefetch<BN>(p, quad, half, lane, m0, n0);
-    }
     for (int tile = first; tile < num_tiles; tile += stride) {
       int m_blk, n_blk;
       pair_tile(tile, m_blk, n_blk);
-      if (tile + stride < num_tiles && p.tma_store) {  // one tile ahead
-        int m1, n1;
-        pair_tile(tile + stride, m1, n1);
-        epilogue_prefetch<BN>(p, quad, half, lane, m1, n1);
-      }
       if (p.tma_store) {  // these wait for the accumulator themselves, after requesting what they read from global memory
         epilogue_dispatch<BN>(p, &map_c, slab, tmem_base + acc * BN, quad, half, lane, m_blk, n_blk, &s.tmem_full[acc], acc_phase);
       } else {
@@ -1211,18 +1120,7 @@ int launch_gemm(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap 
   }
   p.n_blocks = (p.N + BN - 1) / BN;
   p.n_fastest = p.n_blocks <= 8;  // few column blocks: keep the A rows of a group hot instead of re-reading A per column block
-  // short K loop: keep one operand in shared memory (see GemmParams::resident); APE_GEMM_RESIDENT=0 switches it off (A/B runs)
-  static const int resident_mask = [] {  // bit 0: W resident, bit 1: A resident
-    const char *e = getenv("APE_GEMM_RESIDENT");
-    return e != nullptr ? atoi(e) : 0;
-  }();
-  p.resident = 0;
-  if (CL == 1 && resident_mask && !p.conv && p.k_blocks <= STAGES) {
-    if (p.n_blocks == 1 && p.m_blocks > num_sms() && (resident_mask & 1)) p.resident = 1;        // several row tiles per CTA share the weights
-    else if (p.n_blocks > 1 && p.m_blocks >= num_sms() && (resident_mask & 2)) p.resident = 2;   // a CTA keeps a row block for all its column blocks
-  }
-  int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
-  if (p.resident == 2) groups = p.m_blocks;  // work items are whole row blocks
+  const int groups = (p.m_blocks + CL - 1) / CL * p.n_blocks;
   const int max_clusters = num_sms() / CL;
   const int clusters = groups < max_clusters ? groups : max_clusters;
   cudaLaunchConfig_t cfg{};
@@ -1340,7 +1238,6 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   const bool single = (tile_n & 0x1000) != 0 || M <= BM || (auto_single && (tile_n & 0xE000) == 0);
   // kernel variant: default = cluster of 2 along M sharing the weight tile by TMA multicast (1-CTA MMA); 0x2000 = CTA-pair
   // MMA (cta_group::2, 256 x bn tiles; measured equal or slower on B200 for these shapes, kept selectable);
-  // 0x8000 = cluster of 4 along M (weight tile split four ways)
   // measured (profiles/r02_gemm_phases.jsonl): the CTA pair is the fastest variant for the long K loops (w3 4096x1024x2730:
   // 33.6 us against 37.7 single / 38.6 multicast; FFN2 87296x256x2048: 105.9 against 113.3 / 116.3)
   // with the lean epilogues (profiles/r02_gemm_phases_lean.jsonl) it also wins where a CTA has few column blocks to walk
@@ -1349,8 +1246,7 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   const int n_blocks_bn = (N + bn - 1) / bn;
   const bool auto_pair = K >= 2048 || (n_blocks_bn <= 4 && M >= 4096) || N >= 4096;
   const bool pair = !single && ((tile_n & 0x2000) != 0 || (policy == 0 && auto_pair && (tile_n & 0xC000) == 0));
-  const bool quad = !single && !pair && (tile_n & 0x8000) != 0 && M > 2 * BM;
-  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : quad ? bn / 4 : bn / 2)) return rc;
+  if (int rc = make_map(&mb, W, in_dtype, N, K, ldw, single ? bn : bn / 2)) return rc;
   GemmParams p{};
   p.C = C; p.bias = bias; p.residual = residual; p.ldc = ldc; p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
@@ -1358,11 +1254,6 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   p.k_blocks = (K + BK - 1) / BK;
   p.out_dtype = out_dtype; p.act = act; p.res_dtype = res_dtype;
   p.trace = g_gemm_trace;
-  static const int prefetch_mask = [] {
-    const char *e = getenv("APE_GEMM_PREFETCH");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  p.prefetch = prefetch_mask;
   p.idesc = tc::make_idesc_f16(BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
   // 16-bit outputs with 16-byte aligned rows leave through shared memory + TMA stores
   const int n_out = act == ACT_SWIGLU ? N / 2 : N;
@@ -1415,10 +1306,6 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   if (single) {
     if (bn == 256) return launch_gemm<256, 4, 1>(ma, mb, mc, p, st);
     return launch_gemm<128, 6, 1>(ma, mb, mc, p, st);
-  }
-  if (quad) {
-    if (bn == 256) return launch_gemm<256, 4, 4>(ma, mb, mc, p, st);
-    return launch_gemm<128, 6, 4>(ma, mb, mc, p, st);
   }
   if (bn == 256) return launch_gemm<256, 4, 2>(ma, mb, mc, p, st);
   return launch_gemm<128, 6, 2>(ma, mb, mc, p, st);

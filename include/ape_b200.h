@@ -146,7 +146,7 @@ int ape_msda_bwd(const void *value, const int64_t *spatial_shapes, const int64_t
  * act: 0 none, 1 ReLU, 2 GELU(erf), 3 SwiGLU over interleaved (gate, up) column pairs -> C is [M, N/2],
  *      4 clamp to +-50000 (VisionLanguageAlign, vision_language_align.py:49-51).
  * out_dtype: APE_DTYPE_* of C (pitch ldc elements).  tile_n: 0 = auto, or 128 / 256 (| 0x1000 single CTA, 0x4000 cluster of
- * two CTAs sharing the weight tile by TMA multicast, 0x2000 CTA-pair MMA, 0x8000 cluster of four).
+ * two CTAs sharing the weight tile by TMA multicast, 0x2000 CTA-pair MMA; 0x4000 forces the multicast cluster).
  */
 int ape_gemm_tn(const void *A, int64_t lda, const void *W, int64_t ldw, void *C, int64_t ldc, const float *bias,
                 const void *residual, int64_t ldr, int M, int N, int K, int in_dtype, int out_dtype, int act,

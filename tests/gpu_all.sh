@@ -3,7 +3,7 @@
 # the driver's sequence (smoke, suite in one process, bench, reference arm) + configs 3 / 4, CUPTI table, predictor timings,
 # ncu --set full of the attention / GEMM kernels.  Outputs land in gpurun_out/; what is kept goes to profiles/ (see its README).
 # A/B switches for whole-step comparisons (python bench.py --no-cpu-baseline --no-microbench under each): APE_PDL, APE_GEMM_POLICY,
-# APE_GEMM_LEAN, APE_GEMM_RESIDENT, APE_GEMM_PREFETCH, APE_ATTN_VARIANT, APE_MSDA_PAIR, APE_CONV3X3, APE_CONV_PAIR, APE_FUSED_ROPE.
+# APE_GEMM_LEAN, APE_ATTN_VARIANT, APE_MSDA_PAIR, APE_CONV3X3, APE_CONV_PAIR, APE_FUSED_ROPE.
 # Multi-GPU: gpurun --gpus N -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1
 #   --master-port 29517 bench.py --gpus N'.
 set -u

@@ -87,7 +87,7 @@ def test_vit_swiglu_shape_16bit_out(ops, dtype):
     assert ((pad == 9.0) | (pad == 0.0)).all()
 
 
-@pytest.mark.parametrize("tile", [128, 256, 128 | 0x1000, 256 | 0x1000, 128 | 0x2000, 256 | 0x2000, 128 | 0x8000, 256 | 0x8000])  # default: cluster of 2 (multicast); 0x1000: single CTA; 0x2000: CTA-pair MMA; 0x8000: cluster of 4
+@pytest.mark.parametrize("tile", [128, 256, 128 | 0x1000, 256 | 0x1000, 128 | 0x2000, 256 | 0x2000, 128 | 0x4000, 256 | 0x4000])  # default: per-shape policy; 0x1000: single CTA; 0x2000: CTA-pair MMA; 0x4000: cluster of 2 (TMA multicast)
 def test_tma_store_epilogue_edges(ops, tile):
     # M and N both ragged, bias + relu + residual, 16-bit output with an aligned pitch
     M, N, K = 777, 840, 192
@@ -113,7 +113,7 @@ def test_cluster_pairs_with_odd_row_block_counts(ops, M, tile):
     torch.testing.assert_close(y, ref_linear(x, w, b), rtol=2e-4, atol=2e-4)
     y1 = ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile | 0x1000)
     assert torch.equal(y, y1)  # same accumulation order with and without the cluster
-    for flag in (0x2000, 0x8000):  # CTA-pair MMA (cta_group::2) and cluster of 4
+    for flag in (0x2000, 0x4000):  # CTA-pair MMA (cta_group::2) and the multicast cluster of 2
         assert torch.equal(y, ops.linear_tc(x, w, b, out_dtype=torch.float32, tile_n=tile | flag))
 
 
@@ -245,16 +245,16 @@ def test_conv3x3_implicit_gemm_matches_conv2d(ops, dtype, B, H, W, Cin, Cout):
 
 
 @pytest.mark.parametrize("M,N,K,act,out32", [
-    (19100, 256, 256, None, False),     # W resident: one column block, 150 row tiles on 148 CTAs (second round for two of them)
-    (40000, 256, 192, "relu", False),   # W resident, 3 k blocks, several tiles per CTA, ragged last tile
-    (25000, 200, 256, None, True),      # W resident, N < tile, fp32 output + residual
-    (19000, 2048, 256, "relu", False),  # A resident: 149 row blocks x 8 column blocks (encoder FFN1 geometry)
-    (30000, 480, 256, None, False),     # A resident, ragged second column block (stacked offsets / logits projection)
-    (20000, 1024, 200, None, True),     # A resident, K not a multiple of 64, fp32 output + residual
+    (19100, 256, 256, None, False),     # one column block, 150 row tiles on 148 CTAs (second round for two of them)
+    (40000, 256, 192, "relu", False),   # 3 k blocks, several tiles per CTA, ragged last tile
+    (25000, 200, 256, None, True),      # N < tile, fp32 output + residual
+    (19000, 2048, 256, "relu", False),  # 149 row blocks x 8 column blocks (encoder FFN1 geometry)
+    (30000, 480, 256, None, False),     # ragged second column block (stacked offsets / logits projection)
+    (20000, 1024, 200, None, True),     # K not a multiple of 64, fp32 output + residual
 ])
-def test_resident_operand_schedules(ops, M, N, K, act, out32):
-    """K <= 256: one operand stays in shared memory (GemmParams::resident) — the weights when there is a single column block,
-    the A rows of a row block otherwise.  Same results as the streaming schedule, row block by row block."""
+def test_short_k_many_tiles_per_cta(ops, M, N, K, act, out32):
+    """K <= 256 with tens of tiles per CTA (the encoder's GEMMs): main loops of 2-4 k blocks back to back with the lean epilogues,
+    every row block written exactly once with its own rows."""
     dtype = torch.float16
     x = rnd(M, K + (-K) % 8, dtype=dtype, seed=11)[:, :K]
     w = rnd(N, K + (-K) % 8, dtype=dtype, seed=12, scale=K ** -0.5)[:, :K]
