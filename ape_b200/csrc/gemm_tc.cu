@@ -1300,6 +1300,7 @@ static int gemm_impl(const void *A, int64_t lda, const void *W, int64_t ldw, voi
   }
   if (pair) {
     p.idesc = tc::make_idesc_f16(2 * BM, bn, in_dtype == APE_DTYPE_BF16 ? 1 : 0);
+    // 5 stages of 32 KB: a sixth was measured slower in the step (13.68 against 13.36 ms)
     if (bn == 256) return launch_gemm_pair<256, 5>(ma, mb, mc, p, st);
     return launch_gemm_pair<128, 6>(ma, mb, mc, p, st);
   }
