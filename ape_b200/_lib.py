@@ -118,6 +118,10 @@ def _declare(lib):
     lib.ape_mask_crop.argtypes = [_vp] * 5 + [_i] * 7 + [_vp]
     lib.ape_mask_paste.restype = _i
     lib.ape_mask_paste.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp]
+    lib.ape_mask_paste_rle.restype = _i
+    lib.ape_mask_paste_rle.argtypes = [_vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp]
+    lib.ape_rle_to_string.restype = _i
+    lib.ape_rle_to_string.argtypes = [_vp, _i, _vp]
     lib.ape_resample_ksize.restype = _i
     lib.ape_resample_ksize.argtypes = [_i, _i]
     lib.ape_resample_coeffs_u8.restype = _i
@@ -169,6 +173,8 @@ EXPORTS = (
     "ape_mask_crop_workspace_bytes",
     "ape_mask_crop",
     "ape_mask_paste",
+    "ape_mask_paste_rle",
+    "ape_rle_to_string",
     "ape_resample_ksize",
     "ape_resample_coeffs_u8",
     "ape_resample_u8",

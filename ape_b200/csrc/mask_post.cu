@@ -99,7 +99,31 @@ __global__ void __launch_bounds__(256) mask_roialign_kernel(const uint32_t *__re
   out[(size_t)k * S * S + idx] = (acc / count) >= 0.5f ? 1 : 0;
 }
 
-// detectron2 _do_paste_mask: out[n, y, x] = grid_sample(mask_n, normalised (x, y) relative to box n) >= threshold
+// detectron2 _do_paste_mask for ONE output pixel: grid_sample(mask_n, normalised (x, y) relative to box b, bilinear, zeros padding,
+// align_corners = false) >= threshold.  Shared by the dense paste and the run-length kernels, so both see the same booleans.
+__device__ __forceinline__ bool paste_px(const uint8_t *__restrict__ m, const float4 &b, int S, int y, int x, float threshold) {
+  const float gy = ((float)y + 0.5f - b.y) / (b.w - b.y) * 2.f - 1.f;
+  const float iy = ((gy + 1.f) * (float)S - 1.f) / 2.f;  // grid_sampler_unnormalize, align_corners = false
+  const float fy = floorf(iy);
+  const int y_n = (int)fy, y_s = y_n + 1;
+  const float wy_s = iy - fy, wy_n = (fy + 1.f) - iy;  // (iy - iy_nw), (iy_se - iy) as ATen's grid_sampler
+  const float gx = ((float)x + 0.5f - b.x) / (b.z - b.x) * 2.f - 1.f;
+  const float ixf = ((gx + 1.f) * (float)S - 1.f) / 2.f;
+  const float fx = floorf(ixf);
+  const int x_w = (int)fx, x_e = x_w + 1;
+  const float wx_e = ixf - fx, wx_w = (fx + 1.f) - ixf;
+  float v = 0.f;
+  // isfinite: a degenerate box gives inf / nan coordinates, which grid_sample treats as out of bounds
+  if (isfinite(ixf) && isfinite(iy) && x_e >= 0 && x_w < S && y_s >= 0 && y_n < S) {
+    const bool wn = y_n >= 0, ws = y_s < S, ww = x_w >= 0, we = x_e < S;
+    if (wn && ww) v += (float)__ldg(m + y_n * S + x_w) * (wx_w * wy_n);
+    if (wn && we) v += (float)__ldg(m + y_n * S + x_e) * (wx_e * wy_n);
+    if (ws && ww) v += (float)__ldg(m + y_s * S + x_w) * (wx_w * wy_s);
+    if (ws && we) v += (float)__ldg(m + y_s * S + x_e) * (wx_e * wy_s);
+  }
+  return v >= threshold;
+}
+
 __global__ void __launch_bounds__(256) mask_paste_kernel(const uint8_t *__restrict__ masks, const float *__restrict__ boxes,
                                                          uint8_t *__restrict__ out, int S, int img_h, int img_w, float threshold) {
   pdl_prologue();
@@ -108,37 +132,83 @@ __global__ void __launch_bounds__(256) mask_paste_kernel(const uint8_t *__restri
   if (x4 >= img_w) return;
   const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
   const uint8_t *m = masks + (size_t)n * S * S;
-  const float gy = ((float)y + 0.5f - b.y) / (b.w - b.y) * 2.f - 1.f;
-  const float iy = ((gy + 1.f) * (float)S - 1.f) / 2.f;  // grid_sampler_unnormalize, align_corners = false
-  const float fy = floorf(iy);
-  const int y_n = (int)fy, y_s = y_n + 1;
-  const float wy_s = iy - fy, wy_n = (fy + 1.f) - iy;  // (iy_se - iy), (iy - iy_nw) as ATen's grid_sampler
   uint8_t r[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = x4 + i;
-    const float gx = ((float)x + 0.5f - b.x) / (b.z - b.x) * 2.f - 1.f;
-    const float ixf = ((gx + 1.f) * (float)S - 1.f) / 2.f;
-    const float fx = floorf(ixf);
-    const int x_w = (int)fx, x_e = x_w + 1;
-    const float wx_e = ixf - fx, wx_w = (fx + 1.f) - ixf;
-    float v = 0.f;
-    // isfinite: a degenerate box gives inf / nan coordinates, which grid_sample treats as out of bounds
-    if (isfinite(ixf) && isfinite(iy) && x_e >= 0 && x_w < S && y_s >= 0 && y_n < S) {
-      const bool wn = y_n >= 0, ws = y_s < S, ww = x_w >= 0, we = x_e < S;
-      if (wn && ww) v += (float)__ldg(m + y_n * S + x_w) * (wx_w * wy_n);
-      if (wn && we) v += (float)__ldg(m + y_n * S + x_e) * (wx_e * wy_n);
-      if (ws && ww) v += (float)__ldg(m + y_s * S + x_w) * (wx_w * wy_s);
-      if (ws && we) v += (float)__ldg(m + y_s * S + x_e) * (wx_e * wy_s);
-    }
-    r[i] = v >= threshold ? 1 : 0;
-  }
+  for (int i = 0; i < 4; ++i) r[i] = paste_px(m, b, S, y, x4 + i, threshold) ? 1 : 0;
   uint8_t *dst = out + ((size_t)n * img_h + y) * img_w + x4;
   if (x4 + 4 <= img_w && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
     *reinterpret_cast<uint32_t *>(dst) = (uint32_t)r[0] | ((uint32_t)r[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)r[3] << 24);
   } else {
     for (int i = 0; i < 4 && x4 + i < img_w; ++i) dst[i] = r[i];
   }
+}
+
+// ---- pasted masks as COCO run-length codes, without the dense masks -------------------------------------------------------
+// The evaluators turn every pasted mask into cocoapi's RLE right away (mask_util.encode(np.array(mask[:, :, None], order="F")),
+// ape/evaluation/{d3,refcoco}_evaluation.py:466-468 and detectron2's instances_to_coco_json for COCO / LVIS): runs of equal
+// pixels in COLUMN-major order, the first run counting zeros.  300 pasted 1024^2 masks are 314 MB of booleans to write, copy to
+// the host and scan there; their run boundaries are a few hundred kilobytes.  Two passes over (mask, column) CTAs, each pixel
+// recomputed from the 128 x 128 mask with the paste arithmetic above:
+//   pass 1  number of boundaries in the column (a pixel differs from its predecessor in column-major order; the predecessor of
+//           the first pixel of a column is the last pixel of the previous column, of the very first pixel a 0)
+//   (exclusive scan of the per-column numbers, on the caller's side)
+//   pass 2  the positions j = x * H + y of the boundaries, written in order at the column's offset.
+// Run lengths are the differences of consecutive positions (plus the leading and the trailing run).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) mask_rle_kernel(const uint8_t *__restrict__ masks, const float *__restrict__ boxes, int S,
+                                                       int img_h, int img_w, float threshold, int *__restrict__ col_count,
+                                                       const long long *__restrict__ col_offset, int *__restrict__ positions) {
+  pdl_prologue();
+  const int n = blockIdx.y, x = blockIdx.x;
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + n);
+  const uint8_t *m = masks + (size_t)n * S * S;
+  long long out0 = 0;
+  if (WRITE) out0 = col_offset[(size_t)n * img_w + x];
+  // value of the pixel before this column's first one in column-major order
+  const bool carry_in = x > 0 ? paste_px(m, b, S, img_h - 1, x - 1, threshold) : false;
+  {  // columns the box does not reach are all zeros: at most the boundary that ends a run of the previous column
+    const float gx = ((float)x + 0.5f - b.x) / (b.z - b.x) * 2.f - 1.f;
+    const float ixf = ((gx + 1.f) * (float)S - 1.f) / 2.f;
+    const float fx = floorf(ixf);
+    if (!(isfinite(ixf) && (int)fx + 1 >= 0 && (int)fx < S)) {
+      if (threadIdx.x == 0) {
+        if (WRITE) { if (carry_in) positions[out0] = x * img_h; }
+        else col_count[(size_t)n * img_w + x] = carry_in ? 1 : 0;
+      }
+      return;
+    }
+  }
+  __shared__ int s_warp[8];
+  __shared__ int s_last[8];
+  __shared__ int s_base;
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) { s_base = 0; s_carry = carry_in ? 1 : 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int y0 = 0; y0 < img_h; y0 += 256) {  // 256 rows per step, boundaries kept in row order
+    const int y = y0 + threadIdx.x;
+    const bool cur = y < img_h ? paste_px(m, b, S, y, x, threshold) : false;
+    if (lane == 31) s_last[warp] = cur ? 1 : 0;
+    __syncthreads();
+    bool prev = __shfl_up_sync(0xffffffffu, cur ? 1 : 0, 1) != 0;
+    if (lane == 0) prev = (warp == 0 ? s_carry : s_last[warp - 1]) != 0;
+    const bool flag = y < img_h && cur != prev;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (WRITE && flag) positions[out0 + before + __popc(bal & ((1u << lane) - 1))] = x * img_h + y;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_warp[w];
+      s_base += t;
+      s_carry = s_last[7];  // the step is full (y0 + 255 < img_h) whenever another step follows
+    }
+    __syncthreads();
+  }
+  if (!WRITE && threadIdx.x == 0) col_count[(size_t)n * img_w + x] = s_base;
 }
 
 }  // namespace
@@ -187,4 +257,48 @@ extern "C" int ape_mask_paste(const uint8_t *masks, const float *boxes, uint8_t 
   APE_LAUNCH(mask_paste_kernel, dim3(((img_w + 3) / 4 + 255) / 256, img_h, N), 256, 0, (cudaStream_t)stream, masks, boxes, out, S,
              img_h, img_w, threshold);
   return check_launch("mask_paste_kernel");
+}
+
+// pass 1 (positions == NULL): col_count [N, img_w] int32 <- boundaries per column; pass 2: positions <- boundary positions at
+// col_offset [N, img_w] int64 (exclusive scan of col_count over the whole [N, img_w] array).
+extern "C" int ape_mask_paste_rle(const uint8_t *masks, const float *boxes, int N, int S, int img_h, int img_w, float threshold,
+                                  int *col_count, const int64_t *col_offset, int *positions, void *stream) {
+  if (N == 0) return APE_OK;
+  if (!masks || !boxes) return fail(APE_ERR_NULL_PTR, "mask_paste_rle: null pointer");
+  if (N < 0 || N > 65535 || S <= 0 || img_h <= 0 || img_w <= 0 || (long long)img_h * img_w > 0x7fffffffLL)
+    return fail(APE_ERR_INVALID_ARG, "mask_paste_rle: bad geometry N=%d S=%d image %dx%d", N, S, img_h, img_w);
+  if (reinterpret_cast<uintptr_t>(boxes) & 15) return fail(APE_ERR_INVALID_ARG, "mask_paste_rle: boxes must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (positions == nullptr) {
+    if (!col_count) return fail(APE_ERR_NULL_PTR, "mask_paste_rle: null col_count");
+    APE_LAUNCH(mask_rle_kernel<false>, dim3(img_w, N), 256, 0, st, masks, boxes, S, img_h, img_w, threshold, col_count,
+               (const long long *)nullptr, (int *)nullptr);
+  } else {
+    if (!col_offset) return fail(APE_ERR_NULL_PTR, "mask_paste_rle: null col_offset");
+    APE_LAUNCH(mask_rle_kernel<true>, dim3(img_w, N), 256, 0, st, masks, boxes, S, img_h, img_w, threshold, (int *)nullptr,
+               (const long long *)col_offset, positions);
+  }
+  return check_launch("mask_rle_kernel");
+}
+
+// cocoapi rleToString (maskApi.c): run lengths -> the compressed ASCII string of the "counts" field (HOST function).
+// Every count from the fourth on is stored as the difference to the count two places earlier; 5 bits per character plus a
+// continuation bit, offset 48.  Returns the number of characters written (out must hold 7 * m), < 0 on bad arguments.
+extern "C" int ape_rle_to_string(const uint32_t *counts, int m, char *out) {
+  if (m < 0 || (m > 0 && (!counts || !out))) return fail(APE_ERR_INVALID_ARG, "rle_to_string: bad arguments");
+  int p = 0;
+  for (int i = 0; i < m; ++i) {
+    long long x = (long long)counts[i];
+    if (i > 2) x -= (long long)counts[i - 2];
+    bool more = true;
+    while (more) {
+      char c = (char)(x & 0x1f);
+      x >>= 5;
+      more = (c & 0x10) ? x != -1 : x != 0;
+      if (more) c |= 0x20;
+      c += 48;
+      out[p++] = c;
+    }
+  }
+  return p;
 }

@@ -123,8 +123,9 @@ def fast_rcnn_inference_single_image(boxes, scores, image_shape, score_thresh, n
     return boxes, scores, filter_inds[:, 1], filter_inds[:, 0]
 
 
-def detector_postprocess(result: Instances, out_h, out_w):
-    """detectron2 detector_postprocess for box fields: rescale, clip, drop empty boxes."""
+def detector_postprocess(result: Instances, out_h, out_w, mask_format="bitmask"):
+    """detectron2 detector_postprocess for box fields: rescale, clip, drop empty boxes.  mask_format "rle": the pasted masks leave
+    as COCO run-length codes (`pred_masks_rle`: what the evaluators turn every mask into right away) instead of [N,H,W] booleans."""
     sx, sy = out_w / result.image_size[1], out_h / result.image_size[0]
     b = result.pred_boxes.tensor.clone()
     b[:, 0::2] *= sx
@@ -134,7 +135,10 @@ def detector_postprocess(result: Instances, out_h, out_w):
     keep = ((b[:, 2] - b[:, 0]) > 0) & ((b[:, 3] - b[:, 1]) > 0)
     extra = {k: v[keep] for k, v in result.get_fields().items() if k not in ("pred_boxes", "scores", "pred_classes")}
     if "pred_masks" in extra:  # ROIMasks(pred_masks[:, 0]).to_bitmasks(boxes, H, W, 0.5): paste into the rescaled boxes
-        extra["pred_masks"] = paste_masks_in_image(extra["pred_masks"][:, 0], b[keep], (out_h, out_w), 0.5)
+        if mask_format == "rle" and extra["pred_masks"].is_cuda:
+            extra["pred_masks_rle"] = ops.paste_masks_rle(extra.pop("pred_masks")[:, 0], b[keep], (out_h, out_w), 0.5)
+        else:
+            extra["pred_masks"] = paste_masks_in_image(extra["pred_masks"][:, 0], b[keep], (out_h, out_w), 0.5)
     return Instances((out_h, out_w), pred_boxes=Boxes(b[keep]), scores=result.scores[keep],
                      pred_classes=result.pred_classes[keep], **extra)
 
@@ -275,6 +279,10 @@ class DeformableDETRSegmVL(nn.Module):
 
         self.instance_on, self.semantic_on, self.panoptic_on = instance_on, semantic_on, panoptic_on
         self.test_mask_on = test_mask_on
+        # "bitmask": `pred_masks` [N,H,W] booleans as the reference returns them; "rle": `pred_masks_rle`, COCO run-length codes
+        # computed on the device from the 128 x 128 masks (what the evaluators encode every mask into: d3_evaluation.py:466-468),
+        # 314 MB of booleans per 300 detections at 1024^2 that are never written or copied
+        self.mask_format = "bitmask"
         self.semantic_post_nms = semantic_post_nms
         self.panoptic_post_nms = panoptic_post_nms
         self.panoptic_configs = panoptic_configs if panoptic_configs is not None else {
@@ -562,7 +570,7 @@ class DeformableDETRSegmVL(nn.Module):
         out = []
         for r, inp, size in zip(results, batched_inputs, image_sizes):
             h, w = inp.get("height", size[0]), inp.get("width", size[1])
-            out.append({"instances": detector_postprocess(r, h, w).to("cpu")} if instance_on else {})
+            out.append({"instances": detector_postprocess(r, h, w, getattr(self, "mask_format", "bitmask")).to("cpu")} if instance_on else {})
         # the semantic / panoptic branches select queries with the same threshold + NMS + top-k as the instance branch; when their
         # class logits are the instance branch's (no thing-class slicing, no "things" stuff column) the kept queries are reused
         # instead of running the selection two more times

@@ -639,6 +639,55 @@ def paste_masks_in_image(masks, boxes, image_shape, threshold=0.5):
     return out.view(torch.bool)
 
 
+def rle_counts_to_string(counts):
+    """cocoapi rleToString (ape_rle_to_string, host): uint32 run lengths -> the compressed `counts` bytes of a COCO RLE."""
+    import numpy as np
+
+    c = np.ascontiguousarray(counts, dtype=np.uint32)
+    out = np.empty((7 * max(len(c), 1),), dtype=np.uint8)
+    n = int(_lib.lib.ape_rle_to_string(c.ctypes.data, len(c), out.ctypes.data))
+    _lib.check(0 if n >= 0 else n, "ape_rle_to_string")
+    return out[:n].tobytes()
+
+
+def paste_masks_rle(masks, boxes, image_shape, threshold=0.5):
+    """`[mask_util.encode(np.asfortranarray(m)) for m in paste_masks_in_image(masks, boxes, image_shape)]` without the dense
+    masks (ape_mask_paste_rle): list of {"size": [H, W], "counts": bytes} — the run boundaries of every pasted mask are found on the
+    device in column-major order (two passes over (mask, column) CTAs) and only they cross to the host."""
+    import numpy as np
+
+    N, S = masks.shape[0], masks.shape[-1]
+    H, W = int(image_shape[0]), int(image_shape[1])
+    if N == 0:
+        return []
+    _require(masks.is_cuda and masks.dim() == 3 and masks.shape[1] == S, "paste_masks_rle: CUDA masks [N,S,S]")
+    m8 = (masks.view(torch.uint8) if masks.dtype == torch.bool else (masks >= 0.5).to(torch.uint8)).contiguous()
+    boxes = boxes.to(device=masks.device, dtype=torch.float32).contiguous()
+    stream = _lib.current_stream_ptr()
+    col_count = torch.empty((N, W), dtype=torch.int32, device=masks.device)
+    with torch.cuda.device(masks.device), _timed(("mask_rle", N, H, W)):
+        rc = _lib.lib.ape_mask_paste_rle(m8.data_ptr(), boxes.data_ptr(), N, S, H, W, float(threshold), col_count.data_ptr(), None,
+                                         None, stream)
+        _lib.check(rc, "ape_mask_paste_rle")
+        csum = col_count.view(-1).to(torch.int64).cumsum(0)
+        col_offset = (csum - col_count.view(-1)).contiguous()
+        per_mask = csum.view(N, W)[:, -1].cpu()           # boundaries up to the end of every mask (the one synchronisation)
+        total = int(per_mask[-1])
+        positions = torch.empty((max(total, 1),), dtype=torch.int32, device=masks.device)
+        rc = _lib.lib.ape_mask_paste_rle(m8.data_ptr(), boxes.data_ptr(), N, S, H, W, float(threshold), None, col_offset.data_ptr(),
+                                         positions.data_ptr(), stream)
+        _lib.check(rc, "ape_mask_paste_rle")
+    pos = positions[:total].cpu().numpy().astype(np.int64)
+    ends = per_mask.numpy()
+    out, lo = [], 0
+    for n in range(N):
+        p = pos[lo:int(ends[n])]
+        lo = int(ends[n])
+        counts = np.diff(np.concatenate(([0], p, [H * W])))  # leading run of zeros, ..., trailing run
+        out.append({"size": [H, W], "counts": rle_counts_to_string(counts)})
+    return out
+
+
 _RESAMPLE_TABLES = {}
 
 

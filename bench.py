@@ -409,6 +409,9 @@ def model_bench(args, rank, local_rank, world):
     masks_on = args.workload == "ape_l_d_masks"  # BASELINE.json configs[2]: boxes + instance masks + semantic map
     if masks_on:
         model.test_mask_on, model.semantic_on = True, True
+        model.mask_format = args.mask_format  # "rle": the pasted masks leave as COCO run-length codes (what the evaluators encode them into)
+        if args.mask_format == "rle":
+            config["mask_format"] = "COCO run-length codes computed on the device (pred_masks_rle) instead of [N,H,W] booleans"
         config["workload"] = config["workload"].replace("boxes only", "boxes + instance masks (128^2 per box, pasted) + semantic map (1203 x 1024^2)")
     g = torch.Generator().manual_seed(rank)
     NIMG = 4
@@ -560,8 +563,14 @@ def model_bench(args, rank, local_rank, world):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(f"msda_fused_enc_{args.dtype}")
         inst = out[0]["instances"]
-        d2h = sum(v.tensor.numel() * 4 if hasattr(v, "tensor") else v.numel() * v.element_size()
-                  for v in inst.get_fields().values()) if world == 1 else world * 300 * 13 * 4
+        def field_bytes(v):
+            if hasattr(v, "tensor"):
+                return v.tensor.numel() * 4
+            if isinstance(v, list):  # run-length codes: the boundary positions crossed as int32, 4 bytes per run
+                return sum(4 * len(r["counts"]) for r in v)
+            return v.numel() * v.element_size()
+
+        d2h = sum(field_bytes(v) for v in inst.get_fields().values()) if world == 1 else world * 300 * 13 * 4
         line = {
             "metric": "images_per_sec", "value": world * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -627,6 +636,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4, help="ape_l_d_1536_phrase: images per step")
     ap.add_argument("--impl", default="ape_b200", choices=["ape_b200", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--mask-format", default="bitmask", choices=["bitmask", "rle"], help="ape_l_d_masks: instance masks as booleans (reference contract) or COCO RLE")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true", help="skip the config-5 ms_deform_attn microbench keys")
     ap.add_argument("--quick-microbench", action="store_true")

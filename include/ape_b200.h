@@ -363,6 +363,19 @@ int ape_mask_crop(const void *logits, const int64_t *index, const float *boxes, 
                   int Hp, int Wp, int S, int dtype, void *stream);
 int ape_mask_paste(const uint8_t *masks, const float *boxes, uint8_t *out, int N, int S, int img_h, int img_w, float threshold,
                    void *stream);
+/*
+ * The pasted masks as COCO run-length codes without ever writing the dense masks (the evaluators encode every pasted mask with
+ * cocoapi's mask_util.encode(np.array(mask[:, :, None], order="F")) right away: ape/evaluation/d3_evaluation.py:466-468,
+ * refcoco_evaluation.py:450-452, detectron2 instances_to_coco_json): runs of equal pixels in COLUMN-major order.
+ *   ape_mask_paste_rle  pass 1 (positions == NULL): col_count [N,img_w] int32 <- run boundaries per (mask, column);
+ *                       pass 2: positions <- the boundary positions x*img_h + y, in order, at col_offset [N,img_w] int64 =
+ *                       exclusive scan of col_count over the whole array.  Same pixel arithmetic as ape_mask_paste.
+ *   ape_rle_to_string   HOST: run lengths (first run = zeros) -> cocoapi's compressed "counts" string (rleToString); returns
+ *                       the number of characters (out holds up to 7 per count).
+ */
+int ape_mask_paste_rle(const uint8_t *masks, const float *boxes, int N, int S, int img_h, int img_w, float threshold,
+                       int *col_count, const int64_t *col_offset, int *positions, void *stream);
+int ape_rle_to_string(const uint32_t *counts, int m, char *out);
 
 #ifdef __cplusplus
 }

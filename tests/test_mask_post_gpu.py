@@ -81,3 +81,56 @@ def test_paste_matches_grid_sample(built, hw):
     assert frac < 1e-4
     assert torch.equal(ape_b200.ops.paste_masks_in_image(masks.float(), boxes, hw), got)  # 0 / 1 floats as detector_postprocess passes them
     assert ape_b200.ops.paste_masks_in_image(masks[:0], boxes[:0], hw).shape == (0, H, W)
+
+
+@pytest.mark.parametrize("hw", [(480, 640), (1024, 1024), (37, 53), (300, 1)])
+def test_paste_rle_decodes_to_the_dense_paste(built, hw):
+    """ape_mask_paste_rle (run boundaries found on the device, column-major) against the dense paste kernel: the decoded run-length
+    code IS the dense mask, and the code equals the oracle's encoding of it (cocoapi's rleEncode + rleToString restated)."""
+    import ape_b200
+    from oracle import rle as R
+
+    g = torch.Generator().manual_seed(7)
+    N, S = 19, 128
+    masks = (_smooth_logits(N, S, S, seed=13) > 0)
+    H, W = hw
+    c = torch.rand(N, 2, generator=g) * torch.tensor([W, H])
+    wh = torch.rand(N, 2, generator=g) * torch.tensor([W, H]) * 0.8 + 1.0
+    boxes = torch.cat([(c - wh / 2), (c + wh / 2)], 1).cuda()
+    boxes[0] = torch.tensor([0.0, 0.0, float(W), float(H)])          # the whole image
+    boxes[1] = torch.tensor([-5.0, -5.0, W + 5.0, H + 5.0])           # first and last pixel inside the mask's support
+    masks[2] = True                                                   # a solid box
+    masks[3] = False                                                  # an empty mask: a single run of zeros
+    dense = ape_b200.ops.paste_masks_in_image(masks, boxes, hw).cpu().numpy().astype("uint8")
+    rles = ape_b200.ops.paste_masks_rle(masks, boxes, hw)
+    assert len(rles) == N
+    for n in range(N):
+        assert rles[n]["size"] == [H, W]
+        assert (R.decode(rles[n]) == dense[n]).all(), f"mask {n}"
+        assert rles[n]["counts"] == R.encode(dense[n])["counts"]
+    assert rles[3]["counts"] == R.counts_to_string([H * W])
+    assert ape_b200.ops.paste_masks_rle(masks[:0], boxes[:0], hw) == []
+
+
+def test_model_returns_run_length_masks_when_asked(built):
+    """mask_format = "rle": `pred_masks_rle` of the detections decode to the `pred_masks` the default format returns."""
+    from ape_b200 import configs
+    from ape_b200.modeling import build_model
+    from oracle import rle as R
+    from oracle import synth
+
+    spec = configs.MINI
+    model = build_model(spec)
+    synth.fill_state_dict(model)
+    model = model.cuda().eval()
+    model.test_mask_on = True
+    img = synth.image(56, 64, seed=7)
+    inp = [{"image": img, "height": 112, "width": 128}]
+    want = model(inp)[0]["instances"]
+    model.mask_format = "rle"
+    got = model(inp)[0]["instances"]
+    assert len(got) == len(want) > 0 and not got.has("pred_masks")
+    assert torch.equal(got.pred_boxes.tensor, want.pred_boxes.tensor)
+    for rle, m in zip(got.pred_masks_rle, want.pred_masks):
+        assert rle["size"] == [112, 128]
+        assert (torch.from_numpy(R.decode(rle)).bool() == m.cpu()).all()
